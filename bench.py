@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched IPOfunc forward+backward LP solves per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--thr T]
+
+A "step" is one pass of the hot path over one batch of synthetic cost vectors of the Energy-scheduling
+LP (BASELINE.json configs[1]: ICON load1, standard form 172 x 1582): `x = IPOfunc(...)(c)` for B
+instances followed by the backward for dL/dc.  One process per GPU (torchrun for N > 1), instances
+sharded across ranks with no data-path collective (weak scaling: B per GPU is fixed).
+
+Prints ONE JSON line (rank 0).  `value` is whole-job LP/s with inputs resident in HBM, `e2e` the same
+through host (pinned) buffers with the copies inside the timed region, `roofline` the FP64 roofline of
+the dominant kernel with ALGORITHMIC flops (SURVEY.md §8d formula, dense m^3/3 Cholesky count), and
+`cpu_baseline` the reference's CPU path (as-executed oracle port) timed on this box's host cores.
+`--impl reference` times only that CPU path, on the same config/metric/unit.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "batched IPOfunc fwd+bwd LP solves/sec"
+UNIT = "LP/s"
+OPTS = dict(bounds=[(0.0, None)], thr=0.1, damping=1e-6, max_iter=None, pc=True, method=1)  # exp_run.py:61-63
+
+
+def energy_problem():
+    from neuripsintopt_b200.data import icon
+    A, b, G, h, F = icon.make_matrix_intopt(**icon.load1_day01())
+    return A, b, G, h, F
+
+
+def synthetic_costs(F, B, seed):
+    """P ~ U[20,120] per 48-slot day, c = P @ F^T; upstream gradient c_true/1440."""
+    rng = np.random.default_rng(seed)
+    P_true = rng.uniform(20.0, 120.0, (B, 48))
+    P_pred = P_true * np.abs(1.0 + 0.2 * rng.standard_normal((B, 48)))
+    c = np.asarray((F @ P_pred.T).T, dtype=np.float32)
+    g = np.asarray((F @ P_true.T).T / F.shape[0], dtype=np.float32)
+    return c, g
+
+
+def algorithmic_flops(info, iters_total, B, k_bwd=2):
+    """F_it = 2S + m^3/3 + 6m^2 + 20 nnz + 30 n ;  F_bw = 2S + m^3/3 + 2k m^2 + 12 nnz + 20 n."""
+    m, n, nnz, S = info["m"], info["n"], info["nnz"], info["asm_terms"]
+    f_it = 2 * S + m ** 3 / 3 + 6 * m * m + 20 * nnz + 30 * n
+    f_bw = 2 * S + m ** 3 / 3 + 2 * k_bwd * m * m + 12 * nnz + 20 * n
+    return f_it * iters_total, f_bw * B, f_it, f_bw
+
+
+def executed_flops(info, iters_total, B, k_bwd=2):
+    """Same formula with the envelope Cholesky/solve counts actually executed (reported beside the contract figure)."""
+    m, n, nnz, S = info["m"], info["n"], info["nnz"], info["asm_terms"]
+    chol, env = 2 * info["chol_macs"], info["envelope"]
+    f_it = 2 * S + chol + 3 * 4 * env + 20 * nnz + 30 * n
+    f_bw = 2 * S + chol + k_bwd * 4 * env + 12 * nnz + 20 * n
+    return f_it * iters_total + f_bw * B
+
+
+def cpu_reference_pass(A, b, G, h, c, g, count):
+    """The reference's CPU path as executed (oracle port): per instance host prep + HSD forward + float32
+    n-right-hand-side backward, BLAS threads = all host cores, like Interior/intopt_energy_mlp.py:409-432."""
+    from oracle import hsd_numpy as O
+    t0 = time.perf_counter()
+    for i in range(count):
+        O.ipofunc(c[i], g[i], A=A, b=b, G=G, h=h, bounds=OPTS["bounds"], variant="whole", thr=OPTS["thr"],
+                  max_iter=OPTS["max_iter"], damping=OPTS["damping"], asref=True)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    A, b, G, h, F = energy_problem()
+    Ad, Gd = A.toarray(), G.toarray()
+    per_step = args.ref_sample
+    c, g = synthetic_costs(F, per_step, 0)
+    for _ in range(args.warmup):
+        cpu_reference_pass(Ad, b, Gd, h, c, g, min(2, per_step))
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_reference_pass(Ad, b, Gd, h, c, g, per_step)
+    value = per_step * args.steps / t
+    cores = os.cpu_count()
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * t / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload="Energy ICON load1 LP (172x1582 standard form), thr=0.1, damping=1e-6",
+                            batch_per_step=per_step),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
+                                  sample="%d LPs per step x %d steps, serial loop, BLAS threads=all cores, "
+                                         "as-executed oracle port (float32 n-RHS backward)" % (per_step, args.steps)),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            hi = [v for v in sm if v >= 0.5 * max(sm)]
+            out = dict(sm_mhz=float(np.median(hi)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from neuripsintopt_b200 import _capi
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, args.warmup
+
+    A, b, G, h, F = energy_problem()
+    tt = lambda M: torch.as_tensor(M.toarray() if hasattr(M, "toarray") else M, dtype=torch.float32)  # noqa: E731
+    opts = dict(OPTS, thr=args.thr)
+    f = IPOfunc(tt(A), tt(b), tt(G), tt(h), check_finite=False, **opts)
+    c_np, g_np = synthetic_costs(F, B, 1000 + rank)  # every rank owns a different shard of the global batch
+    c_dev = torch.tensor(c_np, device=dev)
+    g_dev = torch.tensor(g_np, device=dev)
+    c_host = torch.tensor(c_np).pin_memory()
+    g_host = torch.tensor(g_np).pin_memory()
+    x_host = torch.empty_like(c_host).pin_memory()
+    gc_host = torch.empty_like(c_host).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        c = c_dev.detach().requires_grad_(True)
+        x = f(c)
+        x.backward(g_dev)
+        return x, c.grad
+
+    def step_e2e():
+        c = c_host.to(dev, non_blocking=True).requires_grad_(True)
+        g = g_host.to(dev, non_blocking=True)
+        x = f(c)
+        x.backward(g)
+        x_host.copy_(x.detach(), non_blocking=True)
+        gc_host.copy_(c.grad, non_blocking=True)
+
+    # ---- parity gate on the same inputs before timing (rank 0, a few instances) ----------------------
+    x, gc = step_resident()
+    torch.cuda.synchronize()
+    status, iters = IPOfunc.status()
+    iters_total = int(iters.sum().item())
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import hsd_numpy as O  # checker only
+        Ad, Gd = A.toarray(), G.toarray()
+        ex = eg = 0.0
+        for i in range(min(2, B)):
+            r = O.ipofunc(c_np[i], g_np[i], A=Ad, b=b, G=Gd, h=h, bounds=opts["bounds"], thr=opts["thr"],
+                          max_iter=opts["max_iter"], damping=opts["damping"])
+            ex = max(ex, float(np.abs(x[i].double().cpu().numpy() - r["x"]).max() / max(1.0, np.abs(r["x"]).max())))
+            eg = max(eg, float(np.linalg.norm(gc[i].double().cpu().numpy() - r["grad"]) / np.linalg.norm(r["grad"])))
+            assert int(iters[i]) == r["iters"], (int(iters[i]), r["iters"])
+        assert ex < 1e-6 and eg < 1e-5, ("parity gate failed", ex, eg)
+        parity = dict(x_rel=ex, grad_rel=eg, checked=min(2, B))
+    assert int((status != 0).sum().item()) == 0, "non-zero status words in the benchmark batch"
+
+    dp = None
+    info = None
+    from neuripsintopt_b200 import ipofunc as _ipo
+    for v in _ipo._PROBLEM_CACHE.values():
+        if hasattr(v, "info"):
+            info = v.info
+    fp64_peak = _capi.measure_fp64_peak(5) * 1e-3  # TFLOP/s, measured now on this device
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, split=False):
+        for _ in range(W):
+            step_fn()
+        barrier()
+        tot = 0.0
+        fwd_ms = bwd_ms = 0.0
+        for _ in range(K):
+            flush.zero_()  # evict L2 between timed iterations (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if split:
+                em = torch.cuda.Event(enable_timing=True)
+                c = c_dev.detach().requires_grad_(True)
+                e0.record()
+                xx = f(c)
+                em.record()
+                xx.backward(g_dev)
+                e1.record()
+                e1.synchronize()
+                fwd_ms += e0.elapsed_time(em)
+                bwd_ms += em.elapsed_time(e1)
+            else:
+                e0.record()
+                step_fn()
+                e1.record()
+                e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([tot, fwd_ms, bwd_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    tot_ms, fwd_ms, bwd_ms = timed(step_resident, split=True)
+    clocks = sampler.stop() if sampler else None
+    e2e_ms, _, _ = timed(step_e2e)
+
+    if rank == 0:
+        value = world * B * K / (tot_ms * 1e-3)
+        e2e = world * B * K / (e2e_ms * 1e-3)
+        f_fwd, f_bwd, f_it, f_bw = algorithmic_flops(info, iters_total, B)
+        ach_fwd = f_fwd / (fwd_ms / K * 1e-3) * 1e-12
+        ach_bwd = f_bwd / (bwd_ms / K * 1e-3) * 1e-12
+        ach_all = (f_fwd + f_bwd) / (tot_ms / K * 1e-3) * 1e-12
+        exe_all = executed_flops(info, iters_total, B) / (tot_ms / K * 1e-3) * 1e-12
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        n_x, n, m = c_np.shape[1], info["n"], info["m"]
+        alg_bytes = 8.0 * (8 * n + 2 * m) * B  # SURVEY §8(d) algorithmic bytes per LP
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=tot_ms / K,
+            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload="Energy ICON load1 LP (172x1582 standard form, nnz 22188), thr=%g, damping=1e-6, "
+                                 "whole (HSD) backward" % args.thr,
+                        batch_per_gpu=B, global_batch=B * world, iters_per_lp=iters_total / B,
+                        l2="flushed between timed steps (256 MB write)", parallelism="dp%d" % world),
+            e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int(c_host.numel() * 4 + g_host.numel() * 4),
+                     d2h_bytes_per_step=int(x_host.numel() * 4 + gc_host.numel() * 4)),
+            gpu_launches=2 * K,
+            roofline=dict(bound="fp64", kernel="intopt_forward_kernel", achieved=ach_fwd, peak=fp64_peak,
+                          unit="TFLOP/s", frac=ach_fwd / fp64_peak, traffic=None,
+                          peak_source="DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
+                          flops_per_iter=f_it, flops_backward=f_bw,
+                          backward=dict(kernel="intopt_backward_kernel", achieved=ach_bwd, frac=ach_bwd / fp64_peak),
+                          step=dict(achieved=ach_all, frac=ach_all / fp64_peak,
+                                    executed_achieved=exe_all, executed_frac=exe_all / fp64_peak,
+                                    note="achieved uses the contract's dense m^3/3 Cholesky count; executed_* uses the "
+                                         "envelope factorisation's real MAC count"),
+                          hbm=dict(algorithmic_bytes_per_step=alg_bytes,
+                                   achieved_gbs=alg_bytes / (tot_ms / K * 1e-3) * 1e-9, peak_gbs=hbm_peak),
+                          fwd_ms=fwd_ms / K, bwd_ms=bwd_ms / K),
+            problem=info, parity=parity, clocks=clocks)
+        if not args.no_cpu and world == 1:
+            Ad, Gd = A.toarray(), G.toarray()
+            cnt = args.ref_sample
+            cpu_reference_pass(Ad, b, Gd, h, c_np, g_np, 1)
+            t = cpu_reference_pass(Ad, b, Gd, h, c_np, g_np, cnt)
+            from oracle import hsd_numpy as O
+            t1 = time.perf_counter()
+            for i in range(cnt):
+                O.ipofunc(c_np[i], g_np[i], A=Ad, b=b, G=Gd, h=h, bounds=opts["bounds"], thr=opts["thr"],
+                          max_iter=opts["max_iter"], damping=opts["damping"])
+            t_vjp = time.perf_counter() - t1
+            line["cpu_baseline"] = dict(value=cnt / t, unit=UNIT, cores=os.cpu_count(), kind="port",
+                                        sample="%d LPs of the same batch, serial loop, BLAS threads=all cores, "
+                                               "as-executed oracle port incl. per-call host prep" % cnt,
+                                        fp64_vjp_port_value=cnt / t_vjp)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="LP instances per GPU per step")
+    ap.add_argument("--thr", type=float, default=0.1)
+    ap.add_argument("--ref-sample", type=int, default=8, help="LPs per CPU-baseline pass")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,116 @@
+/*
+ * intopt_b200 — C ABI of the B200-native differentiable interior-point LP layer.
+ *
+ * This is the drop-in boundary for the hot path of JayMan91/NeurIPSIntopt:
+ *   forward  = IPOfunc_cls.forward's solver loop, Interior/ip_model_whole.py:1385-1447
+ *              (_initialization :647, _get_delta :761, _get_step :870, _do_step :861,
+ *              _indicators :880, termination tests :1408-1423)
+ *   backward = IPOfunc_cls.backward, Interior/ip_model_whole.py:1502-1560 (mode 0, "whole") and
+ *              Interior/ip_model_alter.py:1516-1624 (mode 1, "alter")
+ * operating on the standard form  min c.x  s.t.  A x = b, x >= 0  that the reference builds on
+ * the host (_clean_inputs/_presolve/_get_Abc, :67,:918,:333) — that part stays on the host
+ * (neuripsintopt_b200/problem.py).
+ *
+ * The reference is pure Python and has no FFI; the Python binding a maintainer would add is
+ * the ctypes stub shown in INTEGRATION.md (neuripsintopt_b200/_capi.py is that stub).
+ *
+ * Conventions: plain C types only.  Pointers named *_dev are device pointers owned by the
+ * caller (PyTorch allocations) and only borrowed for the call; *_host are host pointers.
+ * All work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises
+ * the device except intopt_problem_create/destroy.  Return value: 0 = ok, <0 = error
+ * (see intopt_last_error()).  Per-instance outcomes go to status_dev[B]:
+ *   0 ok/stopped by the go test, 1 max_iter reached (:1414), 2 infeasibility/unboundedness
+ *   indicators fired (:1409-1413), 3 factorisation breakdown (:855-857,:1419), 4 non-finite c.
+ * There is no CPU fallback: every entry point fails if no CUDA device is usable.
+ */
+#ifndef INTOPT_B200_H
+#define INTOPT_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INTOPT_B200_VERSION 1
+
+typedef struct IntoptProblem IntoptProblem; /* opaque, immutable after create, one per device */
+
+/* Solver options = the IPOfunc keyword arguments that reach the loop (ip_model_whole.py:1287-1290). */
+typedef struct IntoptOpts {
+  double alpha0;      /* step damping, default 0.9995 (:1287, used at :1402) */
+  double tol;         /* termination tolerance, default 1e-8 (:1288, :1408-1410) */
+  double thr;         /* early stop: loop ends when mu <= thr (:1408); thr=None -> 0 (:1319) */
+  double damping_fwd; /* diagonal damping of A.diag(x/t).A^T: 1e-6 in whole (:774), `damping` in alter */
+  int max_iter;       /* up to max_iter+1 iterations run (:1414) */
+  int reserved;
+} IntoptOpts;
+
+/* Static facts about a problem after structure analysis (host side, no GPU needed to read). */
+typedef struct IntoptInfo {
+  int m, n, nnz;
+  int envelope;           /* doubles in the skyline (envelope) storage of chol(A D A^T) after row ordering */
+  int dense_lower;        /* m(m+1)/2, for comparison */
+  long long asm_terms;    /* S = sum over columns of nnz_k(nnz_k+1)/2: MACs to assemble A D A^T */
+  long long chol_macs;    /* MACs executed by the envelope Cholesky */
+  int smem_bytes;         /* dynamic shared memory the solver kernel requests per CTA */
+  int factor_in_smem;     /* 1 if the factor lives in shared memory, 0 if it spills to the workspace */
+  int threads;            /* CTA size */
+  int ordering;           /* 0 natural, 1 reverse Cuthill-McKee, 2 dense rows last */
+} IntoptInfo;
+
+int intopt_version(void);
+const char* intopt_last_error(void);
+
+/* Host-only structure analysis of a standard-form A (CSR, m x n).  Fills `info` and, if non-NULL,
+ * row_perm_host[m] (internal row i = original row row_perm_host[i]).  Needs no GPU. */
+int intopt_analyze(int m, int n, const int* rowptr_host, const int* colidx_host, const double* val_host,
+                   IntoptInfo* info, int* row_perm_host);
+
+/* Build the device-resident problem on the current CUDA device: CSR/CSC copies of A, row ordering,
+ * envelope layout and the gather lists that assemble A.diag(d).A^T.
+ * b_host may be NULL when every call passes b_batch_dev (per-instance right-hand sides,
+ * shortespath/shortespath.py:407-413).  flags: reserved, pass 0. */
+int intopt_problem_create(IntoptProblem** out, int m, int n, const int* rowptr_host, const int* colidx_host,
+                          const double* val_host, const double* b_host, int flags);
+int intopt_problem_destroy(IntoptProblem* p);
+int intopt_problem_info(const IntoptProblem* p, IntoptInfo* info);
+
+/* Bytes of device workspace a forward/backward call over B instances needs. */
+size_t intopt_workspace_bytes(const IntoptProblem* p, int B);
+
+/* Forward: B independent LPs sharing A.  Replaces the loop at ip_model_whole.py:1385-1447.
+ *   c_dev        B x n standard-form costs, instance stride c_stride doubles (0 = one shared c)
+ *   b_batch_dev  B x m right-hand sides, instance stride b_stride doubles (0 = one shared b), or NULL
+ *                (use the problem's b)
+ *   init_dev     optional warm start, B x (2n+m+2) in the `state` layout (init_val, :655-660), or NULL
+ *   xhat_dev     out, B x n:  x / tau  (:1441)
+ *   state_dev    out, B x (2n+m+2): x[n], y[m], t[n], tau, kappa — what forward saves for backward (:1463)
+ *   status_dev, iters_dev  out, int32[B]
+ */
+int intopt_forward(const IntoptProblem* p, int B, const double* c_dev, long long c_stride,
+                   const double* b_batch_dev, long long b_stride, const IntoptOpts* opts,
+                   const double* init_dev,
+                   double* xhat_dev, double* state_dev, int* status_dev, int* iters_dev,
+                   void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Backward: dL/dc at the saved iterate.  mode 0 = ip_model_whole.py:1502-1560 (HSD embedding, uses the
+ * un-normalised iterate), mode 1 = ip_model_alter.py:1516-1624 (log barrier, uses x/tau, t/tau).
+ *   grad_x_dev   B x nvar  upstream gradient w.r.t. the leading nvar standard-form variables
+ *   grad_c_dev   out, B x nvar  (:1555-1556: only J[:nvar,:nvar] is used)
+ *   status_dev   out, int32[B]: 0 ok, 3 factorisation breakdown
+ */
+int intopt_backward(const IntoptProblem* p, int B, int mode, double damping_bwd, int nvar,
+                    const double* state_dev, const double* c_dev, long long c_stride,
+                    const double* b_batch_dev, long long b_stride, const double* grad_x_dev,
+                    double* grad_c_dev,
+                    int* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Measured FP64 FMA throughput of the current device (GFLOP/s) with a register-resident DFMA kernel;
+ * the roofline denominator MEASURED_PEAKS.json lacks.  Synchronises the device. */
+int intopt_measure_fp64_peak(double* gflops_out, int repeats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INTOPT_B200_H */

@@ -1,0 +1,103 @@
+"""ctypes binding of the C ABI declared in include/intopt_b200.h (libintopt_b200.so).
+
+This is the reference-side stub a maintainer would add: the reference is pure
+Python with no FFI, so the binding is ctypes over plain pointers and sizes — no torch types cross the
+boundary.  There is deliberately no fallback: if the CUDA library is missing or no device is usable
+every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libintopt_b200.so")
+
+
+class IntoptOpts(ctypes.Structure):
+    _fields_ = [("alpha0", ctypes.c_double), ("tol", ctypes.c_double), ("thr", ctypes.c_double),
+                ("damping_fwd", ctypes.c_double), ("max_iter", ctypes.c_int), ("reserved", ctypes.c_int)]
+
+
+class IntoptInfo(ctypes.Structure):
+    _fields_ = [("m", ctypes.c_int), ("n", ctypes.c_int), ("nnz", ctypes.c_int), ("envelope", ctypes.c_int),
+                ("dense_lower", ctypes.c_int), ("asm_terms", ctypes.c_longlong), ("chol_macs", ctypes.c_longlong),
+                ("smem_bytes", ctypes.c_int), ("factor_in_smem", ctypes.c_int), ("threads", ctypes.c_int),
+                ("ordering", ctypes.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["intopt_version", "intopt_last_error", "intopt_analyze", "intopt_problem_create",
+           "intopt_problem_destroy", "intopt_problem_info", "intopt_workspace_bytes", "intopt_forward",
+           "intopt_backward", "intopt_measure_fp64_peak"]
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libintopt_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    script = os.path.join(_HERE, "csrc", "build.sh")
+    out = subprocess.run(["bash", script], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("nvcc build of libintopt_b200.so failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout.strip())
+    return LIB_PATH
+
+
+def lib():
+    """Load the shared library (once) and declare the prototypes of include/intopt_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libintopt_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or neuripsintopt_b200/csrc/build.sh. There is no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cd, cll, csz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_longlong, ctypes.c_size_t
+    L.intopt_version.restype = ci
+    L.intopt_last_error.restype = ctypes.c_char_p
+    L.intopt_analyze.argtypes = [ci, ci, vp, vp, vp, ctypes.POINTER(IntoptInfo), vp]
+    L.intopt_problem_create.argtypes = [ctypes.POINTER(vp), ci, ci, vp, vp, vp, vp, ci]
+    L.intopt_problem_destroy.argtypes = [vp]
+    L.intopt_problem_info.argtypes = [vp, ctypes.POINTER(IntoptInfo)]
+    L.intopt_workspace_bytes.argtypes = [vp, ci]
+    L.intopt_workspace_bytes.restype = csz
+    L.intopt_forward.argtypes = [vp, ci, vp, cll, vp, cll, ctypes.POINTER(IntoptOpts), vp, vp, vp, vp, vp, vp, csz, vp]
+    L.intopt_backward.argtypes = [vp, ci, ci, cd, ci, vp, vp, cll, vp, cll, vp, vp, vp, vp, csz, vp]
+    L.intopt_measure_fp64_peak.argtypes = [ctypes.POINTER(cd), ci]
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError here means the library and the header disagree
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().intopt_last_error()
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def analyze(csr):
+    """Host-only structure analysis of a scipy CSR matrix -> (info dict, row permutation)."""
+    import numpy as np
+    L = lib()
+    m, n = csr.shape
+    rp = np.ascontiguousarray(csr.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(csr.indices, dtype=np.int32)
+    val = np.ascontiguousarray(csr.data, dtype=np.float64)
+    info = IntoptInfo()
+    perm = np.zeros(m, dtype=np.int32)
+    check(L.intopt_analyze(m, n, rp.ctypes.data, ci.ctypes.data, val.ctypes.data, ctypes.byref(info),
+                           perm.ctypes.data), "intopt_analyze")
+    return info.as_dict(), perm
+
+
+def measure_fp64_peak(repeats=5):
+    out = ctypes.c_double(0.0)
+    check(lib().intopt_measure_fp64_peak(ctypes.byref(out), repeats), "intopt_measure_fp64_peak")
+    return out.value

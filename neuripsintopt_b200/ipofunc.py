@@ -1,0 +1,392 @@
+"""`IPOfunc` — the reference's differentiable LP layer, batched, on B200.
+
+Host-side mirror of `IPOfunc` (Interior/ip_model_whole.py:1287-1592 and Interior/ip_model_alter.py
+:1287-1655): same factory signature, same positional order `(A, b, G, h)` = (equality, rhs, inequality,
+rhs), same defaults, returns `torch.autograd.Function.apply` mapping a cost vector `c` to the solution
+`x` with a hand-written backward returning dL/dc.  Additive extensions: `c` may be `(B, n_x)` (a minibatch
+of cost vectors, solved concurrently, one CTA each) and `b` may be `(B, n_eq)` (per-instance right-hand
+sides, shortespath/shortespath.py:407-413).
+
+All arithmetic of the solver loop and of the backward runs in fp64 inside libintopt_b200.so (hand-written
+sm_100a CUDA, reached through the C ABI of include/intopt_b200.h).  PyTorch is only used for device
+memory, the current stream, and the index gathers around the call.  No CPU fallback exists: a CPU tensor
+or a missing library raises.
+
+The drivers re-create `IPOfunc(...)` for every instance (Interior/intopt_energy_mlp.py:422,
+shortespath/shortespath.py:421); the expensive part — presolve, standard form, structure analysis, the
+device-resident problem — is therefore cached on the *content* of (A, G, h, bounds), and the right-hand
+side `b` only enters through a cached linear map.
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from scipy.linalg import LinAlgError
+
+from . import _capi
+from . import problem as _problem
+
+STATUS_OK, STATUS_MAXITER, STATUS_INFEAS, STATUS_BREAKDOWN, STATUS_NONFINITE = 0, 1, 2, 3, 4
+
+_PROBLEM_CACHE: "OrderedDict[tuple, object]" = OrderedDict()
+_PROBLEM_CACHE_MAX = 16
+
+
+def clear_cache():
+    _PROBLEM_CACHE.clear()
+
+
+def _to_numpy(v):
+    if v is None:
+        return None
+    if isinstance(v, torch.Tensor):
+        v = v.detach().cpu().numpy()
+    v = np.asarray(v)
+    if v.ndim == 0 or v.shape[0] == 0:  # empty torch.Tensor() means "no such constraints" (:1300-1316)
+        return None
+    return np.ascontiguousarray(v, dtype=np.float64)
+
+
+def _digest(*arrays):
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        if a is None:
+            h.update(b"<none>")
+        else:
+            h.update(str(a.shape).encode())
+            h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class DeviceProblem:
+    """A StandardForm plus its device-resident IntoptProblem handle and index tensors (one per device)."""
+
+    def __init__(self, sf, device):
+        self.sf = sf
+        self.device = device
+        L = _capi.lib()
+        A = sf.A
+        rp = np.ascontiguousarray(A.indptr, dtype=np.int32)
+        ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+        val = np.ascontiguousarray(A.data, dtype=np.float64)
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _capi.check(L.intopt_problem_create(ctypes.byref(self.handle), sf.m, sf.n, rp.ctypes.data,
+                                                ci.ctypes.data, val.ctypes.data, None, 0),
+                        "intopt_problem_create")
+        info = _capi.IntoptInfo()
+        _capi.check(L.intopt_problem_info(self.handle, ctypes.byref(info)), "intopt_problem_info")
+        self.info = info.as_dict()
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=device)
+        kept = sf.c_src >= 0
+        cols = np.nonzero(kept)[0]
+        self.c_cols = t(cols, torch.long)                 # standard-form columns fed by user costs
+        self.c_src = t(sf.c_src[kept], torch.long)
+        self.c_sign = t(sf.c_sign[kept], torch.float64)
+        self.identity_vars = bool(sf.nvar == sf.n_x and sf.fixed_idx.size == 0)
+        self.c_plain = bool((sf.c_sign[kept] == 1).all() and cols.size == sf.nvar)
+        self.var_index = t(sf.var_index, torch.long)
+        self.fixed_idx = t(sf.fixed_idx, torch.long)
+        self.x_shift = t(sf.x_shift, torch.float64) if np.any(sf.x_shift != 0) else None
+        self.x_flip = t(sf.x_flip_ub, torch.float64) if np.isfinite(sf.x_flip_ub).any() else None
+        self.free_cols = t(sf.free_cols, torch.long) if (sf.free_cols >= 0).any() else None
+        self._ws = {}
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _capi.lib().intopt_problem_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def workspace(self, B):
+        ws = self._ws.get(B)
+        if ws is None:
+            nbytes = _capi.lib().intopt_workspace_bytes(self.handle, B)
+            ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=self.device)
+            self._ws = {B: ws}  # keep one size only
+        return ws
+
+
+def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.1, pc=True, tol=1e-8,
+                 max_iter=1000, init_val=None, method=1, mu0=None, smoothing=False, bounds=None, thr=None,
+                 new_grad=True, presolve=True, A_eq_rr=True, damping=1e-2, check_finite=True):
+    """Shared implementation behind ip_model_whole.IPOfunc / ip_model_alter.IPOfunc.
+
+    Unused upstream keywords are accepted and ignored exactly as upstream does: `beta` (only if pc=False),
+    `mu0`, `new_grad`, `A_eq_rr` are never read, `smoothing` is only logged (ip_model_whole.py:1339).
+    `check_finite` (additive): True reproduces upstream's LinAlgError on non-finite `c` (:1332-1341) at the
+    price of one device->host sync per call; False leaves it to the per-instance status word (4).
+    """
+    if variant not in ("whole", "alter"):
+        raise ValueError(variant)
+    if not pc:
+        raise NotImplementedError("pc=False (plain path-following) is not used by any reference driver")
+    if method != 1:
+        raise NotImplementedError("method 2/3 (sliced saved tensors, ip_model_whole.py:1467-1482) not implemented")
+    if not presolve:
+        raise NotImplementedError("presolve=False is not used by any reference driver")
+    A_np, b_np, G_np, h_np = _to_numpy(A), _to_numpy(b), _to_numpy(G), _to_numpy(h)
+    assert (A_np is not None or G_np is not None) and (b_np is not None or h_np is not None)  # :1209
+    if A_np is not None and b_np is None:
+        raise ValueError("A was given without b")
+    if bounds is None:  # whole :1318, alter ip_model_alter.py:1331
+        bounds = [(0.0, None)] if variant == "whole" else [(0.0, 1.0)]
+    thr_ = 0.0 if thr is None else float(thr)
+    max_iter_ = 1000 if max_iter is None else int(max_iter)
+    damping_fwd = 1e-6 if variant == "whole" else float(damping)  # :774 | ip_model_alter.py:775
+    mode = 0 if variant == "whole" else 1
+    n_x = (A_np if A_np is not None else G_np).shape[1]
+    b_batched = b_np is not None and b_np.ndim == 2
+    structure_key = _digest(A_np, G_np, h_np) + repr([tuple(bd) for bd in bounds])
+    zero_cols = _problem.zero_columns(A_np, G_np, n_x)
+    state = {"events": [], "time_ms": 0.0, "last": []}
+    b_cache = {}
+
+    def get_problem(device, sign_key):
+        """Cached DeviceProblem (or the PresolveComplete outcome) for this structure on `device`."""
+        key = (structure_key, str(device), sign_key)
+        hit = _PROBLEM_CACHE.get(key)
+        if hit is None:
+            try:
+                sf = _problem.build_standard_form(
+                    n_x, A_np, None, G_np, h_np, bounds,
+                    None if not zero_cols.size else np.asarray(sign_key, dtype=np.float64))
+                hit = DeviceProblem(sf, device)
+            except _problem.PresolveComplete as done:
+                hit = done
+            _PROBLEM_CACHE[key] = hit
+            while len(_PROBLEM_CACHE) > _PROBLEM_CACHE_MAX:
+                _PROBLEM_CACHE.popitem(last=False)
+        else:
+            _PROBLEM_CACHE.move_to_end(key)
+        return hit
+
+    def b_on_device(dp, device):
+        """Standard-form right-hand side(s) (1 or B rows, fp64) and the per-instance infeasibility mask."""
+        key = (id(dp), str(device))
+        if key not in b_cache:
+            sf = dp.sf
+            bs = np.atleast_2d(sf.b_std(b_np) if sf.n_eq_user else sf.b_const)
+            bad = sf.infeasible_mask(b_np) if sf.n_eq_user else np.zeros(1, dtype=bool)
+            fixed = np.atleast_2d(sf.fixed_values(b_np) if sf.n_eq_user else sf.fixed_const0)
+            b_cache[key] = (torch.as_tensor(np.ascontiguousarray(bs), dtype=torch.float64, device=device),
+                            bad,
+                            torch.as_tensor(np.ascontiguousarray(fixed), dtype=torch.float64, device=device))
+        return b_cache[key]
+
+    def pack_init(dp, B, device):
+        if init_val is None:
+            return None
+        sf = dp.sf
+        n, m = sf.n, sf.m
+        buf = torch.empty(B, 2 * n + m + 2, dtype=torch.float64, device=device)
+        for lo, hi, k in ((0, n, "x"), (n, n + m, "y"), (n + m, 2 * n + m, "t"), (2 * n + m, 2 * n + m + 1, "tau"),
+                          (2 * n + m + 1, 2 * n + m + 2, "kappa")):
+            v = init_val[k]
+            v = v.detach() if isinstance(v, torch.Tensor) else torch.as_tensor(np.asarray(v, dtype=np.float64))
+            buf[:, lo:hi] = v.to(device=device, dtype=torch.float64).reshape(-1, hi - lo)
+        return buf
+
+    def solve_group(dp, c2, sel):
+        """c2: (Bg, n_x) fp64 on device.  Returns x_user (Bg, n_x) fp64 and the tensors backward needs."""
+        sf = dp.sf
+        L = _capi.lib()
+        Bg = c2.shape[0]
+        device = c2.device
+        c_std = torch.zeros(Bg, sf.n, dtype=torch.float64, device=device)
+        if dp.c_plain:
+            c_std[:, :sf.nvar] = c2 if dp.identity_vars else c2[:, dp.c_src]
+        else:
+            c_std[:, dp.c_cols] = c2[:, dp.c_src] * dp.c_sign
+        b_all, bad, fixed_all = b_on_device(dp, device)
+        if b_all.shape[0] == 1:
+            b_std, b_stride, fixed = b_all, 0, fixed_all
+        else:
+            b_std = b_all if sel is None else b_all[sel].contiguous()
+            fixed = fixed_all if sel is None else fixed_all[sel]
+            b_stride = sf.m
+            if b_std.shape[0] != Bg:
+                raise ValueError("b has %d instances but c has %d" % (b_std.shape[0], Bg))
+        xhat = torch.empty(Bg, sf.n, dtype=torch.float64, device=device)
+        st = torch.empty(Bg, 2 * sf.n + sf.m + 2, dtype=torch.float64, device=device)
+        status = torch.empty(Bg, dtype=torch.int32, device=device)
+        iters = torch.empty(Bg, dtype=torch.int32, device=device)
+        ws = dp.workspace(Bg)
+        init = pack_init(dp, Bg, device)
+        opts = _capi.IntoptOpts(alpha0, tol, thr_, damping_fwd, max_iter_, 0)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _capi.check(L.intopt_forward(dp.handle, Bg, _ptr(c_std), sf.n, _ptr(b_std), b_stride, ctypes.byref(opts),
+                                     _ptr(init), _ptr(xhat), _ptr(st), _ptr(status), _ptr(iters), _ptr(ws),
+                                     ws.numel() * 8, ctypes.c_void_p(stream)), "intopt_forward")
+        # _postprocess (:1241-1285): undo substitutions, re-insert fixed variables
+        xk = xhat[:, :sf.nvar]
+        if dp.free_cols is not None:
+            neg = torch.where(dp.free_cols >= 0, xhat[:, dp.free_cols.clamp(min=0)], torch.zeros_like(xk))
+            xk = xk - neg
+        if dp.x_flip is not None:
+            xk = torch.where(torch.isnan(dp.x_flip), xk, dp.x_flip - xk)
+        if dp.x_shift is not None:
+            xk = xk + dp.x_shift
+        if dp.identity_vars:
+            x_user = xk
+        else:
+            x_user = torch.zeros(Bg, n_x, dtype=torch.float64, device=device)
+            x_user[:, dp.var_index] = xk
+            if sf.fixed_idx.size:
+                x_user[:, dp.fixed_idx] = fixed
+        if bad.any():  # presolve-infeasible instances return the presolve x (zeros) upstream (:1483-1488)
+            badsel = bad if sel is None or bad.size == 1 else bad[sel.cpu().numpy()]
+            x_user[torch.as_tensor(np.broadcast_to(badsel, (Bg,)).copy(), device=device)] = 0.0
+        return x_user, (c_std, b_std, b_stride, st, status, iters)
+
+    class IPOfunc_cls(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, c):
+            if not isinstance(c, torch.Tensor) or not c.is_cuda:
+                raise RuntimeError("IPOfunc (B200): c must be a CUDA tensor; there is no CPU fallback")
+            device = c.device
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            squeeze = c.dim() == 1
+            c2 = c.detach().reshape(-1, c.shape[-1]).double()
+            if c2.shape[1] != n_x:
+                raise ValueError("c must have %d entries per instance" % n_x)
+            if check_finite and not bool(torch.isfinite(c2).all()):
+                raise LinAlgError("c contains inf, nan, or None")  # :1332-1341
+            B = c2.shape[0]
+            if b_batched and B == 1 and b_np.shape[0] > 1:  # one shared c, per-instance b (Twitter)
+                B = b_np.shape[0]
+                c2 = c2.expand(B, -1)
+                squeeze = False
+            # group by the sign pattern of c on unconstrained columns (presolve zero-column rule, :995-1016)
+            if zero_cols.size:
+                signs = torch.sign(c2[:, torch.as_tensor(zero_cols, device=device)]).to(torch.int8).cpu().numpy()
+                keys, inverse = np.unique(signs, axis=0, return_inverse=True)
+                inverse = np.asarray(inverse).reshape(-1)
+                groups = [(tuple(int(v) for v in k), np.nonzero(inverse == gi)[0]) for gi, k in enumerate(keys)]
+            else:
+                groups = [((), None)]
+            single = len(groups) == 1
+            x_out = None if single else torch.empty(B, n_x, dtype=torch.float64, device=device)
+            saved = []
+            for sign_key, idx in groups:
+                dp = get_problem(device, sign_key)
+                sel = None if single else torch.as_tensor(idx, device=device)
+                cg = c2 if single else c2[sel]
+                if isinstance(dp, _problem.PresolveComplete):
+                    # decided in presolve: upstream returns presolve's x and saves nothing (:1483-1488);
+                    # the gradient of such instances is zero here
+                    xg = torch.as_tensor(dp.x, dtype=torch.float64, device=device).expand(cg.shape[0], -1)
+                    saved.append((None, sel, None))
+                else:
+                    xg, pack = solve_group(dp, cg.contiguous(), sel)
+                    saved.append((dp, sel, pack))
+                if single:
+                    x_out = xg
+                else:
+                    x_out[sel] = xg
+            ctx.saved = saved
+            ctx.in_shape = c.shape
+            ctx.B = B
+            ctx.in_dtype = c.dtype
+            state["last"] = saved
+            ev1.record()
+            state["events"].append((ev0, ev1))
+            out = x_out.to(c.dtype)
+            return out[0] if squeeze else out
+
+        @staticmethod
+        def backward(ctx, del_x):
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            L = _capi.lib()
+            device = del_x.device
+            B = ctx.B
+            g2 = del_x.detach().reshape(-1, n_x).double()
+            if g2.shape[0] != B:
+                g2 = g2.expand(B, -1)
+            single = len(ctx.saved) == 1
+            grad = None if single else torch.zeros(B, n_x, dtype=torch.float64, device=device)
+            for dp, sel, pack in ctx.saved:
+                if dp is None:
+                    if single:
+                        grad = torch.zeros(B, n_x, dtype=torch.float64, device=device)
+                    continue
+                sf = dp.sf
+                c_std, b_std, b_stride, st, status, iters = pack
+                gg = g2 if sel is None else g2[sel]
+                gk = (gg if dp.identity_vars else gg[:, dp.var_index]).contiguous()  # del_x[var_index] (:1518)
+                Bg = gk.shape[0]
+                gc = torch.empty(Bg, sf.nvar, dtype=torch.float64, device=device)
+                bstat = torch.empty(Bg, dtype=torch.int32, device=device)
+                ws = dp.workspace(Bg)
+                stream = torch.cuda.current_stream(device).cuda_stream
+                _capi.check(L.intopt_backward(dp.handle, Bg, mode, float(damping), sf.nvar, _ptr(st), _ptr(c_std),
+                                              sf.n, _ptr(b_std), b_stride, _ptr(gk), _ptr(gc), _ptr(bstat),
+                                              _ptr(ws), ws.numel() * 8, ctypes.c_void_p(stream)),
+                            "intopt_backward")
+                if dp.identity_vars:
+                    gfull = gc
+                else:
+                    gfull = torch.zeros(Bg, n_x, dtype=torch.float64, device=device)
+                    gfull[:, dp.var_index] = gc  # c_grad[var_index] = dc (:1559-1560)
+                if single:
+                    grad = gfull
+                else:
+                    grad[sel] = gfull
+            if len(ctx.in_shape) == 1 and B > 1:  # one shared c, per-instance b: the gradients add up
+                grad = grad.sum(dim=0)
+            ev1.record()
+            state["events"].append((ev0, ev1))
+            return grad.reshape(ctx.in_shape).to(ctx.in_dtype)
+
+    def Runtime():
+        """Accumulated device time of forward+backward in seconds (CUDA events; upstream: wall clock,
+        ip_model_whole.py:1291,1498-1499,1574-1575).  Synchronises."""
+        torch.cuda.synchronize()
+        for e0, e1 in state["events"]:
+            state["time_ms"] += e0.elapsed_time(e1)
+        state["events"] = []
+        return state["time_ms"] * 1e-3
+
+    def _last_packs():
+        return [(dp, sel, pack) for dp, sel, pack in state["last"] if dp is not None]
+
+    def status():
+        """(status, iters) int32 tensors of the last forward: 0 ok, 1 max_iter, 2 infeasible/unbounded
+        indicators, 3 factorisation breakdown, 4 non-finite c."""
+        packs = _last_packs()
+        if len(packs) == 1 and packs[0][1] is None:
+            return packs[0][2][4], packs[0][2][5]
+        raise RuntimeError("status(): the last batch was split by presolve sign patterns")
+
+    def forward_solved():
+        """Upstream always returns True (dead plumbing); here: every instance of the last
+        forward left the loop through its own `go` test.  Synchronises."""
+        return all(bool((pack[4] == 0).all()) for _, _, pack in _last_packs())
+
+    def end_vectors():
+        """Final iterate of the last forward as an `init_val` dict (upstream's raises NameError)."""
+        packs = _last_packs()
+        if len(packs) != 1 or packs[0][1] is not None:
+            raise RuntimeError("end_vectors(): the last batch was split by presolve sign patterns")
+        dp, _, pack = packs[0]
+        n, m, st = dp.sf.n, dp.sf.m, pack[3]
+        return {"x": st[:, :n], "y": st[:, n:n + m], "t": st[:, n + m:2 * n + m], "tau": st[:, 2 * n + m],
+                "kappa": st[:, 2 * n + m + 1]}
+
+    hooks = dict(Runtime=Runtime, end_vectors=end_vectors, forward_solved=forward_solved, status=status,
+                 get_problem=get_problem)
+    return IPOfunc_cls.apply, hooks

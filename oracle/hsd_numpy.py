@@ -261,16 +261,29 @@ def forward(A, b, c, alpha0=0.9995, tol=1e-8, thr=0.0, max_iter=1000, damping_fw
         M = A.dot(D.reshape(-1, 1) * A.T)  # :773
         M[np.diag_indices(m)] += damping_fwd  # :774-775
         solved = True
+        # _get_solver (:683-759): Cholesky first; on failure the reference's retry ladder (:798-822)
+        # re-solves with scipy.linalg.solve(assume_a = 'sym', then 'pos', then 'gen').
+        solver = None
         try:
-            L = sla.cho_factor(M)  # :742
+            Lc = sla.cho_factor(M)  # :742
+            solver = lambda r: sla.cho_solve(Lc, r)  # noqa: E731
         except (sla.LinAlgError, ValueError):
-            solved = False
+            for assume in ("sym", "pos", "gen"):  # :819-822
+                try:
+                    sla.solve(M, b, assume_a=assume)
+                    solver = (lambda a_: lambda r: sla.solve(M, r, assume_a=a_))(assume)
+                    break
+                except (sla.LinAlgError, ValueError):
+                    continue
+            if solver is None:
+                solved = False
         if solved:
             def sym_solve(ra, rb):  # :663-681
-                v = sla.cho_solve(L, rb + A.dot(D * ra))
+                v = solver(rb + A.dot(D * ra))
                 return D * (A.T.dot(v) - ra), v
 
-            p, q = sym_solve(c, b)  # :800
+            with np.errstate(all="ignore"):
+                p, q = sym_solve(c, b)  # :800
             if not (np.isfinite(p).all() and np.isfinite(q).all()):
                 solved = False
         if solved:

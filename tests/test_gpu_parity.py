@@ -1,0 +1,205 @@
+"""GPU parity tests: the CUDA path (through IPOfunc -> C ABI -> sm_100a kernels) against the CPU oracle and
+against the reference's own outputs (tests/golden).  Tolerances are BASELINE.json's: relative 1e-6 on x*
+and the objective, 1e-5 on dL/dc (both against the fp64 oracle); iteration counts must be equal for
+early-stopped runs (thr > 0) and may differ by one for converged runs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hsd_numpy as O
+from tests import golden_util as GU
+
+pytestmark = pytest.mark.gpu
+
+X_TOL = 1e-6
+G_TOL = 1e-5
+
+
+def _relinf(a, b):
+    return np.abs(a - b).max() / max(1.0, np.abs(b).max())
+
+
+def _rel2(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _module(variant):
+    from neuripsintopt_b200 import ip_model_alter, ip_model_whole
+    return ip_model_whole if variant == "whole" else ip_model_alter
+
+
+def _tt(v):
+    return torch.Tensor() if v is None else torch.as_tensor(np.asarray(v), dtype=torch.float32)
+
+
+def _run_gpu(variant, kw, inp, c, g):
+    mod = _module(variant)
+    ct = torch.tensor(np.asarray(c), dtype=torch.float32, device="cuda", requires_grad=True)
+    f = mod.IPOfunc(_tt(inp["A"]), _tt(inp["b"]), _tt(inp["G"]), _tt(inp["h"]), **kw)
+    x = f(ct)
+    (x * torch.tensor(np.asarray(g), dtype=torch.float32, device="cuda")).sum().backward()
+    torch.cuda.synchronize()
+    status, iters = mod.IPOfunc.status()
+    end = {k: v.cpu().numpy() for k, v in mod.IPOfunc.end_vectors().items()}
+    return (x.detach().cpu().numpy().astype(np.float64), ct.grad.cpu().numpy().astype(np.float64),
+            status.cpu().numpy(), iters.cpu().numpy(), end)
+
+
+def _check_case(name, z, case, batched_inp, per_instance_inp):
+    kw = dict(case["kw"])
+    variant = case["variant"]
+    thr = kw.get("thr") or 0.0
+    damping = kw.get("damping", 1e-2)
+    k = len(case["c"])
+    if batched_inp is not None:
+        xs, gs, status, iters, end = _run_gpu(variant, kw, batched_inp, case["c"], case["g"])
+    else:
+        outs = [_run_gpu(variant, kw, per_instance_inp(i), case["c"][i], case["g"][i]) for i in range(k)]
+        xs = np.stack([o[0] for o in outs])
+        gs = np.stack([o[1] for o in outs])
+        iters = np.concatenate([o[3] for o in outs])
+        end = {kk: np.concatenate([o[4][kk] for o in outs]) for kk in outs[0][4]}
+    for i in range(k):
+        inp = per_instance_inp(i)
+        r = O.ipofunc(case["c"][i], case["g"][i], variant=variant, bounds=kw.get("bounds"), thr=kw.get("thr"),
+                      max_iter=kw.get("max_iter", 1000), damping=damping, **inp)
+        sf = r["sf"]
+        # x* and objective
+        assert _relinf(xs[i], r["x"]) < X_TOL, (name, variant, thr, i, _relinf(xs[i], r["x"]))
+        c64 = case["c"][i].astype(np.float64)
+        assert abs(c64 @ xs[i] - c64 @ r["x"]) <= X_TOL * max(1.0, abs(c64 @ r["x"])), (name, i)
+        # the reference's own float32 output
+        assert _relinf(xs[i], case["x"][i].astype(np.float64)) < 5e-6, (name, i)
+        if thr > 0:
+            assert iters[i] == r["iters"] == case["iters"][i], (name, i, iters[i], r["iters"])
+            assert _rel2(gs[i], r["grad"]) < G_TOL, (name, variant, thr, i, _rel2(gs[i], r["grad"]))
+        else:
+            assert abs(int(iters[i]) - r["iters"]) <= 1, (name, i, iters[i], r["iters"])
+            # converged runs: the gradient is a 0/0-type function of the last iterate (mu ~ 1e-13), so the
+            # backward kernel is checked against the oracle backward evaluated at the SAME (GPU) iterate
+            st = dict(x=end["x"][i], y=end["y"][i], t=end["t"][i], tau=float(end["tau"][i]),
+                      kappa=float(end["kappa"][i]))
+            fn = O.backward_whole if variant == "whole" else O.backward_alter
+            dc = fn(sf["A"], sf["b"], sf["c"], st, case["g"][i].astype(np.float64)[sf["var_index"]], damping,
+                    sf["nvar"])
+            assert _rel2(gs[i][sf["var_index"]], dc) < 1e-4, (name, variant, i, _rel2(gs[i][sf["var_index"]], dc))
+
+
+@pytest.mark.parametrize("name", ["energy_load1", "dense_m16", "dense_m64"])
+def test_shared_problem_batches(name):
+    z = GU.load(name)
+    inp = GU.problem_inputs(name, z, 0)
+    for case in GU.cases(z):
+        _check_case(name, z, case, inp, lambda i: inp)
+
+
+def test_twitter_per_instance_b():
+    z = GU.load("twitter_sp")
+    for case in GU.cases(z):
+        k = len(case["c"])
+        A = GU.problem_inputs("twitter_sp", z, 0)["A"]
+        batched = dict(A=A, b=z["b_rr"][:k], G=None, h=None)
+        _check_case("twitter_sp", z, case, batched, lambda i: GU.problem_inputs("twitter_sp", z, i))
+
+
+def test_knapsack_per_instance_A():
+    z = GU.load("knapsack")
+    for case in GU.cases(z):
+        _check_case("knapsack", z, case, None, lambda i: GU.problem_inputs("knapsack", z, i))
+
+
+def test_one_dimensional_c_and_dtype():
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = GU.load("dense_m16")
+    case = GU.cases(z)[0]
+    f = IPOfunc(_tt(z["A"]), _tt(z["b"]), torch.Tensor(), torch.Tensor(), **case["kw"])
+    c1 = torch.tensor(case["c"][0], device="cuda", requires_grad=True)
+    x1 = f(c1)
+    assert x1.shape == c1.shape and x1.dtype == torch.float32
+    x1.sum().backward()
+    assert c1.grad.shape == c1.shape
+    cb = torch.tensor(case["c"], device="cuda", dtype=torch.float64)
+    xb = f(cb)
+    assert xb.dtype == torch.float64
+    np.testing.assert_allclose(xb[0].cpu().numpy(), x1.detach().double().cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_error_conventions():
+    from scipy.linalg import LinAlgError
+
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = GU.load("dense_m16")
+    case = GU.cases(z)[0]
+    f = IPOfunc(_tt(z["A"]), _tt(z["b"]), torch.Tensor(), torch.Tensor(), **case["kw"])
+    with pytest.raises(RuntimeError):
+        f(torch.tensor(case["c"][0]))  # CPU tensor: no fallback
+    bad = torch.tensor(case["c"][0], device="cuda")
+    bad[3] = float("nan")
+    with pytest.raises(LinAlgError):
+        f(bad)  # ip_model_whole.py:1332-1341
+    f2 = IPOfunc(_tt(z["A"]), _tt(z["b"]), torch.Tensor(), torch.Tensor(), check_finite=False, **case["kw"])
+    cb = torch.tensor(case["c"], device="cuda")
+    cb[1, 2] = float("inf")
+    f2(cb)
+    status, _ = IPOfunc.status()
+    assert status.cpu().tolist() == [0, 4]
+
+
+def test_batch_position_independence():
+    """Instances are independent: the same LP gives bitwise identical results wherever it sits in a batch
+    (this is what makes 1-GPU and N-GPU shards agree exactly)."""
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = GU.load("energy_load1")
+    inp = GU.problem_inputs("energy_load1", z, 0)
+    case = GU.cases(z)[0]
+    f = IPOfunc(_tt(inp["A"]), _tt(inp["b"]), _tt(inp["G"]), _tt(inp["h"]), **case["kw"])
+    rng = np.random.default_rng(1)
+    P = rng.uniform(20, 120, (37, 48))
+    F = GU.dense(z, "F")
+    c = torch.tensor((P @ F.T).astype(np.float32), device="cuda")
+    xa = f(c)
+    perm = torch.randperm(37, device="cuda")
+    xb = f(c[perm])
+    assert torch.equal(xa[perm], xb)
+    xc = f(c[5:6])
+    assert torch.equal(xc[0], xa[5])
+
+
+def test_converged_energy_matches_highs():
+    from scipy.optimize import linprog
+
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = GU.load("energy_load1")
+    inp = GU.problem_inputs("energy_load1", z, 0)
+    F = GU.dense(z, "F")
+    P = z["price_days"][:8].astype(np.float64)
+    c = (P @ F.T).astype(np.float32)
+    f = IPOfunc(_tt(inp["A"]), _tt(inp["b"]), _tt(inp["G"]), _tt(inp["h"]), bounds=[(0.0, None)], thr=None,
+                damping=1e-6)
+    x = f(torch.tensor(c, device="cuda")).double().cpu().numpy()
+    for i in range(0, 8, 3):
+        hs = linprog(c[i].astype(np.float64), A_ub=inp["G"], b_ub=inp["h"], A_eq=inp["A"], b_eq=inp["b"],
+                     bounds=(0, None), method="highs")
+        assert abs(c[i].astype(np.float64) @ x[i] - hs.fun) <= 1e-6 * abs(hs.fun)
+        assert np.abs(inp["A"] @ x[i] - inp["b"]).max() < 1e-5
+        assert (inp["G"] @ x[i] - inp["h"]).max() < 1e-5
+
+
+def test_warm_start_roundtrip():
+    """end_vectors() -> init_val continues from the saved iterate (upstream's end_vectors is broken)."""
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = GU.load("dense_m64")
+    case = GU.cases(z)[0]
+    A, b = _tt(z["A"]), _tt(z["b"])
+    c = torch.tensor(case["c"], device="cuda")
+    kw = dict(case["kw"])
+    kw["thr"] = 0.1
+    IPOfunc(A, b, torch.Tensor(), torch.Tensor(), **kw)(c)
+    init = {k: v.clone() for k, v in IPOfunc.end_vectors().items()}
+    kw["thr"] = None
+    x_cold = IPOfunc(A, b, torch.Tensor(), torch.Tensor(), **kw)(c)
+    _, it_cold = IPOfunc.status()
+    x_warm = IPOfunc(A, b, torch.Tensor(), torch.Tensor(), init_val=init, **kw)(c)
+    _, it_warm = IPOfunc.status()
+    assert (it_warm < it_cold).all()
+    np.testing.assert_allclose(x_warm.cpu().numpy(), x_cold.cpu().numpy(), rtol=1e-4, atol=1e-5)

@@ -1,0 +1,106 @@
+"""CPU tests of the host side: presolve/standard form (neuripsintopt_b200/problem.py) against the
+reference's own standard forms (tests/golden) and against the oracle restatement on random LPs."""
+import numpy as np
+import pytest
+
+from neuripsintopt_b200 import problem as PR
+from oracle import hsd_numpy as O
+from tests import golden_util as GU
+
+f32 = lambda v: None if v is None else np.asarray(v, np.float32).astype(np.float64)  # noqa: E731
+
+
+def _build(name, z, case, b=True):
+    inp = GU.problem_inputs(name, z, 0)
+    n_x = case["c"].shape[1]
+    zc = PR.zero_columns(f32(inp["A"]), f32(inp["G"]), n_x)
+    sgn = np.sign(case["c"][0].astype(np.float64)[zc])
+    sf = PR.build_standard_form(n_x, f32(inp["A"]), f32(inp["b"]) if b else None, f32(inp["G"]), f32(inp["h"]),
+                                case["kw"].get("bounds"), sgn)
+    return sf, inp
+
+
+@pytest.mark.parametrize("name", GU.ALL)
+def test_standard_form_equals_reference(name):
+    z = GU.load(name)
+    case = GU.cases(z)[0]
+    sf, _ = _build(name, z, case)
+    np.testing.assert_array_equal(sf.A.toarray(), GU.dense(z, "stdA"))
+    np.testing.assert_array_equal(sf.b, z["std_b"])
+    c = case["c"][0].astype(np.float64)
+    c_std = np.where(sf.c_src >= 0, c[np.maximum(sf.c_src, 0)] * sf.c_sign, 0.0)
+    np.testing.assert_array_equal(c_std, z["std_c"])
+
+
+def test_per_instance_b_is_a_linear_map():
+    z = GU.load("twitter_sp")
+    case = GU.cases(z)[0]
+    sf, inp = _build("twitter_sp", z, case, b=False)
+    assert sf.b is None
+    bb = sf.b_std(f32(z["b_rr"]))
+    assert bb.shape == (len(z["b_rr"]), sf.m)
+    for i in range(len(z["b_rr"])):
+        ref = O.standard_form(case["c"][i].astype(np.float64), f32(inp["A"]), f32(z["b_rr"][i]),
+                              bounds=case["kw"]["bounds"])
+        np.testing.assert_allclose(bb[i], ref["b"], rtol=0, atol=1e-15)
+        np.testing.assert_array_equal(sf.fixed_idx, ref["fixed_idx"])
+        np.testing.assert_allclose(sf.fixed_values(f32(z["b_rr"][i])), ref["fixed_val"], atol=1e-15)
+    assert not sf.infeasible_mask(f32(z["b_rr"])).any()
+
+
+def test_zero_column_rule_depends_on_sign_of_c():
+    # ip_model_whole.py:995-1016 — Twitter's A has one unconstrained column
+    z = GU.load("twitter_sp")
+    case = GU.cases(z)[0]
+    inp = GU.problem_inputs("twitter_sp", z, 0)
+    n_x = case["c"].shape[1]
+    zc = PR.zero_columns(f32(inp["A"]), None, n_x)
+    assert zc.tolist() == [1852]
+    pos = PR.build_standard_form(n_x, f32(inp["A"]), f32(inp["b"]), None, None, [(0.0, None)], [1.0])
+    zero = PR.build_standard_form(n_x, f32(inp["A"]), f32(inp["b"]), None, None, [(0.0, None)], [0.0])
+    assert pos.n + 1 == zero.n and 1852 in pos.fixed_idx and 1852 not in zero.fixed_idx
+    with pytest.raises(PR.PresolveComplete) as e:  # c<0 and no upper bound: unbounded, status 3
+        PR.build_standard_form(n_x, f32(inp["A"]), f32(inp["b"]), None, None, [(0.0, None)], [-1.0])
+    assert e.value.status == 3
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_lps_match_oracle_restatement(seed):
+    """Mixed bounds (finite, one-sided below, free), inequality + equality rows, a singleton row."""
+    rng = np.random.default_rng(seed)
+    n, me, mu = 9, 3, 4
+    A = rng.integers(-2, 3, (me, n)).astype(float)
+    A[0] = 0
+    A[0, 2] = 2.0  # singleton equality row fixes x2
+    G = rng.integers(-2, 3, (mu, n)).astype(float)
+    G[1] = 0
+    G[1, 4] = -1.0  # singleton inequality row: lower bound on x4
+    b = rng.uniform(0.5, 2.0, me)
+    h = rng.uniform(1.0, 3.0, mu)
+    bounds = [(0, None), (0, 2.0), (0, 3), (None, 5.0), (-1.0, None), (None, None), (1.0, 4.0), (0, None), (None, None)]
+    c = rng.standard_normal(n)
+    ref = O.standard_form(c, A, b, G, h, bounds)
+    zc = PR.zero_columns(A, G, n)
+    sf = PR.build_standard_form(n, A, b, G, h, bounds, np.sign(c[zc]))
+    assert not ref["complete"]
+    np.testing.assert_allclose(sf.A.toarray(), ref["A"], atol=0)
+    np.testing.assert_allclose(sf.b, ref["b"], atol=1e-14)
+    c_std = np.where(sf.c_src >= 0, c[np.maximum(sf.c_src, 0)] * sf.c_sign, 0.0)
+    np.testing.assert_allclose(c_std, ref["c"], atol=0)
+    np.testing.assert_array_equal(sf.var_index, ref["var_index"])
+    np.testing.assert_allclose(sf.fixed_const, ref["fixed_val"], atol=1e-15)
+
+
+def test_presolve_outcomes():
+    with pytest.raises(PR.PresolveComplete) as e:  # zero row, non-zero rhs (:957-970)
+        PR.build_standard_form(3, np.array([[0.0, 0, 0], [1, 1, 1]]), np.array([1.0, 1.0]))
+    assert e.value.status == 2
+    with pytest.raises(PR.PresolveComplete) as e:  # singleton row outside the bounds (:1026-1034)
+        PR.build_standard_form(3, np.array([[1.0, 0, 0], [1, 1, 1]]), np.array([-1.0, 1.0]))
+    assert e.value.status == 2
+    sf = PR.build_standard_form(3, np.array([[1.0, 0, 0], [1, 1, 1]]), None)
+    assert sf.infeasible_mask(np.array([[-1.0, 1.0], [0.5, 1.0]])).tolist() == [True, False]
+    with pytest.raises(ValueError):
+        PR.clean_bounds([(2.0, 1.0)], 3)
+    with pytest.raises(ValueError):
+        PR.build_standard_form(3, np.array([[1.0, np.nan, 0]]), np.array([1.0]))
