@@ -49,14 +49,20 @@ typedef struct IntoptOpts {
 /* Static facts about a problem after structure analysis (host side, no GPU needed to read). */
 typedef struct IntoptInfo {
   int m, n, nnz;
-  int envelope;           /* doubles in the skyline (envelope) storage of chol(A D A^T) after row ordering */
+  int envelope;           /* doubles in the 8x8 block-skyline storage of chol(A D A^T) after row ordering */
   int dense_lower;        /* m(m+1)/2, for comparison */
   long long asm_terms;    /* S = sum over columns of nnz_k(nnz_k+1)/2: MACs to assemble A D A^T */
-  long long chol_macs;    /* MACs executed by the envelope Cholesky */
+  long long chol_macs;    /* MACs executed by the block-skyline Cholesky */
   int smem_bytes;         /* dynamic shared memory the solver kernel requests per CTA */
   int factor_in_smem;     /* 1 if the factor lives in shared memory, 0 if it spills to the workspace */
-  int threads;            /* CTA size */
+  int threads;            /* CTA size (env INTOPT_THREADS, default 256) */
   int ordering;           /* 0 natural, 1 reverse Cuthill-McKee, 2 dense rows last */
+  int gather_in_smem;     /* 1 if the n-vector gather buffer lives in shared memory */
+  int ctas_per_sm;        /* resident CTAs per SM (set by intopt_problem_create, 0 from intopt_analyze) */
+  int scalar_envelope;    /* doubles a scalar skyline would need (for comparison) */
+  int reserved;
+  long long asm_padded;   /* gather-list slots incl. padding of the warp-interleaved layout */
+  long long solve_macs;   /* MACs of one blocked L L^T solve */
 } IntoptInfo;
 
 int intopt_version(void);

@@ -24,7 +24,9 @@ class IntoptInfo(ctypes.Structure):
     _fields_ = [("m", ctypes.c_int), ("n", ctypes.c_int), ("nnz", ctypes.c_int), ("envelope", ctypes.c_int),
                 ("dense_lower", ctypes.c_int), ("asm_terms", ctypes.c_longlong), ("chol_macs", ctypes.c_longlong),
                 ("smem_bytes", ctypes.c_int), ("factor_in_smem", ctypes.c_int), ("threads", ctypes.c_int),
-                ("ordering", ctypes.c_int)]
+                ("ordering", ctypes.c_int), ("gather_in_smem", ctypes.c_int), ("ctas_per_sm", ctypes.c_int),
+                ("scalar_envelope", ctypes.c_int), ("reserved", ctypes.c_int), ("asm_padded", ctypes.c_longlong),
+                ("solve_macs", ctypes.c_longlong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -1,0 +1,52 @@
+// Binds a HostStructure to the pointer-only ProblemDev the solver code consumes.  `Up` maps a host
+// std::vector to a pointer usable by the solver: identity for the single-threaded test build,
+// cudaMalloc + cudaMemcpy for the CUDA build.
+#pragma once
+#include "intopt_solver.cuh"
+#include "intopt_structure.hpp"
+
+namespace intopt {
+
+template <class Up>
+inline void bind_problem(const HostStructure& S, ProblemDev& D, Up&& up) {
+  D.m = S.m;
+  D.n = S.n;
+  D.nnz = S.nnz;
+  D.mb = S.mb;
+  D.m8 = S.m8;
+  D.mv = S.m8 + 8;
+  D.csr_ptr = up(S.csr_ptr);
+  D.csr_col = up(S.csr_col);
+  D.a_unit = S.a_unit ? 1 : 0;
+  D.csr_val = S.a_unit ? nullptr : up(S.csr_val);
+  D.csc_gptr = up(S.csc_gptr);
+  D.csc_glen = up(S.csc_glen);
+  D.csc_row = up(S.csc_row);
+  D.csc_val = S.a_unit ? nullptr : up(S.csc_val);
+  D.perm = up(S.perm);
+  D.fb = up(S.fb);
+  D.boff = up(S.boff);
+  D.bsize = S.bsize;
+  D.dummy_pos = up(S.dummy_pos);
+  D.n_dummy = (int)S.dummy_pos.size();
+  D.act_ptr = up(S.act_ptr);
+  D.act_blk = up(S.act_blk);
+  D.pair_ptr = up(S.pair_ptr);
+  D.pair_dst = up(S.pair_dst);
+  D.pair_a = up(S.pair_a);
+  D.pair_b = up(S.pair_b);
+  D.next_diag_first = up(S.next_diag_first);
+  D.n_asm = S.n_asm;
+  D.asm_gptr = up(S.asm_gptr);
+  D.asm_glen = up(S.asm_glen);
+  D.asm_pos = up(S.asm_pos);
+  D.asm_diag = up(S.asm_diag);
+  D.asm_k = up(S.asm_k);
+  D.asm_unit = S.asm_unit ? 1 : 0;
+  D.asm_w = S.asm_unit ? nullptr : up(S.asm_w);
+}
+
+// doubles of shared memory the solver needs beyond the (optional) factor and gather buffer
+inline size_t smem_fixed_doubles(const HostStructure& S) { return (size_t)S_NVEC * (S.m8 + 8) + S_SCRATCH; }
+
+}  // namespace intopt

@@ -2,15 +2,14 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "../../include/intopt_b200.h"
-#include "intopt_solver.cuh"
-#include "intopt_structure.hpp"
+#include "intopt_bind.hpp"
 
 namespace {
 
@@ -26,33 +25,59 @@ int fail(int code, const std::string& msg) {
       return fail(-100 - (int)e_, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
   } while (0)
 
-constexpr int kThreads = 256;
-constexpr int kMaxDynSmem = 232448;  // 227 KB opt-in per CTA on sm_100
+constexpr int kMaxThreads = 512;
+constexpr int kMaxDynSmem = 232448 - 256;  // 227 KB opt-in per CTA on sm_100, minus the kernels' static smem
+constexpr size_t kCounterBytes = 256;
 
-size_t smem_vec_bytes(int m) { return (size_t)(intopt::S_NVEC * m + 1 + 8 * 32) * sizeof(double); }
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v && *v ? std::atoi(v) : dflt;
+}
+
+// Decide what lives in shared memory.  Preference: factor + gather buffer; then factor only; then neither.
+void plan_smem(const intopt::HostStructure& S, int* factor_in_smem, int* gather_in_smem, int* smem_bytes) {
+  const size_t fixed = intopt::smem_fixed_doubles(S);
+  const size_t fac = (size_t)S.bsize, gat = (size_t)intopt::gather_len(S.n);
+  *factor_in_smem = 1;
+  *gather_in_smem = 1;
+  if ((fixed + fac + gat) * 8 > (size_t)kMaxDynSmem) {
+    *gather_in_smem = 0;
+    if ((fixed + fac) * 8 > (size_t)kMaxDynSmem) {
+      *factor_in_smem = 0;
+      if ((fixed + gat) * 8 <= (size_t)kMaxDynSmem) *gather_in_smem = 1;
+    }
+  }
+  *smem_bytes = (int)((fixed + (*factor_in_smem ? fac : 0) + (*gather_in_smem ? gat : 0)) * 8);
+}
 
 void fill_info(const intopt::HostStructure& S, IntoptInfo* info) {
   info->m = S.m;
   info->n = S.n;
   info->nnz = S.nnz;
-  info->envelope = S.sky_size;
+  info->envelope = S.bsize;
   info->dense_lower = (int)((long long)S.m * (S.m + 1) / 2);
   info->asm_terms = S.asm_terms;
   info->chol_macs = S.chol_macs;
-  size_t with_factor = smem_vec_bytes(S.m) + (size_t)S.sky_size * sizeof(double);
-  info->factor_in_smem = with_factor <= (size_t)kMaxDynSmem ? 1 : 0;
-  info->smem_bytes = (int)(info->factor_in_smem ? with_factor : smem_vec_bytes(S.m));
-  info->threads = kThreads;
+  int g = 0;
+  plan_smem(S, &info->factor_in_smem, &g, &info->smem_bytes);
+  info->gather_in_smem = g;
+  info->threads = env_int("INTOPT_THREADS", 256);
   info->ordering = S.ordering;
+  info->scalar_envelope = S.sky_size;
+  info->asm_padded = S.asm_padded;
+  info->solve_macs = S.solve_macs;
 }
 
 template <class T>
-cudaError_t upload(const std::vector<T>& h, T** d) {
+cudaError_t upload(const std::vector<T>& h, const T** d, std::vector<void*>& allocs) {
   *d = nullptr;
   if (h.empty()) return cudaSuccess;
-  cudaError_t e = cudaMalloc((void**)d, h.size() * sizeof(T));
+  T* p = nullptr;
+  cudaError_t e = cudaMalloc((void**)&p, h.size() * sizeof(T));
   if (e != cudaSuccess) return e;
-  return cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  allocs.push_back(p);
+  *d = p;
+  return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
 }
 
 }  // namespace
@@ -60,37 +85,59 @@ cudaError_t upload(const std::vector<T>& h, T** d) {
 struct IntoptProblem {
   intopt::ProblemDev dev{};
   IntoptInfo info{};
+  const double* b_dev = nullptr;
   int device = 0;
+  int sms = 0;
+  int slots = 0;  // persistent CTAs per launch
   std::vector<void*> allocs;
 };
 
-__global__ void __launch_bounds__(kThreads) intopt_forward_kernel(intopt::ProblemDev P, intopt::FwdParams a) {
-  extern __shared__ double smem[];
+__device__ __forceinline__ CtaCtx make_ctx(double* red) {
   CtaCtx cx;
   cx.tid = threadIdx.x;
   cx.nthreads = blockDim.x;
   cx.lane = threadIdx.x & 31;
   cx.warp = threadIdx.x >> 5;
   cx.nwarps = blockDim.x >> 5;
-  cx.red = smem + (a.factor_in_smem ? P.sky_size : 0) + intopt::S_NVEC * P.m + 1;
-  for (int inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
-    intopt::forward_instance(cx, P, a, inst, smem);
+  cx.red = red;
+  return cx;
+}
+
+// Persistent CTAs: each pulls the next LP instance from an atomic counter until the batch is exhausted,
+// so finished LPs free their SM slot without any host involvement.
+template <int TMAX>
+__global__ void __launch_bounds__(TMAX) intopt_forward_kernel(intopt::ProblemDev P, intopt::FwdParams a) {
+  extern __shared__ double smem[];
+  __shared__ int s_inst;
+  double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
+  const intopt::SmemLayout S =
+      intopt::carve(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
+  const CtaCtx cx = make_ctx(S.red);
+  for (;;) {
+    if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
     __syncthreads();
+    const int inst = s_inst;
+    __syncthreads();
+    if (inst >= a.B) break;
+    intopt::forward_instance(cx, P, a, inst, wsi, S);
   }
 }
 
-__global__ void __launch_bounds__(kThreads) intopt_backward_kernel(intopt::ProblemDev P, intopt::BwdParams a) {
+template <int TMAX>
+__global__ void __launch_bounds__(TMAX) intopt_backward_kernel(intopt::ProblemDev P, intopt::BwdParams a) {
   extern __shared__ double smem[];
-  CtaCtx cx;
-  cx.tid = threadIdx.x;
-  cx.nthreads = blockDim.x;
-  cx.lane = threadIdx.x & 31;
-  cx.warp = threadIdx.x >> 5;
-  cx.nwarps = blockDim.x >> 5;
-  cx.red = smem + (a.factor_in_smem ? P.sky_size : 0) + intopt::S_NVEC * P.m + 1;
-  for (int inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
-    intopt::backward_instance(cx, P, a, inst, smem);
+  __shared__ int s_inst;
+  double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
+  const intopt::SmemLayout S =
+      intopt::carve(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
+  const CtaCtx cx = make_ctx(S.red);
+  for (;;) {
+    if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
     __syncthreads();
+    const int inst = s_inst;
+    __syncthreads();
+    if (inst >= a.B) break;
+    intopt::backward_instance(cx, P, a, inst, wsi, S);
   }
 }
 
@@ -114,6 +161,15 @@ __global__ void __launch_bounds__(256) intopt_fp64_peak_kernel(double* out, int 
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+
+namespace {
+size_t ws_per_slot_doubles(const IntoptProblem* p) {
+  size_t per = (size_t)intopt::W_NVEC * p->info.n;
+  if (!p->info.factor_in_smem) per += (size_t)p->info.envelope;
+  if (!p->info.gather_in_smem) per += (size_t)intopt::gather_len(p->info.n);
+  return (per + 1) & ~(size_t)1;
+}
+}  // namespace
 
 extern "C" {
 
@@ -140,61 +196,53 @@ int intopt_problem_create(IntoptProblem** out, int m, int n, const int* rowptr, 
   int rc = intopt::analyze(m, n, rowptr, colidx, val, S);
   if (rc) return fail(rc, "malformed CSR input");
   int ndev = 0;
-  CU_TRY(cudaGetDeviceCount(&ndev));
-  if (ndev <= 0) return fail(-10, "no CUDA device: intopt_b200 has no CPU fallback");
+  cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  if (e0 != cudaSuccess || ndev <= 0) return fail(-10, "no CUDA device: intopt_b200 has no CPU fallback");
   IntoptProblem* p = new (std::nothrow) IntoptProblem();
   if (!p) return fail(-2, "out of host memory");
-  CU_TRY(cudaGetDevice(&p->device));
+  cudaError_t err = cudaSuccess;
+  auto up = [&](const auto& v) {
+    using T = typename std::decay<decltype(v)>::type::value_type;
+    const T* d = nullptr;
+    cudaError_t e = upload(v, &d, p->allocs);
+    if (e != cudaSuccess) err = e;
+    return d;
+  };
   fill_info(S, &p->info);
-  intopt::ProblemDev& D = p->dev;
-  D.m = m;
-  D.n = n;
-  D.nnz = S.nnz;
-  D.sky_size = S.sky_size;
-  D.n_asm = (int)S.asm_pos.size();
-  D.asm_unit = S.asm_unit ? 1 : 0;
-  std::vector<double> bperm;
+  intopt::bind_problem(S, p->dev, up);
   if (b) {
-    bperm.resize(m);
+    std::vector<double> bperm(m);
     for (int i = 0; i < m; ++i) bperm[i] = b[S.perm[i]];
+    p->b_dev = up(bperm);
   }
-  std::vector<double> wdummy;
-  int *d_i = nullptr;
-  double* d_d = nullptr;
-  unsigned char* d_u = nullptr;
-#define UP_I(vec, field)                    \
-  CU_TRY(upload(vec, &d_i));                \
-  D.field = d_i;                            \
-  p->allocs.push_back(d_i);
-#define UP_D(vec, field)                    \
-  CU_TRY(upload(vec, &d_d));                \
-  D.field = d_d;                            \
-  p->allocs.push_back(d_d);
-  UP_I(S.csr_ptr, csr_ptr)
-  UP_I(S.csr_col, csr_col)
-  UP_D(S.csr_val, csr_val)
-  UP_I(S.csc_ptr, csc_ptr)
-  UP_I(S.csc_row, csc_row)
-  UP_D(S.csc_val, csc_val)
-  UP_D(bperm, b)
-  UP_I(S.perm, perm)
-  UP_I(S.sky_first, sky_first)
-  UP_I(S.sky_off, sky_off)
-  UP_I(S.asm_ptr, asm_ptr)
-  UP_I(S.asm_pos, asm_pos)
-  UP_I(S.asm_k, asm_k)
-  if (!S.asm_unit) {
-    UP_D(S.asm_w, asm_w)
-  } else {
-    D.asm_w = nullptr;
+  if (err != cudaSuccess) {
+    intopt_problem_destroy(p);
+    return fail(-100 - (int)err, std::string("device upload: ") + cudaGetErrorString(err));
   }
-  CU_TRY(upload(S.asm_diag, &d_u));
-  D.asm_diag = d_u;
-  p->allocs.push_back(d_u);
-#undef UP_I
-#undef UP_D
-  CU_TRY(cudaFuncSetAttribute(intopt_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  CU_TRY(cudaFuncSetAttribute(intopt_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  CU_TRY(cudaGetDevice(&p->device));
+  CU_TRY(cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, p->device));
+  if (p->info.threads < 32 || p->info.threads > kMaxThreads || p->info.threads % 32) {
+    intopt_problem_destroy(p);
+    return fail(-12, "INTOPT_THREADS must be a multiple of 32 in [32, 512]");
+  }
+  CU_TRY(cudaFuncSetAttribute(intopt_forward_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  CU_TRY(cudaFuncSetAttribute(intopt_backward_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  CU_TRY(cudaFuncSetAttribute(intopt_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  CU_TRY(cudaFuncSetAttribute(intopt_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  int occ = 0;
+  if (p->info.threads <= 256)
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intopt_forward_kernel<256>, p->info.threads,
+                                                         (size_t)p->info.smem_bytes));
+  else
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intopt_forward_kernel<512>, p->info.threads,
+                                                         (size_t)p->info.smem_bytes));
+  if (occ < 1) {
+    intopt_problem_destroy(p);
+    return fail(-11, "solver kernel does not fit on an SM (shared memory / registers)");
+  }
+  occ = std::min(occ, env_int("INTOPT_MAX_CTAS_PER_SM", 8));
+  p->info.ctas_per_sm = occ;
+  p->slots = p->sms * occ;
   CU_TRY(cudaDeviceSynchronize());
   *out = p;
   return 0;
@@ -216,16 +264,16 @@ int intopt_problem_info(const IntoptProblem* p, IntoptInfo* info) {
 
 size_t intopt_workspace_bytes(const IntoptProblem* p, int B) {
   if (!p || B <= 0) return 0;
-  size_t per = (size_t)intopt::W_NVEC * p->info.n + (p->info.factor_in_smem ? 0 : (size_t)p->info.envelope);
-  return per * sizeof(double) * (size_t)B;
+  const size_t slots = (size_t)std::min(B, p->slots);
+  return kCounterBytes + ws_per_slot_doubles(p) * sizeof(double) * slots;
 }
 
 int intopt_forward(const IntoptProblem* p, int B, const double* c, long long c_stride, const double* b_batch,
-                   long long b_stride, const IntoptOpts* o, const double* init, double* xhat, double* state, int* status, int* iters,
-                   void* ws, size_t ws_bytes, void* stream) {
+                   long long b_stride, const IntoptOpts* o, const double* init, double* xhat, double* state,
+                   int* status, int* iters, void* ws, size_t ws_bytes, void* stream) {
   if (!p || !c || !o || !xhat || !state || !status || !iters || !ws) return fail(-1, "NULL argument");
   if (B <= 0) return 0;
-  if (!p->dev.b && !b_batch) return fail(-3, "problem has no b and no b_batch was given");
+  if (!p->b_dev && !b_batch) return fail(-3, "problem has no b and no b_batch was given");
   if (ws_bytes < intopt_workspace_bytes(p, B)) return fail(-4, "workspace too small");
   intopt::FwdParams a{};
   a.B = B;
@@ -233,33 +281,40 @@ int intopt_forward(const IntoptProblem* p, int B, const double* c, long long c_s
   a.c_stride = c_stride;
   a.b_batch = b_batch;
   a.b_stride = b_stride;
+  a.b_problem = p->b_dev;
   a.init = init;
   a.xhat = xhat;
   a.state = state;
   a.status = status;
   a.iters = iters;
-  a.ws = (double*)ws;
+  a.counter = (int*)ws;
+  a.ws = (double*)((char*)ws + kCounterBytes);
   a.factor_in_smem = p->info.factor_in_smem;
-  a.ws_stride = (long long)intopt::W_NVEC * p->info.n + (a.factor_in_smem ? 0 : p->info.envelope);
+  a.gather_in_smem = p->info.gather_in_smem;
+  a.ws_stride = (long long)ws_per_slot_doubles(p);
   a.alpha0 = o->alpha0;
   a.tol = o->tol;
   a.thr = o->thr;
   a.damping = o->damping_fwd;
   a.max_iter = o->max_iter;
-  intopt_forward_kernel<<<B, kThreads, p->info.smem_bytes, (cudaStream_t)stream>>>(p->dev, a);
+  const int grid = std::min(B, p->slots);
+  CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
+  if (p->info.threads <= 256)
+    intopt_forward_kernel<256><<<grid, p->info.threads, p->info.smem_bytes, (cudaStream_t)stream>>>(p->dev, a);
+  else
+    intopt_forward_kernel<512><<<grid, p->info.threads, p->info.smem_bytes, (cudaStream_t)stream>>>(p->dev, a);
   CU_TRY(cudaGetLastError());
   return 0;
 }
 
 int intopt_backward(const IntoptProblem* p, int B, int mode, double damping, int nvar, const double* state,
                     const double* c, long long c_stride, const double* b_batch, long long b_stride,
-                    const double* gx, double* gc,
-                    int* status, void* ws, size_t ws_bytes, void* stream) {
+                    const double* gx, double* gc, int* status, void* ws, size_t ws_bytes, void* stream) {
   if (!p || !c || !state || !gx || !gc || !status || !ws) return fail(-1, "NULL argument");
   if (B <= 0) return 0;
   if (mode != 0 && mode != 1) return fail(-5, "mode must be 0 (whole) or 1 (alter)");
   if (nvar < 0 || nvar > p->info.n) return fail(-6, "nvar out of range");
-  if (mode == 0 && !p->dev.b && !b_batch) return fail(-3, "problem has no b and no b_batch was given");
+  if (mode == 0 && !p->b_dev && !b_batch) return fail(-3, "problem has no b and no b_batch was given");
   if (ws_bytes < intopt_workspace_bytes(p, B)) return fail(-4, "workspace too small");
   intopt::BwdParams a{};
   a.B = B;
@@ -271,13 +326,21 @@ int intopt_backward(const IntoptProblem* p, int B, int mode, double damping, int
   a.c_stride = c_stride;
   a.b_batch = b_batch;
   a.b_stride = b_stride;
+  a.b_problem = p->b_dev;
   a.gx = gx;
   a.gc = gc;
   a.status = status;
-  a.ws = (double*)ws;
+  a.counter = (int*)ws;
+  a.ws = (double*)((char*)ws + kCounterBytes);
   a.factor_in_smem = p->info.factor_in_smem;
-  a.ws_stride = (long long)intopt::W_NVEC * p->info.n + (a.factor_in_smem ? 0 : p->info.envelope);
-  intopt_backward_kernel<<<B, kThreads, p->info.smem_bytes, (cudaStream_t)stream>>>(p->dev, a);
+  a.gather_in_smem = p->info.gather_in_smem;
+  a.ws_stride = (long long)ws_per_slot_doubles(p);
+  const int grid = std::min(B, p->slots);
+  CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
+  if (p->info.threads <= 256)
+    intopt_backward_kernel<256><<<grid, p->info.threads, p->info.smem_bytes, (cudaStream_t)stream>>>(p->dev, a);
+  else
+    intopt_backward_kernel<512><<<grid, p->info.threads, p->info.smem_bytes, (cudaStream_t)stream>>>(p->dev, a);
   CU_TRY(cudaGetLastError());
   return 0;
 }

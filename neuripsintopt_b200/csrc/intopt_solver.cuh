@@ -1,8 +1,10 @@
 // Per-instance interior-point solver: one CTA owns one LP for the whole IPM loop.
 //
-// The factor of M = A.diag(d).A^T + delta.I lives in shared memory in envelope (skyline) form, the
-// m-vectors live in shared memory, the n-vectors in a per-instance global workspace that stays in
-// L1/L2.  A (CSR + CSC) and the assembly gather lists are shared by every instance and stay in L2.
+// Data placement (Energy LP, m=172, n=1582): the factor of M = A.diag(d).A^T + delta.I lives in shared
+// memory as an 8x8 block skyline (~60-80 KB), together with the m-vectors and one n-vector gather buffer;
+// the element-wise n-vectors live in a per-CTA global workspace that stays L2 resident (CTAs are
+// persistent and pull instances from an atomic counter).  A (by rows / by interleaved column groups) and
+// the gather lists that assemble M are shared by every instance and stay in L2.
 //
 // The code is written against a tiny "CTA execution" vocabulary (CTA_FOR / WARP_ROWS / cta_sum ...)
 // so the same source also compiles as plain single-threaded C++ (-DINTOPT_HOST_EMU) for the CPU
@@ -14,9 +16,11 @@
 //   backward Interior/ip_model_whole.py:1502-1560, Interior/ip_model_alter.py:1516-1624
 #pragma once
 #include <math.h>
+#include <stdint.h>
 
 #ifdef INTOPT_HOST_EMU
 #define IO_DEV inline
+#define IO_HD inline
 #define IO_FORCEINLINE inline
 struct CtaCtx {
   static constexpr int tid = 0, nthreads = 1, lane = 0, warp = 0, nwarps = 1, warpsize = 1;
@@ -28,11 +32,12 @@ IO_DEV double warp_sum(double v) { return v; }
 IO_DEV double warp_min(double v) { return v; }
 #else
 #define IO_DEV __device__ inline
+#define IO_HD __host__ __device__ inline
 #define IO_FORCEINLINE __device__ __forceinline__
 struct CtaCtx {
   int tid, nthreads, lane, warp, nwarps;
   static constexpr int warpsize = 32;
-  double* red;  // >= 4*32 doubles of shared scratch
+  double* red;  // 8*32 doubles of shared scratch
 };
 #define CTA_SYNC() __syncthreads()
 #define WARP_SYNC() __syncwarp()
@@ -50,33 +55,45 @@ IO_FORCEINLINE double warp_min(double v) {
 
 // loops: every thread of the CTA strides over [0,n)
 #define CTA_FOR(i, n) for (int i = cx.tid; i < (n); i += cx.nthreads)
-// one warp per row, lanes stride over the row's entries
+// one warp per item, lanes stride over the item's entries
 #define WARP_ROWS(i, m) for (int i = cx.warp; i < (m); i += cx.nwarps)
 #define LANE_FOR(e, lo, hi) for (int e = (lo) + cx.lane; e < (hi); e += cx.warpsize)
 
 namespace intopt {
 
 enum { ST_OK = 0, ST_MAXITER = 1, ST_INFEAS = 2, ST_BREAKDOWN = 3, ST_NONFINITE = 4 };
+constexpr int KB = 8;  // block edge, == NB of intopt_structure.hpp
 
 struct ProblemDev {
-  int m, n, nnz;
+  int m, n, nnz, mb, m8, mv;  // mv = m8 + 8: length of every m-vector (slot m8 is always zero)
   const int* csr_ptr;
   const int* csr_col;
-  const double* csr_val;
-  const int* csc_ptr;
-  const int* csc_row;
-  const double* csc_val;
-  const double* b;  // internal row order, may be null
+  const double* csr_val;  // null if a_unit
+  const int* csc_gptr;
+  const int* csc_glen;
+  const uint16_t* csc_row;
+  const double* csc_val;  // null if a_unit
+  int a_unit;
   const int* perm;  // internal row -> original row
-  const int* sky_first;
-  const int* sky_off;
-  int sky_size;
+  const int* fb;
+  const int* boff;
+  int bsize;
+  const int* dummy_pos;
+  int n_dummy;
+  const int* act_ptr;
+  const int* act_blk;
+  const int* pair_ptr;
+  const int* pair_dst;
+  const int* pair_a;
+  const int* pair_b;
+  const unsigned char* next_diag_first;
   int n_asm;
-  const int* asm_ptr;
+  const int* asm_gptr;
+  const int* asm_glen;
   const int* asm_pos;
   const unsigned char* asm_diag;
   const int* asm_k;
-  const double* asm_w;
+  const double* asm_w;  // null if asm_unit
   int asm_unit;
 };
 
@@ -85,6 +102,7 @@ template <int N>
 IO_DEV void cta_sum(const CtaCtx& cx, double (&v)[N]) {
 #ifdef INTOPT_HOST_EMU
   (void)cx;
+  (void)v;
 #else
 #pragma unroll
   for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
@@ -107,6 +125,7 @@ template <int N>
 IO_DEV void cta_min(const CtaCtx& cx, double (&v)[N]) {
 #ifdef INTOPT_HOST_EMU
   (void)cx;
+  (void)v;
 #else
 #pragma unroll
   for (int k = 0; k < N; ++k) v[k] = warp_min(v[k]);
@@ -126,124 +145,311 @@ IO_DEV void cta_min(const CtaCtx& cx, double (&v)[N]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// M = A diag(d) A^T + delta I, assembled entry by entry into the envelope storage L (K1).
+// K1: M = A diag(d) A^T + delta I, assembled entry by entry into the block skyline L.
+// `g` is the gather buffer holding d (g[n] == 0 is the padding slot).  Each warp walks whole groups
+// of 32 entries whose term lists are interleaved, so index loads are fully coalesced.
 // ---------------------------------------------------------------------------------------------
-IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const double* __restrict__ d,
-                                   double delta, double* L) {
-  CTA_FOR(e, P.sky_size) L[e] = 0.0;
+IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const double* g, double delta,
+                                   double* L) {
+  CTA_FOR(e, P.bsize) L[e] = 0.0;
   CTA_SYNC();
-  CTA_FOR(e, P.n_asm) {
-    const int lo = P.asm_ptr[e], hi = P.asm_ptr[e + 1];
-    double s = 0.0;
-    if (P.asm_unit) {
-      for (int t = lo; t < hi; ++t) s += d[P.asm_k[t]];
-    } else {
-      for (int t = lo; t < hi; ++t) s = fma(P.asm_w[t], d[P.asm_k[t]], s);
+  CTA_FOR(e, P.n_dummy) L[P.dummy_pos[e]] = 1.0;
+  const int ngrp = P.n_asm >> 5;
+  WARP_ROWS(grp, ngrp) {
+    const int len = P.asm_glen[grp];
+    const int* __restrict__ kk = P.asm_k + (size_t)P.asm_gptr[grp] * 32;
+    LANE_FOR(l, 0, 32) {
+      const int e = grp * 32 + l;
+      double s = 0.0;
+      if (P.asm_unit) {
+        for (int t = 0; t < len; ++t) s += g[kk[t * 32 + l]];
+      } else {
+        const double* __restrict__ ww = P.asm_w + (size_t)P.asm_gptr[grp] * 32;
+        for (int t = 0; t < len; ++t) s = fma(ww[t * 32 + l], g[kk[t * 32 + l]], s);
+      }
+      const int pos = P.asm_pos[e];
+      if (pos >= 0) L[pos] = P.asm_diag[e] ? s + delta : s;
     }
-    if (P.asm_diag[e]) s += delta;
-    L[P.asm_pos[e]] = s;
   }
   CTA_SYNC();
 }
 
-// ---------------------------------------------------------------------------------------------
-// Envelope Cholesky, left-looking by columns (K2).  On exit L holds the strict lower factor in
-// place, dg[j] = L_jj and dgi[j] = 1/L_jj.  Returns false (for every thread) on a non-positive or
-// non-finite pivot (the reference's cho_factor failure, ip_model_whole.py:742,755-758).
-// ---------------------------------------------------------------------------------------------
-IO_DEV bool envelope_cholesky(const CtaCtx& cx, const ProblemDev& P, double* L, double* dg, double* dgi,
-                              int* fail_flag) {
-  const int m = P.m;
-  const int* __restrict__ first = P.sky_first;
-  const int* __restrict__ off = P.sky_off;
-  if (cx.tid == 0) *fail_flag = 0;
-  CTA_SYNC();
-  for (int j = 0; j < m; ++j) {
-    const int fj = first[j];
-    const double* Lj = L + off[j] - fj;  // Lj[k] = L(j,k)
-    // phase 1: s_ij = M_ij - sum_k L_ik L_jk for every row i >= j that reaches column j
-    CTA_FOR(r, m - j) {
-      const int i = j + r;
-      const int fi = first[i];
-      if (fi <= j) {
-        double* Li = L + off[i] - fi;
-        const int k0 = fi > fj ? fi : fj;
-        double s = Li[j];
-        for (int k = k0; k < j; ++k) s = fma(-Li[k], Lj[k], s);
-        Li[j] = s;
-      }
+// Cholesky of one 8x8 diagonal block (lower part of row-major `blk`), then its inverse written over it:
+// on exit blk holds Linv = L_KK^-1 (lower).  Executed by ONE warp: lane i owns row i (factor) / column i
+// (inverse).  `scr` is 8 + 64 doubles of scratch.  A non-positive / non-finite pivot sets *fail and
+// continues with pivot 1.
+IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr, int* fail) {
+  double* col = scr;
+  double* inv = scr + KB;
+  for (int j = 0; j < KB; ++j) {
+    LANE_FOR(i, j, KB) {
+      double s = blk[i * KB + j];
+      for (int k = 0; k < j; ++k) s = fma(-blk[i * KB + k], blk[j * KB + k], s);
+      col[i] = s;
     }
-    CTA_SYNC();
-    // phase 2: pivot and scale the column
-    double piv = Lj[j];
+    WARP_SYNC();
+    double piv = col[j];
     if (!(piv > 0.0) || !(piv < 1e300)) {
-      if (cx.tid == 0) *fail_flag = 1;
+      if (cx.lane == 0) *fail = 1;
       piv = 1.0;
     }
     const double dj = sqrt(piv);
     const double rinv = 1.0 / dj;
-    CTA_FOR(r, m - j) {
-      const int i = j + r;
-      if (r == 0) {
-        dg[j] = dj;
-        dgi[j] = rinv;
-      } else if (first[i] <= j) {
-        L[off[i] - first[i] + j] *= rinv;
+    LANE_FOR(i, j, KB) blk[i * KB + j] = (i == j) ? dj : col[i] * rinv;
+    WARP_SYNC();
+  }
+  // inverse, one column per lane: X(:,c) = L^-1 e_c by forward substitution
+  LANE_FOR(c, 0, KB) {
+    double x[KB];
+#pragma unroll
+    for (int i = 0; i < KB; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < KB; ++k)
+        if (k < i && k >= c) s = fma(-blk[i * KB + k], x[k], s);
+      x[i] = (i >= c) ? s / blk[i * KB + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < KB; ++i) inv[i * KB + c] = x[i];
+  }
+  WARP_SYNC();
+  LANE_FOR(e, 0, KB * KB) {
+    if ((e & 7) <= (e >> 3)) blk[e] = inv[e];
+  }
+  WARP_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: blocked right-looking Cholesky on the block skyline with one-step look-ahead.
+// Step K:  (a) panel: L_IK = C_IK * Linv_KK^T for the active block rows I > K (one thread per row);
+//          (b) trailing update C_IJ -= L_IK L_JK^T over the precomputed pair list; warp 0 takes the
+//              update of the next diagonal block first and then factors + inverts it while the other
+//              warps finish the remaining pairs.
+// On exit: strictly-lower blocks hold L, diagonal blocks hold Linv_KK (what the solves need).
+// Returns false (for every thread) on a bad pivot (the reference's cho_factor failure,
+// ip_model_whole.py:742,755-758).
+// ---------------------------------------------------------------------------------------------
+IO_DEV void chol_update_task(const ProblemDev& P, double* L, int p0, int task) {
+  // task = (pair, row r, half h): 4 entries of row r of the destination block
+  const int p = p0 + (task >> 4), r = (task >> 1) & 7, h = task & 1;
+  const double* __restrict__ A = L + P.pair_a[p] + r * KB;
+  const double* __restrict__ Bm = L + P.pair_b[p] + h * 4 * KB;
+  double* dst = L + P.pair_dst[p] + r * KB + h * 4;
+  double a[KB];
+#pragma unroll
+  for (int k = 0; k < KB; ++k) a[k] = A[k];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) s = fma(a[k], Bm[c * KB + k], s);
+    dst[c] -= s;
+  }
+}
+
+IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, double* L, double* scratch, int* fail_flag) {
+  const int mb = P.mb;
+  if (cx.tid == 0) *fail_flag = 0;
+  CTA_SYNC();
+  if (cx.warp == 0) diag_block_factor_invert(cx, L + P.boff[0] + (0 - P.fb[0]) * 64, scratch, fail_flag);
+  CTA_SYNC();
+  const int o_tid = cx.nwarps > 1 ? cx.tid - cx.warpsize : 0;
+  const int o_n = cx.nwarps > 1 ? cx.nthreads - cx.warpsize : 1;
+  for (int K = 0; K < mb; ++K) {
+    const double* __restrict__ Linv = L + P.boff[K] + (K - P.fb[K]) * 64;
+    // (a) panel rows
+    const int a0 = P.act_ptr[K], na = P.act_ptr[K + 1] - a0;
+    CTA_FOR(idx, na * KB) {
+      const int I = P.act_blk[a0 + (idx >> 3)];
+      double* row = L + P.boff[I] + (K - P.fb[I]) * 64 + (idx & 7) * KB;
+      double cin[KB], out[KB];
+#pragma unroll
+      for (int k = 0; k < KB; ++k) cin[k] = row[k];
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < KB; ++k)
+          if (k <= c) s = fma(cin[k], Linv[c * KB + k], s);
+        out[c] = s;
       }
+#pragma unroll
+      for (int k = 0; k < KB; ++k) row[k] = out[k];
+    }
+    CTA_SYNC();
+    // (b) trailing update with look-ahead
+    const int p0 = P.pair_ptr[K], np = P.pair_ptr[K + 1] - p0;
+    const int lead = P.next_diag_first[K] ? 1 : 0;  // pair p0 updates block (K+1,K+1)
+    if (cx.warp == 0) {
+      if (lead) {
+        LANE_FOR(task, 0, 16) chol_update_task(P, L, p0, task);
+        WARP_SYNC();
+      }
+      if (K + 1 < mb)
+        diag_block_factor_invert(cx, L + P.boff[K + 1] + (K + 1 - P.fb[K + 1]) * 64, scratch, fail_flag);
+    }
+    if (cx.nwarps == 1 || cx.warp > 0) {
+      for (int task = lead * 16 + o_tid; task < np * 16; task += o_n) chol_update_task(P, L, p0, task);
     }
     CTA_SYNC();
   }
   return *fail_flag == 0;
 }
 
-// Solve L L^T z = r in place (r -> z), column-oriented substitution over the envelope.
-// r[j] is kept unscaled while a sweep runs (consumers multiply by 1/L_jj themselves), so one
-// barrier per column suffices; a parallel scaling pass finishes each sweep.
-IO_DEV void envelope_solve(const CtaCtx& cx, const ProblemDev& P, const double* L, const double* dg,
-                           const double* dgi, double* r) {
-  const int m = P.m;
-  const int* __restrict__ first = P.sky_first;
-  const int* __restrict__ off = P.sky_off;
-  (void)dg;
+// ---------------------------------------------------------------------------------------------
+// Solve L L^T z = r in place for NR right-hand sides at once (blocked substitution; the diagonal
+// blocks hold Linv).  `ybuf` is NR*8 doubles of scratch.
+// ---------------------------------------------------------------------------------------------
+template <int NR>
+IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const double* L, double* const (&r)[NR],
+                        double* ybuf) {
+  const int mb = P.mb;
   // forward: L y = r
-  for (int j = 0; j < m - 1; ++j) {
-    const double yj = r[j] * dgi[j];
-    CTA_FOR(q, m - j - 1) {
-      const int i = j + 1 + q;
-      if (first[i] <= j) r[i] = fma(-L[off[i] - first[i] + j], yj, r[i]);
+  for (int K = 0; K < mb; ++K) {
+    const double* __restrict__ Linv = L + P.boff[K] + (K - P.fb[K]) * 64;
+    CTA_FOR(idx, NR * KB) {
+      const int q = idx >> 3, i = idx & 7;
+      const double* rk = r[q] + K * KB;
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < KB; ++j)
+        if (j <= i) s = fma(Linv[i * KB + j], rk[j], s);
+      ybuf[idx] = s;
+    }
+    CTA_SYNC();
+    const int a0 = P.act_ptr[K], na = P.act_ptr[K + 1] - a0;
+    CTA_FOR(idx, NR * KB) r[idx >> 3][K * KB + (idx & 7)] = ybuf[idx];
+    CTA_FOR(idx, na * KB * NR) {
+      const int q = idx / (na * KB), rem = idx - q * (na * KB);
+      const int I = P.act_blk[a0 + (rem >> 3)], rr = rem & 7;
+      const double* __restrict__ row = L + P.boff[I] + (K - P.fb[I]) * 64 + rr * KB;
+      const double* yk = ybuf + q * KB;
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < KB; ++k) s = fma(row[k], yk[k], s);
+      r[q][I * KB + rr] -= s;
     }
     CTA_SYNC();
   }
-  CTA_FOR(j, m) r[j] *= dgi[j];
-  CTA_SYNC();
-  // backward: L^T z = y ; row i of L is column i of L^T
-  for (int i = m - 1; i > 0; --i) {
-    const double zi = r[i] * dgi[i];
-    const int fi = first[i];
-    const double* Li = L + off[i] - fi;
-    CTA_FOR(q, i - fi) {
-      const int k = fi + q;
-      r[k] = fma(-Li[k], zi, r[k]);
+  // backward: L^T z = y
+  for (int I = mb - 1; I >= 0; --I) {
+    const int f = P.fb[I];
+    const double* __restrict__ Linv = L + P.boff[I] + (I - f) * 64;
+    CTA_FOR(idx, NR * KB) {
+      const int q = idx >> 3, i = idx & 7;
+      const double* ri = r[q] + I * KB;
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < KB; ++j)
+        if (j >= i) s = fma(Linv[j * KB + i], ri[j], s);
+      ybuf[idx] = s;
+    }
+    CTA_SYNC();
+    const int nk = I - f;
+    CTA_FOR(idx, NR * KB) r[idx >> 3][I * KB + (idx & 7)] = ybuf[idx];
+    CTA_FOR(idx, nk * KB * NR) {
+      const int q = idx / (nk * KB), rem = idx - q * (nk * KB);
+      const int Kc = f + (rem >> 3), k = rem & 7;
+      const double* __restrict__ blk = L + P.boff[I] + (Kc - f) * 64 + k;
+      const double* zi = ybuf + q * KB;
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < KB; ++i) s = fma(blk[i * KB], zi[i], s);
+      r[q][Kc * KB + k] -= s;
     }
     CTA_SYNC();
   }
-  CTA_FOR(j, m) r[j] *= dgi[j];
-  CTA_SYNC();
 }
 
-// out[i] = base[i]*scale + sum_e A_ie * src[col_e]   (row-wise, one warp per row)
-IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const double* __restrict__ src, double* out) {
+// out[i] = sum_e A_ie * src[col_e]   (row-wise, one warp per row)
+IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const double* src, double* out) {
   WARP_ROWS(i, P.m) {
     double s = 0.0;
-    LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s = fma(P.csr_val[e], src[P.csr_col[e]], s);
+    if (P.a_unit) {
+      LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s += src[P.csr_col[e]];
+    } else {
+      LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s = fma(P.csr_val[e], src[P.csr_col[e]], s);
+    }
     s = warp_sum(s);
     if (cx.lane == 0) out[i] = s;
   }
 }
 
+// (A^T y)_k through the interleaved column groups (lanes of a warp own 32 consecutive columns)
 IO_FORCEINLINE double col_dot(const ProblemDev& P, int k, const double* yv) {
+  const int g = k >> 5, l = k & 31, len = P.csc_glen[g];
+  const size_t base = (size_t)P.csc_gptr[g] * 32 + l;
   double s = 0.0;
-  for (int e = P.csc_ptr[k]; e < P.csc_ptr[k + 1]; ++e) s = fma(P.csc_val[e], yv[P.csc_row[e]], s);
+  if (P.a_unit) {
+    for (int t = 0; t < len; ++t) s += yv[P.csc_row[base + (size_t)t * 32]];
+  } else {
+    for (int t = 0; t < len; ++t) s = fma(P.csc_val[base + (size_t)t * 32], yv[P.csc_row[base + (size_t)t * 32]], s);
+  }
+  return s;
+}
+
+IO_FORCEINLINE void col_dot2(const ProblemDev& P, int k, const double* y1, const double* y2, double& s1, double& s2) {
+  const int g = k >> 5, l = k & 31, len = P.csc_glen[g];
+  const size_t base = (size_t)P.csc_gptr[g] * 32 + l;
+  s1 = 0.0;
+  s2 = 0.0;
+  if (P.a_unit) {
+    for (int t = 0; t < len; ++t) {
+      const int row = P.csc_row[base + (size_t)t * 32];
+      s1 += y1[row];
+      s2 += y2[row];
+    }
+  } else {
+    for (int t = 0; t < len; ++t) {
+      const int row = P.csc_row[base + (size_t)t * 32];
+      const double a = P.csc_val[base + (size_t)t * 32];
+      s1 = fma(a, y1[row], s1);
+      s2 = fma(a, y2[row], s2);
+    }
+  }
+}
+
+// workspace n-vector slots (global, per CTA)
+enum { W_X = 0, W_T, W_D, W_R2, W_P, W_W, W_DX, W_DXDT, W_NVEC };
+// shared-memory m-vector slots
+enum { S_B = 0, S_Y, S_R1, S_Q, S_V, S_NVEC };
+constexpr int S_SCRATCH = 2 * KB + (KB + KB * KB) + 8 * 32 + 2;  // ybuf + diag scratch + red + flag
+
+struct SmemLayout {
+  double *L, *G, *bs, *y, *r1, *q, *v, *ybuf, *dscr, *red;
+  int* flag;
+};
+
+IO_HD int gather_len(int n) { return (n + 2) & ~1; }
+
+// Carve shared memory (and, for spilled pieces, the tail of the per-CTA workspace).
+IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int factor_in_smem, int gather_in_smem) {
+  SmemLayout s;
+  double* p = smem;
+  if (factor_in_smem) {
+    s.L = p;
+    p += P.bsize;
+  } else {
+    s.L = ws_tail;
+    ws_tail += P.bsize;
+  }
+  if (gather_in_smem) {
+    s.G = p;
+    p += gather_len(P.n);
+  } else {
+    s.G = ws_tail;
+    ws_tail += gather_len(P.n);
+  }
+  s.bs = p + S_B * P.mv;
+  s.y = p + S_Y * P.mv;
+  s.r1 = p + S_R1 * P.mv;
+  s.q = p + S_Q * P.mv;
+  s.v = p + S_V * P.mv;
+  p += S_NVEC * P.mv;
+  s.ybuf = p;
+  s.dscr = p + 2 * KB;
+  s.red = s.dscr + KB + KB * KB;
+  s.flag = (int*)(s.red + 8 * 32);
   return s;
 }
 
@@ -253,55 +459,48 @@ struct FwdParams {
   long long c_stride;
   const double* b_batch;  // original row order, B x m, or null
   long long b_stride;
-  const double* init;     // B x (2n+m+2) or null
+  const double* b_problem;  // internal row order or null
+  const double* init;       // B x (2n+m+2) or null
   double* xhat;
   double* state;
   int* status;
   int* iters;
-  double* ws;  // per instance: 9 n-vectors (+ sky_size if the factor spills)
+  double* ws;  // per CTA slot: W_NVEC n-vectors (+ spilled factor / gather buffer)
   long long ws_stride;
-  int factor_in_smem;
+  int* counter;  // instance dispenser (zeroed before launch)
+  int factor_in_smem, gather_in_smem;
   double alpha0, tol, thr, damping;
   int max_iter;
 };
 
-// workspace n-vector slots
-enum { W_X = 0, W_T, W_D, W_R2, W_P, W_W, W_DW, W_DX, W_DXDT, W_NVEC };
-
-// shared-memory m-vector slots (after the factor)
-enum { S_B = 0, S_Y, S_R1, S_Q, S_V, S_DG, S_DGI, S_NVEC };
-
-IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdParams& a, int inst, double* smem) {
-  const int m = P.m, n = P.n;
-  double* wsi = a.ws + (long long)inst * a.ws_stride;
-  double* L = a.factor_in_smem ? smem : wsi + (long long)W_NVEC * n;
-  double* sv = a.factor_in_smem ? smem + P.sky_size : smem;
-  double* bs = sv + S_B * m;
-  double* y = sv + S_Y * m;
-  double* r1 = sv + S_R1 * m;
-  double* q = sv + S_Q * m;
-  double* v = sv + S_V * m;
-  double* dg = sv + S_DG * m;
-  double* dgi = sv + S_DGI * m;
-  int* fail_flag = (int*)(sv + S_NVEC * m);  // one double slot; cx.red follows it
-
+IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdParams& a, int inst, double* wsi,
+                             const SmemLayout& S) {
+  const int m = P.m, n = P.n, mv = P.mv;
+  double *L = S.L, *G = S.G, *bs = S.bs, *y = S.y, *r1 = S.r1, *q = S.q, *v = S.v;
   double* x = wsi + (long long)W_X * n;
   double* t = wsi + (long long)W_T * n;
   double* D = wsi + (long long)W_D * n;
   double* r2 = wsi + (long long)W_R2 * n;
   double* p = wsi + (long long)W_P * n;
   double* w = wsi + (long long)W_W * n;
-  double* dw = wsi + (long long)W_DW * n;
   double* dx = wsi + (long long)W_DX * n;
   double* dxdt = wsi + (long long)W_DXDT * n;
   const double* __restrict__ c = a.c + (long long)inst * a.c_stride;
 
-  // ---- load b, initial point (_initialization :647-661) -----------------------------------------
-  CTA_FOR(i, m) {
-    bs[i] = a.b_batch ? a.b_batch[(long long)inst * a.b_stride + P.perm[i]] : P.b[i];
+  // ---- load b, initial point (_initialization :647-661); padded slots of m-vectors are zero ---------
+  CTA_FOR(i, mv) {
+    double bv = 0.0;
+    if (i < m) bv = a.b_batch ? a.b_batch[(long long)inst * a.b_stride + P.perm[i]] : a.b_problem[i];
+    bs[i] = bv;
+    y[i] = 0.0;
+    r1[i] = 0.0;
+    q[i] = 0.0;
+    v[i] = 0.0;
   }
+  if (cx.tid == 0) G[n] = 0.0;
   double tau = 1.0, kappa = 1.0;
   const long long slen = 2LL * n + m + 2;
+  CTA_SYNC();
   if (a.init) {
     const double* s0 = a.init + (long long)inst * slen;
     CTA_FOR(k, n) {
@@ -316,7 +515,6 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
       x[k] = 1.0;
       t[k] = 1.0;
     }
-    CTA_FOR(i, m) y[i] = 0.0;
   }
   CTA_SYNC();
 
@@ -332,11 +530,14 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
       acc[1] += ck;
       if (!(fabs(ck) < 1e300)) acc[2] += 1.0;
     }
-    // ||b - A 1||
-    double accp = 0.0;
+    double accp = 0.0;  // ||b - A 1||
     WARP_ROWS(i, m) {
       double s = 0.0;
-      LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s += P.csr_val[e];
+      if (P.a_unit) {
+        LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s += 1.0;
+      } else {
+        LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s += P.csr_val[e];
+      }
       s = warp_sum(s);
       if (cx.lane == 0) {
         const double e = bs[i] - s;
@@ -353,127 +554,149 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
 
   int iters = 0, status = ST_OK;
   bool solved = true;
-  if (nonfinite) {
-    // the reference raises LinAlgError for non-finite c (:1332-1341); here: status word, x untouched
-    status = ST_NONFINITE;
-  }
+  if (nonfinite) status = ST_NONFINITE;  // the reference raises LinAlgError here (:1332-1341)
 
   while (status != ST_NONFINITE) {
-    // ---- residuals at the current iterate (:765-770; identical to _indicators' r_p, r_d :887-894) --
-    double xt_, cx_, nd2;
-    {
-      double acc[3] = {0.0, 0.0, 0.0};
-      CTA_FOR(k, n) {
-        const double xk = x[k], tk = t[k], ck = c[k];
-        const double aty = col_dot(P, k, y);
-        const double r = -(aty + tk - ck * tau);  // :766
-        r2[k] = r;
-        D[k] = xk / tk;  // :772
-        acc[0] = fma(xk, tk, acc[0]);
-        acc[1] = fma(ck, xk, acc[1]);
-        acc[2] = fma(r, r, acc[2]);
-      }
-      double accm[2] = {0.0, 0.0};
-      WARP_ROWS(i, m) {
-        double s = 0.0;
+    // ---- residuals at the current iterate (:765-770; the same r_p, r_d as _indicators :887-894) ----
+    double acc[3] = {0.0, 0.0, 0.0};
+    CTA_FOR(k, n) {
+      const double xk = x[k], tk = t[k], ck = c[k];
+      const double aty = col_dot(P, k, y);
+      const double r = -(aty + tk - ck * tau);  // :766
+      const double dk = xk / tk;                // :772
+      r2[k] = r;
+      D[k] = dk;
+      G[k] = dk;
+      acc[0] = fma(xk, tk, acc[0]);
+      acc[1] = fma(ck, xk, acc[1]);
+      acc[2] = fma(r, r, acc[2]);
+    }
+    double accm[2] = {0.0, 0.0};
+    WARP_ROWS(i, m) {
+      double s = 0.0;
+      if (P.a_unit) {
+        LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s += x[P.csr_col[e]];
+      } else {
         LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s = fma(P.csr_val[e], x[P.csr_col[e]], s);
-        s = warp_sum(s);
-        if (cx.lane == 0) {
-          const double r = -(s - bs[i] * tau);  // :765
-          r1[i] = r;
-          accm[0] = fma(r, r, accm[0]);
-          accm[1] = fma(bs[i], y[i], accm[1]);
-        }
       }
-      double red[5] = {acc[0], acc[1], acc[2], accm[0], accm[1]};
-      cta_sum<5>(cx, red);
-      xt_ = red[0];
-      cx_ = red[1];
-      nd2 = red[2];
-      const double np2 = red[3], by_ = red[4];
-      const double mu = (xt_ + tau * kappa) / (double)(n + 1);  // :770
-      if (iters > 0) {
-        // _indicators (:880-917) and the loop tests (:1408-1423), in the reference's order
-        const double rho_p = sqrt(np2) / rp0;
-        const double rho_d = sqrt(nd2) / rd0;
-        const double rho_A = fabs(cx_ - by_) / (tau + fabs(by_));
-        const double rho_g = fabs(kappa + cx_ - by_) / rg0;
-        const double rho_mu = mu;  // mu_0 = 1
-        const bool go = (rho_p > a.tol || rho_d > a.tol || rho_A > a.tol) && (mu > a.thr);
-        const bool inf1 = rho_p < a.tol && rho_d < a.tol && rho_g < a.tol && tau < a.tol * fmax(1.0, kappa);
-        const bool inf2 = rho_mu < a.tol && tau < a.tol * fmin(1.0, kappa);
-        if (inf1 || inf2) {
-          status = ST_INFEAS;
-          break;
-        }
-        if (a.max_iter < iters) {
-          status = ST_MAXITER;
-          break;
-        }
-        if (!solved) {
-          status = ST_BREAKDOWN;
-          break;
-        }
-        if (!go) break;
+      s = warp_sum(s);
+      if (cx.lane == 0) {
+        const double r = -(s - bs[i] * tau);  // :765
+        r1[i] = r;
+        accm[0] = fma(r, r, accm[0]);
+        accm[1] = fma(bs[i], y[i], accm[1]);
       }
-      ++iters;
-      const double r3 = -(-cx_ + by_ - kappa);  // :767
+    }
+    double red[5] = {acc[0], acc[1], acc[2], accm[0], accm[1]};
+    cta_sum<5>(cx, red);  // (its barriers also order the G writes before the assembly reads)
+    const double xt_ = red[0], cx_ = red[1], nd2 = red[2], np2 = red[3], by_ = red[4];
+    const double mu = (xt_ + tau * kappa) / (double)(n + 1);  // :770
+    if (iters > 0) {
+      // _indicators (:880-917) and the loop tests (:1408-1423), in the reference's order
+      const double rho_p = sqrt(np2) / rp0;
+      const double rho_d = sqrt(nd2) / rd0;
+      const double rho_A = fabs(cx_ - by_) / (tau + fabs(by_));
+      const double rho_g = fabs(kappa + cx_ - by_) / rg0;
+      const double rho_mu = mu;  // mu_0 = 1
+      const bool go = (rho_p > a.tol || rho_d > a.tol || rho_A > a.tol) && (mu > a.thr);
+      const bool inf1 = rho_p < a.tol && rho_d < a.tol && rho_g < a.tol && tau < a.tol * fmax(1.0, kappa);
+      const bool inf2 = rho_mu < a.tol && tau < a.tol * fmin(1.0, kappa);
+      if (inf1 || inf2) {
+        status = ST_INFEAS;
+        break;
+      }
+      if (a.max_iter < iters) {
+        status = ST_MAXITER;
+        break;
+      }
+      if (!solved) {
+        status = ST_BREAKDOWN;
+        break;
+      }
+      if (!go) break;
+    }
+    ++iters;
+    const double r3 = -(-cx_ + by_ - kappa);  // :767
 
-      // ---- M = A D A^T + delta I, factor (:772-777) ------------------------------------------------
-      assemble_normal_matrix(cx, P, D, a.damping, L);
-      solved = envelope_cholesky(cx, P, L, dg, dgi, fail_flag);
-      if (!solved) continue;  // deltas = 0 (:855-857): the iterate is unchanged, tests run at loop top
+    // ---- M = A D A^T + delta I, factor (:772-777) ------------------------------------------------
+    assemble_normal_matrix(cx, P, G, a.damping, L);
+    // right-hand side of the (p,q) solve (:800): G = D*c, built while the factorisation runs
+    CTA_FOR(k, n) G[k] = D[k] * c[k];
+    solved = block_cholesky(cx, P, L, S.dscr, S.flag);  // (its barriers order the G writes)
+    if (!solved) continue;  // deltas = 0 (:855-857): the iterate is unchanged, the tests run at loop top
+    spmv_rows(cx, P, G, q);
+    CTA_SYNC();
+    // predictor: gamma = 0, eta = 1
+    CTA_FOR(k, n) {
+      const double rxt = -(x[k] * t[k]);               // :788 with gamma = 0
+      const double wk = r2[k] - (1.0 / x[k]) * rxt;    // :801 with eta(0) = 1
+      w[k] = wk;
+      G[k] = D[k] * wk;
+    }
+    CTA_FOR(i, m) q[i] = bs[i] + q[i];  // r = r2 + A(Dinv r1), :666 with (r1,r2) = (c,b)
+    CTA_SYNC();
+    spmv_rows(cx, P, G, v);
+    CTA_SYNC();
+    CTA_FOR(i, m) v[i] = r1[i] + v[i];
+    CTA_SYNC();
+    {
+      double* const rhs2[2] = {q, v};
+      block_solve<2>(cx, P, L, rhs2, S.ybuf);
+    }
+    double cp_, bq_, cu_, bv_;
+    {
+      double acc2[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      CTA_FOR(k, n) {
+        double atq, atv;
+        col_dot2(P, k, q, v, atq, atv);
+        const double dk = D[k], ck = c[k];
+        const double pk = dk * (atq - ck);    // :678 for (c,b)
+        const double uk = dk * (atv - w[k]);  // :678 for the predictor
+        p[k] = pk;
+        dx[k] = uk;
+        acc2[0] = fma(ck, pk, acc2[0]);
+        acc2[2] = fma(ck, uk, acc2[2]);
+        if (!(fabs(pk) < 1e300)) acc2[4] += 1.0;
+      }
+      CTA_FOR(i, m) {
+        acc2[1] = fma(bs[i], q[i], acc2[1]);
+        acc2[3] = fma(bs[i], v[i], acc2[3]);
+        if (!(fabs(q[i]) < 1e300)) acc2[4] += 1.0;
+      }
+      cta_sum<5>(cx, acc2);
+      cp_ = acc2[0];
+      bq_ = acc2[1];
+      cu_ = acc2[2];
+      bv_ = acc2[3];
+      if (acc2[4] > 0.0) {  // NaN in p or q (:805-806) -> unsolved
+        solved = false;
+        continue;
+      }
+    }
 
-      // ---- (p,q) = sym_solve(c, b) (:800, :663-681), once per iteration ---------------------------
-      CTA_FOR(k, n) dw[k] = D[k] * c[k];
-      CTA_SYNC();
-      spmv_rows(cx, P, dw, q);
-      CTA_SYNC();
-      CTA_FOR(i, m) q[i] = bs[i] + q[i];
-      CTA_SYNC();
-      envelope_solve(cx, P, L, dg, dgi, q);
-      double cp_, bq_;
-      {
-        double acc2[3] = {0.0, 0.0, 0.0};
+    // ---- predictor (pass 0) and corrector (pass 1) (:783-847) ---------------------------------------
+    double gamma = 0.0, dtau = 0.0, dkappa = 0.0, minr = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+      const double eta = 1.0 - gamma;
+      const double gm = gamma * mu;
+      double rtk = -(tau * kappa - gm);     // :789
+      if (pass == 1) rtk -= dtau * dkappa;  // :795
+      if (pass == 1) {
         CTA_FOR(k, n) {
-          const double pk = D[k] * (col_dot(P, k, q) - c[k]);
-          p[k] = pk;
-          acc2[0] = fma(c[k], pk, acc2[0]);
-          if (!(fabs(pk) < 1e300)) acc2[2] += 1.0;
-        }
-        CTA_FOR(i, m) {
-          acc2[1] = fma(bs[i], q[i], acc2[1]);
-          if (!(fabs(q[i]) < 1e300)) acc2[2] += 1.0;
-        }
-        cta_sum<3>(cx, acc2);
-        cp_ = acc2[0];
-        bq_ = acc2[1];
-        if (acc2[2] > 0.0) {  // NaN in p or q (:805-806) -> unsolved
-          solved = false;
-          continue;
-        }
-      }
-
-      // ---- predictor (i=0) and corrector (i=1) passes (:783-847) -----------------------------------
-      double gamma = 0.0, dtau = 0.0, dkappa = 0.0, minr = 0.0;
-      for (int pass = 0; pass < 2; ++pass) {
-        const double eta = 1.0 - gamma;
-        const double gm = gamma * mu;
-        double rtk = -(tau * kappa - gm);          // :789
-        if (pass == 1) rtk -= dtau * dkappa;       // :795
-        CTA_FOR(k, n) {
-          double rxt = -(x[k] * t[k] - gm);        // :788
-          if (pass == 1) rxt -= dxdt[k];           // :793
+          const double rxt = -(x[k] * t[k] - gm) - dxdt[k];    // :788,793
           const double wk = eta * r2[k] - (1.0 / x[k]) * rxt;  // :801
           w[k] = wk;
-          dw[k] = D[k] * wk;
+          G[k] = D[k] * wk;
         }
         CTA_SYNC();
-        spmv_rows(cx, P, dw, v);
+        spmv_rows(cx, P, G, v);
         CTA_SYNC();
-        CTA_FOR(i, m) v[i] = eta * r1[i] + v[i];   // r = r2 + A(Dinv r1), :666
+        CTA_FOR(i, m) v[i] = eta * r1[i] + v[i];
         CTA_SYNC();
-        envelope_solve(cx, P, L, dg, dgi, v);
+        {
+          double* const rhs1[1] = {v};
+          block_solve<1>(cx, P, L, rhs1, S.ybuf);
+        }
         double acc3[2] = {0.0, 0.0};
         CTA_FOR(k, n) {
           const double uk = D[k] * (col_dot(P, k, v) - w[k]);  // :678
@@ -482,47 +705,48 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
         }
         CTA_FOR(i, m) acc3[1] = fma(bs[i], v[i], acc3[1]);
         cta_sum<2>(cx, acc3);
-        const double cu_ = acc3[0], bv_ = acc3[1];
-        dtau = ((eta * r3 + 1.0 / tau * rtk - (-cu_ + bv_)) / (1.0 / tau * kappa + (-cp_ + bq_)));  // :837-838
-        dkappa = (rtk - kappa * dtau) / tau;  // :842
-        double mn[1] = {INFINITY};
+        cu_ = acc3[0];
+        bv_ = acc3[1];
+      }
+      dtau = ((eta * r3 + 1.0 / tau * rtk - (-cu_ + bv_)) / (1.0 / tau * kappa + (-cp_ + bq_)));  // :837-838
+      dkappa = (rtk - kappa * dtau) / tau;                                                         // :842
+      double mn[1] = {INFINITY};
+      CTA_FOR(k, n) {
+        const double xk = x[k], tk = t[k];
+        double rxt = -(xk * tk - gm);
+        if (pass == 1) rxt -= dxdt[k];
+        const double dxk = dx[k] + p[k] * dtau;            // :839
+        const double dtk = (1.0 / xk) * (rxt - tk * dxk);  // :841
+        dx[k] = dxk;
+        if (pass == 0) dxdt[k] = dxk * dtk;
+        if (dxk < 0.0) mn[0] = fmin(mn[0], xk / -dxk);  // :871-875
+        if (dtk < 0.0) mn[0] = fmin(mn[0], tk / -dtk);
+      }
+      cta_min<1>(cx, mn);
+      minr = mn[0];
+      // _get_step (:870-878) with alpha0 = 1 (:843); an empty candidate set contributes 1
+      double alpha = fmin(1.0, minr);
+      if (dtau < 0.0) alpha = fmin(alpha, tau / -dtau);
+      if (dkappa < 0.0) alpha = fmin(alpha, kappa / -dkappa);
+      const double oma = 1.0 - alpha;
+      gamma = oma * oma * fmin(0.1, oma);  // :844
+      if (pass == 1) {
+        // ---- step (:1402-1403).  alpha0*min(x/-dx) == min(alpha0*x/-dx) bit for bit
+        double al = fmin(1.0, a.alpha0 * minr);
+        if (dtau < 0.0) al = fmin(al, a.alpha0 * tau / -dtau);  // evaluation order of :874,876
+        if (dkappa < 0.0) al = fmin(al, a.alpha0 * kappa / -dkappa);
         CTA_FOR(k, n) {
           const double xk = x[k], tk = t[k];
-          double rxt = -(xk * tk - gm);
-          if (pass == 1) rxt -= dxdt[k];
-          const double dxk = dx[k] + p[k] * dtau;           // :839
-          const double dtk = (1.0 / xk) * (rxt - tk * dxk);  // :841
-          dx[k] = dxk;
-          if (pass == 0) dxdt[k] = dxk * dtk;
-          if (dxk < 0.0) mn[0] = fmin(mn[0], xk / -dxk);     // :871-875
-          if (dtk < 0.0) mn[0] = fmin(mn[0], tk / -dtk);
+          const double rxt = -(xk * tk - gm) - dxdt[k];
+          const double dxk = dx[k];
+          const double dtk = (1.0 / xk) * (rxt - tk * dxk);
+          x[k] = xk + al * dxk;
+          t[k] = tk + al * dtk;
         }
-        cta_min<1>(cx, mn);
-        minr = mn[0];
-        // _get_step (:870-878) with alpha0 = 1 (:843); an empty candidate set contributes 1
-        double alpha = fmin(1.0, minr);
-        if (dtau < 0.0) alpha = fmin(alpha, tau / -dtau);
-        if (dkappa < 0.0) alpha = fmin(alpha, kappa / -dkappa);
-        const double oma = 1.0 - alpha;
-        gamma = oma * oma * fmin(0.1, oma);                   // :844
-        if (pass == 1) {
-          // ---- step (:1402-1403).  alpha0*min(x/-dx) == min(alpha0*x/-dx) bit for bit
-          double al = fmin(1.0, a.alpha0 * minr);
-          if (dtau < 0.0) al = fmin(al, a.alpha0 * tau / -dtau);        // evaluation order of :874,876
-          if (dkappa < 0.0) al = fmin(al, a.alpha0 * kappa / -dkappa);
-          CTA_FOR(k, n) {
-            const double xk = x[k], tk = t[k];
-            const double rxt = -(xk * tk - gm) - dxdt[k];
-            const double dxk = dx[k];
-            const double dtk = (1.0 / xk) * (rxt - tk * dxk);
-            x[k] = xk + al * dxk;
-            t[k] = tk + al * dtk;
-          }
-          CTA_FOR(i, m) y[i] = y[i] + al * (v[i] + q[i] * dtau);  // d_y = v + q d_tau (:840)
-          tau = tau + al * dtau;
-          kappa = kappa + al * dkappa;
-          CTA_SYNC();
-        }
+        CTA_FOR(i, m) y[i] = y[i] + al * (v[i] + q[i] * dtau);  // d_y = v + q d_tau (:840)
+        tau = tau + al * dtau;
+        kappa = kappa + al * dkappa;
+        CTA_SYNC();
       }
     }
   }
@@ -543,6 +767,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
     a.status[inst] = status;
     a.iters[inst] = iters;
   }
+  CTA_SYNC();
 }
 
 struct BwdParams {
@@ -553,12 +778,14 @@ struct BwdParams {
   long long c_stride;
   const double* b_batch;
   long long b_stride;
+  const double* b_problem;
   const double* gx;  // B x nvar
   double* gc;        // B x nvar
   int* status;
   double* ws;
   long long ws_stride;
-  int factor_in_smem;
+  int* counter;
+  int factor_in_smem, gather_in_smem;
 };
 
 // K5: dL/dc at the saved iterate, VJP form:
@@ -566,20 +793,11 @@ struct BwdParams {
 //          s = (x.g + c.ug - b.w)/(b.q - c.p + mu/tau^2), dc = ug + p s        (ip_model_whole.py:1515-1556)
 //   alter: dc = -X2 (g - A^T M^-1 A (X2 g)) / mu  with x,t normalised by tau   (ip_model_alter.py:1524-1620)
 // with M = A diag(x^2) A^T + damping I in both.
-IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const BwdParams& a, int inst, double* smem) {
-  const int m = P.m, n = P.n, nvar = a.nvar;
-  double* wsi = a.ws + (long long)inst * a.ws_stride;
-  double* L = a.factor_in_smem ? smem : wsi + (long long)W_NVEC * n;
-  double* sv = a.factor_in_smem ? smem + P.sky_size : smem;
-  double* bs = sv + S_B * m;
-  double* q = sv + S_Q * m;
-  double* v = sv + S_V * m;
-  double* dg = sv + S_DG * m;
-  double* dgi = sv + S_DGI * m;
-  int* fail_flag = (int*)(sv + S_NVEC * m);
+IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const BwdParams& a, int inst, double* wsi,
+                              const SmemLayout& S) {
+  const int m = P.m, n = P.n, nvar = a.nvar, mv = P.mv;
+  double *L = S.L, *G = S.G, *bs = S.bs, *q = S.q, *v = S.v;
   double* x2 = wsi + (long long)W_D * n;
-  double* tmp = wsi + (long long)W_DW * n;
-  double* ug = wsi + (long long)W_DX * n;
   const long long slen = 2LL * n + m + 2;
   const double* st = a.state + (long long)inst * slen;
   const double* __restrict__ c = a.c + (long long)inst * a.c_stride;
@@ -589,60 +807,72 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const BwdPa
   const double* ts = st + n + m;
   const double tau = st[2 * n + m], kappa = st[2 * n + m + 1];
   const bool whole = a.mode == 0;
-  const double scale = whole ? 1.0 : 1.0 / tau;  // alter saves x/tau, t/tau (ip_model_alter.py:1459-1461)
 
-  CTA_FOR(i, m) bs[i] = a.b_batch ? a.b_batch[(long long)inst * a.b_stride + P.perm[i]] : (P.b ? P.b[i] : 0.0);
+  CTA_FOR(i, mv) {
+    double bv = 0.0;
+    if (i < m)
+      bv = a.b_batch ? a.b_batch[(long long)inst * a.b_stride + P.perm[i]] : (a.b_problem ? a.b_problem[i] : 0.0);
+    bs[i] = bv;
+    q[i] = 0.0;
+    v[i] = 0.0;
+  }
+  if (cx.tid == 0) G[n] = 0.0;
   double xt[2] = {0.0, 0.0};
   CTA_FOR(k, n) {
-    const double xk = whole ? xs[k] : xs[k] / tau;
+    const double xk = whole ? xs[k] : xs[k] / tau;  // alter saves x/tau, t/tau (ip_model_alter.py:1459-1461)
     const double tk = whole ? ts[k] : ts[k] / tau;
-    x2[k] = xk * xk;
+    const double xx = xk * xk;
+    x2[k] = xx;
+    G[k] = xx;
     xt[0] = fma(xk, tk, xt[0]);
     if (k < nvar) xt[1] = fma(xk, g[k], xt[1]);
   }
   cta_sum<2>(cx, xt);
-  (void)scale;
   const double mu = whole ? (xt[0] + tau * kappa) / (double)(n + 1) : xt[0] / (double)n;  // :1517 | alter :1525
   const double xg = xt[1];
 
-  assemble_normal_matrix(cx, P, x2, a.damping, L);  // :1525-1527,1535
-  const bool ok = envelope_cholesky(cx, P, L, dg, dgi, fail_flag);
+  assemble_normal_matrix(cx, P, G, a.damping, L);  // :1525-1527,1535
+  CTA_FOR(k, n) G[k] = (k < nvar) ? x2[k] * g[k] : 0.0;
+  const bool ok = block_cholesky(cx, P, L, S.dscr, S.flag);
   if (!ok) {
     // the reference raises LinAlgError (:1546-1547); here: zero gradient + status
     CTA_FOR(k, nvar) gc[k] = 0.0;
     if (cx.tid == 0) a.status[inst] = ST_BREAKDOWN;
+    CTA_SYNC();
     return;
   }
-  // w = M^-1 (tau * A (X2 g_hat))
-  CTA_FOR(k, n) tmp[k] = (k < nvar) ? x2[k] * g[k] : 0.0;
+  spmv_rows(cx, P, G, v);  // A (X2 g_hat)
   CTA_SYNC();
-  spmv_rows(cx, P, tmp, v);
-  CTA_SYNC();
-  if (whole) {
-    CTA_FOR(i, m) v[i] = tau * v[i];
-    CTA_SYNC();
-  }
-  envelope_solve(cx, P, L, dg, dgi, v);
   if (!whole) {
+    double* const rhs1[1] = {v};
+    block_solve<1>(cx, P, L, rhs1, S.ybuf);
     CTA_FOR(k, nvar) gc[k] = -x2[k] * (g[k] - col_dot(P, k, v)) / mu;
     if (cx.tid == 0) a.status[inst] = ST_OK;
+    CTA_SYNC();
     return;
   }
-  // q = M^-1 (mu b + A (X2 c))   (:1530,1542)
-  CTA_FOR(k, n) tmp[k] = x2[k] * c[k];
+  CTA_FOR(k, n) G[k] = x2[k] * c[k];
+  CTA_FOR(i, m) v[i] = tau * v[i];  // r1 g = tau A X2 g (:1529)
   CTA_SYNC();
-  spmv_rows(cx, P, tmp, q);
+  spmv_rows(cx, P, G, q);
   CTA_SYNC();
-  CTA_FOR(i, m) q[i] = mu * bs[i] + q[i];
+  CTA_FOR(i, m) q[i] = mu * bs[i] + q[i];  // r2 = mu b + A(X2 c) (:1530)
   CTA_SYNC();
-  envelope_solve(cx, P, L, dg, dgi, q);
+  {
+    double* const rhs2[2] = {q, v};
+    block_solve<2>(cx, P, L, rhs2, S.ybuf);
+  }
+  double* ug = wsi + (long long)W_DX * n;
+  double* pp = wsi + (long long)W_P * n;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   CTA_FOR(k, n) {
+    double atq, atv;
+    col_dot2(P, k, q, v, atq, atv);
     const double gk = (k < nvar) ? g[k] : 0.0;
-    const double ugk = x2[k] * (col_dot(P, k, v) - tau * gk) / mu;  // :1549 applied to g
-    const double pk = x2[k] * (col_dot(P, k, q) - c[k]) / mu;       // :1548
+    const double ugk = x2[k] * (atv - tau * gk) / mu;  // :1549 applied to g
+    const double pk = x2[k] * (atq - c[k]) / mu;       // :1548
     ug[k] = ugk;
-    tmp[k] = pk;
+    pp[k] = pk;
     acc[0] = fma(c[k], ugk, acc[0]);
     acc[1] = fma(c[k], pk, acc[1]);
   }
@@ -652,8 +882,9 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const BwdPa
   }
   cta_sum<4>(cx, acc);
   const double s = (xg + acc[0] - acc[2]) / (acc[3] - acc[1] + mu / (tau * tau));  // :1552-1553
-  CTA_FOR(k, nvar) gc[k] = ug[k] + tmp[k] * s;  // :1554-1556
+  CTA_FOR(k, nvar) gc[k] = ug[k] + pp[k] * s;                                      // :1554-1556
   if (cx.tid == 0) a.status[inst] = ST_OK;
+  CTA_SYNC();
 }
 
 }  // namespace intopt

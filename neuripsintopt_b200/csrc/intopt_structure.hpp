@@ -2,9 +2,14 @@
 //
 // Everything that depends only on the sparsity pattern of the standard-form A is computed once
 // per problem here (the reference redoes its whole host prep per call, Interior/
-// intopt_energy_mlp.py:422): row ordering, the envelope (skyline) layout of chol(A D A^T), and the
-// gather lists that assemble A.diag(d).A^T entry by entry (replaces the dense
-// `A.dot(Dinv.reshape(-1,1)*A.T)` of Interior/ip_model_whole.py:773 and :1525-1527).
+// intopt_energy_mlp.py:422):
+//   * a row ordering that minimises the envelope of M = A D A^T (natural / reverse Cuthill-McKee /
+//     dense-rows-last, the smallest wins);
+//   * the 8x8 block-skyline layout of chol(M) and the static schedule of the blocked right-looking
+//     factorisation (panel rows and trailing block pairs per block column);
+//   * warp-interleaved (ELL-style) gather lists that assemble M entry by entry, replacing the dense
+//     `A.dot(Dinv.reshape(-1,1)*A.T)` of Interior/ip_model_whole.py:773 and :1525-1527;
+//   * A by rows (CSR, one warp per row) and by columns (32-column interleaved groups).
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -14,22 +19,40 @@
 
 namespace intopt {
 
+constexpr int NB = 8;           // block edge of the block-skyline factor
+constexpr int NBB = NB * NB;    // doubles per block
+
 struct HostStructure {
-  int m = 0, n = 0, nnz = 0;
+  int m = 0, n = 0, nnz = 0, mb = 0, m8 = 0;
   std::vector<int> perm;  // internal row i == original row perm[i]
+  // A by rows (internal order): one warp per row
   std::vector<int> csr_ptr, csr_col;
-  std::vector<double> csr_val;  // rows in internal order
-  std::vector<int> csc_ptr, csc_row;
-  std::vector<double> csc_val;  // row indices internal
-  std::vector<int> sky_first, sky_off;  // row i stores columns first[i]..i at off[i]..off[i+1]-1
+  std::vector<double> csr_val;
+  bool a_unit = true;  // every non-zero of A equals 1: value streams are skipped
+  // A by columns, 32 consecutive columns per group, entries interleaved: entry t of column 32g+l sits at
+  // (csc_gptr[g] + t) * 32 + l ; padded with row = m8 (a guaranteed-zero slot of every m-vector) / value 0
+  std::vector<int> csc_gptr, csc_glen;
+  std::vector<uint16_t> csc_row;
+  std::vector<double> csc_val;
+  // scalar envelope (first non-zero column of each row of M in internal order)
+  std::vector<int> sky_first;
   int sky_size = 0;
-  // assembly: entry e (e < n_asm) lives at skyline position asm_pos[e] and equals
-  //   sum_{t in [asm_ptr[e], asm_ptr[e+1])} asm_w[t] * d[asm_k[t]]      (+ damping on the diagonal)
-  std::vector<int> asm_ptr, asm_pos, asm_k;
+  // block skyline: block row I holds block columns fb[I]..I, 64 doubles each (row-major), at boff[I]
+  std::vector<int> fb, boff;
+  int bsize = 0;
+  std::vector<int> dummy_pos;  // diagonal positions of the padding rows m..m8-1 (set to 1)
+  // factorisation schedule
+  std::vector<int> act_ptr, act_blk;               // block rows I > K with fb[I] <= K
+  std::vector<int> pair_ptr, pair_dst, pair_a, pair_b;  // trailing updates of step K: dst -= a * b^T
+  std::vector<unsigned char> next_diag_first;      // pair_ptr[K] is the update of block (K+1,K+1)
+  // assembly gather lists, entries sorted by length (descending), 32 entries per group, interleaved like csc
+  int n_asm = 0;  // padded to a multiple of 32
+  std::vector<int> asm_gptr, asm_glen, asm_pos;  // asm_pos < 0: padding entry
   std::vector<unsigned char> asm_diag;
+  std::vector<int> asm_k;  // index into the gather buffer; n = the zero slot
   std::vector<double> asm_w;
-  bool asm_unit = true;  // every asm_w == 1 (0/1 matrices): the kernel skips the weight stream
-  long long asm_terms = 0, chol_macs = 0;
+  bool asm_unit = true;
+  long long asm_terms = 0, asm_padded = 0, chol_macs = 0, solve_macs = 0;
   int ordering = 0;
 };
 
@@ -55,17 +78,22 @@ inline std::vector<std::vector<int>> row_graph(int m, int n, const int* rp, cons
   return adj;
 }
 
-inline long long envelope_of(const std::vector<std::vector<int>>& adj, const std::vector<int>& perm) {
+// doubles of block-skyline storage for a given ordering (the quantity that decides residency)
+inline long long block_envelope_of(const std::vector<std::vector<int>>& adj, const std::vector<int>& perm) {
   int m = (int)perm.size();
   std::vector<int> inv(m);
   for (int i = 0; i < m; ++i) inv[perm[i]] = i;
-  long long env = 0;
+  int mb = (m + NB - 1) / NB;
+  std::vector<int> fbk(mb);
+  for (int I = 0; I < mb; ++I) fbk[I] = I;
   for (int i = 0; i < m; ++i) {
     int f = i;
     for (int r : adj[perm[i]]) f = std::min(f, inv[r]);
-    env += i - f + 1;
+    fbk[i / NB] = std::min(fbk[i / NB], f / NB);
   }
-  return env;
+  long long blocks = 0;
+  for (int I = 0; I < mb; ++I) blocks += I - fbk[I] + 1;
+  return blocks * NBB;
 }
 
 inline std::vector<int> rcm(const std::vector<std::vector<int>>& adj) {
@@ -75,7 +103,6 @@ inline std::vector<int> rcm(const std::vector<std::vector<int>>& adj) {
   std::vector<char> seen(m, 0);
   auto deg = [&](int v) { return (int)adj[v].size(); };
   auto bfs_levels = [&](int root, std::vector<int>& lvl_nodes) {
-    // returns eccentricity; lvl_nodes = last level
     std::vector<int> dist(m, -1);
     std::queue<int> q;
     q.push(root);
@@ -98,8 +125,7 @@ inline std::vector<int> rcm(const std::vector<std::vector<int>>& adj) {
   };
   for (int start = 0; start < m; ++start) {
     if (seen[start]) continue;
-    // pseudo-peripheral root of this component (George & Liu)
-    int root = start;
+    int root = start;  // pseudo-peripheral root of this component (George & Liu)
     std::vector<int> last;
     int ecc = bfs_levels(root, last);
     for (int it = 0; it < 8; ++it) {
@@ -113,8 +139,7 @@ inline std::vector<int> rcm(const std::vector<std::vector<int>>& adj) {
       ecc = ecc2;
       last.swap(last2);
     }
-    // Cuthill-McKee from root
-    std::queue<int> q;
+    std::queue<int> q;  // Cuthill-McKee from root
     q.push(root);
     seen[root] = 1;
     while (!q.empty()) {
@@ -146,7 +171,7 @@ inline std::vector<int> dense_rows_last(const std::vector<std::vector<int>>& adj
 
 }  // namespace detail
 
-// Returns 0 on success, negative on malformed input.  `force_order`: -1 choose the smallest envelope.
+// Returns 0 on success, negative on malformed input.  `force_order`: -1 = smallest block envelope.
 inline int analyze(int m, int n, const int* rp, const int* ci, const double* val, HostStructure& S,
                    int force_order = -1) {
   if (m <= 0 || n <= 0 || !rp || !ci || !val) return -1;
@@ -156,25 +181,27 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   const int nnz = rp[m];
   for (int e = 0; e < nnz; ++e)
     if (ci[e] < 0 || ci[e] >= n) return -3;
+  if (m + 2 * NB >= 65535) return -4;  // row indices travel as uint16
+  S = HostStructure();
   S.m = m;
   S.n = n;
   S.nnz = nnz;
+  S.mb = (m + NB - 1) / NB;
+  S.m8 = S.mb * NB;
+  const int mb = S.mb;
 
-  // ---- choose the row ordering with the smallest envelope --------------------------------
+  // ---- row ordering ------------------------------------------------------------------------------
   auto adj = detail::row_graph(m, n, rp, ci);
   std::vector<std::vector<int>> cand(3);
   cand[0].resize(m);
   std::iota(cand[0].begin(), cand[0].end(), 0);
   cand[1] = detail::rcm(adj);
-  {
-    // border threshold: rows coupled to more than half of the rows
-    cand[2] = detail::dense_rows_last(adj, std::max(8, m / 2));
-  }
+  cand[2] = detail::dense_rows_last(adj, std::max(8, m / 2));
   int best = 0;
   long long best_env = -1;
   for (int k = 0; k < 3; ++k) {
     if (force_order >= 0 && k != force_order) continue;
-    long long env = detail::envelope_of(adj, cand[k]);
+    long long env = detail::block_envelope_of(adj, cand[k]);
     if (best_env < 0 || env < best_env) {
       best_env = env;
       best = k;
@@ -185,7 +212,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   std::vector<int> inv(m);
   for (int i = 0; i < m; ++i) inv[S.perm[i]] = i;
 
-  // ---- permuted CSR and CSC ---------------------------------------------------------------
+  // ---- A by rows (internal order, columns ascending) ------------------------------------------------
   S.csr_ptr.assign(m + 1, 0);
   S.csr_col.resize(nnz);
   S.csr_val.resize(nnz);
@@ -200,85 +227,152 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
       S.csr_val[dst + t] = val[src + idx[t]];
     }
   }
-  S.csc_ptr.assign(n + 1, 0);
-  for (int e = 0; e < nnz; ++e) S.csc_ptr[S.csr_col[e] + 1]++;
-  for (int k = 0; k < n; ++k) S.csc_ptr[k + 1] += S.csc_ptr[k];
-  S.csc_row.resize(nnz);
-  S.csc_val.resize(nnz);
+  S.a_unit = true;
+  for (double v : S.csr_val)
+    if (v != 1.0) S.a_unit = false;
+
+  // ---- A by columns: plain CSC first, then the interleaved groups ------------------------------------
+  std::vector<int> cptr(n + 1, 0), crow(nnz);
+  std::vector<double> cval(nnz);
+  for (int e = 0; e < nnz; ++e) cptr[S.csr_col[e] + 1]++;
+  for (int k = 0; k < n; ++k) cptr[k + 1] += cptr[k];
   {
-    std::vector<int> fill(S.csc_ptr.begin(), S.csc_ptr.end() - 1);
+    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
     for (int i = 0; i < m; ++i)
       for (int e = S.csr_ptr[i]; e < S.csr_ptr[i + 1]; ++e) {
         int k = S.csr_col[e], d = fill[k]++;
-        S.csc_row[d] = i;  // ascending in i because rows are visited in order
-        S.csc_val[d] = S.csr_val[e];
+        crow[d] = i;  // ascending in i
+        cval[d] = S.csr_val[e];
       }
   }
+  const int ngrp = (n + 31) / 32;
+  S.csc_gptr.assign(ngrp + 1, 0);
+  S.csc_glen.assign(ngrp, 0);
+  for (int g = 0; g < ngrp; ++g) {
+    int len = 0;
+    for (int k = 32 * g; k < std::min(n, 32 * g + 32); ++k) len = std::max(len, cptr[k + 1] - cptr[k]);
+    S.csc_glen[g] = len;
+    S.csc_gptr[g + 1] = S.csc_gptr[g] + len;
+  }
+  S.csc_row.assign((size_t)S.csc_gptr[ngrp] * 32, (uint16_t)S.m8);
+  S.csc_val.assign((size_t)S.csc_gptr[ngrp] * 32, 0.0);
+  for (int k = 0; k < n; ++k) {
+    int g = k >> 5, l = k & 31;
+    for (int t = 0; t < cptr[k + 1] - cptr[k]; ++t) {
+      size_t d = ((size_t)S.csc_gptr[g] + t) * 32 + l;
+      S.csc_row[d] = (uint16_t)crow[cptr[k] + t];
+      S.csc_val[d] = cval[cptr[k] + t];
+    }
+  }
 
-  // ---- envelope layout -----------------------------------------------------------------------
+  // ---- scalar envelope, block skyline -------------------------------------------------------------------
   S.sky_first.assign(m, 0);
+  S.sky_size = 0;
   for (int i = 0; i < m; ++i) {
     int f = i;
     for (int r : adj[S.perm[i]]) f = std::min(f, inv[r]);
     S.sky_first[i] = f;
+    S.sky_size += i - f + 1;
   }
-  S.sky_off.assign(m + 1, 0);
-  for (int i = 0; i < m; ++i) S.sky_off[i + 1] = S.sky_off[i] + (i - S.sky_first[i] + 1);
-  S.sky_size = S.sky_off[m];
+  S.fb.resize(mb);
+  for (int I = 0; I < mb; ++I) S.fb[I] = I;
+  for (int i = 0; i < m; ++i) S.fb[i / NB] = std::min(S.fb[i / NB], S.sky_first[i] / NB);
+  S.boff.assign(mb + 1, 0);
+  for (int I = 0; I < mb; ++I) S.boff[I + 1] = S.boff[I] + (I - S.fb[I] + 1) * NBB;
+  S.bsize = S.boff[mb];
+  auto pos_of = [&](int i, int j) {  // entry (i,j), j <= i, inside the block skyline
+    int I = i / NB, J = j / NB;
+    return S.boff[I] + (J - S.fb[I]) * NBB + (i % NB) * NB + (j % NB);
+  };
+  for (int i = m; i < S.m8; ++i) S.dummy_pos.push_back(pos_of(i, i));
 
-  // ---- assembly gather lists: one list per structurally non-zero lower entry (i >= j) -------
-  // count terms per (i,j): walk the columns; rows inside a column are ascending
+  // ---- factorisation schedule ------------------------------------------------------------------------------
+  S.act_ptr.assign(mb + 1, 0);
+  S.pair_ptr.assign(mb + 1, 0);
+  S.next_diag_first.assign(mb, 0);
+  S.chol_macs = 0;
+  S.solve_macs = 0;
+  for (int K = 0; K < mb; ++K) {
+    std::vector<int> act;
+    for (int I = K + 1; I < mb; ++I)
+      if (S.fb[I] <= K) act.push_back(I);
+    for (int I : act) S.act_blk.push_back(I);
+    S.act_ptr[K + 1] = (int)S.act_blk.size();
+    // pairs (I >= J), the update of the next diagonal block first (look-ahead)
+    std::vector<std::pair<int, int>> pairs;
+    if (!act.empty() && act[0] == K + 1) {
+      pairs.push_back({K + 1, K + 1});
+      S.next_diag_first[K] = 1;
+    }
+    for (size_t a = 0; a < act.size(); ++a)
+      for (size_t b2 = 0; b2 <= a; ++b2) {
+        if (act[a] == K + 1 && act[b2] == K + 1) continue;
+        pairs.push_back({act[a], act[b2]});
+      }
+    for (auto& pr : pairs) {
+      int I = pr.first, J = pr.second;
+      S.pair_dst.push_back(S.boff[I] + (J - S.fb[I]) * NBB);
+      S.pair_a.push_back(S.boff[I] + (K - S.fb[I]) * NBB);
+      S.pair_b.push_back(S.boff[J] + (K - S.fb[J]) * NBB);
+    }
+    S.pair_ptr[K + 1] = (int)S.pair_dst.size();
+    S.chol_macs += (long long)pairs.size() * NB * NB * NB + (long long)act.size() * NB * 36 + 120 + 120;
+    S.solve_macs += 2 * ((long long)act.size() * NBB + 36);
+  }
+
+  // ---- assembly gather lists -------------------------------------------------------------------------------
   S.asm_terms = 0;
   for (int k = 0; k < n; ++k) {
-    long long c = S.csc_ptr[k + 1] - S.csc_ptr[k];
+    long long c = cptr[k + 1] - cptr[k];
     S.asm_terms += c * (c + 1) / 2;
   }
-  // position -> entry id map over the skyline (dense in the envelope)
-  std::vector<int> cnt(S.sky_size, 0);
+  std::vector<int> cnt(S.bsize, 0);
   for (int k = 0; k < n; ++k)
-    for (int a = S.csc_ptr[k]; a < S.csc_ptr[k + 1]; ++a)
-      for (int b2 = S.csc_ptr[k]; b2 <= a; ++b2) {
-        int i = S.csc_row[a], j = S.csc_row[b2];
-        cnt[S.sky_off[i] + (j - S.sky_first[i])]++;
-      }
-  std::vector<int> entry_of(S.sky_size, -1);
-  S.asm_pos.clear();
-  S.asm_ptr.assign(1, 0);
-  S.asm_diag.clear();
+    for (int a = cptr[k]; a < cptr[k + 1]; ++a)
+      for (int b2 = cptr[k]; b2 <= a; ++b2) cnt[pos_of(crow[a], crow[b2])]++;
+  struct Ent {
+    int pos, len;
+    unsigned char diag;
+  };
+  std::vector<Ent> ents;
   for (int i = 0; i < m; ++i)
     for (int j = S.sky_first[i]; j <= i; ++j) {
-      int pos = S.sky_off[i] + (j - S.sky_first[i]);
-      if (cnt[pos] > 0 || i == j) {  // the diagonal is always assembled (it carries the damping)
-        entry_of[pos] = (int)S.asm_pos.size();
-        S.asm_pos.push_back(pos);
-        S.asm_diag.push_back(i == j ? 1 : 0);
-        S.asm_ptr.push_back(S.asm_ptr.back() + cnt[pos]);
-      }
+      int pos = pos_of(i, j);
+      if (cnt[pos] > 0 || i == j) ents.push_back({pos, cnt[pos], (unsigned char)(i == j)});
     }
-  S.asm_k.resize((size_t)S.asm_terms);
-  S.asm_w.resize((size_t)S.asm_terms);
+  std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.len > b.len; });
+  const int ne = (int)ents.size();
+  const int nag = (ne + 31) / 32;
+  S.n_asm = nag * 32;
+  S.asm_pos.assign(S.n_asm, -1);
+  S.asm_diag.assign(S.n_asm, 0);
+  S.asm_gptr.assign(nag + 1, 0);
+  S.asm_glen.assign(nag, 0);
+  std::vector<int> entry_of(S.bsize, -1);
+  for (int e = 0; e < ne; ++e) {
+    S.asm_pos[e] = ents[e].pos;
+    S.asm_diag[e] = ents[e].diag;
+    entry_of[ents[e].pos] = e;
+    S.asm_glen[e / 32] = std::max(S.asm_glen[e / 32], ents[e].len);
+  }
+  for (int g = 0; g < nag; ++g) S.asm_gptr[g + 1] = S.asm_gptr[g] + S.asm_glen[g];
+  S.asm_padded = (long long)S.asm_gptr[nag] * 32;
+  S.asm_k.assign((size_t)S.asm_padded, n);  // n = the zero slot of the gather buffer
+  S.asm_w.assign((size_t)S.asm_padded, 0.0);
   S.asm_unit = true;
   {
-    std::vector<int> fill(S.asm_ptr.begin(), S.asm_ptr.end() - 1);
+    std::vector<int> fill(ne, 0);
     for (int k = 0; k < n; ++k)
-      for (int a = S.csc_ptr[k]; a < S.csc_ptr[k + 1]; ++a)
-        for (int b2 = S.csc_ptr[k]; b2 <= a; ++b2) {
-          int i = S.csc_row[a], j = S.csc_row[b2];
-          int e = entry_of[S.sky_off[i] + (j - S.sky_first[i])];
-          int d = fill[e]++;
-          double w = S.csc_val[a] * S.csc_val[b2];
+      for (int a = cptr[k]; a < cptr[k + 1]; ++a)
+        for (int b2 = cptr[k]; b2 <= a; ++b2) {
+          int e = entry_of[pos_of(crow[a], crow[b2])];
+          int t = fill[e]++;
+          size_t d = ((size_t)S.asm_gptr[e / 32] + t) * 32 + (e % 32);
+          double w = cval[a] * cval[b2];
           S.asm_k[d] = k;
           S.asm_w[d] = w;
           if (w != 1.0) S.asm_unit = false;
         }
-  }
-
-  // ---- MAC count of the envelope Cholesky -------------------------------------------------------
-  S.chol_macs = 0;
-  {
-    // for column j, rows i > j with first[i] <= j contribute (j - max(first[i], first[j])) MACs
-    for (int i = 0; i < m; ++i)
-      for (int j = S.sky_first[i]; j <= i; ++j) S.chol_macs += j - std::max(S.sky_first[i], S.sky_first[j]);
   }
   return 0;
 }

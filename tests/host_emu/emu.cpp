@@ -5,24 +5,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../neuripsintopt_b200/csrc/intopt_solver.cuh"
-#include "../../neuripsintopt_b200/csrc/intopt_structure.hpp"
-
-namespace {
-intopt::ProblemDev view(const intopt::HostStructure& S, const std::vector<double>& b) {
-  intopt::ProblemDev D{};
-  D.m = S.m; D.n = S.n; D.nnz = S.nnz;
-  D.csr_ptr = S.csr_ptr.data(); D.csr_col = S.csr_col.data(); D.csr_val = S.csr_val.data();
-  D.csc_ptr = S.csc_ptr.data(); D.csc_row = S.csc_row.data(); D.csc_val = S.csc_val.data();
-  D.b = b.empty() ? nullptr : b.data();
-  D.perm = S.perm.data();
-  D.sky_first = S.sky_first.data(); D.sky_off = S.sky_off.data(); D.sky_size = S.sky_size;
-  D.n_asm = (int)S.asm_pos.size();
-  D.asm_ptr = S.asm_ptr.data(); D.asm_pos = S.asm_pos.data(); D.asm_diag = S.asm_diag.data();
-  D.asm_k = S.asm_k.data(); D.asm_w = S.asm_w.data(); D.asm_unit = S.asm_unit ? 1 : 0;
-  return D;
-}
-}  // namespace
+#include "../../neuripsintopt_b200/csrc/intopt_bind.hpp"
 
 extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const double* val, const double* b,
                          int force_order, int B, const double* c, long long c_stride, const double* b_batch,
@@ -33,28 +16,33 @@ extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const doubl
   intopt::HostStructure S;
   int rc = intopt::analyze(m, n, rp, ci, val, S, force_order);
   if (rc) return rc;
-  if (envelope_out) *envelope_out = S.sky_size;
+  if (envelope_out) *envelope_out = S.bsize;
   std::vector<double> bperm;
   if (b) {
     bperm.resize(m);
     for (int i = 0; i < m; ++i) bperm[i] = b[S.perm[i]];
   }
-  intopt::ProblemDev P = view(S, bperm);
-  std::vector<double> smem((size_t)S.sky_size + intopt::S_NVEC * m + 1 + 8 * 32);
-  std::vector<double> ws((size_t)intopt::W_NVEC * n * B);
+  intopt::ProblemDev P{};
+  intopt::bind_problem(S, P, [](const auto& v) { return v.data(); });
+  std::vector<double> smem((size_t)S.bsize + intopt::gather_len(n) + intopt::smem_fixed_doubles(S));
+  std::vector<double> ws((size_t)intopt::W_NVEC * n);
+  const intopt::SmemLayout L = intopt::carve(P, smem.data(), nullptr, 1, 1);
   CtaCtx cx;
-  cx.red = smem.data() + S.sky_size + intopt::S_NVEC * m + 1;
+  cx.red = L.red;
   intopt::FwdParams a{};
-  a.B = B; a.c = c; a.c_stride = c_stride; a.b_batch = b_batch; a.b_stride = m; a.init = init; a.xhat = xhat; a.state = state;
-  a.status = status; a.iters = iters; a.ws = ws.data(); a.ws_stride = (long long)intopt::W_NVEC * n;
-  a.factor_in_smem = 1; a.alpha0 = alpha0; a.tol = tol; a.thr = thr; a.damping = damping_fwd; a.max_iter = max_iter;
-  for (int i = 0; i < B; ++i) intopt::forward_instance(cx, P, a, i, smem.data());
+  a.B = B; a.c = c; a.c_stride = c_stride; a.b_batch = b_batch; a.b_stride = m;
+  a.b_problem = b ? bperm.data() : nullptr; a.init = init; a.xhat = xhat; a.state = state;
+  a.status = status; a.iters = iters; a.ws = ws.data(); a.ws_stride = 0;
+  a.factor_in_smem = 1; a.gather_in_smem = 1;
+  a.alpha0 = alpha0; a.tol = tol; a.thr = thr; a.damping = damping_fwd; a.max_iter = max_iter;
+  for (int i = 0; i < B; ++i) intopt::forward_instance(cx, P, a, i, ws.data(), L);
   if (gx && gc) {
     intopt::BwdParams g{};
     g.B = B; g.mode = bwd_mode; g.nvar = nvar; g.damping = damping_bwd; g.state = state; g.c = c;
-    g.c_stride = c_stride; g.b_batch = b_batch; g.b_stride = m; g.gx = gx; g.gc = gc; g.status = bstatus; g.ws = ws.data();
-    g.ws_stride = a.ws_stride; g.factor_in_smem = 1;
-    for (int i = 0; i < B; ++i) intopt::backward_instance(cx, P, g, i, smem.data());
+    g.c_stride = c_stride; g.b_batch = b_batch; g.b_stride = m; g.b_problem = b ? bperm.data() : nullptr;
+    g.gx = gx; g.gc = gc; g.status = bstatus; g.ws = ws.data(); g.ws_stride = 0;
+    g.factor_in_smem = 1; g.gather_in_smem = 1;
+    for (int i = 0; i < B; ++i) intopt::backward_instance(cx, P, g, i, ws.data(), L);
   }
   return 0;
 }
