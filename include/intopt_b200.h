@@ -116,6 +116,12 @@ int intopt_backward(const IntoptProblem* p, int B, int mode, double damping_bwd,
  * the roofline denominator MEASURED_PEAKS.json lacks.  Synchronises the device. */
 int intopt_measure_fp64_peak(double* gflops_out, int repeats);
 
+/* Debug aid for profiles/: enable (1) / disable (0) per-phase SM-cycle accounting of the forward kernel;
+ * if out16_host is non-NULL the 16 cycle buckets are copied out (after a device sync) and reset.
+ * Buckets: 0 setup, 1 residuals+tests, 2 assembly, 3 Cholesky, 4 rhs/spmv, 5 solve(2 rhs), 6 p/u loop,
+ * 7 corrector rhs, 8 solve(1 rhs), 9 direction/ratio/update loops, 10 epilogue. */
+int intopt_debug_phase_cycles(int enable, unsigned long long* out16_host);
+
 #ifdef __cplusplus
 }
 #endif

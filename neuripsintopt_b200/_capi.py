@@ -34,7 +34,7 @@ class IntoptInfo(ctypes.Structure):
 
 EXPORTS = ["intopt_version", "intopt_last_error", "intopt_analyze", "intopt_problem_create",
            "intopt_problem_destroy", "intopt_problem_info", "intopt_workspace_bytes", "intopt_forward",
-           "intopt_backward", "intopt_measure_fp64_peak"]
+           "intopt_backward", "intopt_measure_fp64_peak", "intopt_debug_phase_cycles"]
 
 _lib = None
 
@@ -72,6 +72,7 @@ def lib():
     L.intopt_forward.argtypes = [vp, ci, vp, cll, vp, cll, ctypes.POINTER(IntoptOpts), vp, vp, vp, vp, vp, vp, csz, vp]
     L.intopt_backward.argtypes = [vp, ci, ci, cd, ci, vp, vp, cll, vp, cll, vp, vp, vp, vp, csz, vp]
     L.intopt_measure_fp64_peak.argtypes = [ctypes.POINTER(cd), ci]
+    L.intopt_debug_phase_cycles.argtypes = [ci, vp]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here means the library and the header disagree
     _lib = L
@@ -103,3 +104,16 @@ def measure_fp64_peak(repeats=5):
     out = ctypes.c_double(0.0)
     check(lib().intopt_measure_fp64_peak(ctypes.byref(out), repeats), "intopt_measure_fp64_peak")
     return out.value
+
+
+PHASES = ["setup", "residuals+tests", "assembly", "cholesky", "rhs/spmv", "solve2", "p/u loop", "corrector rhs",
+          "solve1", "direction/ratio/update", "epilogue"]
+
+
+def phase_cycles(enable=True, read=False):
+    """Debug aid: toggle per-phase cycle accounting of the forward kernel; optionally read + reset the buckets."""
+    import numpy as np
+    out = np.zeros(16, dtype=np.uint64)
+    check(lib().intopt_debug_phase_cycles(1 if enable else 0, out.ctypes.data if read else None),
+          "intopt_debug_phase_cycles")
+    return dict(zip(PHASES, out[:len(PHASES)].tolist())) if read else None

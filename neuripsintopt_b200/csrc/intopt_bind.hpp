@@ -7,6 +7,10 @@
 
 namespace intopt {
 
+inline int meta_ints(const HostStructure& S) {
+  return S.mb + 2 * (S.mb + 1) + (int)S.act_blk.size() + (S.m + 1) + (int)S.csc_gptr.size() + (int)S.asm_gptr.size();
+}
+
 template <class Up>
 inline void bind_problem(const HostStructure& S, ProblemDev& D, Up&& up) {
   D.m = S.m;
@@ -15,30 +19,25 @@ inline void bind_problem(const HostStructure& S, ProblemDev& D, Up&& up) {
   D.mb = S.mb;
   D.m8 = S.m8;
   D.mv = S.m8 + 8;
-  D.csr_ptr = up(S.csr_ptr);
+  D.g_csr_ptr = up(S.csr_ptr);
   D.csr_col = up(S.csr_col);
   D.a_unit = S.a_unit ? 1 : 0;
   D.csr_val = S.a_unit ? nullptr : up(S.csr_val);
-  D.csc_gptr = up(S.csc_gptr);
-  D.csc_glen = up(S.csc_glen);
+  D.g_csc_gptr = up(S.csc_gptr);
   D.csc_row = up(S.csc_row);
   D.csc_val = S.a_unit ? nullptr : up(S.csc_val);
   D.perm = up(S.perm);
-  D.fb = up(S.fb);
-  D.boff = up(S.boff);
+  D.g_fb = up(S.fb);
+  D.g_boff = up(S.boff);
   D.bsize = S.bsize;
   D.dummy_pos = up(S.dummy_pos);
   D.n_dummy = (int)S.dummy_pos.size();
-  D.act_ptr = up(S.act_ptr);
-  D.act_blk = up(S.act_blk);
-  D.pair_ptr = up(S.pair_ptr);
-  D.pair_dst = up(S.pair_dst);
-  D.pair_a = up(S.pair_a);
-  D.pair_b = up(S.pair_b);
-  D.next_diag_first = up(S.next_diag_first);
+  D.g_act_ptr = up(S.act_ptr);
+  D.g_act_blk = up(S.act_blk);
+  D.n_act = (int)S.act_blk.size();
+  D.meta_ints = meta_ints(S);
   D.n_asm = S.n_asm;
-  D.asm_gptr = up(S.asm_gptr);
-  D.asm_glen = up(S.asm_glen);
+  D.g_asm_gptr = up(S.asm_gptr);
   D.asm_pos = up(S.asm_pos);
   D.asm_diag = up(S.asm_diag);
   D.asm_k = up(S.asm_k);

@@ -35,8 +35,11 @@ int env_int(const char* name, int dflt) {
 }
 
 // Decide what lives in shared memory.  Preference: factor + gather buffer; then factor only; then neither.
+constexpr int kMaxMetaInts = 4096;  // schedule arrays up to 16 KB are staged in shared memory
+
 void plan_smem(const intopt::HostStructure& S, int* factor_in_smem, int* gather_in_smem, int* smem_bytes) {
-  const size_t fixed = intopt::smem_fixed_doubles(S);
+  const int mi = intopt::meta_ints(S);
+  const size_t fixed = intopt::smem_fixed_doubles(S) + (mi <= kMaxMetaInts ? (size_t)(mi + 1) / 2 : 0);
   const size_t fac = (size_t)S.bsize, gat = (size_t)intopt::gather_len(S.n);
   *factor_in_smem = 1;
   *gather_in_smem = 1;
@@ -106,38 +109,42 @@ __device__ __forceinline__ CtaCtx make_ctx(double* red) {
 // Persistent CTAs: each pulls the next LP instance from an atomic counter until the batch is exhausted,
 // so finished LPs free their SM slot without any host involvement.
 template <int TMAX>
-__global__ void __launch_bounds__(TMAX) intopt_forward_kernel(intopt::ProblemDev P, intopt::FwdParams a) {
+__global__ void __launch_bounds__(TMAX) intopt_forward_kernel(const __grid_constant__ intopt::ProblemDev P,
+                                                               const __grid_constant__ intopt::FwdParams a) {
   extern __shared__ double smem[];
   __shared__ int s_inst;
   double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
   const intopt::SmemLayout S =
       intopt::carve(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
+  const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
     __syncthreads();
     const int inst = s_inst;
     __syncthreads();
     if (inst >= a.B) break;
-    intopt::forward_instance(cx, P, a, inst, wsi, S);
+    intopt::forward_instance(cx, P, M, a, inst, wsi, S);
   }
 }
 
 template <int TMAX>
-__global__ void __launch_bounds__(TMAX) intopt_backward_kernel(intopt::ProblemDev P, intopt::BwdParams a) {
+__global__ void __launch_bounds__(TMAX) intopt_backward_kernel(const __grid_constant__ intopt::ProblemDev P,
+                                                                const __grid_constant__ intopt::BwdParams a) {
   extern __shared__ double smem[];
   __shared__ int s_inst;
   double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
   const intopt::SmemLayout S =
       intopt::carve(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
+  const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
     __syncthreads();
     const int inst = s_inst;
     __syncthreads();
     if (inst >= a.B) break;
-    intopt::backward_instance(cx, P, a, inst, wsi, S);
+    intopt::backward_instance(cx, P, M, a, inst, wsi, S);
   }
 }
 
@@ -162,7 +169,10 @@ __global__ void __launch_bounds__(256) intopt_fp64_peak_kernel(double* out, int 
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+__device__ unsigned long long g_phase_cycles[16];
+
 namespace {
+bool g_profile_phases = false;
 size_t ws_per_slot_doubles(const IntoptProblem* p) {
   size_t per = (size_t)intopt::W_NVEC * p->info.n;
   if (!p->info.factor_in_smem) per += (size_t)p->info.envelope;
@@ -297,6 +307,12 @@ int intopt_forward(const IntoptProblem* p, int B, const double* c, long long c_s
   a.thr = o->thr;
   a.damping = o->damping_fwd;
   a.max_iter = o->max_iter;
+  a.phase_cycles = nullptr;
+  if (g_profile_phases) {
+    void* sym = nullptr;
+    CU_TRY(cudaGetSymbolAddress(&sym, g_phase_cycles));
+    a.phase_cycles = (unsigned long long*)sym;
+  }
   const int grid = std::min(B, p->slots);
   CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
   if (p->info.threads <= 256)
@@ -342,6 +358,18 @@ int intopt_backward(const IntoptProblem* p, int B, int mode, double damping, int
   else
     intopt_backward_kernel<512><<<grid, p->info.threads, p->info.smem_bytes, (cudaStream_t)stream>>>(p->dev, a);
   CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int intopt_debug_phase_cycles(int enable, unsigned long long* out16_host) {
+  // debug aid: enable/disable per-phase cycle accounting of the forward kernel and read + reset the buckets
+  g_profile_phases = enable != 0;
+  unsigned long long zero[16] = {0};
+  if (out16_host) {
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpyFromSymbol(out16_host, g_phase_cycles, sizeof(zero)));
+  }
+  CU_TRY(cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)));
   return 0;
 }
 

@@ -65,36 +65,42 @@ enum { ST_OK = 0, ST_MAXITER = 1, ST_INFEAS = 2, ST_BREAKDOWN = 3, ST_NONFINITE 
 constexpr int KB = 8;  // block edge, == NB of intopt_structure.hpp
 
 struct ProblemDev {
-  int m, n, nnz, mb, m8, mv;  // mv = m8 + 8: length of every m-vector (slot m8 is always zero)
-  const int* csr_ptr;
+  int m, n, nnz, mb, m8, mv, n_act;  // mv = m8 + 8: length of every m-vector (slot m8 is always zero)
+  const int* g_csr_ptr;
   const int* csr_col;
   const double* csr_val;  // null if a_unit
-  const int* csc_gptr;
-  const int* csc_glen;
+  const int* g_csc_gptr;
   const uint16_t* csc_row;
   const double* csc_val;  // null if a_unit
   int a_unit;
   const int* perm;  // internal row -> original row
-  const int* fb;
-  const int* boff;
+  const int* g_fb;
+  const int* g_boff;
   int bsize;
   const int* dummy_pos;
   int n_dummy;
-  const int* act_ptr;
-  const int* act_blk;
-  const int* pair_ptr;
-  const int* pair_dst;
-  const int* pair_a;
-  const int* pair_b;
-  const unsigned char* next_diag_first;
+  const int* g_act_ptr;
+  const int* g_act_blk;
+  int meta_ints;  // total ints of {fb, boff, act_ptr, act_blk, csr_ptr, csc_gptr, asm_gptr}: staged in smem if small
   int n_asm;
-  const int* asm_gptr;
-  const int* asm_glen;
+  const int* g_asm_gptr;
   const int* asm_pos;
   const unsigned char* asm_diag;
   const int* asm_k;
   const double* asm_w;  // null if asm_unit
   int asm_unit;
+};
+
+// The small schedule / pointer arrays that sit on the critical path of every blocked step.  They point into
+// shared memory when staged (stage_meta) and into global memory otherwise.
+struct Meta {
+  const int* fb;
+  const int* boff;
+  const int* act_ptr;
+  const int* act_blk;
+  const int* csr_ptr;
+  const int* csc_gptr;
+  const int* asm_gptr;
 };
 
 // Sum N partial values over the CTA; every thread receives the totals (fixed order => deterministic).
@@ -149,22 +155,22 @@ IO_DEV void cta_min(const CtaCtx& cx, double (&v)[N]) {
 // `g` is the gather buffer holding d (g[n] == 0 is the padding slot).  Each warp walks whole groups
 // of 32 entries whose term lists are interleaved, so index loads are fully coalesced.
 // ---------------------------------------------------------------------------------------------
-IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const double* g, double delta,
+IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* g, double delta,
                                    double* L) {
   CTA_FOR(e, P.bsize) L[e] = 0.0;
   CTA_SYNC();
   CTA_FOR(e, P.n_dummy) L[P.dummy_pos[e]] = 1.0;
   const int ngrp = P.n_asm >> 5;
   WARP_ROWS(grp, ngrp) {
-    const int len = P.asm_glen[grp];
-    const int* __restrict__ kk = P.asm_k + (size_t)P.asm_gptr[grp] * 32;
+    const int g0 = M.asm_gptr[grp], len = M.asm_gptr[grp + 1] - g0;
+    const int* __restrict__ kk = P.asm_k + (size_t)g0 * 32;
     LANE_FOR(l, 0, 32) {
       const int e = grp * 32 + l;
       double s = 0.0;
       if (P.asm_unit) {
         for (int t = 0; t < len; ++t) s += g[kk[t * 32 + l]];
       } else {
-        const double* __restrict__ ww = P.asm_w + (size_t)P.asm_gptr[grp] * 32;
+        const double* __restrict__ ww = P.asm_w + (size_t)g0 * 32;
         for (int t = 0; t < len; ++t) s = fma(ww[t * 32 + l], g[kk[t * 32 + l]], s);
       }
       const int pos = P.asm_pos[e];
@@ -229,12 +235,23 @@ IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr,
 // Returns false (for every thread) on a bad pivot (the reference's cho_factor failure,
 // ip_model_whole.py:742,755-758).
 // ---------------------------------------------------------------------------------------------
-IO_DEV void chol_update_task(const ProblemDev& P, double* L, int p0, int task) {
-  // task = (pair, row r, half h): 4 entries of row r of the destination block
-  const int p = p0 + (task >> 4), r = (task >> 1) & 7, h = task & 1;
-  const double* __restrict__ A = L + P.pair_a[p] + r * KB;
-  const double* __restrict__ Bm = L + P.pair_b[p] + h * 4 * KB;
-  double* dst = L + P.pair_dst[p] + r * KB + h * 4;
+// index of the row of the lower triangle that holds flat pair index p (pairs (a,b), b <= a, row-major)
+IO_FORCEINLINE int tri_row(int p) {
+  int a = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+  while ((a + 1) * (a + 2) / 2 <= p) ++a;
+  while (a * (a + 1) / 2 > p) --a;
+  return a;
+}
+
+IO_DEV void chol_update_task(const ProblemDev& P, const Meta& M, double* L, int K, int a0, int task) {
+  // task = (pair of active block rows (I >= J), row r, half h): 4 entries of row r of block (I,J)
+  const int pi = task >> 4, r = (task >> 1) & 7, h = task & 1;
+  const int ia = tri_row(pi), ib = pi - ia * (ia + 1) / 2;
+  const int I = M.act_blk[a0 + ia], J = M.act_blk[a0 + ib];
+  const int fI = M.fb[I], oI = M.boff[I];
+  const double* __restrict__ A = L + oI + (K - fI) * 64 + r * KB;
+  const double* __restrict__ Bm = L + M.boff[J] + (K - M.fb[J]) * 64 + h * 4 * KB;
+  double* dst = L + oI + (J - fI) * 64 + r * KB + h * 4;
   double a[KB];
 #pragma unroll
   for (int k = 0; k < KB; ++k) a[k] = A[k];
@@ -247,21 +264,21 @@ IO_DEV void chol_update_task(const ProblemDev& P, double* L, int p0, int task) {
   }
 }
 
-IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, double* L, double* scratch, int* fail_flag) {
+IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, double* scratch, int* fail_flag) {
   const int mb = P.mb;
   if (cx.tid == 0) *fail_flag = 0;
   CTA_SYNC();
-  if (cx.warp == 0) diag_block_factor_invert(cx, L + P.boff[0] + (0 - P.fb[0]) * 64, scratch, fail_flag);
+  if (cx.warp == 0) diag_block_factor_invert(cx, L + M.boff[0] + (0 - M.fb[0]) * 64, scratch, fail_flag);
   CTA_SYNC();
   const int o_tid = cx.nwarps > 1 ? cx.tid - cx.warpsize : 0;
   const int o_n = cx.nwarps > 1 ? cx.nthreads - cx.warpsize : 1;
   for (int K = 0; K < mb; ++K) {
-    const double* __restrict__ Linv = L + P.boff[K] + (K - P.fb[K]) * 64;
+    const double* __restrict__ Linv = L + M.boff[K] + (K - M.fb[K]) * 64;
     // (a) panel rows
-    const int a0 = P.act_ptr[K], na = P.act_ptr[K + 1] - a0;
+    const int a0 = M.act_ptr[K], na = M.act_ptr[K + 1] - a0;
     CTA_FOR(idx, na * KB) {
-      const int I = P.act_blk[a0 + (idx >> 3)];
-      double* row = L + P.boff[I] + (K - P.fb[I]) * 64 + (idx & 7) * KB;
+      const int I = M.act_blk[a0 + (idx >> 3)];
+      double* row = L + M.boff[I] + (K - M.fb[I]) * 64 + (idx & 7) * KB;
       double cin[KB], out[KB];
 #pragma unroll
       for (int k = 0; k < KB; ++k) cin[k] = row[k];
@@ -278,18 +295,18 @@ IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, double* L, dou
     }
     CTA_SYNC();
     // (b) trailing update with look-ahead
-    const int p0 = P.pair_ptr[K], np = P.pair_ptr[K + 1] - p0;
-    const int lead = P.next_diag_first[K] ? 1 : 0;  // pair p0 updates block (K+1,K+1)
+    const int np = na * (na + 1) / 2;
+    const int lead = (na > 0 && M.act_blk[a0] == K + 1) ? 1 : 0;  // pair 0 updates block (K+1,K+1)
     if (cx.warp == 0) {
       if (lead) {
-        LANE_FOR(task, 0, 16) chol_update_task(P, L, p0, task);
+        LANE_FOR(task, 0, 16) chol_update_task(P, M, L, K, a0, task);
         WARP_SYNC();
       }
       if (K + 1 < mb)
-        diag_block_factor_invert(cx, L + P.boff[K + 1] + (K + 1 - P.fb[K + 1]) * 64, scratch, fail_flag);
+        diag_block_factor_invert(cx, L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64, scratch, fail_flag);
     }
     if (cx.nwarps == 1 || cx.warp > 0) {
-      for (int task = lead * 16 + o_tid; task < np * 16; task += o_n) chol_update_task(P, L, p0, task);
+      for (int task = lead * 16 + o_tid; task < np * 16; task += o_n) chol_update_task(P, M, L, K, a0, task);
     }
     CTA_SYNC();
   }
@@ -301,12 +318,12 @@ IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, double* L, dou
 // blocks hold Linv).  `ybuf` is NR*8 doubles of scratch.
 // ---------------------------------------------------------------------------------------------
 template <int NR>
-IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const double* L, double* const (&r)[NR],
+IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* L, double* const (&r)[NR],
                         double* ybuf) {
   const int mb = P.mb;
   // forward: L y = r
   for (int K = 0; K < mb; ++K) {
-    const double* __restrict__ Linv = L + P.boff[K] + (K - P.fb[K]) * 64;
+    const double* __restrict__ Linv = L + M.boff[K] + (K - M.fb[K]) * 64;
     CTA_FOR(idx, NR * KB) {
       const int q = idx >> 3, i = idx & 7;
       const double* rk = r[q] + K * KB;
@@ -317,12 +334,12 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const double* L, 
       ybuf[idx] = s;
     }
     CTA_SYNC();
-    const int a0 = P.act_ptr[K], na = P.act_ptr[K + 1] - a0;
+    const int a0 = M.act_ptr[K], na = M.act_ptr[K + 1] - a0;
     CTA_FOR(idx, NR * KB) r[idx >> 3][K * KB + (idx & 7)] = ybuf[idx];
     CTA_FOR(idx, na * KB * NR) {
       const int q = idx / (na * KB), rem = idx - q * (na * KB);
-      const int I = P.act_blk[a0 + (rem >> 3)], rr = rem & 7;
-      const double* __restrict__ row = L + P.boff[I] + (K - P.fb[I]) * 64 + rr * KB;
+      const int I = M.act_blk[a0 + (rem >> 3)], rr = rem & 7;
+      const double* __restrict__ row = L + M.boff[I] + (K - M.fb[I]) * 64 + rr * KB;
       const double* yk = ybuf + q * KB;
       double s = 0.0;
 #pragma unroll
@@ -333,8 +350,8 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const double* L, 
   }
   // backward: L^T z = y
   for (int I = mb - 1; I >= 0; --I) {
-    const int f = P.fb[I];
-    const double* __restrict__ Linv = L + P.boff[I] + (I - f) * 64;
+    const int f = M.fb[I];
+    const double* __restrict__ Linv = L + M.boff[I] + (I - f) * 64;
     CTA_FOR(idx, NR * KB) {
       const int q = idx >> 3, i = idx & 7;
       const double* ri = r[q] + I * KB;
@@ -350,7 +367,7 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const double* L, 
     CTA_FOR(idx, nk * KB * NR) {
       const int q = idx / (nk * KB), rem = idx - q * (nk * KB);
       const int Kc = f + (rem >> 3), k = rem & 7;
-      const double* __restrict__ blk = L + P.boff[I] + (Kc - f) * 64 + k;
+      const double* __restrict__ blk = L + M.boff[I] + (Kc - f) * 64 + k;
       const double* zi = ybuf + q * KB;
       double s = 0.0;
 #pragma unroll
@@ -361,24 +378,37 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const double* L, 
   }
 }
 
-// out[i] = sum_e A_ie * src[col_e]   (row-wise, one warp per row)
-IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const double* src, double* out) {
+// out[i] = sum_e A_ie * src[col_e]   (row-wise, one warp per row, two index chunks in flight)
+IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* src, double* out) {
   WARP_ROWS(i, P.m) {
-    double s = 0.0;
+    const int lo = M.csr_ptr[i], hi = M.csr_ptr[i + 1];
+    double s = 0.0, s2 = 0.0;
     if (P.a_unit) {
-      LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s += src[P.csr_col[e]];
+      for (int e = lo + cx.lane; e < hi; e += 2 * cx.warpsize) {
+        const int e2 = e + cx.warpsize;
+        const int c0 = P.csr_col[e];
+        const int c1 = e2 < hi ? P.csr_col[e2] : c0;
+        s += src[c0];
+        if (e2 < hi) s2 += src[c1];
+      }
     } else {
-      LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s = fma(P.csr_val[e], src[P.csr_col[e]], s);
+      for (int e = lo + cx.lane; e < hi; e += 2 * cx.warpsize) {
+        const int e2 = e + cx.warpsize;
+        const int c0 = P.csr_col[e];
+        const int c1 = e2 < hi ? P.csr_col[e2] : c0;
+        s = fma(P.csr_val[e], src[c0], s);
+        if (e2 < hi) s2 = fma(P.csr_val[e2], src[c1], s2);
+      }
     }
-    s = warp_sum(s);
+    s = warp_sum(s + s2);
     if (cx.lane == 0) out[i] = s;
   }
 }
 
 // (A^T y)_k through the interleaved column groups (lanes of a warp own 32 consecutive columns)
-IO_FORCEINLINE double col_dot(const ProblemDev& P, int k, const double* yv) {
-  const int g = k >> 5, l = k & 31, len = P.csc_glen[g];
-  const size_t base = (size_t)P.csc_gptr[g] * 32 + l;
+IO_FORCEINLINE double col_dot(const ProblemDev& P, const Meta& M, int k, const double* yv) {
+  const int g = k >> 5, l = k & 31, g0 = M.csc_gptr[g], len = M.csc_gptr[g + 1] - g0;
+  const size_t base = (size_t)g0 * 32 + l;
   double s = 0.0;
   if (P.a_unit) {
     for (int t = 0; t < len; ++t) s += yv[P.csc_row[base + (size_t)t * 32]];
@@ -388,9 +418,9 @@ IO_FORCEINLINE double col_dot(const ProblemDev& P, int k, const double* yv) {
   return s;
 }
 
-IO_FORCEINLINE void col_dot2(const ProblemDev& P, int k, const double* y1, const double* y2, double& s1, double& s2) {
-  const int g = k >> 5, l = k & 31, len = P.csc_glen[g];
-  const size_t base = (size_t)P.csc_gptr[g] * 32 + l;
+IO_FORCEINLINE void col_dot2(const ProblemDev& P, const Meta& M, int k, const double* y1, const double* y2, double& s1, double& s2) {
+  const int g = k >> 5, l = k & 31, g0 = M.csc_gptr[g], len = M.csc_gptr[g + 1] - g0;
+  const size_t base = (size_t)g0 * 32 + l;
   s1 = 0.0;
   s2 = 0.0;
   if (P.a_unit) {
@@ -409,6 +439,66 @@ IO_FORCEINLINE void col_dot2(const ProblemDev& P, int k, const double* y1, const
   }
 }
 
+IO_DEV Meta global_meta(const ProblemDev& P) {
+  Meta M;
+  M.fb = P.g_fb;
+  M.boff = P.g_boff;
+  M.act_ptr = P.g_act_ptr;
+  M.act_blk = P.g_act_blk;
+  M.csr_ptr = P.g_csr_ptr;
+  M.csc_gptr = P.g_csc_gptr;
+  M.asm_gptr = P.g_asm_gptr;
+  return M;
+}
+
+// Copies the schedule arrays into shared memory (`dst` holds P.meta_ints ints) and returns pointers to the copies.
+IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
+  const int cnt[7] = {P.mb, P.mb + 1, P.mb + 1, P.n_act, P.m + 1, ((P.n + 31) >> 5) + 1, (P.n_asm >> 5) + 1};
+  const int* src[7] = {P.g_fb, P.g_boff, P.g_act_ptr, P.g_act_blk, P.g_csr_ptr, P.g_csc_gptr, P.g_asm_gptr};
+  int* d = dst;
+  for (int a = 0; a < 7; ++a) {
+    CTA_FOR(i, cnt[a]) d[i] = src[a][i];
+    d += cnt[a];
+  }
+  Meta M;
+  d = dst;
+  M.fb = d;
+  d += cnt[0];
+  M.boff = d;
+  d += cnt[1];
+  M.act_ptr = d;
+  d += cnt[2];
+  M.act_blk = d;
+  d += cnt[3];
+  M.csr_ptr = d;
+  d += cnt[4];
+  M.csc_gptr = d;
+  d += cnt[5];
+  M.asm_gptr = d;
+  CTA_SYNC();
+  return M;
+}
+
+// Optional per-phase cycle accounting (debug aid for profiles/): thread 0 of every CTA adds the cycles since
+// the previous mark to bucket `k` of a global array.  Disabled (null pointer) in normal runs.
+struct PhaseTimer {
+  unsigned long long* buckets;
+  long long last;
+};
+#ifdef INTOPT_HOST_EMU
+#define PHASE_MARK(pt, k) ((void)0)
+#define PHASE_START(pt) ((void)0)
+#else
+#define PHASE_START(pt)                                  \
+  if ((pt).buckets && cx.tid == 0) (pt).last = clock64()
+#define PHASE_MARK(pt, k)                                                   \
+  if ((pt).buckets && cx.tid == 0) {                                        \
+    const long long now_ = clock64();                                       \
+    atomicAdd((pt).buckets + (k), (unsigned long long)(now_ - (pt).last));  \
+    (pt).last = now_;                                                       \
+  }
+#endif
+
 // workspace n-vector slots (global, per CTA)
 enum { W_X = 0, W_T, W_D, W_R2, W_P, W_W, W_DX, W_DXDT, W_NVEC };
 // shared-memory m-vector slots
@@ -418,6 +508,7 @@ constexpr int S_SCRATCH = 2 * KB + (KB + KB * KB) + 8 * 32 + 2;  // ybuf + diag 
 struct SmemLayout {
   double *L, *G, *bs, *y, *r1, *q, *v, *ybuf, *dscr, *red;
   int* flag;
+  int* meta;  // P.meta_ints ints when the schedule is staged in shared memory
 };
 
 IO_HD int gather_len(int n) { return (n + 2) & ~1; }
@@ -450,6 +541,7 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
   s.dscr = p + 2 * KB;
   s.red = s.dscr + KB + KB * KB;
   s.flag = (int*)(s.red + 8 * 32);
+  s.meta = (int*)(s.red + 8 * 32 + 2);
   return s;
 }
 
@@ -471,9 +563,10 @@ struct FwdParams {
   int factor_in_smem, gather_in_smem;
   double alpha0, tol, thr, damping;
   int max_iter;
+  unsigned long long* phase_cycles;  // null unless profiling
 };
 
-IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdParams& a, int inst, double* wsi,
+IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst, double* wsi,
                              const SmemLayout& S) {
   const int m = P.m, n = P.n, mv = P.mv;
   double *L = S.L, *G = S.G, *bs = S.bs, *y = S.y, *r1 = S.r1, *q = S.q, *v = S.v;
@@ -487,6 +580,8 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
   double* dxdt = wsi + (long long)W_DXDT * n;
   const double* __restrict__ c = a.c + (long long)inst * a.c_stride;
 
+  PhaseTimer pt{a.phase_cycles, 0};
+  PHASE_START(pt);
   // ---- load b, initial point (_initialization :647-661); padded slots of m-vectors are zero ---------
   CTA_FOR(i, mv) {
     double bv = 0.0;
@@ -534,9 +629,9 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
     WARP_ROWS(i, m) {
       double s = 0.0;
       if (P.a_unit) {
-        LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s += 1.0;
+        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s += 1.0;
       } else {
-        LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s += P.csr_val[e];
+        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s += P.csr_val[e];
       }
       s = warp_sum(s);
       if (cx.lane == 0) {
@@ -556,12 +651,13 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
   bool solved = true;
   if (nonfinite) status = ST_NONFINITE;  // the reference raises LinAlgError here (:1332-1341)
 
+  PHASE_MARK(pt, 0);
   while (status != ST_NONFINITE) {
     // ---- residuals at the current iterate (:765-770; the same r_p, r_d as _indicators :887-894) ----
     double acc[3] = {0.0, 0.0, 0.0};
     CTA_FOR(k, n) {
       const double xk = x[k], tk = t[k], ck = c[k];
-      const double aty = col_dot(P, k, y);
+      const double aty = col_dot(P, M, k, y);
       const double r = -(aty + tk - ck * tau);  // :766
       const double dk = xk / tk;                // :772
       r2[k] = r;
@@ -575,9 +671,9 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
     WARP_ROWS(i, m) {
       double s = 0.0;
       if (P.a_unit) {
-        LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s += x[P.csr_col[e]];
+        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s += x[P.csr_col[e]];
       } else {
-        LANE_FOR(e, P.csr_ptr[i], P.csr_ptr[i + 1]) s = fma(P.csr_val[e], x[P.csr_col[e]], s);
+        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s = fma(P.csr_val[e], x[P.csr_col[e]], s);
       }
       s = warp_sum(s);
       if (cx.lane == 0) {
@@ -617,14 +713,17 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
     }
     ++iters;
     const double r3 = -(-cx_ + by_ - kappa);  // :767
+    PHASE_MARK(pt, 1);
 
     // ---- M = A D A^T + delta I, factor (:772-777) ------------------------------------------------
-    assemble_normal_matrix(cx, P, G, a.damping, L);
+    assemble_normal_matrix(cx, P, M, G, a.damping, L);
+    PHASE_MARK(pt, 2);
     // right-hand side of the (p,q) solve (:800): G = D*c, built while the factorisation runs
     CTA_FOR(k, n) G[k] = D[k] * c[k];
-    solved = block_cholesky(cx, P, L, S.dscr, S.flag);  // (its barriers order the G writes)
+    solved = block_cholesky(cx, P, M, L, S.dscr, S.flag);  // (its barriers order the G writes)
+    PHASE_MARK(pt, 3);
     if (!solved) continue;  // deltas = 0 (:855-857): the iterate is unchanged, the tests run at loop top
-    spmv_rows(cx, P, G, q);
+    spmv_rows(cx, P, M, G, q);
     CTA_SYNC();
     // predictor: gamma = 0, eta = 1
     CTA_FOR(k, n) {
@@ -635,20 +734,22 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
     }
     CTA_FOR(i, m) q[i] = bs[i] + q[i];  // r = r2 + A(Dinv r1), :666 with (r1,r2) = (c,b)
     CTA_SYNC();
-    spmv_rows(cx, P, G, v);
+    spmv_rows(cx, P, M, G, v);
     CTA_SYNC();
     CTA_FOR(i, m) v[i] = r1[i] + v[i];
     CTA_SYNC();
+    PHASE_MARK(pt, 4);
     {
       double* const rhs2[2] = {q, v};
-      block_solve<2>(cx, P, L, rhs2, S.ybuf);
+      block_solve<2>(cx, P, M, L, rhs2, S.ybuf);
     }
+    PHASE_MARK(pt, 5);
     double cp_, bq_, cu_, bv_;
     {
       double acc2[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
       CTA_FOR(k, n) {
         double atq, atv;
-        col_dot2(P, k, q, v, atq, atv);
+        col_dot2(P, M, k, q, v, atq, atv);
         const double dk = D[k], ck = c[k];
         const double pk = dk * (atq - ck);    // :678 for (c,b)
         const double uk = dk * (atv - w[k]);  // :678 for the predictor
@@ -674,6 +775,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
       }
     }
 
+    PHASE_MARK(pt, 6);
     // ---- predictor (pass 0) and corrector (pass 1) (:783-847) ---------------------------------------
     double gamma = 0.0, dtau = 0.0, dkappa = 0.0, minr = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
@@ -689,17 +791,19 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
           G[k] = D[k] * wk;
         }
         CTA_SYNC();
-        spmv_rows(cx, P, G, v);
+        spmv_rows(cx, P, M, G, v);
         CTA_SYNC();
         CTA_FOR(i, m) v[i] = eta * r1[i] + v[i];
         CTA_SYNC();
+        PHASE_MARK(pt, 7);
         {
           double* const rhs1[1] = {v};
-          block_solve<1>(cx, P, L, rhs1, S.ybuf);
+          block_solve<1>(cx, P, M, L, rhs1, S.ybuf);
         }
+        PHASE_MARK(pt, 8);
         double acc3[2] = {0.0, 0.0};
         CTA_FOR(k, n) {
-          const double uk = D[k] * (col_dot(P, k, v) - w[k]);  // :678
+          const double uk = D[k] * (col_dot(P, M, k, v) - w[k]);  // :678
           dx[k] = uk;
           acc3[0] = fma(c[k], uk, acc3[0]);
         }
@@ -749,6 +853,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
         CTA_SYNC();
       }
     }
+    PHASE_MARK(pt, 9);
   }
 
   // ---- epilogue (:1441-1447): x_hat = x / tau, save the iterate ------------------------------------
@@ -768,6 +873,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const FwdPar
     a.iters[inst] = iters;
   }
   CTA_SYNC();
+  PHASE_MARK(pt, 10);
 }
 
 struct BwdParams {
@@ -793,7 +899,7 @@ struct BwdParams {
 //          s = (x.g + c.ug - b.w)/(b.q - c.p + mu/tau^2), dc = ug + p s        (ip_model_whole.py:1515-1556)
 //   alter: dc = -X2 (g - A^T M^-1 A (X2 g)) / mu  with x,t normalised by tau   (ip_model_alter.py:1524-1620)
 // with M = A diag(x^2) A^T + damping I in both.
-IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const BwdParams& a, int inst, double* wsi,
+IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const BwdParams& a, int inst, double* wsi,
                               const SmemLayout& S) {
   const int m = P.m, n = P.n, nvar = a.nvar, mv = P.mv;
   double *L = S.L, *G = S.G, *bs = S.bs, *q = S.q, *v = S.v;
@@ -831,9 +937,9 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const BwdPa
   const double mu = whole ? (xt[0] + tau * kappa) / (double)(n + 1) : xt[0] / (double)n;  // :1517 | alter :1525
   const double xg = xt[1];
 
-  assemble_normal_matrix(cx, P, G, a.damping, L);  // :1525-1527,1535
+  assemble_normal_matrix(cx, P, M, G, a.damping, L);  // :1525-1527,1535
   CTA_FOR(k, n) G[k] = (k < nvar) ? x2[k] * g[k] : 0.0;
-  const bool ok = block_cholesky(cx, P, L, S.dscr, S.flag);
+  const bool ok = block_cholesky(cx, P, M, L, S.dscr, S.flag);
   if (!ok) {
     // the reference raises LinAlgError (:1546-1547); here: zero gradient + status
     CTA_FOR(k, nvar) gc[k] = 0.0;
@@ -841,12 +947,12 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const BwdPa
     CTA_SYNC();
     return;
   }
-  spmv_rows(cx, P, G, v);  // A (X2 g_hat)
+  spmv_rows(cx, P, M, G, v);  // A (X2 g_hat)
   CTA_SYNC();
   if (!whole) {
     double* const rhs1[1] = {v};
-    block_solve<1>(cx, P, L, rhs1, S.ybuf);
-    CTA_FOR(k, nvar) gc[k] = -x2[k] * (g[k] - col_dot(P, k, v)) / mu;
+    block_solve<1>(cx, P, M, L, rhs1, S.ybuf);
+    CTA_FOR(k, nvar) gc[k] = -x2[k] * (g[k] - col_dot(P, M, k, v)) / mu;
     if (cx.tid == 0) a.status[inst] = ST_OK;
     CTA_SYNC();
     return;
@@ -854,20 +960,20 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const BwdPa
   CTA_FOR(k, n) G[k] = x2[k] * c[k];
   CTA_FOR(i, m) v[i] = tau * v[i];  // r1 g = tau A X2 g (:1529)
   CTA_SYNC();
-  spmv_rows(cx, P, G, q);
+  spmv_rows(cx, P, M, G, q);
   CTA_SYNC();
   CTA_FOR(i, m) q[i] = mu * bs[i] + q[i];  // r2 = mu b + A(X2 c) (:1530)
   CTA_SYNC();
   {
     double* const rhs2[2] = {q, v};
-    block_solve<2>(cx, P, L, rhs2, S.ybuf);
+    block_solve<2>(cx, P, M, L, rhs2, S.ybuf);
   }
   double* ug = wsi + (long long)W_DX * n;
   double* pp = wsi + (long long)W_P * n;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   CTA_FOR(k, n) {
     double atq, atv;
-    col_dot2(P, k, q, v, atq, atv);
+    col_dot2(P, M, k, q, v, atq, atv);
     const double gk = (k < nvar) ? g[k] : 0.0;
     const double ugk = x2[k] * (atv - tau * gk) / mu;  // :1549 applied to g
     const double pk = x2[k] * (atq - c[k]) / mu;       // :1548

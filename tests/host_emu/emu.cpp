@@ -24,25 +24,27 @@ extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const doubl
   }
   intopt::ProblemDev P{};
   intopt::bind_problem(S, P, [](const auto& v) { return v.data(); });
-  std::vector<double> smem((size_t)S.bsize + intopt::gather_len(n) + intopt::smem_fixed_doubles(S));
+  std::vector<double> smem((size_t)S.bsize + intopt::gather_len(n) + intopt::smem_fixed_doubles(S) +
+                           (intopt::meta_ints(S) + 1) / 2);
   std::vector<double> ws((size_t)intopt::W_NVEC * n);
   const intopt::SmemLayout L = intopt::carve(P, smem.data(), nullptr, 1, 1);
   CtaCtx cx;
   cx.red = L.red;
+  const intopt::Meta M = intopt::stage_meta(cx, P, L.meta);
   intopt::FwdParams a{};
   a.B = B; a.c = c; a.c_stride = c_stride; a.b_batch = b_batch; a.b_stride = m;
   a.b_problem = b ? bperm.data() : nullptr; a.init = init; a.xhat = xhat; a.state = state;
   a.status = status; a.iters = iters; a.ws = ws.data(); a.ws_stride = 0;
   a.factor_in_smem = 1; a.gather_in_smem = 1;
   a.alpha0 = alpha0; a.tol = tol; a.thr = thr; a.damping = damping_fwd; a.max_iter = max_iter;
-  for (int i = 0; i < B; ++i) intopt::forward_instance(cx, P, a, i, ws.data(), L);
+  for (int i = 0; i < B; ++i) intopt::forward_instance(cx, P, M, a, i, ws.data(), L);
   if (gx && gc) {
     intopt::BwdParams g{};
     g.B = B; g.mode = bwd_mode; g.nvar = nvar; g.damping = damping_bwd; g.state = state; g.c = c;
     g.c_stride = c_stride; g.b_batch = b_batch; g.b_stride = m; g.b_problem = b ? bperm.data() : nullptr;
     g.gx = gx; g.gc = gc; g.status = bstatus; g.ws = ws.data(); g.ws_stride = 0;
     g.factor_in_smem = 1; g.gather_in_smem = 1;
-    for (int i = 0; i < B; ++i) intopt::backward_instance(cx, P, g, i, ws.data(), L);
+    for (int i = 0; i < B; ++i) intopt::backward_instance(cx, P, M, g, i, ws.data(), L);
   }
   return 0;
 }
