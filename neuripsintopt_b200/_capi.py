@@ -107,7 +107,8 @@ def measure_fp64_peak(repeats=5):
 
 
 PHASES = ["setup", "residuals+tests", "assembly", "cholesky", "rhs/spmv", "solve2", "p/u loop", "corrector rhs",
-          "solve1", "direction/ratio/update", "epilogue"]
+          "solve1", "direction/ratio/update", "epilogue", "chol:panel", "chol:lead-update(w0)", "chol:diag(w0)",
+          "chol:wait-others"]
 
 
 def phase_cycles(enable=True, read=False):

@@ -40,7 +40,8 @@ inline void bind_problem(const HostStructure& S, ProblemDev& D, Up&& up) {
   D.g_asm_gptr = up(S.asm_gptr);
   D.asm_pos = up(S.asm_pos);
   D.asm_diag = up(S.asm_diag);
-  D.asm_k = up(S.asm_k);
+  D.asm_k16 = S.asm_k16.empty() ? nullptr : up(S.asm_k16);
+  D.asm_k = S.asm_k16.empty() ? up(S.asm_k) : nullptr;
   D.asm_unit = S.asm_unit ? 1 : 0;
   D.asm_w = S.asm_unit ? nullptr : up(S.asm_w);
 }

@@ -40,7 +40,7 @@ constexpr int kMaxMetaInts = 4096;  // schedule arrays up to 16 KB are staged in
 void plan_smem(const intopt::HostStructure& S, int* factor_in_smem, int* gather_in_smem, int* smem_bytes) {
   const int mi = intopt::meta_ints(S);
   const size_t fixed = intopt::smem_fixed_doubles(S) + (mi <= kMaxMetaInts ? (size_t)(mi + 1) / 2 : 0);
-  const size_t fac = (size_t)S.bsize, gat = (size_t)intopt::gather_len(S.n);
+  const size_t fac = (size_t)S.bsize, gat = 2 * (size_t)intopt::gather_len(S.n);
   *factor_in_smem = 1;
   *gather_in_smem = 1;
   if ((fixed + fac + gat) * 8 > (size_t)kMaxDynSmem) {
@@ -109,9 +109,9 @@ __device__ __forceinline__ CtaCtx make_ctx(double* red) {
 // Persistent CTAs: each pulls the next LP instance from an atomic counter until the batch is exhausted,
 // so finished LPs free their SM slot without any host involvement.
 template <int TMAX>
-__global__ void __launch_bounds__(TMAX) intopt_forward_kernel(const __grid_constant__ intopt::ProblemDev P,
+__global__ void __launch_bounds__(TMAX, 512 / TMAX) intopt_forward_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                const __grid_constant__ intopt::FwdParams a) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ int s_inst;
   double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
   const intopt::SmemLayout S =
@@ -129,9 +129,9 @@ __global__ void __launch_bounds__(TMAX) intopt_forward_kernel(const __grid_const
 }
 
 template <int TMAX>
-__global__ void __launch_bounds__(TMAX) intopt_backward_kernel(const __grid_constant__ intopt::ProblemDev P,
+__global__ void __launch_bounds__(TMAX, 512 / TMAX) intopt_backward_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                 const __grid_constant__ intopt::BwdParams a) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ int s_inst;
   double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
   const intopt::SmemLayout S =
@@ -176,7 +176,7 @@ bool g_profile_phases = false;
 size_t ws_per_slot_doubles(const IntoptProblem* p) {
   size_t per = (size_t)intopt::W_NVEC * p->info.n;
   if (!p->info.factor_in_smem) per += (size_t)p->info.envelope;
-  if (!p->info.gather_in_smem) per += (size_t)intopt::gather_len(p->info.n);
+  if (!p->info.gather_in_smem) per += 2 * (size_t)intopt::gather_len(p->info.n);
   return (per + 1) & ~(size_t)1;
 }
 }  // namespace

@@ -86,7 +86,8 @@ struct ProblemDev {
   const int* g_asm_gptr;
   const int* asm_pos;
   const unsigned char* asm_diag;
-  const int* asm_k;
+  const int* asm_k;          // 32-bit gather indices, or
+  const uint16_t* asm_k16;   // 16-bit ones when n < 65535 (asm_k is then null)
   const double* asm_w;  // null if asm_unit
   int asm_unit;
 };
@@ -155,6 +156,46 @@ IO_DEV void cta_min(const CtaCtx& cx, double (&v)[N]) {
 // `g` is the gather buffer holding d (g[n] == 0 is the padding slot).  Each warp walks whole groups
 // of 32 entries whose term lists are interleaved, so index loads are fully coalesced.
 // ---------------------------------------------------------------------------------------------
+template <class IT>
+IO_FORCEINLINE double gather_sum_unit(const IT* __restrict__ kk, const double* g, int len) {
+  double s0 = 0.0, s1 = 0.0;
+  int t = 0;
+  for (; t + 8 <= len; t += 8) {  // eight independent index loads in flight per lane
+    int k[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) k[u] = kk[(t + u) * 32];
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) {
+      s0 += g[k[u]];
+      s1 += g[k[u + 1]];
+    }
+  }
+  for (; t < len; ++t) s0 += g[kk[t * 32]];
+  return s0 + s1;
+}
+
+template <class IT>
+IO_FORCEINLINE double gather_sum_weighted(const IT* __restrict__ kk, const double* __restrict__ ww, const double* g,
+                                          int len) {
+  double s0 = 0.0, s1 = 0.0;
+  int t = 0;
+  for (; t + 4 <= len; t += 4) {
+    int k[4];
+    double w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      k[u] = kk[(t + u) * 32];
+      w[u] = ww[(t + u) * 32];
+    }
+    s0 = fma(w[0], g[k[0]], s0);
+    s1 = fma(w[1], g[k[1]], s1);
+    s0 = fma(w[2], g[k[2]], s0);
+    s1 = fma(w[3], g[k[3]], s1);
+  }
+  for (; t < len; ++t) s0 = fma(ww[t * 32], g[kk[t * 32]], s0);
+  return s0 + s1;
+}
+
 IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* g, double delta,
                                    double* L) {
   CTA_FOR(e, P.bsize) L[e] = 0.0;
@@ -163,15 +204,16 @@ IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const 
   const int ngrp = P.n_asm >> 5;
   WARP_ROWS(grp, ngrp) {
     const int g0 = M.asm_gptr[grp], len = M.asm_gptr[grp + 1] - g0;
-    const int* __restrict__ kk = P.asm_k + (size_t)g0 * 32;
     LANE_FOR(l, 0, 32) {
       const int e = grp * 32 + l;
-      double s = 0.0;
-      if (P.asm_unit) {
-        for (int t = 0; t < len; ++t) s += g[kk[t * 32 + l]];
+      const size_t base = (size_t)g0 * 32 + l;
+      double s;
+      if (P.asm_k16) {
+        s = P.asm_unit ? gather_sum_unit(P.asm_k16 + base, g, len)
+                       : gather_sum_weighted(P.asm_k16 + base, P.asm_w + base, g, len);
       } else {
-        const double* __restrict__ ww = P.asm_w + (size_t)g0 * 32;
-        for (int t = 0; t < len; ++t) s = fma(ww[t * 32 + l], g[kk[t * 32 + l]], s);
+        s = P.asm_unit ? gather_sum_unit(P.asm_k + base, g, len)
+                       : gather_sum_weighted(P.asm_k + base, P.asm_w + base, g, len);
       }
       const int pos = P.asm_pos[e];
       if (pos >= 0) L[pos] = P.asm_diag[e] ? s + delta : s;
@@ -180,57 +222,167 @@ IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const 
   CTA_SYNC();
 }
 
-// Cholesky of one 8x8 diagonal block (lower part of row-major `blk`), then its inverse written over it:
-// on exit blk holds Linv = L_KK^-1 (lower).  Executed by ONE warp: lane i owns row i (factor) / column i
-// (inverse).  `scr` is 8 + 64 doubles of scratch.  A non-positive / non-finite pivot sets *fail and
-// continues with pivot 1.
+// Optional per-phase cycle accounting (debug aid for profiles/): thread 0 of every CTA adds the cycles since
+// the previous mark to bucket `k` of a global array.  Disabled (null pointer) in normal runs.
+struct PhaseTimer {
+  unsigned long long* buckets;
+  long long last;
+};
+#ifdef INTOPT_HOST_EMU
+#define PHASE_MARK(pt, k) ((void)0)
+#define PHASE_START(pt) ((void)0)
+#else
+#define PHASE_START(pt)                                  \
+  if ((pt).buckets && cx.tid == 0) (pt).last = clock64()
+#define PHASE_MARK(pt, k)                                                   \
+  if ((pt).buckets && cx.tid == 0) {                                        \
+    const long long now_ = clock64();                                       \
+    atomicAdd((pt).buckets + (k), (unsigned long long)(now_ - (pt).last));  \
+    (pt).last = now_;                                                       \
+  }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// 8x8 block storage.  Row-major, but the four 16-byte chunks of row r are XOR-swizzled by (r>>1)&3, so a
+// 128-bit access to the same logical chunk of 8 different rows touches 8 different bank groups
+// (conflict-free), as does a 128-bit access to the four chunks of one row.
+// ---------------------------------------------------------------------------------------------
+#ifdef INTOPT_HOST_EMU
+struct alignas(16) D2 {
+  double x, y;
+};
+#else
+typedef double2 D2;
+#endif
+IO_HD int bswz(int r) { return (r >> 1) & 3; }
+IO_HD int bidx(int r, int k) { return r * 8 + ((((k >> 1) ^ ((r >> 1) & 3))) << 1) + (k & 1); }
+
+IO_FORCEINLINE void load_row(const double* blk, int r, double (&v)[KB]) {
+  const D2* p = reinterpret_cast<const D2*>(blk + r * KB);
+  const int sw = bswz(r);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const D2 t = p[c ^ sw];
+    v[2 * c] = t.x;
+    v[2 * c + 1] = t.y;
+  }
+}
+IO_FORCEINLINE void store_row(double* blk, int r, const double (&v)[KB]) {
+  D2* p = reinterpret_cast<D2*>(blk + r * KB);
+  const int sw = bswz(r);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    D2 t;
+    t.x = v[2 * c];
+    t.y = v[2 * c + 1];
+    p[c ^ sw] = t;
+  }
+}
+IO_FORCEINLINE void load_vec8(const double* v8, double (&v)[KB]) {
+  const D2* p = reinterpret_cast<const D2*>(v8);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const D2 t = p[c];
+    v[2 * c] = t.x;
+    v[2 * c + 1] = t.y;
+  }
+}
+
+// Cholesky of one 8x8 diagonal block (lower part), then its inverse written over it: on exit the block
+// holds Linv = L_KK^-1 (lower).  Executed by ONE warp.  `scr` is 8 + 64 doubles of scratch.
+// A non-positive / non-finite pivot sets *fail and continues with pivot 1.
+#ifdef INTOPT_HOST_EMU
+// single-threaded test build: plain column Cholesky + forward substitution
 IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr, int* fail) {
   double* col = scr;
   double* inv = scr + KB;
   for (int j = 0; j < KB; ++j) {
     LANE_FOR(i, j, KB) {
-      double s = blk[i * KB + j];
-      for (int k = 0; k < j; ++k) s = fma(-blk[i * KB + k], blk[j * KB + k], s);
+      double s = blk[bidx(i, j)];
+      for (int k = 0; k < j; ++k) s = fma(-blk[bidx(i, k)], blk[bidx(j, k)], s);
       col[i] = s;
     }
-    WARP_SYNC();
     double piv = col[j];
     if (!(piv > 0.0) || !(piv < 1e300)) {
-      if (cx.lane == 0) *fail = 1;
+      *fail = 1;
       piv = 1.0;
     }
     const double dj = sqrt(piv);
     const double rinv = 1.0 / dj;
-    LANE_FOR(i, j, KB) blk[i * KB + j] = (i == j) ? dj : col[i] * rinv;
-    WARP_SYNC();
+    LANE_FOR(i, j, KB) blk[bidx(i, j)] = (i == j) ? dj : col[i] * rinv;
   }
-  // inverse, one column per lane: X(:,c) = L^-1 e_c by forward substitution
   LANE_FOR(c, 0, KB) {
     double x[KB];
-#pragma unroll
     for (int i = 0; i < KB; ++i) {
       double s = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < KB; ++k)
-        if (k < i && k >= c) s = fma(-blk[i * KB + k], x[k], s);
-      x[i] = (i >= c) ? s / blk[i * KB + i] : 0.0;
+      for (int k = c; k < i; ++k) s = fma(-blk[bidx(i, k)], x[k], s);
+      x[i] = (i >= c) ? s / blk[bidx(i, i)] : 0.0;
     }
-#pragma unroll
     for (int i = 0; i < KB; ++i) inv[i * KB + c] = x[i];
   }
-  WARP_SYNC();
-  LANE_FOR(e, 0, KB * KB) {
-    if ((e & 7) <= (e >> 3)) blk[e] = inv[e];
-  }
-  WARP_SYNC();
+  for (int i = 0; i < KB; ++i)
+    for (int k = 0; k <= i; ++k) blk[bidx(i, k)] = inv[i * KB + k];
 }
+#else
+// CUDA build: the block lives in registers (lane i & 7 owns row i, lanes 8..31 mirror lanes 0..7), pivots
+// and columns travel by warp shuffles, pivots use rsqrt so the dependent chain has no fp64 divide/sqrt.
+IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr, int* fail) {
+  const unsigned full = 0xffffffffu;
+  const int i = cx.lane & 7;
+  double a[KB], rinv[KB];
+  load_row(blk, i, a);
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < KB; ++j) {
+    double piv = __shfl_sync(full, a[j], j);
+    if (!(piv > 0.0) || !(piv < 1e300)) {
+      bad = true;
+      piv = 1.0;
+    }
+    const double r = rsqrt(piv);
+    rinv[j] = r;
+    a[j] = (i == j) ? piv * r : a[j] * r;  // column j of L (rows above the diagonal hold junk)
+#pragma unroll
+    for (int k = j + 1; k < KB; ++k) {
+      const double lkj = __shfl_sync(full, a[j], k);
+      a[k] = fma(-a[j], lkj, a[k]);
+    }
+  }
+  if (bad && cx.lane == 0) *fail = 1;
+  // publish L (row i, plain row-major) so that every lane can read the rows below its own column
+  double* Ls = scr + KB;
+  if (cx.lane < KB) {
+#pragma unroll
+    for (int k = 0; k < KB; ++k) Ls[i * KB + k] = a[k];
+  }
+  __syncwarp();
+  // column c = i of Linv by forward substitution with reciprocal pivots: x_c = rinv_c,
+  // x_r = -rinv_r * sum_{k=c}^{r-1} L_rk x_k
+  double x[KB];
+#pragma unroll
+  for (int r = 0; r < KB; ++r) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < KB; ++k)
+      if (k < r) s = fma(Ls[r * KB + k], (k >= i) ? x[k] : 0.0, s);
+    x[r] = (r == i) ? rinv[r] : ((r > i) ? -rinv[r] * s : 0.0);
+  }
+  __syncwarp();
+  if (cx.lane < KB) {
+#pragma unroll
+    for (int r = 0; r < KB; ++r)
+      if (r >= i) blk[bidx(r, i)] = x[r];
+  }
+  __syncwarp();
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // K2: blocked right-looking Cholesky on the block skyline with one-step look-ahead.
 // Step K:  (a) panel: L_IK = C_IK * Linv_KK^T for the active block rows I > K (one thread per row);
-//          (b) trailing update C_IJ -= L_IK L_JK^T over the precomputed pair list; warp 0 takes the
+//          (b) trailing update C_IJ -= L_IK L_JK^T, one 4x4 register tile per thread; warp 0 takes the
 //              update of the next diagonal block first and then factors + inverts it while the other
-//              warps finish the remaining pairs.
+//              warps finish the remaining block pairs.
 // On exit: strictly-lower blocks hold L, diagonal blocks hold Linv_KK (what the solves need).
 // Returns false (for every thread) on a bad pivot (the reference's cho_factor failure,
 // ip_model_whole.py:742,755-758).
@@ -244,27 +396,49 @@ IO_FORCEINLINE int tri_row(int p) {
 }
 
 IO_DEV void chol_update_task(const ProblemDev& P, const Meta& M, double* L, int K, int a0, int task) {
-  // task = (pair of active block rows (I >= J), row r, half h): 4 entries of row r of block (I,J)
-  const int pi = task >> 4, r = (task >> 1) & 7, h = task & 1;
+  // task = (pair of active block rows (I >= J), tile row tr, tile col tc): a 4x4 tile of block (I,J)
+  (void)P;
+  const int pi = task >> 2, tr = (task >> 1) & 1, tc = task & 1;
   const int ia = tri_row(pi), ib = pi - ia * (ia + 1) / 2;
   const int I = M.act_blk[a0 + ia], J = M.act_blk[a0 + ib];
   const int fI = M.fb[I], oI = M.boff[I];
-  const double* __restrict__ A = L + oI + (K - fI) * 64 + r * KB;
-  const double* __restrict__ Bm = L + M.boff[J] + (K - M.fb[J]) * 64 + h * 4 * KB;
-  double* dst = L + oI + (J - fI) * 64 + r * KB + h * 4;
-  double a[KB];
+  const double* A = L + oI + (K - fI) * 64 + tr * 32;               // rows 4tr..4tr+3 of L_IK
+  const double* Bm = L + M.boff[J] + (K - M.fb[J]) * 64 + tc * 32;  // rows 4tc..4tc+3 of L_JK
+  double* dst = L + oI + (J - fI) * 64 + tr * 32;
+  double acc[4][4];
 #pragma unroll
-  for (int k = 0; k < KB; ++k) a[k] = A[k];
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    double s = 0.0;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 #pragma unroll
-    for (int k = 0; k < KB; ++k) s = fma(a[k], Bm[c * KB + k], s);
-    dst[c] -= s;
+  for (int c = 0; c < 4; ++c) {  // logical 16-byte chunk of the K dimension
+    D2 av[4], bv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      av[i] = reinterpret_cast<const D2*>(A + i * KB)[c ^ bswz(4 * tr + i)];
+      bv[i] = reinterpret_cast<const D2*>(Bm + i * KB)[c ^ bswz(4 * tc + i)];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i].y, bv[j].y, fma(av[i].x, bv[j].x, acc[i][j]));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    D2* drow = reinterpret_cast<D2*>(dst + i * KB);
+    const int sw = bswz(4 * tr + i);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      D2 t = drow[(2 * tc + h) ^ sw];
+      t.x -= acc[i][2 * h];
+      t.y -= acc[i][2 * h + 1];
+      drow[(2 * tc + h) ^ sw] = t;
+    }
   }
 }
 
-IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, double* scratch, int* fail_flag) {
+IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, double* scratch,
+                           int* fail_flag, PhaseTimer* pt = nullptr) {
   const int mb = P.mb;
   if (cx.tid == 0) *fail_flag = 0;
   CTA_SYNC();
@@ -273,49 +447,51 @@ IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
   const int o_tid = cx.nwarps > 1 ? cx.tid - cx.warpsize : 0;
   const int o_n = cx.nwarps > 1 ? cx.nthreads - cx.warpsize : 1;
   for (int K = 0; K < mb; ++K) {
-    const double* __restrict__ Linv = L + M.boff[K] + (K - M.fb[K]) * 64;
+    const double* Linv = L + M.boff[K] + (K - M.fb[K]) * 64;
     // (a) panel rows
     const int a0 = M.act_ptr[K], na = M.act_ptr[K + 1] - a0;
     CTA_FOR(idx, na * KB) {
       const int I = M.act_blk[a0 + (idx >> 3)];
-      double* row = L + M.boff[I] + (K - M.fb[I]) * 64 + (idx & 7) * KB;
+      double* blk = L + M.boff[I] + (K - M.fb[I]) * 64;
       double cin[KB], out[KB];
-#pragma unroll
-      for (int k = 0; k < KB; ++k) cin[k] = row[k];
+      load_row(blk, idx & 7, cin);
 #pragma unroll
       for (int c = 0; c < KB; ++c) {
         double s = 0.0;
 #pragma unroll
         for (int k = 0; k < KB; ++k)
-          if (k <= c) s = fma(cin[k], Linv[c * KB + k], s);
+          if (k <= c) s = fma(cin[k], Linv[bidx(c, k)], s);
         out[c] = s;
       }
-#pragma unroll
-      for (int k = 0; k < KB; ++k) row[k] = out[k];
+      store_row(blk, idx & 7, out);
     }
     CTA_SYNC();
+    if (pt) { PHASE_MARK(*pt, 11); }
     // (b) trailing update with look-ahead
     const int np = na * (na + 1) / 2;
     const int lead = (na > 0 && M.act_blk[a0] == K + 1) ? 1 : 0;  // pair 0 updates block (K+1,K+1)
     if (cx.warp == 0) {
       if (lead) {
-        LANE_FOR(task, 0, 16) chol_update_task(P, M, L, K, a0, task);
+        LANE_FOR(task, 0, 4) chol_update_task(P, M, L, K, a0, task);
         WARP_SYNC();
       }
+      if (pt) { PHASE_MARK(*pt, 12); }
       if (K + 1 < mb)
         diag_block_factor_invert(cx, L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64, scratch, fail_flag);
+      if (pt) { PHASE_MARK(*pt, 13); }
     }
     if (cx.nwarps == 1 || cx.warp > 0) {
-      for (int task = lead * 16 + o_tid; task < np * 16; task += o_n) chol_update_task(P, M, L, K, a0, task);
+      for (int task = lead * 4 + o_tid; task < np * 4; task += o_n) chol_update_task(P, M, L, K, a0, task);
     }
     CTA_SYNC();
+    if (pt) { PHASE_MARK(*pt, 14); }
   }
   return *fail_flag == 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Solve L L^T z = r in place for NR right-hand sides at once (blocked substitution; the diagonal
-// blocks hold Linv).  `ybuf` is NR*8 doubles of scratch.
+// Solve L L^T z = r in place for NR right-hand sides at once (blocked substitution; the diagonal blocks
+// hold Linv).  `ybuf` is NR*8 doubles of scratch (16-byte aligned).
 // ---------------------------------------------------------------------------------------------
 template <int NR>
 IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* L, double* const (&r)[NR],
@@ -323,14 +499,16 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
   const int mb = P.mb;
   // forward: L y = r
   for (int K = 0; K < mb; ++K) {
-    const double* __restrict__ Linv = L + M.boff[K] + (K - M.fb[K]) * 64;
+    const double* Linv = L + M.boff[K] + (K - M.fb[K]) * 64;
     CTA_FOR(idx, NR * KB) {
       const int q = idx >> 3, i = idx & 7;
-      const double* rk = r[q] + K * KB;
+      double rk[KB], li[KB];
+      load_vec8(r[q] + K * KB, rk);
+      load_row(Linv, i, li);
       double s = 0.0;
 #pragma unroll
       for (int j = 0; j < KB; ++j)
-        if (j <= i) s = fma(Linv[i * KB + j], rk[j], s);
+        if (j <= i) s = fma(li[j], rk[j], s);
       ybuf[idx] = s;
     }
     CTA_SYNC();
@@ -339,8 +517,9 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
     CTA_FOR(idx, na * KB * NR) {
       const int q = idx / (na * KB), rem = idx - q * (na * KB);
       const int I = M.act_blk[a0 + (rem >> 3)], rr = rem & 7;
-      const double* __restrict__ row = L + M.boff[I] + (K - M.fb[I]) * 64 + rr * KB;
-      const double* yk = ybuf + q * KB;
+      double row[KB], yk[KB];
+      load_row(L + M.boff[I] + (K - M.fb[I]) * 64, rr, row);
+      load_vec8(ybuf + q * KB, yk);
       double s = 0.0;
 #pragma unroll
       for (int k = 0; k < KB; ++k) s = fma(row[k], yk[k], s);
@@ -351,56 +530,68 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
   // backward: L^T z = y
   for (int I = mb - 1; I >= 0; --I) {
     const int f = M.fb[I];
-    const double* __restrict__ Linv = L + M.boff[I] + (I - f) * 64;
+    const double* Linv = L + M.boff[I] + (I - f) * 64;
     CTA_FOR(idx, NR * KB) {
       const int q = idx >> 3, i = idx & 7;
-      const double* ri = r[q] + I * KB;
+      double ri[KB];
+      load_vec8(r[q] + I * KB, ri);
       double s = 0.0;
 #pragma unroll
       for (int j = 0; j < KB; ++j)
-        if (j >= i) s = fma(Linv[j * KB + i], ri[j], s);
+        if (j >= i) s = fma(Linv[bidx(j, i)], ri[j], s);
       ybuf[idx] = s;
     }
     CTA_SYNC();
     const int nk = I - f;
     CTA_FOR(idx, NR * KB) r[idx >> 3][I * KB + (idx & 7)] = ybuf[idx];
-    CTA_FOR(idx, nk * KB * NR) {
-      const int q = idx / (nk * KB), rem = idx - q * (nk * KB);
-      const int Kc = f + (rem >> 3), k = rem & 7;
-      const double* __restrict__ blk = L + M.boff[I] + (Kc - f) * 64 + k;
-      const double* zi = ybuf + q * KB;
-      double s = 0.0;
+    CTA_FOR(idx, nk * 4 * NR) {  // one 16-byte chunk (two columns) of block (I,Kc) per thread
+      const int q = idx / (nk * 4), rem = idx - q * (nk * 4);
+      const int Kc = f + (rem >> 2), c = rem & 3;
+      const double* blk = L + M.boff[I] + (Kc - f) * 64;
+      double zi[KB];
+      load_vec8(ybuf + q * KB, zi);
+      double sx = 0.0, sy = 0.0;
 #pragma unroll
-      for (int i = 0; i < KB; ++i) s = fma(blk[i * KB], zi[i], s);
-      r[q][Kc * KB + k] -= s;
+      for (int i = 0; i < KB; ++i) {
+        const D2 t = reinterpret_cast<const D2*>(blk + i * KB)[c ^ bswz(i)];
+        sx = fma(t.x, zi[i], sx);
+        sy = fma(t.y, zi[i], sy);
+      }
+      D2* dst = reinterpret_cast<D2*>(r[q] + Kc * KB) + c;
+      D2 t = *dst;
+      t.x -= sx;
+      t.y -= sy;
+      *dst = t;
     }
     CTA_SYNC();
   }
 }
 
-// out[i] = sum_e A_ie * src[col_e]   (row-wise, one warp per row, two index chunks in flight)
+// out[i] = sum_e A_ie * src[col_e]   (row-wise, one warp per row, four index chunks in flight)
 IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* src, double* out) {
+  const int W = cx.warpsize;
   WARP_ROWS(i, P.m) {
     const int lo = M.csr_ptr[i], hi = M.csr_ptr[i + 1];
-    double s = 0.0, s2 = 0.0;
-    if (P.a_unit) {
-      for (int e = lo + cx.lane; e < hi; e += 2 * cx.warpsize) {
-        const int e2 = e + cx.warpsize;
-        const int c0 = P.csr_col[e];
-        const int c1 = e2 < hi ? P.csr_col[e2] : c0;
-        s += src[c0];
-        if (e2 < hi) s2 += src[c1];
-      }
-    } else {
-      for (int e = lo + cx.lane; e < hi; e += 2 * cx.warpsize) {
-        const int e2 = e + cx.warpsize;
-        const int c0 = P.csr_col[e];
-        const int c1 = e2 < hi ? P.csr_col[e2] : c0;
-        s = fma(P.csr_val[e], src[c0], s);
-        if (e2 < hi) s2 = fma(P.csr_val[e2], src[c1], s2);
+    double s0 = 0.0, s1 = 0.0;
+    for (int e = lo + cx.lane; e < hi; e += 4 * W) {
+      const int e1 = e + W, e2 = e + 2 * W, e3 = e + 3 * W;
+      const int c0 = P.csr_col[e];
+      const int c1 = e1 < hi ? P.csr_col[e1] : c0;
+      const int c2 = e2 < hi ? P.csr_col[e2] : c0;
+      const int c3 = e3 < hi ? P.csr_col[e3] : c0;
+      if (P.a_unit) {
+        s0 += src[c0];
+        if (e1 < hi) s1 += src[c1];
+        if (e2 < hi) s0 += src[c2];
+        if (e3 < hi) s1 += src[c3];
+      } else {
+        s0 = fma(P.csr_val[e], src[c0], s0);
+        if (e1 < hi) s1 = fma(P.csr_val[e1], src[c1], s1);
+        if (e2 < hi) s0 = fma(P.csr_val[e2], src[c2], s0);
+        if (e3 < hi) s1 = fma(P.csr_val[e3], src[c3], s1);
       }
     }
-    s = warp_sum(s + s2);
+    const double s = warp_sum(s0 + s1);
     if (cx.lane == 0) out[i] = s;
   }
 }
@@ -408,35 +599,75 @@ IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, cons
 // (A^T y)_k through the interleaved column groups (lanes of a warp own 32 consecutive columns)
 IO_FORCEINLINE double col_dot(const ProblemDev& P, const Meta& M, int k, const double* yv) {
   const int g = k >> 5, l = k & 31, g0 = M.csc_gptr[g], len = M.csc_gptr[g + 1] - g0;
-  const size_t base = (size_t)g0 * 32 + l;
-  double s = 0.0;
+  const uint16_t* __restrict__ rr = P.csc_row + (size_t)g0 * 32 + l;
+  double s0 = 0.0, s1 = 0.0;
+  int t = 0;
   if (P.a_unit) {
-    for (int t = 0; t < len; ++t) s += yv[P.csc_row[base + (size_t)t * 32]];
+    for (; t + 4 <= len; t += 4) {
+      const int r0 = rr[t * 32], r1 = rr[(t + 1) * 32], r2 = rr[(t + 2) * 32], r3 = rr[(t + 3) * 32];
+      s0 += yv[r0];
+      s1 += yv[r1];
+      s0 += yv[r2];
+      s1 += yv[r3];
+    }
+    for (; t < len; ++t) s0 += yv[rr[t * 32]];
   } else {
-    for (int t = 0; t < len; ++t) s = fma(P.csc_val[base + (size_t)t * 32], yv[P.csc_row[base + (size_t)t * 32]], s);
+    const double* __restrict__ vv = P.csc_val + (size_t)g0 * 32 + l;
+    for (; t + 4 <= len; t += 4) {
+      const int r0 = rr[t * 32], r1 = rr[(t + 1) * 32], r2 = rr[(t + 2) * 32], r3 = rr[(t + 3) * 32];
+      const double a0 = vv[t * 32], a1 = vv[(t + 1) * 32], a2 = vv[(t + 2) * 32], a3 = vv[(t + 3) * 32];
+      s0 = fma(a0, yv[r0], s0);
+      s1 = fma(a1, yv[r1], s1);
+      s0 = fma(a2, yv[r2], s0);
+      s1 = fma(a3, yv[r3], s1);
+    }
+    for (; t < len; ++t) s0 = fma(vv[t * 32], yv[rr[t * 32]], s0);
   }
-  return s;
+  return s0 + s1;
 }
 
-IO_FORCEINLINE void col_dot2(const ProblemDev& P, const Meta& M, int k, const double* y1, const double* y2, double& s1, double& s2) {
+IO_FORCEINLINE void col_dot2(const ProblemDev& P, const Meta& M, int k, const double* y1, const double* y2, double& s1,
+                             double& s2) {
   const int g = k >> 5, l = k & 31, g0 = M.csc_gptr[g], len = M.csc_gptr[g + 1] - g0;
-  const size_t base = (size_t)g0 * 32 + l;
-  s1 = 0.0;
-  s2 = 0.0;
+  const uint16_t* __restrict__ rr = P.csc_row + (size_t)g0 * 32 + l;
+  double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+  int t = 0;
   if (P.a_unit) {
-    for (int t = 0; t < len; ++t) {
-      const int row = P.csc_row[base + (size_t)t * 32];
-      s1 += y1[row];
-      s2 += y2[row];
+    for (; t + 4 <= len; t += 4) {
+      const int r0 = rr[t * 32], r1 = rr[(t + 1) * 32], r2 = rr[(t + 2) * 32], r3 = rr[(t + 3) * 32];
+      a1 += y1[r0];
+      a2 += y2[r0];
+      b1 += y1[r1];
+      b2 += y2[r1];
+      a1 += y1[r2];
+      a2 += y2[r2];
+      b1 += y1[r3];
+      b2 += y2[r3];
+    }
+    for (; t < len; ++t) {
+      const int r0 = rr[t * 32];
+      a1 += y1[r0];
+      a2 += y2[r0];
     }
   } else {
-    for (int t = 0; t < len; ++t) {
-      const int row = P.csc_row[base + (size_t)t * 32];
-      const double a = P.csc_val[base + (size_t)t * 32];
-      s1 = fma(a, y1[row], s1);
-      s2 = fma(a, y2[row], s2);
+    const double* __restrict__ vv = P.csc_val + (size_t)g0 * 32 + l;
+    for (; t + 2 <= len; t += 2) {
+      const int r0 = rr[t * 32], r1 = rr[(t + 1) * 32];
+      const double w0 = vv[t * 32], w1 = vv[(t + 1) * 32];
+      a1 = fma(w0, y1[r0], a1);
+      a2 = fma(w0, y2[r0], a2);
+      b1 = fma(w1, y1[r1], b1);
+      b2 = fma(w1, y2[r1], b2);
+    }
+    for (; t < len; ++t) {
+      const int r0 = rr[t * 32];
+      const double w0 = vv[t * 32];
+      a1 = fma(w0, y1[r0], a1);
+      a2 = fma(w0, y2[r0], a2);
     }
   }
+  s1 = a1 + b1;
+  s2 = a2 + b2;
 }
 
 IO_DEV Meta global_meta(const ProblemDev& P) {
@@ -479,26 +710,6 @@ IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
   return M;
 }
 
-// Optional per-phase cycle accounting (debug aid for profiles/): thread 0 of every CTA adds the cycles since
-// the previous mark to bucket `k` of a global array.  Disabled (null pointer) in normal runs.
-struct PhaseTimer {
-  unsigned long long* buckets;
-  long long last;
-};
-#ifdef INTOPT_HOST_EMU
-#define PHASE_MARK(pt, k) ((void)0)
-#define PHASE_START(pt) ((void)0)
-#else
-#define PHASE_START(pt)                                  \
-  if ((pt).buckets && cx.tid == 0) (pt).last = clock64()
-#define PHASE_MARK(pt, k)                                                   \
-  if ((pt).buckets && cx.tid == 0) {                                        \
-    const long long now_ = clock64();                                       \
-    atomicAdd((pt).buckets + (k), (unsigned long long)(now_ - (pt).last));  \
-    (pt).last = now_;                                                       \
-  }
-#endif
-
 // workspace n-vector slots (global, per CTA)
 enum { W_X = 0, W_T, W_D, W_R2, W_P, W_W, W_DX, W_DXDT, W_NVEC };
 // shared-memory m-vector slots
@@ -506,7 +717,7 @@ enum { S_B = 0, S_Y, S_R1, S_Q, S_V, S_NVEC };
 constexpr int S_SCRATCH = 2 * KB + (KB + KB * KB) + 8 * 32 + 2;  // ybuf + diag scratch + red + flag
 
 struct SmemLayout {
-  double *L, *G, *bs, *y, *r1, *q, *v, *ybuf, *dscr, *red;
+  double *L, *G, *X, *bs, *y, *r1, *q, *v, *ybuf, *dscr, *red;
   int* flag;
   int* meta;  // P.meta_ints ints when the schedule is staged in shared memory
 };
@@ -524,12 +735,14 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
     s.L = ws_tail;
     ws_tail += P.bsize;
   }
-  if (gather_in_smem) {
+  if (gather_in_smem) {  // gather buffer + the primal iterate x
     s.G = p;
-    p += gather_len(P.n);
+    s.X = p + gather_len(P.n);
+    p += 2 * gather_len(P.n);
   } else {
     s.G = ws_tail;
-    ws_tail += gather_len(P.n);
+    s.X = ws_tail + gather_len(P.n);
+    ws_tail += 2 * gather_len(P.n);
   }
   s.bs = p + S_B * P.mv;
   s.y = p + S_Y * P.mv;
@@ -570,7 +783,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
                              const SmemLayout& S) {
   const int m = P.m, n = P.n, mv = P.mv;
   double *L = S.L, *G = S.G, *bs = S.bs, *y = S.y, *r1 = S.r1, *q = S.q, *v = S.v;
-  double* x = wsi + (long long)W_X * n;
+  double* x = S.X;  // the primal iterate lives in shared memory (gathered by A x, read by every n-loop)
   double* t = wsi + (long long)W_T * n;
   double* D = wsi + (long long)W_D * n;
   double* r2 = wsi + (long long)W_R2 * n;
@@ -720,7 +933,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     PHASE_MARK(pt, 2);
     // right-hand side of the (p,q) solve (:800): G = D*c, built while the factorisation runs
     CTA_FOR(k, n) G[k] = D[k] * c[k];
-    solved = block_cholesky(cx, P, M, L, S.dscr, S.flag);  // (its barriers order the G writes)
+    solved = block_cholesky(cx, P, M, L, S.dscr, S.flag, &pt);  // (its barriers order the G writes)
     PHASE_MARK(pt, 3);
     if (!solved) continue;  // deltas = 0 (:855-857): the iterate is unchanged, the tests run at loop top
     spmv_rows(cx, P, M, G, q);

@@ -50,6 +50,7 @@ struct HostStructure {
   std::vector<int> asm_gptr, asm_glen, asm_pos;  // asm_pos < 0: padding entry
   std::vector<unsigned char> asm_diag;
   std::vector<int> asm_k;  // index into the gather buffer; n = the zero slot
+  std::vector<uint16_t> asm_k16;  // the same as 16-bit indices when n < 65535 (then asm_k is not uploaded)
   std::vector<double> asm_w;
   bool asm_unit = true;
   long long asm_terms = 0, asm_padded = 0, chol_macs = 0, solve_macs = 0;
@@ -282,7 +283,8 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   S.bsize = S.boff[mb];
   auto pos_of = [&](int i, int j) {  // entry (i,j), j <= i, inside the block skyline
     int I = i / NB, J = j / NB;
-    return S.boff[I] + (J - S.fb[I]) * NBB + (i % NB) * NB + (j % NB);
+    const int r = i % NB, k = j % NB;  // XOR-swizzled chunk layout, see bidx() in intopt_solver.cuh
+    return S.boff[I] + (J - S.fb[I]) * NBB + r * NB + ((((k >> 1) ^ ((r >> 1) & 3))) << 1) + (k & 1);
   };
   for (int i = m; i < S.m8; ++i) S.dummy_pos.push_back(pos_of(i, i));
 
@@ -373,6 +375,10 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
           S.asm_w[d] = w;
           if (w != 1.0) S.asm_unit = false;
         }
+  }
+  if (n < 65535) {
+    S.asm_k16.resize(S.asm_k.size());
+    for (size_t i = 0; i < S.asm_k.size(); ++i) S.asm_k16[i] = (uint16_t)S.asm_k[i];
   }
   return 0;
 }

@@ -24,7 +24,7 @@ extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const doubl
   }
   intopt::ProblemDev P{};
   intopt::bind_problem(S, P, [](const auto& v) { return v.data(); });
-  std::vector<double> smem((size_t)S.bsize + intopt::gather_len(n) + intopt::smem_fixed_doubles(S) +
+  std::vector<double> smem((size_t)S.bsize + 2 * intopt::gather_len(n) + intopt::smem_fixed_doubles(S) +
                            (intopt::meta_ints(S) + 1) / 2);
   std::vector<double> ws((size_t)intopt::W_NVEC * n);
   const intopt::SmemLayout L = intopt::carve(P, smem.data(), nullptr, 1, 1);
