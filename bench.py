@@ -115,7 +115,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -264,6 +264,8 @@ def run_gpu(args):
         return [float(v) for v in t.tolist()]
 
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.5)  # let nvidia-smi finish its start-up queries before the timed region begins
     tot_ms, fwd_ms, bwd_ms = timed(step_resident, split=True)
     clocks = sampler.stop() if sampler else None
     e2e_ms, _, _ = timed(step_e2e)

@@ -8,7 +8,8 @@
 namespace intopt {
 
 inline int meta_ints(const HostStructure& S) {
-  return S.mb + 2 * (S.mb + 1) + (int)S.act_blk.size() + (S.m + 1) + (int)S.csc_gptr.size() + (int)S.asm_gptr.size();
+  return S.mb + 2 * (S.mb + 1) + (int)S.act_blk.size() + (S.m + 1) + (int)S.csc_gptr.size() +
+         2 * (int)S.asm_gptr.size();
 }
 
 template <class Up>
@@ -41,7 +42,9 @@ inline void bind_problem(const HostStructure& S, ProblemDev& D, Up&& up) {
   D.asm_pos = up(S.asm_pos);
   D.asm_diag = up(S.asm_diag);
   D.asm_k16 = S.asm_k16.empty() ? nullptr : up(S.asm_k16);
-  D.asm_k = S.asm_k16.empty() ? up(S.asm_k) : nullptr;
+  D.asm_k = (S.asm_k16.empty() && !S.asm_k.empty()) ? up(S.asm_k) : nullptr;
+  D.g_asm_rptr = up(S.asm_rptr);
+  D.asm_run = S.asm_run.empty() ? nullptr : up(S.asm_run);
   D.asm_unit = S.asm_unit ? 1 : 0;
   D.asm_w = S.asm_unit ? nullptr : up(S.asm_w);
 }

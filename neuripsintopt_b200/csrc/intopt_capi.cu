@@ -108,14 +108,14 @@ __device__ __forceinline__ CtaCtx make_ctx(double* red) {
 
 // Persistent CTAs: each pulls the next LP instance from an atomic counter until the batch is exhausted,
 // so finished LPs free their SM slot without any host involvement.
-template <int TMAX>
-__global__ void __launch_bounds__(TMAX, 512 / TMAX) intopt_forward_kernel(const __grid_constant__ intopt::ProblemDev P,
+template <int TMAX, bool ALLSMEM>
+__global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_forward_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                const __grid_constant__ intopt::FwdParams a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_inst;
   double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
   const intopt::SmemLayout S =
-      intopt::carve(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
+      intopt::carve<ALLSMEM>(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
   const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   for (;;) {
@@ -128,14 +128,14 @@ __global__ void __launch_bounds__(TMAX, 512 / TMAX) intopt_forward_kernel(const 
   }
 }
 
-template <int TMAX>
-__global__ void __launch_bounds__(TMAX, 512 / TMAX) intopt_backward_kernel(const __grid_constant__ intopt::ProblemDev P,
+template <int TMAX, bool ALLSMEM>
+__global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_backward_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                 const __grid_constant__ intopt::BwdParams a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_inst;
   double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
   const intopt::SmemLayout S =
-      intopt::carve(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
+      intopt::carve<ALLSMEM>(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
   const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   for (;;) {
@@ -170,6 +170,28 @@ __global__ void __launch_bounds__(256) intopt_fp64_peak_kernel(double* out, int 
 }
 
 __device__ unsigned long long g_phase_cycles[16];
+
+// Kernel variants: CTA size cap (192: 2 CTAs/SM x 168 registers, 256: 2 x 128, 512: 1 x 128) x whether every
+// buffer is in shared memory.
+#define INTOPT_VARIANTS(F)                                                                                   \
+  F(192, true) F(192, false) F(256, true) F(256, false) F(512, true) F(512, false)
+static std::vector<const void*> all_kernels() {
+  std::vector<const void*> v;
+#define ADD_(T, A)                                          \
+  v.push_back((const void*)intopt_forward_kernel<T, A>);    \
+  v.push_back((const void*)intopt_backward_kernel<T, A>);
+  INTOPT_VARIANTS(ADD_)
+#undef ADD_
+  return v;
+}
+static const void* pick_kernel(bool forward, int threads, bool allsmem) {
+#define PICK_(T, A)                                                                                        \
+  if (threads <= T && allsmem == A)                                                                        \
+    return forward ? (const void*)intopt_forward_kernel<T, A> : (const void*)intopt_backward_kernel<T, A>;
+  INTOPT_VARIANTS(PICK_)
+#undef PICK_
+  return nullptr;
+}
 
 namespace {
 bool g_profile_phases = false;
@@ -235,17 +257,12 @@ int intopt_problem_create(IntoptProblem** out, int m, int n, const int* rowptr, 
     intopt_problem_destroy(p);
     return fail(-12, "INTOPT_THREADS must be a multiple of 32 in [32, 512]");
   }
-  CU_TRY(cudaFuncSetAttribute(intopt_forward_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  CU_TRY(cudaFuncSetAttribute(intopt_backward_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  CU_TRY(cudaFuncSetAttribute(intopt_forward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  CU_TRY(cudaFuncSetAttribute(intopt_backward_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  for (const void* k : all_kernels())
+    CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   int occ = 0;
-  if (p->info.threads <= 256)
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intopt_forward_kernel<256>, p->info.threads,
-                                                         (size_t)p->info.smem_bytes));
-  else
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, intopt_forward_kernel<512>, p->info.threads,
-                                                         (size_t)p->info.smem_bytes));
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &occ, pick_kernel(true, p->info.threads, p->info.factor_in_smem && p->info.gather_in_smem), p->info.threads,
+      (size_t)p->info.smem_bytes));
   if (occ < 1) {
     intopt_problem_destroy(p);
     return fail(-11, "solver kernel does not fit on an SM (shared memory / registers)");
@@ -308,6 +325,7 @@ int intopt_forward(const IntoptProblem* p, int B, const double* c, long long c_s
   a.damping = o->damping_fwd;
   a.max_iter = o->max_iter;
   a.phase_cycles = nullptr;
+  a.debug = env_int("INTOPT_DEBUG", 0);
   if (g_profile_phases) {
     void* sym = nullptr;
     CU_TRY(cudaGetSymbolAddress(&sym, g_phase_cycles));
@@ -315,10 +333,11 @@ int intopt_forward(const IntoptProblem* p, int B, const double* c, long long c_s
   }
   const int grid = std::min(B, p->slots);
   CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
-  if (p->info.threads <= 256)
-    intopt_forward_kernel<256><<<grid, p->info.threads, p->info.smem_bytes, (cudaStream_t)stream>>>(p->dev, a);
-  else
-    intopt_forward_kernel<512><<<grid, p->info.threads, p->info.smem_bytes, (cudaStream_t)stream>>>(p->dev, a);
+  {
+    void* args[2] = {(void*)&p->dev, (void*)&a};
+    CU_TRY(cudaLaunchKernel(pick_kernel(true, p->info.threads, a.factor_in_smem && a.gather_in_smem), dim3(grid),
+                            dim3(p->info.threads), args, (size_t)p->info.smem_bytes, (cudaStream_t)stream));
+  }
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -353,10 +372,11 @@ int intopt_backward(const IntoptProblem* p, int B, int mode, double damping, int
   a.ws_stride = (long long)ws_per_slot_doubles(p);
   const int grid = std::min(B, p->slots);
   CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
-  if (p->info.threads <= 256)
-    intopt_backward_kernel<256><<<grid, p->info.threads, p->info.smem_bytes, (cudaStream_t)stream>>>(p->dev, a);
-  else
-    intopt_backward_kernel<512><<<grid, p->info.threads, p->info.smem_bytes, (cudaStream_t)stream>>>(p->dev, a);
+  {
+    void* args[2] = {(void*)&p->dev, (void*)&a};
+    CU_TRY(cudaLaunchKernel(pick_kernel(false, p->info.threads, a.factor_in_smem && a.gather_in_smem), dim3(grid),
+                            dim3(p->info.threads), args, (size_t)p->info.smem_bytes, (cudaStream_t)stream));
+  }
   CU_TRY(cudaGetLastError());
   return 0;
 }

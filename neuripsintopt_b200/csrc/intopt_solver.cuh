@@ -31,7 +31,7 @@ struct CtaCtx {
 IO_DEV double warp_sum(double v) { return v; }
 IO_DEV double warp_min(double v) { return v; }
 #else
-#define IO_DEV __device__ inline
+#define IO_DEV __device__ __forceinline__
 #define IO_HD __host__ __device__ inline
 #define IO_FORCEINLINE __device__ __forceinline__
 struct CtaCtx {
@@ -51,6 +51,14 @@ IO_FORCEINLINE double warp_min(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+#endif
+
+#ifdef INTOPT_HOST_EMU
+struct alignas(16) U4 {
+  uint32_t x, y, z, w;
+};
+#else
+typedef uint4 U4;
 #endif
 
 // loops: every thread of the CTA strides over [0,n)
@@ -84,6 +92,8 @@ struct ProblemDev {
   int meta_ints;  // total ints of {fb, boff, act_ptr, act_blk, csr_ptr, csc_gptr, asm_gptr}: staged in smem if small
   int n_asm;
   const int* g_asm_gptr;
+  const int* g_asm_rptr;
+  const uint32_t* asm_run;  // run-length gather lists (unit weights only), null otherwise
   const int* asm_pos;
   const unsigned char* asm_diag;
   const int* asm_k;          // 32-bit gather indices, or
@@ -102,6 +112,7 @@ struct Meta {
   const int* csr_ptr;
   const int* csc_gptr;
   const int* asm_gptr;
+  const int* asm_rptr;
 };
 
 // Sum N partial values over the CTA; every thread receives the totals (fixed order => deterministic).
@@ -196,12 +207,86 @@ IO_FORCEINLINE double gather_sum_weighted(const IT* __restrict__ kk, const doubl
   return s0 + s1;
 }
 
+// sum of g over one run (start | len << 16; len = 0 is padding); eight loads in flight per lane
+IO_FORCEINLINE void run_sum(uint32_t h, const double* g, double& s0, double& s1) {
+  const double* gp = g + (h & 0xffffu);
+  const int len = (int)(h >> 16);
+  int j = 0;
+  double s2 = 0.0, s3 = 0.0;
+  for (; j + 8 <= len; j += 8) {
+    const double a0 = gp[j], a1 = gp[j + 1], a2 = gp[j + 2], a3 = gp[j + 3];
+    const double a4 = gp[j + 4], a5 = gp[j + 5], a6 = gp[j + 6], a7 = gp[j + 7];
+    s0 += a0;
+    s1 += a1;
+    s2 += a2;
+    s3 += a3;
+    s0 += a4;
+    s1 += a5;
+    s2 += a6;
+    s3 += a7;
+  }
+  if (j + 4 <= len) {
+    const double a0 = gp[j], a1 = gp[j + 1], a2 = gp[j + 2], a3 = gp[j + 3];
+    s0 += a0;
+    s1 += a1;
+    s2 += a2;
+    s3 += a3;
+    j += 4;
+  }
+  if (j + 2 <= len) {
+    const double a0 = gp[j], a1 = gp[j + 1];
+    s0 += a0;
+    s1 += a1;
+    j += 2;
+  }
+  if (j < len) s0 += gp[j];
+  s0 += s2;
+  s1 += s3;
+}
+
 IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* g, double delta,
-                                   double* L) {
+                                   double* L, int dbg = 0) {
   CTA_FOR(e, P.bsize) L[e] = 0.0;
   CTA_SYNC();
   CTA_FOR(e, P.n_dummy) L[P.dummy_pos[e]] = 1.0;
-  const int ngrp = P.n_asm >> 5;
+  const int ngrp = (dbg & 1) ? 0 : (P.n_asm >> 5);
+  if (P.asm_run) {
+    // run-length lists: a handful of headers per entry instead of one index per term.  Lane l of a warp owns
+    // entry 32*grp + l; its R headers are contiguous, fetched 12 at a time with three 16-byte loads that are
+    // all in flight together (one L2 round trip per group instead of one per run).
+    WARP_ROWS(grp, ngrp) {
+      const int r0 = M.asm_rptr[grp], R = M.asm_rptr[grp + 1] - r0;
+      LANE_FOR(l, 0, 32) {
+        const uint32_t* __restrict__ hp = P.asm_run + (size_t)r0 * 32 + (size_t)l * R;
+        double s0 = 0.0, s1 = 0.0;
+        for (int rb = 0; rb < R; rb += 12) {
+          uint32_t h[12];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            if (rb + 4 * c < R && !(dbg & 4)) {
+              const U4 q = *reinterpret_cast<const U4*>(hp + rb + 4 * c);
+              h[4 * c] = q.x;
+              h[4 * c + 1] = q.y;
+              h[4 * c + 2] = q.z;
+              h[4 * c + 3] = q.w;
+            } else {
+              h[4 * c] = h[4 * c + 1] = h[4 * c + 2] = h[4 * c + 3] = 0u;
+            }
+          }
+          const int cnt = R - rb < 12 ? R - rb : 12;
+          for (int u = 0; u < cnt; ++u) {
+            if (!(dbg & 2)) run_sum(h[0], g, s0, s1);
+#pragma unroll
+            for (int v = 0; v < 11; ++v) h[v] = h[v + 1];  // rotate the register queue
+          }
+        }
+        const int e = grp * 32 + l, pos = P.asm_pos[e];
+        if (pos >= 0) L[pos] = P.asm_diag[e] ? (s0 + s1) + delta : (s0 + s1);
+      }
+    }
+    CTA_SYNC();
+    return;
+  }
   WARP_ROWS(grp, ngrp) {
     const int g0 = M.asm_gptr[grp], len = M.asm_gptr[grp + 1] - g0;
     LANE_FOR(l, 0, 32) {
@@ -494,6 +579,11 @@ IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
 // hold Linv).  `ybuf` is NR*8 doubles of scratch (16-byte aligned).
 // ---------------------------------------------------------------------------------------------
 template <int NR>
+IO_FORCEINLINE double* rhs_sel(double* const (&r)[NR], int q) {
+  return (NR > 1 && q) ? r[NR - 1] : r[0];  // NR is 1 or 2
+}
+
+template <int NR>
 IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* L, double* const (&r)[NR],
                         double* ybuf) {
   const int mb = P.mb;
@@ -503,7 +593,7 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
     CTA_FOR(idx, NR * KB) {
       const int q = idx >> 3, i = idx & 7;
       double rk[KB], li[KB];
-      load_vec8(r[q] + K * KB, rk);
+      load_vec8(rhs_sel<NR>(r, q) + K * KB, rk);
       load_row(Linv, i, li);
       double s = 0.0;
 #pragma unroll
@@ -513,7 +603,7 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
     }
     CTA_SYNC();
     const int a0 = M.act_ptr[K], na = M.act_ptr[K + 1] - a0;
-    CTA_FOR(idx, NR * KB) r[idx >> 3][K * KB + (idx & 7)] = ybuf[idx];
+    CTA_FOR(idx, NR * KB) rhs_sel<NR>(r, idx >> 3)[K * KB + (idx & 7)] = ybuf[idx];
     CTA_FOR(idx, na * KB * NR) {
       const int q = idx / (na * KB), rem = idx - q * (na * KB);
       const int I = M.act_blk[a0 + (rem >> 3)], rr = rem & 7;
@@ -523,7 +613,7 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
       double s = 0.0;
 #pragma unroll
       for (int k = 0; k < KB; ++k) s = fma(row[k], yk[k], s);
-      r[q][I * KB + rr] -= s;
+      rhs_sel<NR>(r, q)[I * KB + rr] -= s;
     }
     CTA_SYNC();
   }
@@ -534,7 +624,7 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
     CTA_FOR(idx, NR * KB) {
       const int q = idx >> 3, i = idx & 7;
       double ri[KB];
-      load_vec8(r[q] + I * KB, ri);
+      load_vec8(rhs_sel<NR>(r, q) + I * KB, ri);
       double s = 0.0;
 #pragma unroll
       for (int j = 0; j < KB; ++j)
@@ -543,7 +633,7 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
     }
     CTA_SYNC();
     const int nk = I - f;
-    CTA_FOR(idx, NR * KB) r[idx >> 3][I * KB + (idx & 7)] = ybuf[idx];
+    CTA_FOR(idx, NR * KB) rhs_sel<NR>(r, idx >> 3)[I * KB + (idx & 7)] = ybuf[idx];
     CTA_FOR(idx, nk * 4 * NR) {  // one 16-byte chunk (two columns) of block (I,Kc) per thread
       const int q = idx / (nk * 4), rem = idx - q * (nk * 4);
       const int Kc = f + (rem >> 2), c = rem & 3;
@@ -557,7 +647,7 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
         sx = fma(t.x, zi[i], sx);
         sy = fma(t.y, zi[i], sy);
       }
-      D2* dst = reinterpret_cast<D2*>(r[q] + Kc * KB) + c;
+      D2* dst = reinterpret_cast<D2*>(rhs_sel<NR>(r, q) + Kc * KB) + c;
       D2 t = *dst;
       t.x -= sx;
       t.y -= sy;
@@ -679,15 +769,18 @@ IO_DEV Meta global_meta(const ProblemDev& P) {
   M.csr_ptr = P.g_csr_ptr;
   M.csc_gptr = P.g_csc_gptr;
   M.asm_gptr = P.g_asm_gptr;
+  M.asm_rptr = P.g_asm_rptr;
   return M;
 }
 
 // Copies the schedule arrays into shared memory (`dst` holds P.meta_ints ints) and returns pointers to the copies.
 IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
-  const int cnt[7] = {P.mb, P.mb + 1, P.mb + 1, P.n_act, P.m + 1, ((P.n + 31) >> 5) + 1, (P.n_asm >> 5) + 1};
-  const int* src[7] = {P.g_fb, P.g_boff, P.g_act_ptr, P.g_act_blk, P.g_csr_ptr, P.g_csc_gptr, P.g_asm_gptr};
+  const int cnt[8] = {P.mb, P.mb + 1, P.mb + 1, P.n_act, P.m + 1, ((P.n + 31) >> 5) + 1, (P.n_asm >> 5) + 1,
+                      (P.n_asm >> 5) + 1};
+  const int* src[8] = {P.g_fb, P.g_boff, P.g_act_ptr, P.g_act_blk, P.g_csr_ptr, P.g_csc_gptr, P.g_asm_gptr,
+                       P.g_asm_rptr};
   int* d = dst;
-  for (int a = 0; a < 7; ++a) {
+  for (int a = 0; a < 8; ++a) {
     CTA_FOR(i, cnt[a]) d[i] = src[a][i];
     d += cnt[a];
   }
@@ -706,6 +799,8 @@ IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
   M.csc_gptr = d;
   d += cnt[5];
   M.asm_gptr = d;
+  d += cnt[6];
+  M.asm_rptr = d;
   CTA_SYNC();
   return M;
 }
@@ -724,25 +819,36 @@ struct SmemLayout {
 
 IO_HD int gather_len(int n) { return (n + 2) & ~1; }
 
-// Carve shared memory (and, for spilled pieces, the tail of the per-CTA workspace).
+// Carve shared memory (and, for spilled pieces, the tail of the per-CTA workspace).  ALLSMEM = factor and
+// gather buffers both live in shared memory: every pointer is then derived unconditionally from the shared
+// array, which lets the compiler emit LDS/STS instead of generic loads (the common, fast instantiation).
+template <bool ALLSMEM>
 IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int factor_in_smem, int gather_in_smem) {
   SmemLayout s;
   double* p = smem;
-  if (factor_in_smem) {
+  if (ALLSMEM) {
     s.L = p;
     p += P.bsize;
-  } else {
-    s.L = ws_tail;
-    ws_tail += P.bsize;
-  }
-  if (gather_in_smem) {  // gather buffer + the primal iterate x
     s.G = p;
     s.X = p + gather_len(P.n);
     p += 2 * gather_len(P.n);
   } else {
-    s.G = ws_tail;
-    s.X = ws_tail + gather_len(P.n);
-    ws_tail += 2 * gather_len(P.n);
+    if (factor_in_smem) {
+      s.L = p;
+      p += P.bsize;
+    } else {
+      s.L = ws_tail;
+      ws_tail += P.bsize;
+    }
+    if (gather_in_smem) {  // gather buffer + the primal iterate x
+      s.G = p;
+      s.X = p + gather_len(P.n);
+      p += 2 * gather_len(P.n);
+    } else {
+      s.G = ws_tail;
+      s.X = ws_tail + gather_len(P.n);
+      ws_tail += 2 * gather_len(P.n);
+    }
   }
   s.bs = p + S_B * P.mv;
   s.y = p + S_Y * P.mv;
@@ -755,6 +861,21 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
   s.red = s.dscr + KB + KB * KB;
   s.flag = (int*)(s.red + 8 * 32);
   s.meta = (int*)(s.red + 8 * 32 + 2);
+#ifndef INTOPT_HOST_EMU
+  if (ALLSMEM) {
+    __builtin_assume(__isShared(s.L));
+    __builtin_assume(__isShared(s.G));
+    __builtin_assume(__isShared(s.X));
+  }
+  __builtin_assume(__isShared(s.bs));
+  __builtin_assume(__isShared(s.y));
+  __builtin_assume(__isShared(s.r1));
+  __builtin_assume(__isShared(s.q));
+  __builtin_assume(__isShared(s.v));
+  __builtin_assume(__isShared(s.ybuf));
+  __builtin_assume(__isShared(s.dscr));
+  __builtin_assume(__isShared(s.red));
+#endif
   return s;
 }
 
@@ -777,6 +898,7 @@ struct FwdParams {
   double alpha0, tol, thr, damping;
   int max_iter;
   unsigned long long* phase_cycles;  // null unless profiling
+  int debug;                         // debug switches for bottleneck isolation (env INTOPT_DEBUG), 0 in production
 };
 
 IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst, double* wsi,
@@ -784,13 +906,13 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
   const int m = P.m, n = P.n, mv = P.mv;
   double *L = S.L, *G = S.G, *bs = S.bs, *y = S.y, *r1 = S.r1, *q = S.q, *v = S.v;
   double* x = S.X;  // the primal iterate lives in shared memory (gathered by A x, read by every n-loop)
-  double* t = wsi + (long long)W_T * n;
-  double* D = wsi + (long long)W_D * n;
-  double* r2 = wsi + (long long)W_R2 * n;
-  double* p = wsi + (long long)W_P * n;
-  double* w = wsi + (long long)W_W * n;
-  double* dx = wsi + (long long)W_DX * n;
-  double* dxdt = wsi + (long long)W_DXDT * n;
+  double* __restrict__ t = wsi + (long long)W_T * n;
+  double* __restrict__ D = wsi + (long long)W_D * n;
+  double* __restrict__ r2 = wsi + (long long)W_R2 * n;
+  double* __restrict__ p = wsi + (long long)W_P * n;
+  double* __restrict__ w = wsi + (long long)W_W * n;
+  double* __restrict__ dx = wsi + (long long)W_DX * n;
+  double* __restrict__ dxdt = wsi + (long long)W_DXDT * n;
   const double* __restrict__ c = a.c + (long long)inst * a.c_stride;
 
   PhaseTimer pt{a.phase_cycles, 0};
@@ -929,7 +1051,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     PHASE_MARK(pt, 1);
 
     // ---- M = A D A^T + delta I, factor (:772-777) ------------------------------------------------
-    assemble_normal_matrix(cx, P, M, G, a.damping, L);
+    assemble_normal_matrix(cx, P, M, G, a.damping, L, a.debug);
     PHASE_MARK(pt, 2);
     // right-hand side of the (p,q) solve (:800): G = D*c, built while the factorisation runs
     CTA_FOR(k, n) G[k] = D[k] * c[k];

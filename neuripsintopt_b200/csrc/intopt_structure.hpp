@@ -53,6 +53,11 @@ struct HostStructure {
   std::vector<uint16_t> asm_k16;  // the same as 16-bit indices when n < 65535 (then asm_k is not uploaded)
   std::vector<double> asm_w;
   bool asm_unit = true;
+  // run-length form of the unit-weight lists (consecutive gather indices collapse to start | len << 16);
+  // group g holds R = asm_rptr[g+1]-asm_rptr[g] run slots per lane (R % 4 == 0), lane-major, padded with len = 0
+  std::vector<int> asm_rptr;
+  std::vector<uint32_t> asm_run;
+  long long asm_runs = 0;
   long long asm_terms = 0, asm_padded = 0, chol_macs = 0, solve_macs = 0;
   int ordering = 0;
 };
@@ -328,55 +333,106 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
     long long c = cptr[k + 1] - cptr[k];
     S.asm_terms += c * (c + 1) / 2;
   }
-  std::vector<int> cnt(S.bsize, 0);
-  for (int k = 0; k < n; ++k)
-    for (int a = cptr[k]; a < cptr[k + 1]; ++a)
-      for (int b2 = cptr[k]; b2 <= a; ++b2) cnt[pos_of(crow[a], crow[b2])]++;
+  // entry ids over the envelope positions that are structurally non-zero (plus every diagonal)
+  std::vector<int> id_of(S.bsize, -1);
   struct Ent {
-    int pos, len;
+    int pos;
     unsigned char diag;
+    std::vector<int> k;
+    std::vector<double> w;
+    std::vector<uint32_t> runs;  // start | len << 16, longest first
   };
   std::vector<Ent> ents;
-  for (int i = 0; i < m; ++i)
-    for (int j = S.sky_first[i]; j <= i; ++j) {
-      int pos = pos_of(i, j);
-      if (cnt[pos] > 0 || i == j) ents.push_back({pos, cnt[pos], (unsigned char)(i == j)});
+  {
+    std::vector<char> present(S.bsize, 0);
+    for (int k = 0; k < n; ++k)
+      for (int a = cptr[k]; a < cptr[k + 1]; ++a)
+        for (int b2 = cptr[k]; b2 <= a; ++b2) present[pos_of(crow[a], crow[b2])] = 1;
+    for (int i = 0; i < m; ++i)
+      for (int j = S.sky_first[i]; j <= i; ++j) {
+        const int pos = pos_of(i, j);
+        if (present[pos] || i == j) {
+          id_of[pos] = (int)ents.size();
+          ents.push_back({pos, (unsigned char)(i == j), {}, {}, {}});
+        }
+      }
+  }
+  S.asm_unit = true;
+  for (int k = 0; k < n; ++k)  // ascending k => every term list is ascending in k
+    for (int a = cptr[k]; a < cptr[k + 1]; ++a)
+      for (int b2 = cptr[k]; b2 <= a; ++b2) {
+        Ent& en = ents[id_of[pos_of(crow[a], crow[b2])]];
+        const double w = cval[a] * cval[b2];
+        en.k.push_back(k);
+        en.w.push_back(w);
+        if (w != 1.0) S.asm_unit = false;
+      }
+  const bool rle = S.asm_unit && n < 65535;
+  if (rle)
+    for (Ent& en : ents) {
+      size_t t = 0;
+      while (t < en.k.size()) {
+        size_t len = 1;
+        while (t + len < en.k.size() && en.k[t + len] == en.k[t] + (int)len && len < 65535) ++len;
+        en.runs.push_back((uint32_t)en.k[t] | ((uint32_t)len << 16));
+        t += len;
+      }
+      std::stable_sort(en.runs.begin(), en.runs.end(), [](uint32_t a, uint32_t b) { return (a >> 16) > (b >> 16); });
+      S.asm_runs += (long long)en.runs.size();
     }
-  std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.len > b.len; });
+  // order: lanes of a warp should do the same amount of work in the same shape.  Run-length form: sort by the
+  // sequence of run lengths (lexicographic, descending) so that run slot u has similar length on every lane;
+  // plain form: sort by term count.
+  std::vector<int> order(ents.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    if (rle) {
+      const auto &ra = ents[a].runs, &rb = ents[b].runs;
+      const size_t c = std::min(ra.size(), rb.size());
+      for (size_t u = 0; u < c; ++u)
+        if ((ra[u] >> 16) != (rb[u] >> 16)) return (ra[u] >> 16) > (rb[u] >> 16);
+      return ra.size() > rb.size();
+    }
+    return ents[a].k.size() > ents[b].k.size();
+  });
   const int ne = (int)ents.size();
   const int nag = (ne + 31) / 32;
   S.n_asm = nag * 32;
   S.asm_pos.assign(S.n_asm, -1);
   S.asm_diag.assign(S.n_asm, 0);
   S.asm_gptr.assign(nag + 1, 0);
-  S.asm_glen.assign(nag, 0);
-  std::vector<int> entry_of(S.bsize, -1);
+  S.asm_rptr.assign(nag + 1, 0);
+  for (int g = 0; g < nag; ++g) {
+    size_t len = 0, R = 0;
+    for (int e = 32 * g; e < std::min(ne, 32 * g + 32); ++e) {
+      len = std::max(len, ents[order[e]].k.size());
+      R = std::max(R, ents[order[e]].runs.size());
+    }
+    S.asm_gptr[g + 1] = S.asm_gptr[g] + (rle ? 0 : (int)len);  // the per-term lists are dropped when RLE applies
+    S.asm_rptr[g + 1] = S.asm_rptr[g] + (int)((R + 3) & ~(size_t)3);  // multiple of 4: 16-byte header loads
+  }
+  S.asm_padded = rle ? (long long)S.asm_rptr[nag] * 32 : (long long)S.asm_gptr[nag] * 32;
+  S.asm_k.assign((size_t)S.asm_gptr[nag] * 32, n);  // n = the zero slot of the gather buffer
+  S.asm_w.assign((size_t)S.asm_gptr[nag] * 32, 0.0);
+  S.asm_run.assign((size_t)S.asm_rptr[nag] * 32, 0u);
   for (int e = 0; e < ne; ++e) {
-    S.asm_pos[e] = ents[e].pos;
-    S.asm_diag[e] = ents[e].diag;
-    entry_of[ents[e].pos] = e;
-    S.asm_glen[e / 32] = std::max(S.asm_glen[e / 32], ents[e].len);
+    const Ent& en = ents[order[e]];
+    S.asm_pos[e] = en.pos;
+    S.asm_diag[e] = en.diag;
+    const int g = e / 32, l = e % 32;
+    if (rle) {
+      // lane-major inside the group: lane l owns R consecutive slots (R = slots per lane of this group)
+      const size_t R = (size_t)(S.asm_rptr[g + 1] - S.asm_rptr[g]);
+      for (size_t r = 0; r < en.runs.size(); ++r) S.asm_run[(size_t)S.asm_rptr[g] * 32 + (size_t)l * R + r] = en.runs[r];
+    } else {
+      for (size_t t = 0; t < en.k.size(); ++t) {
+        const size_t d = ((size_t)S.asm_gptr[g] + t) * 32 + l;
+        S.asm_k[d] = en.k[t];
+        S.asm_w[d] = en.w[t];
+      }
+    }
   }
-  for (int g = 0; g < nag; ++g) S.asm_gptr[g + 1] = S.asm_gptr[g] + S.asm_glen[g];
-  S.asm_padded = (long long)S.asm_gptr[nag] * 32;
-  S.asm_k.assign((size_t)S.asm_padded, n);  // n = the zero slot of the gather buffer
-  S.asm_w.assign((size_t)S.asm_padded, 0.0);
-  S.asm_unit = true;
-  {
-    std::vector<int> fill(ne, 0);
-    for (int k = 0; k < n; ++k)
-      for (int a = cptr[k]; a < cptr[k + 1]; ++a)
-        for (int b2 = cptr[k]; b2 <= a; ++b2) {
-          int e = entry_of[pos_of(crow[a], crow[b2])];
-          int t = fill[e]++;
-          size_t d = ((size_t)S.asm_gptr[e / 32] + t) * 32 + (e % 32);
-          double w = cval[a] * cval[b2];
-          S.asm_k[d] = k;
-          S.asm_w[d] = w;
-          if (w != 1.0) S.asm_unit = false;
-        }
-  }
-  if (n < 65535) {
+  if (!rle && n < 65535) {
     S.asm_k16.resize(S.asm_k.size());
     for (size_t i = 0; i < S.asm_k.size(); ++i) S.asm_k16[i] = (uint16_t)S.asm_k[i];
   }

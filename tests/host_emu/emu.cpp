@@ -27,7 +27,7 @@ extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const doubl
   std::vector<double> smem((size_t)S.bsize + 2 * intopt::gather_len(n) + intopt::smem_fixed_doubles(S) +
                            (intopt::meta_ints(S) + 1) / 2);
   std::vector<double> ws((size_t)intopt::W_NVEC * n);
-  const intopt::SmemLayout L = intopt::carve(P, smem.data(), nullptr, 1, 1);
+  const intopt::SmemLayout L = intopt::carve<true>(P, smem.data(), nullptr, 1, 1);
   CtaCtx cx;
   cx.red = L.red;
   const intopt::Meta M = intopt::stage_meta(cx, P, L.meta);
