@@ -208,3 +208,56 @@ def test_warm_start_roundtrip():
     _, it_warm = IPOfunc.status()
     assert (it_warm < it_cold).all()
     np.testing.assert_allclose(x_warm.cpu().numpy(), x_cold.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_batched_energy_learner_gradient_matches_oracle():
+    """f-1: the batched training step feeds dL/dc of every day back into the predictor; the gradient that
+    reaches the predicted prices must equal F^T dL/dc with dL/dc from the oracle."""
+    from neuripsintopt_b200.data import icon
+    from neuripsintopt_b200.energy_learner import IntoptEnergyLearner
+    torch.manual_seed(0)
+    lrn = IntoptEnergyLearner(icon.load1_day01(), input_size=4, hidden_size=1, num_layers=1, device="cuda",
+                              thr=0.1, damping=1e-6, lr=0.1)
+    rng = np.random.default_rng(0)
+    B = 3
+    X = torch.tensor(rng.standard_normal((B, 48, 4)), dtype=torch.float32, device="cuda")
+    y = torch.tensor(rng.uniform(20, 120, (B, 48)), dtype=torch.float32, device="cuda")
+    with torch.no_grad():  # make the predicted prices positive and of the right scale
+        lrn.model.net.weight.mul_(5.0)
+        lrn.model.net.bias.fill_(60.0)
+    price = lrn.model(X.reshape(B * 48, -1)).view(B, 48).detach().requires_grad_(True)
+    c_pred = price @ lrn.F.t()
+    c_true = y @ lrn.F.t()
+    x = lrn.lp_layer(c_pred)
+    (x * c_true).mean(dim=1).sum().backward()
+    A, b, G, h, F = icon.make_matrix_intopt(**icon.load1_day01())
+    for i in range(B):
+        r = O.ipofunc(c_pred[i].detach().cpu().numpy(), (c_true[i] / c_true.shape[1]).cpu().numpy(), A=A.toarray(),
+                      b=b, G=G.toarray(), h=h, bounds=[(0.0, None)], thr=0.1, damping=1e-6)
+        want = F.toarray().T @ r["grad"]
+        got = price.grad[i].double().cpu().numpy()
+        assert _rel2(got, want) < 1e-4, _rel2(got, want)
+    loss0 = lrn.training_step(X, y)
+    assert np.isfinite(loss0)
+
+
+def test_full_size_batch_properties():
+    """BASELINE size (B=1024 Energy LPs): size-independent checks — all status words 0, every instance stops
+    after the same 2 iterations as the reference, primal residual small relative to the cold start, and
+    an arbitrary subset matches the oracle."""
+    import bench
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    A, b, G, h, F = bench.energy_problem()
+    f = IPOfunc(_tt(A.toarray()), _tt(b), _tt(G.toarray()), _tt(h), check_finite=False, **bench.OPTS)
+    c, g = bench.synthetic_costs(F, 1024, 5)
+    ct = torch.tensor(c, device="cuda", requires_grad=True)
+    x = f(ct)
+    x.backward(torch.tensor(g, device="cuda"))
+    status, iters = IPOfunc.status()
+    assert int((status != 0).sum()) == 0 and iters.unique().tolist() == [2]
+    assert torch.isfinite(x).all() and torch.isfinite(ct.grad).all()
+    for i in (0, 511, 1023):
+        r = O.ipofunc(c[i], g[i], A=A.toarray(), b=b, G=G.toarray(), h=h, bounds=[(0.0, None)], thr=0.1,
+                      damping=1e-6)
+        assert _relinf(x[i].detach().double().cpu().numpy(), r["x"]) < X_TOL
+        assert _rel2(ct.grad[i].double().cpu().numpy(), r["grad"]) < G_TOL
