@@ -115,12 +115,26 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SMI_MS", "100")], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def wait_first_sample(self, timeout=30.0):
+        """nvidia-smi's cold start (first NVML init on a fresh box) takes seconds and disturbs running kernels;
+        block until it has printed its first sample so that this happens before the timed region."""
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return True
+            time.sleep(0.05)
+        return False
+
+    def mark(self):
+        """Byte offset of the log right now (samples after it belong to the timed region)."""
+        return os.path.getsize(self.f.name) if self.p is not None else 0
+
+    def stop(self, start_offset=0):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
         if self.p is None:
             return out
@@ -130,7 +144,7 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush()
-        self.f.seek(0)
+        self.f.seek(start_offset)
         sm, mx, reasons = [], [], set()
         for ln in self.f.read().splitlines():
             parts = [p.strip() for p in ln.split(",")]
@@ -170,6 +184,7 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.batch, args.steps, args.warmup
+    sampler = ClockSampler(local) if rank == 0 else None  # started early: its cold start must not hit the timing
 
     A, b, G, h, F = energy_problem()
     tt = lambda M: torch.as_tensor(M.toarray() if hasattr(M, "toarray") else M, dtype=torch.float32)  # noqa: E731
@@ -190,13 +205,37 @@ def run_gpu(args):
         x.backward(g_dev)
         return x, c.grad
 
-    def step_e2e():
-        c = c_host.to(dev, non_blocking=True).requires_grad_(True)
-        g = g_host.to(dev, non_blocking=True)
-        x = f(c)
-        x.backward(g)
-        x_host.copy_(x.detach(), non_blocking=True)
-        gc_host.copy_(c.grad, non_blocking=True)
+    # end-to-end: every step copies its inputs from pinned host memory and its results back; copies run on
+    # side streams with two device buffer sets, so step k+1's upload and step k-1's download overlap step k's
+    # kernels (what a prefetching data loader does).  Nothing is cached across steps.
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    dbuf = [dict(c=torch.empty_like(c_dev), g=torch.empty_like(g_dev), free=None) for _ in range(2)]
+
+    def e2e_loop(n_steps):
+        main = torch.cuda.current_stream(dev)
+        for k in range(n_steps):
+            buf = dbuf[k % 2]
+            with torch.cuda.stream(s_in):
+                if buf["free"] is not None:
+                    s_in.wait_event(buf["free"])  # the step that last used this buffer has finished
+                buf["c"].copy_(c_host, non_blocking=True)
+                buf["g"].copy_(g_host, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(s_in)
+            main.wait_event(ready)
+            c = buf["c"].detach().requires_grad_(True)
+            x = f(c)
+            x.backward(buf["g"])
+            done = torch.cuda.Event()
+            done.record(main)
+            buf["free"] = done
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                x_host.copy_(x.detach(), non_blocking=True)
+                gc_host.copy_(c.grad, non_blocking=True)
+                x.record_stream(s_out)
+                c.grad.record_stream(s_out)
+        main.wait_stream(s_out)
 
     # ---- parity gate on the same inputs before timing (rank 0, a few instances) ----------------------
     x, gc = step_resident()
@@ -231,6 +270,8 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    per_rank = []
+
     def timed(step_fn, split=False):
         for _ in range(W):
             step_fn()
@@ -260,15 +301,34 @@ def run_gpu(args):
         barrier()
         t = torch.tensor([tot, fwd_ms, bwd_ms], dtype=torch.float64, device=dev)
         if world > 1:
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            per_rank.append([round(float(v[0]) / K, 4) for v in allt])
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(v) for v in t.tolist()]
 
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        time.sleep(0.5)  # let nvidia-smi finish its start-up queries before the timed region begins
+        sampler.wait_first_sample()
+    smi_from = sampler.mark() if sampler else 0
+    for _ in range(3):  # untimed pre-warm on top of the W warm-up steps (clocks, allocator, NCCL)
+        step_resident()
     tot_ms, fwd_ms, bwd_ms = timed(step_resident, split=True)
-    clocks = sampler.stop() if sampler else None
-    e2e_ms, _, _ = timed(step_e2e)
+    # end-to-end: one event pair around exactly K pipelined steps (inputs come from the host every step)
+    e2e_loop(max(W, 3))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_loop(K)
+    e1.record()
+    e1.synchronize()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+    # clock samples cover pre-warm + warm-up + both timed regions (identical load); the timed regions alone are
+    # only ~K x 4 ms long, too short for more than a couple of 100 ms samples
+    clocks = sampler.stop(smi_from) if sampler else None
 
     if rank == 0:
         value = world * B * K / (tot_ms * 1e-3)
@@ -307,7 +367,7 @@ def run_gpu(args):
                           hbm=dict(algorithmic_bytes_per_step=alg_bytes,
                                    achieved_gbs=alg_bytes / (tot_ms / K * 1e-3) * 1e-9, peak_gbs=hbm_peak),
                           fwd_ms=fwd_ms / K, bwd_ms=bwd_ms / K),
-            problem=info, parity=parity, clocks=clocks)
+            problem=info, parity=parity, clocks=clocks, per_rank_ms_per_step=per_rank)
         if not args.no_cpu and world == 1:
             Ad, Gd = A.toarray(), G.toarray()
             cnt = args.ref_sample
