@@ -193,10 +193,10 @@ def run_gpu(args):
     c_np, g_np = synthetic_costs(F, B, 1000 + rank)  # every rank owns a different shard of the global batch
     c_dev = torch.tensor(c_np, device=dev)
     g_dev = torch.tensor(g_np, device=dev)
-    c_host = torch.tensor(c_np).pin_memory()
-    g_host = torch.tensor(g_np).pin_memory()
-    x_host = torch.empty_like(c_host).pin_memory()
-    gc_host = torch.empty_like(c_host).pin_memory()
+    c_host = torch.empty(c_np.shape, dtype=torch.float32, pin_memory=True).copy_(torch.from_numpy(c_np))
+    g_host = torch.empty(g_np.shape, dtype=torch.float32, pin_memory=True).copy_(torch.from_numpy(g_np))
+    x_host = torch.empty(c_np.shape, dtype=torch.float32, pin_memory=True)
+    gc_host = torch.empty(c_np.shape, dtype=torch.float32, pin_memory=True)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def step_resident():
