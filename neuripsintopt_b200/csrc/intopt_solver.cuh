@@ -54,6 +54,13 @@ IO_FORCEINLINE double warp_min(double v) {
 #endif
 
 #ifdef INTOPT_HOST_EMU
+struct alignas(16) D2 {
+  double x, y;
+};
+#else
+typedef double2 D2;
+#endif
+#ifdef INTOPT_HOST_EMU
 struct alignas(16) U4 {
   uint32_t x, y, z, w;
 };
@@ -207,53 +214,109 @@ IO_FORCEINLINE double gather_sum_weighted(const IT* __restrict__ kk, const doubl
   return s0 + s1;
 }
 
-// sum of g over one run (start | len << 16; len = 0 is padding); eight loads in flight per lane
-IO_FORCEINLINE void run_sum(uint32_t h, const double* g, double& s0, double& s1) {
-  const double* gp = g + (h & 0xffffu);
-  const int len = (int)(h >> 16);
-  int j = 0;
-  double s2 = 0.0, s3 = 0.0;
-  for (; j + 8 <= len; j += 8) {
-    const double a0 = gp[j], a1 = gp[j + 1], a2 = gp[j + 2], a3 = gp[j + 3];
-    const double a4 = gp[j + 4], a5 = gp[j + 5], a6 = gp[j + 6], a7 = gp[j + 7];
-    s0 += a0;
-    s1 += a1;
-    s2 += a2;
-    s3 += a3;
-    s0 += a4;
-    s1 += a5;
-    s2 += a6;
-    s3 += a7;
-  }
-  if (j + 4 <= len) {
-    const double a0 = gp[j], a1 = gp[j + 1], a2 = gp[j + 2], a3 = gp[j + 3];
-    s0 += a0;
-    s1 += a1;
-    s2 += a2;
-    s3 += a3;
-    j += 4;
-  }
-  if (j + 2 <= len) {
-    const double a0 = gp[j], a1 = gp[j + 1];
-    s0 += a0;
-    s1 += a1;
-    j += 2;
-  }
-  if (j < len) s0 += gp[j];
-  s0 += s2;
-  s1 += s3;
+// ---------------------------------------------------------------------------------------------
+// Double-double helpers for the prefix-sum assembly.  A run of consecutive gather indices sums to
+// P[start+len] - P[start]; keeping the prefix sums P as unevaluated pairs hi+lo (about 106 bits) makes that
+// difference exact to ~1e-32 * P[n], i.e. far below one ulp of any run sum, however wide the dynamic range
+// of d is (d = x/t spans 1e-12..1e12 near convergence).
+// ---------------------------------------------------------------------------------------------
+IO_FORCEINLINE void two_sum(double a, double b, double& s, double& e) {
+  s = a + b;
+  const double bb = s - a;
+  e = (a - (s - bb)) + (b - bb);
+}
+IO_FORCEINLINE D2 dd_add_d(D2 a, double b) {  // (hi,lo) + double
+  double s, e;
+  two_sum(a.x, b, s, e);
+  e += a.y;
+  D2 r;
+  r.x = s + e;
+  r.y = e - (r.x - s);
+  return r;
+}
+IO_FORCEINLINE D2 dd_add(D2 a, D2 b) {  // (hi,lo) + (hi,lo)
+  double s, e;
+  two_sum(a.x, b.x, s, e);
+  e += a.y + b.y;
+  D2 r;
+  r.x = s + e;
+  r.y = e - (r.x - s);
+  return r;
+}
+IO_FORCEINLINE double dd_diff(D2 hi, D2 lo) {  // hi - lo rounded to double
+  double s, e;
+  two_sum(hi.x, -lo.x, s, e);
+  return s + (e + (hi.y - lo.y));
 }
 
-IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* g, double delta,
-                                   double* L, int dbg = 0) {
-  CTA_FOR(e, P.bsize) L[e] = 0.0;
+// Exclusive double-double prefix sums of d[0..n) into PP[0..n] (PP[k] = sum_{k'<k} d[k']).  Chunks of 8
+// consecutive elements per thread, chunk totals scanned in two more levels.  `tot` holds ceil(n/8) + 40 D2.
+IO_DEV void dd_prefix_scan(const CtaCtx& cx, const double* __restrict__ d, int n, D2* PP, D2* tot) {
+  const int nch = (n + 7) >> 3, ngr = (nch + 31) >> 5;
+  D2* tot2 = tot + nch;
+  CTA_FOR(t, nch) {
+    D2 acc;
+    acc.x = 0.0;
+    acc.y = 0.0;
+    const int k0 = t << 3, k1 = k0 + 8 < n ? k0 + 8 : n;
+    for (int k = k0; k < k1; ++k) {
+      PP[k] = acc;  // exclusive, local to the chunk
+      acc = dd_add_d(acc, d[k]);
+    }
+    tot[t] = acc;
+  }
   CTA_SYNC();
-  CTA_FOR(e, P.n_dummy) L[P.dummy_pos[e]] = 1.0;
+  CTA_FOR(gq, ngr) {  // exclusive scan of 32 chunk totals each
+    D2 acc;
+    acc.x = 0.0;
+    acc.y = 0.0;
+    const int t0 = gq << 5, t1 = t0 + 32 < nch ? t0 + 32 : nch;
+    for (int t = t0; t < t1; ++t) {
+      const D2 v = tot[t];
+      tot[t] = acc;
+      acc = dd_add(acc, v);
+    }
+    tot2[gq] = acc;
+  }
+  CTA_SYNC();
+  if (cx.tid == 0) {  // exclusive scan of the group totals (a handful), grand total to PP[n]
+    D2 acc;
+    acc.x = 0.0;
+    acc.y = 0.0;
+    for (int gq = 0; gq < ngr; ++gq) {
+      const D2 v = tot2[gq];
+      tot2[gq] = acc;
+      acc = dd_add(acc, v);
+    }
+    PP[n] = acc;
+  }
+  CTA_SYNC();
+  CTA_FOR(t, nch) {
+    const D2 off = dd_add(tot2[t >> 5], tot[t]);
+    const int k0 = t << 3, k1 = k0 + 8 < n ? k0 + 8 : n;
+    for (int k = k0; k < k1; ++k) PP[k] = dd_add(off, PP[k]);
+  }
+  CTA_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: M = A diag(d) A^T + delta I, assembled entry by entry into the block skyline L.
+// `d` is the (global) weight vector, `region` the shared gather region of 2*gather_len(n) doubles.
+//  * unit-weight problems (0/1 matrices): the term list of an entry is a few runs of consecutive indices;
+//    a run costs two 16-byte gathers from the double-double prefix sums of d instead of one gather per term;
+//  * general problems: one gather per term from a copy of d in `region`, indices warp-interleaved.
+// ---------------------------------------------------------------------------------------------
+IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* __restrict__ d,
+                                   double* region, D2* scan_tmp, double delta, double* L, int dbg = 0) {
+  const int n = P.n;
+  CTA_FOR(e, P.bsize) L[e] = 0.0;
   const int ngrp = (dbg & 1) ? 0 : (P.n_asm >> 5);
   if (P.asm_run) {
-    // run-length lists: a handful of headers per entry instead of one index per term.  Lane l of a warp owns
-    // entry 32*grp + l; its R headers are contiguous, fetched 12 at a time with three 16-byte loads that are
-    // all in flight together (one L2 round trip per group instead of one per run).
+    D2* PP = reinterpret_cast<D2*>(region);
+    dd_prefix_scan(cx, d, n, PP, scan_tmp);  // (its barriers also order the zero fill)
+    CTA_FOR(e, P.n_dummy) L[P.dummy_pos[e]] = 1.0;
+    // Lane l of a warp owns entry 32*grp + l; its R run headers are contiguous and fetched 12 at a time with
+    // three 16-byte loads that are all in flight together (one L2 round trip per group).
     WARP_ROWS(grp, ngrp) {
       const int r0 = M.asm_rptr[grp], R = M.asm_rptr[grp + 1] - r0;
       LANE_FOR(l, 0, 32) {
@@ -263,7 +326,7 @@ IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const 
           uint32_t h[12];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            if (rb + 4 * c < R && !(dbg & 4)) {
+            if (rb + 4 * c < R) {
               const U4 q = *reinterpret_cast<const U4*>(hp + rb + 4 * c);
               h[4 * c] = q.x;
               h[4 * c + 1] = q.y;
@@ -273,11 +336,13 @@ IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const 
               h[4 * c] = h[4 * c + 1] = h[4 * c + 2] = h[4 * c + 3] = 0u;
             }
           }
-          const int cnt = R - rb < 12 ? R - rb : 12;
-          for (int u = 0; u < cnt; ++u) {
-            if (!(dbg & 2)) run_sum(h[0], g, s0, s1);
 #pragma unroll
-            for (int v = 0; v < 11; ++v) h[v] = h[v + 1];  // rotate the register queue
+          for (int u = 0; u < 12; u += 2) {  // padding headers (len 0) contribute exactly 0
+            const int a0 = (int)(h[u] & 0xffffu), a1 = (int)(h[u + 1] & 0xffffu);
+            const D2 lo0 = PP[a0], hi0 = PP[a0 + (int)(h[u] >> 16)];
+            const D2 lo1 = PP[a1], hi1 = PP[a1 + (int)(h[u + 1] >> 16)];
+            s0 += dd_diff(hi0, lo0);
+            s1 += dd_diff(hi1, lo1);
           }
         }
         const int e = grp * 32 + l, pos = P.asm_pos[e];
@@ -287,6 +352,11 @@ IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const 
     CTA_SYNC();
     return;
   }
+  CTA_FOR(k, n) region[k] = d[k];
+  if (cx.tid == 0) region[n] = 0.0;
+  CTA_SYNC();
+  CTA_FOR(e, P.n_dummy) L[P.dummy_pos[e]] = 1.0;
+  const double* g = region;
   WARP_ROWS(grp, ngrp) {
     const int g0 = M.asm_gptr[grp], len = M.asm_gptr[grp + 1] - g0;
     LANE_FOR(l, 0, 32) {
@@ -332,13 +402,6 @@ struct PhaseTimer {
 // 128-bit access to the same logical chunk of 8 different rows touches 8 different bank groups
 // (conflict-free), as does a 128-bit access to the four chunks of one row.
 // ---------------------------------------------------------------------------------------------
-#ifdef INTOPT_HOST_EMU
-struct alignas(16) D2 {
-  double x, y;
-};
-#else
-typedef double2 D2;
-#endif
 IO_HD int bswz(int r) { return (r >> 1) & 3; }
 IO_HD int bidx(int r, int k) { return r * 8 + ((((k >> 1) ^ ((r >> 1) & 3))) << 1) + (k & 1); }
 
@@ -812,12 +875,14 @@ enum { S_B = 0, S_Y, S_R1, S_Q, S_V, S_NVEC };
 constexpr int S_SCRATCH = 2 * KB + (KB + KB * KB) + 8 * 32 + 2;  // ybuf + diag scratch + red + flag
 
 struct SmemLayout {
-  double *L, *G, *X, *bs, *y, *r1, *q, *v, *ybuf, *dscr, *red;
+  double *L, *G, *bs, *y, *r1, *q, *v, *ybuf, *dscr, *red;  // G: gather region of 2*gather_len(n) doubles
+  D2* scan;  // scratch of the double-double prefix scan: scan_len(n) D2
   int* flag;
   int* meta;  // P.meta_ints ints when the schedule is staged in shared memory
 };
 
 IO_HD int gather_len(int n) { return (n + 2) & ~1; }
+IO_HD int scan_len(int n) { return ((n + 7) >> 3) + 40; }  // D2 entries of prefix-scan scratch
 
 // Carve shared memory (and, for spilled pieces, the tail of the per-CTA workspace).  ALLSMEM = factor and
 // gather buffers both live in shared memory: every pointer is then derived unconditionally from the shared
@@ -830,7 +895,6 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
     s.L = p;
     p += P.bsize;
     s.G = p;
-    s.X = p + gather_len(P.n);
     p += 2 * gather_len(P.n);
   } else {
     if (factor_in_smem) {
@@ -842,11 +906,9 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
     }
     if (gather_in_smem) {  // gather buffer + the primal iterate x
       s.G = p;
-      s.X = p + gather_len(P.n);
       p += 2 * gather_len(P.n);
     } else {
       s.G = ws_tail;
-      s.X = ws_tail + gather_len(P.n);
       ws_tail += 2 * gather_len(P.n);
     }
   }
@@ -860,12 +922,12 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
   s.dscr = p + 2 * KB;
   s.red = s.dscr + KB + KB * KB;
   s.flag = (int*)(s.red + 8 * 32);
-  s.meta = (int*)(s.red + 8 * 32 + 2);
+  s.scan = reinterpret_cast<D2*>(s.red + 8 * 32 + 2);
+  s.meta = (int*)(s.red + 8 * 32 + 2 + 2 * scan_len(P.n));
 #ifndef INTOPT_HOST_EMU
   if (ALLSMEM) {
     __builtin_assume(__isShared(s.L));
     __builtin_assume(__isShared(s.G));
-    __builtin_assume(__isShared(s.X));
   }
   __builtin_assume(__isShared(s.bs));
   __builtin_assume(__isShared(s.y));
@@ -905,7 +967,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
                              const SmemLayout& S) {
   const int m = P.m, n = P.n, mv = P.mv;
   double *L = S.L, *G = S.G, *bs = S.bs, *y = S.y, *r1 = S.r1, *q = S.q, *v = S.v;
-  double* x = S.X;  // the primal iterate lives in shared memory (gathered by A x, read by every n-loop)
+  double* __restrict__ x = wsi + (long long)W_X * n;
   double* __restrict__ t = wsi + (long long)W_T * n;
   double* __restrict__ D = wsi + (long long)W_D * n;
   double* __restrict__ r2 = wsi + (long long)W_R2 * n;
@@ -935,6 +997,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     const double* s0 = a.init + (long long)inst * slen;
     CTA_FOR(k, n) {
       x[k] = s0[k];
+      G[k] = s0[k];
       t[k] = s0[n + m + k];
     }
     CTA_FOR(i, m) y[i] = s0[n + P.perm[i]];
@@ -943,6 +1006,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
   } else {
     CTA_FOR(k, n) {
       x[k] = 1.0;
+      G[k] = 1.0;  // G mirrors x at every loop top: the residual A x gathers from shared memory
       t[k] = 1.0;
     }
   }
@@ -997,7 +1061,6 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
       const double dk = xk / tk;                // :772
       r2[k] = r;
       D[k] = dk;
-      G[k] = dk;
       acc[0] = fma(xk, tk, acc[0]);
       acc[1] = fma(ck, xk, acc[1]);
       acc[2] = fma(r, r, acc[2]);
@@ -1006,9 +1069,9 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     WARP_ROWS(i, m) {
       double s = 0.0;
       if (P.a_unit) {
-        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s += x[P.csr_col[e]];
+        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s += G[P.csr_col[e]];
       } else {
-        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s = fma(P.csr_val[e], x[P.csr_col[e]], s);
+        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s = fma(P.csr_val[e], G[P.csr_col[e]], s);
       }
       s = warp_sum(s);
       if (cx.lane == 0) {
@@ -1051,13 +1114,17 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     PHASE_MARK(pt, 1);
 
     // ---- M = A D A^T + delta I, factor (:772-777) ------------------------------------------------
-    assemble_normal_matrix(cx, P, M, G, a.damping, L, a.debug);
+    assemble_normal_matrix(cx, P, M, D, G, S.scan, a.damping, L, a.debug);
     PHASE_MARK(pt, 2);
     // right-hand side of the (p,q) solve (:800): G = D*c, built while the factorisation runs
     CTA_FOR(k, n) G[k] = D[k] * c[k];
     solved = block_cholesky(cx, P, M, L, S.dscr, S.flag, &pt);  // (its barriers order the G writes)
     PHASE_MARK(pt, 3);
-    if (!solved) continue;  // deltas = 0 (:855-857): the iterate is unchanged, the tests run at loop top
+    if (!solved) {  // deltas = 0 (:855-857): the iterate is unchanged, the tests run at loop top
+      CTA_FOR(k, n) G[k] = x[k];  // G must mirror x again
+      CTA_SYNC();
+      continue;
+    }
     spmv_rows(cx, P, M, G, q);
     CTA_SYNC();
     // predictor: gamma = 0, eta = 1
@@ -1106,6 +1173,8 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
       bv_ = acc2[3];
       if (acc2[4] > 0.0) {  // NaN in p or q (:805-806) -> unsolved
         solved = false;
+        CTA_FOR(k, n) G[k] = x[k];
+        CTA_SYNC();
         continue;
       }
     }
@@ -1179,7 +1248,9 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
           const double rxt = -(xk * tk - gm) - dxdt[k];
           const double dxk = dx[k];
           const double dtk = (1.0 / xk) * (rxt - tk * dxk);
-          x[k] = xk + al * dxk;
+          const double xn = xk + al * dxk;
+          x[k] = xn;
+          G[k] = xn;
           t[k] = tk + al * dtk;
         }
         CTA_FOR(i, m) y[i] = y[i] + al * (v[i] + q[i] * dtau);  // d_y = v + q d_tau (:840)
@@ -1264,7 +1335,6 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
     const double tk = whole ? ts[k] : ts[k] / tau;
     const double xx = xk * xk;
     x2[k] = xx;
-    G[k] = xx;
     xt[0] = fma(xk, tk, xt[0]);
     if (k < nvar) xt[1] = fma(xk, g[k], xt[1]);
   }
@@ -1272,7 +1342,8 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   const double mu = whole ? (xt[0] + tau * kappa) / (double)(n + 1) : xt[0] / (double)n;  // :1517 | alter :1525
   const double xg = xt[1];
 
-  assemble_normal_matrix(cx, P, M, G, a.damping, L);  // :1525-1527,1535
+  CTA_SYNC();
+  assemble_normal_matrix(cx, P, M, x2, G, S.scan, a.damping, L);  // :1525-1527,1535
   CTA_FOR(k, n) G[k] = (k < nvar) ? x2[k] * g[k] : 0.0;
   const bool ok = block_cholesky(cx, P, M, L, S.dscr, S.flag);
   if (!ok) {
