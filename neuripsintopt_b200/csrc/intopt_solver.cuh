@@ -88,6 +88,11 @@ struct ProblemDev {
   const uint16_t* csc_row;
   const double* csc_val;  // null if a_unit
   int a_unit;
+  const uint32_t* rs_hdr;  // run-length rows (unit A): slot-packed headers, null if unavailable
+  const uint16_t* rs_row;
+  int rs_slots;
+  const int* g_cr_gptr;   // run-length columns (unit A)
+  const uint32_t* cr_hdr;  // null if unavailable
   const int* perm;  // internal row -> original row
   const int* g_fb;
   const int* g_boff;
@@ -120,6 +125,7 @@ struct Meta {
   const int* csc_gptr;
   const int* asm_gptr;
   const int* asm_rptr;
+  const int* cr_gptr;
 };
 
 // Sum N partial values over the CTA; every thread receives the totals (fixed order => deterministic).
@@ -721,7 +727,63 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
 }
 
 // out[i] = sum_e A_ie * src[col_e]   (row-wise, one warp per row, four index chunks in flight)
+IO_FORCEINLINE double run_total(const double* gp, int len) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int j = 0;
+  for (; j + 4 <= len; j += 4) {
+    const double a0 = gp[j], a1 = gp[j + 1], a2 = gp[j + 2], a3 = gp[j + 3];
+    s0 += a0;
+    s1 += a1;
+    s2 += a2;
+    s3 += a3;
+  }
+  for (; j < len; ++j) s0 += gp[j];
+  return (s0 + s1) + (s2 + s3);
+}
+
 IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* src, double* out) {
+  if (P.rs_hdr) {
+    // unit-weight A in run-length form: every lane sums one run of consecutive src entries, rows are whole
+    // lane ranges of a slot and are combined by a segmented shuffle scan (fixed order => deterministic)
+#ifdef INTOPT_HOST_EMU
+    for (int slot = 0; slot < P.rs_slots; ++slot)
+      for (int l = 0; l < 32; ++l) {
+        const uint32_t h = P.rs_hdr[slot * 32 + l];
+        const int row = P.rs_row[slot * 32 + l];
+        if (row == 0xffff) continue;
+        const double s = run_total(src + (h & 0xffffu), (int)(h >> 16));
+        const bool first = l == 0 || P.rs_row[slot * 32 + l - 1] != row;
+        out[row] = first ? s : out[row] + s;
+      }
+#else
+    int slot = cx.warp;
+    uint32_t hn = 0u;
+    int rown = 0xffff;
+    if (slot < P.rs_slots) {
+      hn = P.rs_hdr[slot * 32 + cx.lane];
+      rown = P.rs_row[slot * 32 + cx.lane];
+    }
+    for (; slot < P.rs_slots; slot += cx.nwarps) {
+      const uint32_t h = hn;
+      const int row = rown;
+      const int nxt = slot + cx.nwarps;
+      if (nxt < P.rs_slots) {  // next slot's headers are in flight while this one is summed
+        hn = P.rs_hdr[nxt * 32 + cx.lane];
+        rown = P.rs_row[nxt * 32 + cx.lane];
+      }
+      double s = run_total(src + (h & 0xffffu), (int)(h >> 16));
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, s, off);
+        const int r = __shfl_up_sync(0xffffffffu, row, off);
+        if (cx.lane >= off && r == row) s += v;
+      }
+      const int rnext = __shfl_down_sync(0xffffffffu, row, 1);
+      if (row != 0xffff && (cx.lane == 31 || rnext != row)) out[row] = s;
+    }
+#endif
+    return;
+  }
   const int W = cx.warpsize;
   WARP_ROWS(i, P.m) {
     const int lo = M.csr_ptr[i], hi = M.csr_ptr[i + 1];
@@ -823,6 +885,80 @@ IO_FORCEINLINE void col_dot2(const ProblemDev& P, const Meta& M, int k, const do
   s2 = a2 + b2;
 }
 
+// Run-length columns: first 16-byte header block (four runs) of column k; zero if the path is unavailable.
+IO_FORCEINLINE U4 cr_fetch(const ProblemDev& P, const Meta& M, int k) {
+  U4 q;
+  q.x = q.y = q.z = q.w = 0u;
+  if (P.cr_hdr && k < P.n) {
+    const int g = k >> 5, r0 = M.cr_gptr[g], R = M.cr_gptr[g + 1] - r0;
+    q = *reinterpret_cast<const U4*>(P.cr_hdr + (size_t)r0 * 32 + (size_t)(k & 31) * R);
+  }
+  return q;
+}
+// (A^T y)_k for NY vectors from the prefetched header block `q` (further blocks, if any, are loaded here).
+template <int NY>
+IO_FORCEINLINE void cr_dot(const ProblemDev& P, const Meta& M, int k, U4 q, const double* y1, const double* y2,
+                           double& a, double& b2) {
+  a = 0.0;
+  b2 = 0.0;
+  const int g = k >> 5, r0 = M.cr_gptr[g], R = M.cr_gptr[g + 1] - r0;
+  const uint32_t* __restrict__ hp = P.cr_hdr + (size_t)r0 * 32 + (size_t)(k & 31) * R;
+  for (int rb = 0; rb < R; rb += 4) {
+    if (rb) q = *reinterpret_cast<const U4*>(hp + rb);
+    const uint32_t h[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int st = (int)(h[u] & 0xffffu), len = (int)(h[u] >> 16);
+      a += run_total(y1 + st, len);
+      if (NY == 2) b2 += run_total(y2 + st, len);
+    }
+  }
+}
+
+// out[k] = (A^T y)_k for every column k (NY = 1 or 2 vectors at once).  Unit-weight problems use the
+// run-length columns: one 16-byte header load per column (four runs), the next group's header in flight.
+template <int NY>
+IO_DEV void at_mult(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* y1, const double* y2,
+                    double* out1, double* out2) {
+  const int n = P.n;
+  if (P.cr_hdr) {
+    const int ngrp = (n + 31) >> 5;
+    WARP_ROWS(g, ngrp) {
+      const int r0 = M.cr_gptr[g], R = M.cr_gptr[g + 1] - r0;
+      LANE_FOR(l, 0, 32) {
+        const uint32_t* __restrict__ hp = P.cr_hdr + (size_t)r0 * 32 + (size_t)l * R;
+        double a = 0.0, b2 = 0.0;
+        for (int rb = 0; rb < R; rb += 4) {
+          const U4 q = *reinterpret_cast<const U4*>(hp + rb);
+          const uint32_t h[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int st = (int)(h[u] & 0xffffu), len = (int)(h[u] >> 16);
+            a += run_total(y1 + st, len);
+            if (NY == 2) b2 += run_total(y2 + st, len);
+          }
+        }
+        const int k = g * 32 + l;
+        if (k < n) {
+          out1[k] = a;
+          if (NY == 2) out2[k] = b2;
+        }
+      }
+    }
+    return;
+  }
+  CTA_FOR(k, n) {
+    if (NY == 2) {
+      double a, b2;
+      col_dot2(P, M, k, y1, y2, a, b2);
+      out1[k] = a;
+      out2[k] = b2;
+    } else {
+      out1[k] = col_dot(P, M, k, y1);
+    }
+  }
+}
+
 IO_DEV Meta global_meta(const ProblemDev& P) {
   Meta M;
   M.fb = P.g_fb;
@@ -833,17 +969,18 @@ IO_DEV Meta global_meta(const ProblemDev& P) {
   M.csc_gptr = P.g_csc_gptr;
   M.asm_gptr = P.g_asm_gptr;
   M.asm_rptr = P.g_asm_rptr;
+  M.cr_gptr = P.g_cr_gptr;
   return M;
 }
 
 // Copies the schedule arrays into shared memory (`dst` holds P.meta_ints ints) and returns pointers to the copies.
 IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
-  const int cnt[8] = {P.mb, P.mb + 1, P.mb + 1, P.n_act, P.m + 1, ((P.n + 31) >> 5) + 1, (P.n_asm >> 5) + 1,
-                      (P.n_asm >> 5) + 1};
-  const int* src[8] = {P.g_fb, P.g_boff, P.g_act_ptr, P.g_act_blk, P.g_csr_ptr, P.g_csc_gptr, P.g_asm_gptr,
-                       P.g_asm_rptr};
+  const int cnt[9] = {P.mb, P.mb + 1, P.mb + 1, P.n_act, P.m + 1, ((P.n + 31) >> 5) + 1, (P.n_asm >> 5) + 1,
+                      (P.n_asm >> 5) + 1, ((P.n + 31) >> 5) + 1};
+  const int* src[9] = {P.g_fb, P.g_boff, P.g_act_ptr, P.g_act_blk, P.g_csr_ptr, P.g_csc_gptr, P.g_asm_gptr,
+                       P.g_asm_rptr, P.g_cr_gptr};
   int* d = dst;
-  for (int a = 0; a < 8; ++a) {
+  for (int a = 0; a < 9; ++a) {
     CTA_FOR(i, cnt[a]) d[i] = src[a][i];
     d += cnt[a];
   }
@@ -864,6 +1001,8 @@ IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
   M.asm_gptr = d;
   d += cnt[6];
   M.asm_rptr = d;
+  d += cnt[7];
+  M.cr_gptr = d;
   CTA_SYNC();
   return M;
 }
@@ -1054,9 +1193,17 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
   while (status != ST_NONFINITE) {
     // ---- residuals at the current iterate (:765-770; the same r_p, r_d as _indicators :887-894) ----
     double acc[3] = {0.0, 0.0, 0.0};
+    U4 hq = cr_fetch(P, M, cx.tid);
     CTA_FOR(k, n) {
       const double xk = x[k], tk = t[k], ck = c[k];
-      const double aty = col_dot(P, M, k, y);
+      double aty, unused_;
+      if (P.cr_hdr) {
+        const U4 q0 = hq;
+        hq = cr_fetch(P, M, k + cx.nthreads);  // next column's header in flight during this column's work
+        cr_dot<1>(P, M, k, q0, y, nullptr, aty, unused_);
+      } else {
+        aty = col_dot(P, M, k, y);
+      }
       const double r = -(aty + tk - ck * tau);  // :766
       const double dk = xk / tk;                // :772
       r2[k] = r;
@@ -1149,9 +1296,16 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     double cp_, bq_, cu_, bv_;
     {
       double acc2[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      U4 hq2 = cr_fetch(P, M, cx.tid);
       CTA_FOR(k, n) {
         double atq, atv;
-        col_dot2(P, M, k, q, v, atq, atv);
+        if (P.cr_hdr) {
+          const U4 q0 = hq2;
+          hq2 = cr_fetch(P, M, k + cx.nthreads);
+          cr_dot<2>(P, M, k, q0, q, v, atq, atv);
+        } else {
+          col_dot2(P, M, k, q, v, atq, atv);
+        }
         const double dk = D[k], ck = c[k];
         const double pk = dk * (atq - ck);    // :678 for (c,b)
         const double uk = dk * (atv - w[k]);  // :678 for the predictor
@@ -1206,8 +1360,17 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
         }
         PHASE_MARK(pt, 8);
         double acc3[2] = {0.0, 0.0};
+        U4 hq3 = cr_fetch(P, M, cx.tid);
         CTA_FOR(k, n) {
-          const double uk = D[k] * (col_dot(P, M, k, v) - w[k]);  // :678
+          double atv, unused_;
+          if (P.cr_hdr) {
+            const U4 q0 = hq3;
+            hq3 = cr_fetch(P, M, k + cx.nthreads);
+            cr_dot<1>(P, M, k, q0, v, nullptr, atv, unused_);
+          } else {
+            atv = col_dot(P, M, k, v);
+          }
+          const double uk = D[k] * (atv - w[k]);  // :678
           dx[k] = uk;
           acc3[0] = fma(c[k], uk, acc3[0]);
         }
@@ -1358,7 +1521,9 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   if (!whole) {
     double* const rhs1[1] = {v};
     block_solve<1>(cx, P, M, L, rhs1, S.ybuf);
-    CTA_FOR(k, nvar) gc[k] = -x2[k] * (g[k] - col_dot(P, M, k, v)) / mu;
+    at_mult<1>(cx, P, M, v, nullptr, G, nullptr);
+    CTA_SYNC();
+    CTA_FOR(k, nvar) gc[k] = -x2[k] * (g[k] - G[k]) / mu;
     if (cx.tid == 0) a.status[inst] = ST_OK;
     CTA_SYNC();
     return;
@@ -1377,9 +1542,10 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   double* ug = wsi + (long long)W_DX * n;
   double* pp = wsi + (long long)W_P * n;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  at_mult<2>(cx, P, M, q, v, G, G + gather_len(n));
+  CTA_SYNC();
   CTA_FOR(k, n) {
-    double atq, atv;
-    col_dot2(P, M, k, q, v, atq, atv);
+    const double atq = G[k], atv = G[gather_len(n) + k];
     const double gk = (k < nvar) ? g[k] : 0.0;
     const double ugk = x2[k] * (atv - tau * gk) / mu;  // :1549 applied to g
     const double pk = x2[k] * (atq - c[k]) / mu;       // :1548

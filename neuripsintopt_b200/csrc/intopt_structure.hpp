@@ -34,6 +34,14 @@ struct HostStructure {
   std::vector<int> csc_gptr, csc_glen;
   std::vector<uint16_t> csc_row;
   std::vector<double> csc_val;
+  // run-length forms for unit-weight A (consecutive indices collapse to start | len << 16):
+  //  * rows: whole rows packed into 32-lane slots, one run per lane (rs_row = row id, 0xffff = padding lane);
+  //  * columns: per 32-column group, R = cr_gptr[g+1]-cr_gptr[g] run slots per lane (R % 4 == 0), lane-major
+  std::vector<uint32_t> rs_hdr;
+  std::vector<uint16_t> rs_row;
+  int rs_slots = 0;
+  std::vector<int> cr_gptr;
+  std::vector<uint32_t> cr_hdr;
   // scalar envelope (first non-zero column of each row of M in internal order)
   std::vector<int> sky_first;
   int sky_size = 0;
@@ -268,6 +276,72 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
       size_t d = ((size_t)S.csc_gptr[g] + t) * 32 + l;
       S.csc_row[d] = (uint16_t)crow[cptr[k] + t];
       S.csc_val[d] = cval[cptr[k] + t];
+    }
+  }
+
+  // ---- run-length forms of A (unit weights only) -----------------------------------------------------
+  S.cr_gptr.assign(ngrp + 1, 0);
+  if (S.a_unit && n < 65535) {
+    auto runs_of = [](const int* idx, int len) {
+      std::vector<uint32_t> r;
+      int t = 0;
+      while (t < len) {
+        int l = 1;
+        while (t + l < len && idx[t + l] == idx[t] + l && l < 65535) ++l;
+        r.push_back((uint32_t)idx[t] | ((uint32_t)l << 16));
+        t += l;
+      }
+      return r;
+    };
+    // rows -> slots
+    bool ok = true;
+    std::vector<uint32_t> hdr;
+    std::vector<uint16_t> rid;
+    int used = 32;  // lanes used in the current slot (start a new slot first)
+    for (int i = 0; i < m && ok; ++i) {
+      auto r = runs_of(S.csr_col.data() + S.csr_ptr[i], S.csr_ptr[i + 1] - S.csr_ptr[i]);
+      if (r.size() > 32) ok = false;
+      if (used + (int)r.size() > 32) {
+        while (used < 32 && !hdr.empty()) {
+          hdr.push_back(0u);
+          rid.push_back(0xffff);
+          ++used;
+        }
+        used = 0;
+      }
+      for (uint32_t h : r) {
+        hdr.push_back(h);
+        rid.push_back((uint16_t)i);
+      }
+      if (r.empty()) {  // a row without entries still has to produce out[i] = 0
+        hdr.push_back(0u);
+        rid.push_back((uint16_t)i);
+        used += 1;
+      }
+      used += (int)r.size();
+    }
+    while (hdr.size() % 32) {
+      hdr.push_back(0u);
+      rid.push_back(0xffff);
+    }
+    if (ok) {
+      S.rs_hdr = hdr;
+      S.rs_row = rid;
+      S.rs_slots = (int)hdr.size() / 32;
+    }
+    // columns -> lane-major run slots per 32-column group
+    std::vector<std::vector<uint32_t>> cruns(n);
+    for (int k = 0; k < n; ++k) cruns[k] = runs_of(crow.data() + cptr[k], cptr[k + 1] - cptr[k]);
+    for (int g = 0; g < ngrp; ++g) {
+      size_t R = 0;
+      for (int k = 32 * g; k < std::min(n, 32 * g + 32); ++k) R = std::max(R, cruns[k].size());
+      S.cr_gptr[g + 1] = S.cr_gptr[g] + (int)((R + 3) & ~(size_t)3);
+    }
+    S.cr_hdr.assign((size_t)S.cr_gptr[ngrp] * 32, 0u);
+    for (int k = 0; k < n; ++k) {
+      const int g = k >> 5, l = k & 31;
+      const size_t R = (size_t)(S.cr_gptr[g + 1] - S.cr_gptr[g]);
+      for (size_t r = 0; r < cruns[k].size(); ++r) S.cr_hdr[(size_t)S.cr_gptr[g] * 32 + (size_t)l * R + r] = cruns[k][r];
     }
   }
 
