@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Secondary benchmark: batched IPOfunc fwd+bwd throughput on every BASELINE.json config shape
+(bench.py stays the contract benchmark on the Energy LP).  Prints one JSON line per config.
+
+    python bench_configs.py [--batch B] [--steps K]
+
+Configs: knapsack (32x62, per-instance cost row => one problem per instance, shared structure cache),
+energy (172x1582), twitter (221x2852, per-instance b, shared c), dense m in {16, 64} (n = 2m).
+Inputs come from tests/golden/*.npz (problem data) with synthetic cost batches."""
+import argparse, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT)
+import torch
+from tests import golden_util as GU
+
+
+def time_steps(fn, steps, warmup=3):
+    for _ in range(warmup): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps): fn()
+    e1.record(); e1.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=1024); ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--thr", type=float, default=0.1)
+    args = ap.parse_args()
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    from neuripsintopt_b200 import ipofunc as _ipo
+    tt = lambda v: torch.Tensor() if v is None else torch.as_tensor(np.asarray(v), dtype=torch.float32)
+    rng = np.random.default_rng(0)
+    B = args.batch
+    out = []
+    for name in ("energy_load1", "twitter_sp", "dense_m16", "dense_m64", "knapsack"):
+        z = GU.load(name); case = GU.cases(z)[0]; kw = dict(case["kw"]); kw["thr"] = args.thr
+        inp = GU.problem_inputs(name, z, 0)
+        n_x = case["c"].shape[1]
+        c0 = case["c"][0].astype(np.float64)
+        if name == "twitter_sp":
+            pairs = z["train_pairs"]; nb = z["b_rr"].shape[1]
+            bb = np.tile(z["b_rr"], (B // len(z["b_rr"]) + 1, 1))[:B]
+            c = torch.tensor((c0 * np.abs(1 + 0.3 * rng.standard_normal((B, n_x)))).astype(np.float32), device="cuda")
+            f = IPOfunc(tt(inp["A"]), tt(bb), torch.Tensor(), torch.Tensor(), check_finite=False, **kw)
+        elif name == "knapsack":
+            # one cost row per instance => B different problems; run the reference-style loop over a few of them
+            Bk = 10  # the experiment has 10 minibatches of 31 items (ModelRun.py:17,60): 10 distinct cost rows, cached
+            costs = rng.uniform(20, 1000, (Bk, n_x)).astype(np.float32)
+            c = torch.tensor(-(rng.standard_normal((Bk, n_x)) + 0.3 * rng.standard_normal((Bk, n_x))).astype(np.float32), device="cuda")
+            fs = [IPOfunc(tt(costs[i][None, :]), tt(z["budget_rhs"]), torch.Tensor(), torch.Tensor(), check_finite=False, **kw) for i in range(Bk)]
+            g = torch.ones(n_x, device="cuda")
+            def step():
+                for i in range(Bk):
+                    ci = c[i].detach().requires_grad_(True); fs[i](ci).backward(g)
+            ms = time_steps(step, max(2, args.steps // 3))
+            out.append(dict(config=name, shape="32x62 (per-instance A: one problem per instance, looped)", batch=Bk,
+                            lp_per_s=Bk / ms * 1e3, ms_per_step=ms, thr=args.thr))
+            print(json.dumps(out[-1])); continue
+        else:
+            scale = np.abs(c0).mean()
+            c = torch.tensor((c0 + 0.05 * scale * rng.standard_normal((B, n_x))).astype(np.float32), device="cuda")
+            f = IPOfunc(tt(inp["A"]), tt(inp["b"]), tt(inp["G"]), tt(inp["h"]), check_finite=False, **kw)
+        g = torch.ones(B, n_x, device="cuda") / n_x
+        def step():
+            cc = c.detach().requires_grad_(True); f(cc).backward(g)
+        step(); torch.cuda.synchronize()
+        status, iters = IPOfunc.status()
+        ms = time_steps(step, args.steps)
+        info = [v.info for v in _ipo._PROBLEM_CACHE.values() if hasattr(v, "info")][-1]
+        out.append(dict(config=name, shape="%dx%d nnz %d" % (info["m"], info["n"], info["nnz"]), batch=B,
+                        lp_per_s=B / ms * 1e3, ms_per_step=ms, thr=args.thr, mean_iters=float(iters.float().mean()),
+                        bad_status=int((status != 0).sum()), smem_bytes=info["smem_bytes"], ctas_per_sm=info["ctas_per_sm"],
+                        envelope=info["envelope"]))
+        print(json.dumps(out[-1]))
+
+
+if __name__ == "__main__":
+    main()

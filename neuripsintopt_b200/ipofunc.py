@@ -33,7 +33,7 @@ from . import problem as _problem
 STATUS_OK, STATUS_MAXITER, STATUS_INFEAS, STATUS_BREAKDOWN, STATUS_NONFINITE = 0, 1, 2, 3, 4
 
 _PROBLEM_CACHE: "OrderedDict[tuple, object]" = OrderedDict()
-_PROBLEM_CACHE_MAX = 16
+_PROBLEM_CACHE_MAX = 64  # e.g. the knapsack experiment cycles through 10 minibatch cost rows (one problem each)
 
 
 def clear_cache():
