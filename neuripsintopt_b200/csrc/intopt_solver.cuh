@@ -447,9 +447,17 @@ IO_FORCEINLINE void load_vec8(const double* v8, double (&v)[KB]) {
 // A non-positive / non-finite pivot sets *fail and continues with pivot 1.
 #ifdef INTOPT_HOST_EMU
 // single-threaded test build: plain column Cholesky + forward substitution
-IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr, int* fail) {
+IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr, int* fail,
+                                     const double* panel = nullptr) {
   double* col = scr;
   double* inv = scr + KB;
+  if (panel)  // fused look-ahead update: C -= P P^T with P = L_(K+1,K)
+    for (int i = 0; i < KB; ++i)
+      for (int k = 0; k <= i; ++k) {
+        double s = 0.0;
+        for (int j = 0; j < KB; ++j) s = fma(panel[bidx(i, j)], panel[bidx(k, j)], s);
+        blk[bidx(i, k)] -= s;
+      }
   for (int j = 0; j < KB; ++j) {
     LANE_FOR(i, j, KB) {
       double s = blk[bidx(i, j)];
@@ -480,11 +488,25 @@ IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr,
 #else
 // CUDA build: the block lives in registers (lane i & 7 owns row i, lanes 8..31 mirror lanes 0..7), pivots
 // and columns travel by warp shuffles, pivots use rsqrt so the dependent chain has no fp64 divide/sqrt.
-IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr, int* fail) {
+IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr, int* fail,
+                                     const double* panel = nullptr) {
   const unsigned full = 0xffffffffu;
   const int i = cx.lane & 7;
   double a[KB], rinv[KB];
   load_row(blk, i, a);
+  if (panel) {  // fused look-ahead update in registers: row i of C -= P_i . P_k^T with P = L_(K+1,K)
+    double own[KB];
+    load_row(panel, i, own);
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      double pk[KB];
+      load_row(panel, k, pk);  // same address on every lane: broadcast
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < KB; ++j) s = fma(own[j], pk[j], s);
+      a[k] -= s;
+    }
+  }
   bool bad = false;
 #pragma unroll
   for (int j = 0; j < KB; ++j) {
@@ -625,13 +647,12 @@ IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
     const int np = na * (na + 1) / 2;
     const int lead = (na > 0 && M.act_blk[a0] == K + 1) ? 1 : 0;  // pair 0 updates block (K+1,K+1)
     if (cx.warp == 0) {
-      if (lead) {
-        LANE_FOR(task, 0, 4) chol_update_task(P, M, L, K, a0, task);
-        WARP_SYNC();
-      }
       if (pt) { PHASE_MARK(*pt, 12); }
-      if (K + 1 < mb)
-        diag_block_factor_invert(cx, L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64, scratch, fail_flag);
+      if (K + 1 < mb) {
+        // the update of the next diagonal block by this step's panel block (K+1,K) is fused into its factorisation
+        const double* lead_panel = lead ? L + M.boff[K + 1] + (K - M.fb[K + 1]) * 64 : nullptr;
+        diag_block_factor_invert(cx, L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64, scratch, fail_flag, lead_panel);
+      }
       if (pt) { PHASE_MARK(*pt, 13); }
     }
     if (cx.nwarps == 1 || cx.warp > 0) {
@@ -645,88 +666,154 @@ IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
 
 // ---------------------------------------------------------------------------------------------
 // Solve L L^T z = r in place for NR right-hand sides at once (blocked substitution; the diagonal blocks
-// hold Linv).  `ybuf` is NR*8 doubles of scratch (16-byte aligned).
+// hold Linv).  One barrier per block step: while the CTA applies block K's update to the rows below,
+// warp 0 first updates the rows of the NEXT pivot block and immediately multiplies them by its inverted
+// diagonal block, so the next step's pivot values are ready when the barrier opens.
+// `ybuf` is 2*NR*8 doubles of scratch (double buffered, 16-byte aligned).
 // ---------------------------------------------------------------------------------------------
 template <int NR>
 IO_FORCEINLINE double* rhs_sel(double* const (&r)[NR], int q) {
   return (NR > 1 && q) ? r[NR - 1] : r[0];  // NR is 1 or 2
 }
 
+// y[idx] (idx = q*8 + i) = row i of Linv (or of Linv^T) times the 8-vector v_q
+template <int NR, bool TRANS>
+IO_FORCEINLINE void pivot_apply(const double* Linv, double* const (&r)[NR], int blk, int idx, double* yout) {
+  const int q = idx >> 3, i = idx & 7;
+  double rk[KB];
+  load_vec8(rhs_sel<NR>(r, q) + blk * KB, rk);
+  double s = 0.0;
+  if (!TRANS) {
+    double li[KB];
+    load_row(Linv, i, li);
+#pragma unroll
+    for (int j = 0; j < KB; ++j)
+      if (j <= i) s = fma(li[j], rk[j], s);
+  } else {
+#pragma unroll
+    for (int j = 0; j < KB; ++j)
+      if (j >= i) s = fma(Linv[bidx(j, i)], rk[j], s);
+  }
+  yout[idx] = s;
+}
+
 template <int NR>
 IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* L, double* const (&r)[NR],
                         double* ybuf) {
   const int mb = P.mb;
-  // forward: L y = r
+  const int o_tid = cx.nwarps > 1 ? cx.tid - cx.warpsize : 0;
+  const int o_n = cx.nwarps > 1 ? cx.nthreads - cx.warpsize : 1;
+  // ---- forward: L y = r --------------------------------------------------------------------------
+  if (cx.warp == 0) {
+    LANE_FOR(idx, 0, NR * KB) pivot_apply<NR, false>(L + M.boff[0] + (0 - M.fb[0]) * 64, r, 0, idx, ybuf);
+  }
+  CTA_SYNC();
   for (int K = 0; K < mb; ++K) {
-    const double* Linv = L + M.boff[K] + (K - M.fb[K]) * 64;
-    CTA_FOR(idx, NR * KB) {
-      const int q = idx >> 3, i = idx & 7;
-      double rk[KB], li[KB];
-      load_vec8(rhs_sel<NR>(r, q) + K * KB, rk);
-      load_row(Linv, i, li);
-      double s = 0.0;
-#pragma unroll
-      for (int j = 0; j < KB; ++j)
-        if (j <= i) s = fma(li[j], rk[j], s);
-      ybuf[idx] = s;
-    }
-    CTA_SYNC();
+    const double* ycur = ybuf + (K & 1) * NR * KB;
+    double* ynext = ybuf + ((K + 1) & 1) * NR * KB;
     const int a0 = M.act_ptr[K], na = M.act_ptr[K + 1] - a0;
-    CTA_FOR(idx, NR * KB) rhs_sel<NR>(r, idx >> 3)[K * KB + (idx & 7)] = ybuf[idx];
-    CTA_FOR(idx, na * KB * NR) {
-      const int q = idx / (na * KB), rem = idx - q * (na * KB);
-      const int I = M.act_blk[a0 + (rem >> 3)], rr = rem & 7;
-      double row[KB], yk[KB];
-      load_row(L + M.boff[I] + (K - M.fb[I]) * 64, rr, row);
-      load_vec8(ybuf + q * KB, yk);
-      double s = 0.0;
+    const int lead = (na > 0 && M.act_blk[a0] == K + 1) ? 1 : 0;  // the next pivot block is updated by this step
+    if (cx.warp == 0) {
+      LANE_FOR(idx, 0, NR * KB) {
+        rhs_sel<NR>(r, idx >> 3)[K * KB + (idx & 7)] = ycur[idx];  // y_K is final: store it
+        if (lead) {
+          const int q = idx >> 3, rr = idx & 7;
+          double row[KB], yk[KB];
+          load_row(L + M.boff[K + 1] + (K - M.fb[K + 1]) * 64, rr, row);
+          load_vec8(ycur + q * KB, yk);
+          double sacc = 0.0;
 #pragma unroll
-      for (int k = 0; k < KB; ++k) s = fma(row[k], yk[k], s);
-      rhs_sel<NR>(r, q)[I * KB + rr] -= s;
+          for (int k = 0; k < KB; ++k) sacc = fma(row[k], yk[k], sacc);
+          rhs_sel<NR>(r, q)[(K + 1) * KB + rr] -= sacc;
+        }
+      }
+      WARP_SYNC();
+      if (K + 1 < mb) {
+        LANE_FOR(idx, 0, NR * KB)
+        pivot_apply<NR, false>(L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64, r, K + 1, idx, ynext);
+      }
+    }
+    if (cx.nwarps == 1 || cx.warp > 0) {
+      const int nrest = na - lead;
+      for (int idx = o_tid; idx < nrest * KB * NR; idx += o_n) {
+        const int q = idx / (nrest * KB), rem = idx - q * (nrest * KB);
+        const int I = M.act_blk[a0 + lead + (rem >> 3)], rr = rem & 7;
+        double row[KB], yk[KB];
+        load_row(L + M.boff[I] + (K - M.fb[I]) * 64, rr, row);
+        load_vec8(ycur + q * KB, yk);
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < KB; ++k) sacc = fma(row[k], yk[k], sacc);
+        rhs_sel<NR>(r, q)[I * KB + rr] -= sacc;
+      }
     }
     CTA_SYNC();
   }
-  // backward: L^T z = y
+  // ---- backward: L^T z = y -----------------------------------------------------------------------
+  if (cx.warp == 0) {
+    LANE_FOR(idx, 0, NR * KB)
+    pivot_apply<NR, true>(L + M.boff[mb - 1] + (mb - 1 - M.fb[mb - 1]) * 64, r, mb - 1, idx, ybuf + ((mb - 1) & 1) * NR * KB);
+  }
+  CTA_SYNC();
   for (int I = mb - 1; I >= 0; --I) {
     const int f = M.fb[I];
-    const double* Linv = L + M.boff[I] + (I - f) * 64;
-    CTA_FOR(idx, NR * KB) {
-      const int q = idx >> 3, i = idx & 7;
-      double ri[KB];
-      load_vec8(rhs_sel<NR>(r, q) + I * KB, ri);
-      double s = 0.0;
+    const double* zcur = ybuf + (I & 1) * NR * KB;
+    double* znext = ybuf + ((I + 1) & 1) * NR * KB;  // buffer of parity (I-1)&1
+    const int lead = (I > 0 && f <= I - 1) ? 1 : 0;  // block (I, I-1) exists: row block I-1 is updated by this step
+    if (cx.warp == 0) {
+      LANE_FOR(idx, 0, NR * KB) rhs_sel<NR>(r, idx >> 3)[I * KB + (idx & 7)] = zcur[idx];  // z_I is final
+      if (lead) {
+        LANE_FOR(idx, 0, NR * 4) {  // the four 16-byte chunks (two columns each) of block (I, I-1)
+          const int q = idx >> 2, c = idx & 3;
+          const double* blk = L + M.boff[I] + (I - 1 - f) * 64;
+          double zi[KB];
+          load_vec8(zcur + q * KB, zi);
+          double sx = 0.0, sy = 0.0;
 #pragma unroll
-      for (int j = 0; j < KB; ++j)
-        if (j >= i) s = fma(Linv[bidx(j, i)], ri[j], s);
-      ybuf[idx] = s;
-    }
-    CTA_SYNC();
-    const int nk = I - f;
-    CTA_FOR(idx, NR * KB) rhs_sel<NR>(r, idx >> 3)[I * KB + (idx & 7)] = ybuf[idx];
-    CTA_FOR(idx, nk * 4 * NR) {  // one 16-byte chunk (two columns) of block (I,Kc) per thread
-      const int q = idx / (nk * 4), rem = idx - q * (nk * 4);
-      const int Kc = f + (rem >> 2), c = rem & 3;
-      const double* blk = L + M.boff[I] + (Kc - f) * 64;
-      double zi[KB];
-      load_vec8(ybuf + q * KB, zi);
-      double sx = 0.0, sy = 0.0;
-#pragma unroll
-      for (int i = 0; i < KB; ++i) {
-        const D2 t = reinterpret_cast<const D2*>(blk + i * KB)[c ^ bswz(i)];
-        sx = fma(t.x, zi[i], sx);
-        sy = fma(t.y, zi[i], sy);
+          for (int i = 0; i < KB; ++i) {
+            const D2 t2 = reinterpret_cast<const D2*>(blk + i * KB)[c ^ bswz(i)];
+            sx = fma(t2.x, zi[i], sx);
+            sy = fma(t2.y, zi[i], sy);
+          }
+          D2* dst = reinterpret_cast<D2*>(rhs_sel<NR>(r, q) + (I - 1) * KB) + c;
+          D2 t2 = *dst;
+          t2.x -= sx;
+          t2.y -= sy;
+          *dst = t2;
+        }
       }
-      D2* dst = reinterpret_cast<D2*>(rhs_sel<NR>(r, q) + Kc * KB) + c;
-      D2 t = *dst;
-      t.x -= sx;
-      t.y -= sy;
-      *dst = t;
+      WARP_SYNC();
+      if (I > 0) {
+        LANE_FOR(idx, 0, NR * KB)
+        pivot_apply<NR, true>(L + M.boff[I - 1] + (I - 1 - M.fb[I - 1]) * 64, r, I - 1, idx, znext);
+      }
+    }
+    if (cx.nwarps == 1 || cx.warp > 0) {
+      const int nk = I - f - lead;  // block columns f .. I-1-lead
+      for (int idx = o_tid; idx < nk * 4 * NR; idx += o_n) {
+        const int q = idx / (nk * 4), rem = idx - q * (nk * 4);
+        const int Kc = f + (rem >> 2), c = rem & 3;
+        const double* blk = L + M.boff[I] + (Kc - f) * 64;
+        double zi[KB];
+        load_vec8(zcur + q * KB, zi);
+        double sx = 0.0, sy = 0.0;
+#pragma unroll
+        for (int i = 0; i < KB; ++i) {
+          const D2 t2 = reinterpret_cast<const D2*>(blk + i * KB)[c ^ bswz(i)];
+          sx = fma(t2.x, zi[i], sx);
+          sy = fma(t2.y, zi[i], sy);
+        }
+        D2* dst = reinterpret_cast<D2*>(rhs_sel<NR>(r, q) + Kc * KB) + c;
+        D2 t2 = *dst;
+        t2.x -= sx;
+        t2.y -= sy;
+        *dst = t2;
+      }
     }
     CTA_SYNC();
   }
 }
 
-// out[i] = sum_e A_ie * src[col_e]   (row-wise, one warp per row, four index chunks in flight)
 IO_FORCEINLINE double run_total(const double* gp, int len) {
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int j = 0;
@@ -1011,7 +1098,7 @@ IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
 enum { W_X = 0, W_T, W_D, W_R2, W_P, W_W, W_DX, W_DXDT, W_NVEC };
 // shared-memory m-vector slots
 enum { S_B = 0, S_Y, S_R1, S_Q, S_V, S_NVEC };
-constexpr int S_SCRATCH = 2 * KB + (KB + KB * KB) + 8 * 32 + 2;  // ybuf + diag scratch + red + flag
+constexpr int S_SCRATCH = 4 * KB + (KB + KB * KB) + 8 * 32 + 2;  // ybuf (double buffered, 2 rhs) + diag scratch + red + flag
 
 struct SmemLayout {
   double *L, *G, *bs, *y, *r1, *q, *v, *ybuf, *dscr, *red;  // G: gather region of 2*gather_len(n) doubles
@@ -1058,7 +1145,7 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
   s.v = p + S_V * P.mv;
   p += S_NVEC * P.mv;
   s.ybuf = p;
-  s.dscr = p + 2 * KB;
+  s.dscr = p + 4 * KB;
   s.red = s.dscr + KB + KB * KB;
   s.flag = (int*)(s.red + 8 * 32);
   s.scan = reinterpret_cast<D2*>(s.red + 8 * 32 + 2);
