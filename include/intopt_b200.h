@@ -117,10 +117,11 @@ int intopt_backward(const IntoptProblem* p, int B, int mode, double damping_bwd,
 int intopt_measure_fp64_peak(double* gflops_out, int repeats);
 
 /* Debug aid for profiles/: enable (1) / disable (0) per-phase SM-cycle accounting of the forward kernel;
- * if out16_host is non-NULL the 16 cycle buckets are copied out (after a device sync) and reset.
+ * if out32_host is non-NULL the 32 cycle buckets are copied out (after a device sync) and reset.
  * Buckets: 0 setup, 1 residuals+tests, 2 assembly, 3 Cholesky, 4 rhs/spmv, 5 solve(2 rhs), 6 p/u loop,
- * 7 corrector rhs, 8 solve(1 rhs), 9 direction/ratio/update loops, 10 epilogue. */
-int intopt_debug_phase_cycles(int enable, unsigned long long* out16_host);
+ * 7 corrector rhs, 8 solve(1 rhs), 9 direction/ratio/update loops, 10 epilogue, 11-14 Cholesky sub-phases,
+ * 16-23 sub-phases of 1, 4, 7 and 9 (names in neuripsintopt_b200/_capi.py:PHASES). */
+int intopt_debug_phase_cycles(int enable, unsigned long long* out32_host);
 
 #ifdef __cplusplus
 }

@@ -108,13 +108,14 @@ def measure_fp64_peak(repeats=5):
 
 PHASES = ["setup", "residuals+tests", "assembly", "cholesky", "rhs/spmv", "solve2", "p/u loop", "corrector rhs",
           "solve1", "direction/ratio/update", "epilogue", "chol:panel", "chol:lead-update(w0)", "chol:diag(w0)",
-          "chol:wait-others"]
+          "chol:wait-others", "-", "resid:n-loop(A^T y)", "resid:spmv(A x)", "rhs:spmv(q)", "rhs:predictor loop",
+          "rhs:spmv(v)", "corr:n-loop", "corr:spmv(v)", "dir:n-loop+min"]
 
 
 def phase_cycles(enable=True, read=False):
     """Debug aid: toggle per-phase cycle accounting of the forward kernel; optionally read + reset the buckets."""
     import numpy as np
-    out = np.zeros(16, dtype=np.uint64)
+    out = np.zeros(32, dtype=np.uint64)
     check(lib().intopt_debug_phase_cycles(1 if enable else 0, out.ctypes.data if read else None),
           "intopt_debug_phase_cycles")
     return dict(zip(PHASES, out[:len(PHASES)].tolist())) if read else None

@@ -9,7 +9,7 @@ namespace intopt {
 
 inline int meta_ints(const HostStructure& S) {
   return S.mb + 2 * (S.mb + 1) + (int)S.act_blk.size() + (S.m + 1) + (int)S.csc_gptr.size() +
-         2 * (int)S.asm_gptr.size() + (int)S.csc_gptr.size();
+         2 * (int)S.asm_gptr.size();
 }
 
 template <class Up>
@@ -30,10 +30,6 @@ inline void bind_problem(const HostStructure& S, ProblemDev& D, Up&& up) {
   D.rs_hdr = S.rs_slots ? up(S.rs_hdr) : nullptr;
   D.rs_row = S.rs_slots ? up(S.rs_row) : nullptr;
   D.rs_slots = S.rs_slots;
-  D.g_cr_gptr = up(S.cr_gptr);
-  // Run-length columns are built but not used: measured on Energy the divergent per-lane run loops are slower
-  // than the warp-interleaved per-term column lists (74k vs 37k cycles per LP in the p/u loop).
-  D.cr_hdr = nullptr;
   D.perm = up(S.perm);
   D.g_fb = up(S.fb);
   D.g_boff = up(S.boff);

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -85,6 +86,15 @@ cudaError_t upload(const std::vector<T>& h, const T** d, std::vector<void*>& all
 
 }  // namespace
 
+// Cold-start factor cache (see FwdParams::cold_factor): one entry per forward damping value seen.
+struct ColdEntry {
+  double delta;
+  double* factor;  // bsize doubles
+  int* ok;         // device flag: 1 if the factorisation succeeded
+  cudaEvent_t ready;
+  bool done;
+};
+
 struct IntoptProblem {
   intopt::ProblemDev dev{};
   IntoptInfo info{};
@@ -93,6 +103,10 @@ struct IntoptProblem {
   int sms = 0;
   int slots = 0;  // persistent CTAs per launch
   std::vector<void*> allocs;
+  // lazily filled, guarded by `mu`; the problem data itself is immutable after create
+  mutable std::mutex mu;
+  mutable std::vector<ColdEntry> cold;
+  mutable std::vector<void*> cold_allocs;
 };
 
 __device__ __forceinline__ CtaCtx make_ctx(double* red) {
@@ -118,14 +132,30 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_forward_kern
       intopt::carve<ALLSMEM>(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
   const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  const bool cold = a.cold_factor != nullptr && a.init == nullptr && *a.cold_ok != 0;  // launch-uniform
+  if (cold && a.factor_in_smem && threadIdx.x == 0) intopt::mbar_init(S.mbar, 1);
+  unsigned served = 0;  // instances this CTA has run = completed phases of the prefetch mbarrier
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
     __syncthreads();
     const int inst = s_inst;
     __syncthreads();
     if (inst >= a.B) break;
-    intopt::forward_instance(cx, P, M, a, inst, wsi, S);
+    intopt::forward_instance(cx, P, M, a, inst, wsi, S, cold, served & 1u);
+    ++served;
   }
+}
+
+// One CTA computes the cold-start factor chol(A A^T + delta I) with the instance code path (same CTA size).
+template <int TMAX, bool ALLSMEM>
+__global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_coldfactor_kernel(const __grid_constant__ intopt::ProblemDev P,
+                                                                  double delta, double* ws, int factor_in_smem,
+                                                                  int gather_in_smem, double* out, int* ok) {
+  extern __shared__ __align__(16) double smem[];
+  const intopt::SmemLayout S = intopt::carve<ALLSMEM>(P, smem, ws + (long long)intopt::W_NVEC * P.n, factor_in_smem, gather_in_smem);
+  const CtaCtx cx = make_ctx(S.red);
+  const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  intopt::cold_factor_build(cx, P, M, delta, ws, S, out, ok);
 }
 
 template <int TMAX, bool ALLSMEM>
@@ -169,17 +199,22 @@ __global__ void __launch_bounds__(256) intopt_fp64_peak_kernel(double* out, int 
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
-__device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned long long g_phase_cycles[32];
 
 // Kernel variants: CTA size cap (192: 2 CTAs/SM x 168 registers, 256: 2 x 128, 512: 1 x 128) x whether every
 // buffer is in shared memory.
+#ifdef INTOPT_DEV_BUILD  // quick developer builds (INTOPT_NVCC_EXTRA=-DINTOPT_DEV_BUILD): default CTA size only
+#define INTOPT_VARIANTS(F) F(256, true) F(256, false)
+#else
 #define INTOPT_VARIANTS(F)                                                                                   \
   F(192, true) F(192, false) F(256, true) F(256, false) F(512, true) F(512, false)
+#endif
 static std::vector<const void*> all_kernels() {
   std::vector<const void*> v;
 #define ADD_(T, A)                                          \
   v.push_back((const void*)intopt_forward_kernel<T, A>);    \
-  v.push_back((const void*)intopt_backward_kernel<T, A>);
+  v.push_back((const void*)intopt_backward_kernel<T, A>);   \
+  v.push_back((const void*)intopt_coldfactor_kernel<T, A>);
   INTOPT_VARIANTS(ADD_)
 #undef ADD_
   return v;
@@ -192,6 +227,13 @@ static const void* pick_kernel(bool forward, int threads, bool allsmem) {
 #undef PICK_
   return nullptr;
 }
+static const void* pick_cold_kernel(int threads, bool allsmem) {
+#define PICKC_(T, A) \
+  if (threads <= T && allsmem == A) return (const void*)intopt_coldfactor_kernel<T, A>;
+  INTOPT_VARIANTS(PICKC_)
+#undef PICKC_
+  return nullptr;
+}
 
 namespace {
 bool g_profile_phases = false;
@@ -200,6 +242,50 @@ size_t ws_per_slot_doubles(const IntoptProblem* p) {
   if (!p->info.factor_in_smem) per += (size_t)p->info.envelope;
   if (!p->info.gather_in_smem) per += 2 * (size_t)intopt::gather_len(p->info.n);
   return (per + 1) & ~(size_t)1;
+}
+
+// Returns the cold-start factor for `delta` (computing it on `stream` the first time) or nulls if unavailable.
+int cold_factor_for(const IntoptProblem* p, double delta, cudaStream_t stream, const double** factor, const int** ok) {
+  *factor = nullptr;
+  *ok = nullptr;
+  if (env_int("INTOPT_NO_COLD", 0)) return 0;
+  std::lock_guard<std::mutex> lock(p->mu);
+  for (ColdEntry& e : p->cold) {
+    if (std::memcmp(&e.delta, &delta, sizeof(double)) != 0) continue;
+    if (!e.done) {
+      if (cudaEventQuery(e.ready) == cudaSuccess)
+        e.done = true;
+      else
+        CU_TRY(cudaStreamWaitEvent(stream, e.ready, 0));
+    }
+    *factor = e.factor;
+    *ok = e.ok;
+    return 0;
+  }
+  if (p->cold.size() >= 8) return 0;  // unusual: many different dampings on one problem -> plain path
+  ColdEntry e{};
+  e.delta = delta;
+  e.done = false;
+  double* ws = nullptr;
+  CU_TRY(cudaMalloc((void**)&e.factor, sizeof(double) * (size_t)p->info.envelope));
+  p->cold_allocs.push_back(e.factor);
+  CU_TRY(cudaMalloc((void**)&e.ok, sizeof(int)));
+  p->cold_allocs.push_back(e.ok);
+  CU_TRY(cudaMalloc((void**)&ws, sizeof(double) * ws_per_slot_doubles(p)));
+  p->cold_allocs.push_back(ws);
+  CU_TRY(cudaMemsetAsync(e.ok, 0, sizeof(int), stream));
+  CU_TRY(cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming));
+  {
+    int fis = p->info.factor_in_smem, gis = p->info.gather_in_smem;
+    void* args[7] = {(void*)&p->dev, (void*)&delta, (void*)&ws, (void*)&fis, (void*)&gis, (void*)&e.factor, (void*)&e.ok};
+    CU_TRY(cudaLaunchKernel(pick_cold_kernel(p->info.threads, fis && gis), dim3(1), dim3(p->info.threads), args,
+                            (size_t)p->info.smem_bytes, stream));
+  }
+  CU_TRY(cudaEventRecord(e.ready, stream));
+  p->cold.push_back(e);
+  *factor = e.factor;
+  *ok = e.ok;
+  return 0;
 }
 }  // namespace
 
@@ -279,6 +365,9 @@ int intopt_problem_destroy(IntoptProblem* p) {
   if (!p) return 0;
   for (void* a : p->allocs)
     if (a) cudaFree(a);
+  for (void* a : p->cold_allocs)
+    if (a) cudaFree(a);
+  for (ColdEntry& e : p->cold) cudaEventDestroy(e.ready);
   delete p;
   return 0;
 }
@@ -326,6 +415,10 @@ int intopt_forward(const IntoptProblem* p, int B, const double* c, long long c_s
   a.max_iter = o->max_iter;
   a.phase_cycles = nullptr;
   a.debug = env_int("INTOPT_DEBUG", 0);
+  if (!init) {
+    int rc = cold_factor_for(p, a.damping, (cudaStream_t)stream, &a.cold_factor, &a.cold_ok);
+    if (rc) return rc;
+  }
   if (g_profile_phases) {
     void* sym = nullptr;
     CU_TRY(cudaGetSymbolAddress(&sym, g_phase_cycles));
@@ -381,13 +474,13 @@ int intopt_backward(const IntoptProblem* p, int B, int mode, double damping, int
   return 0;
 }
 
-int intopt_debug_phase_cycles(int enable, unsigned long long* out16_host) {
+int intopt_debug_phase_cycles(int enable, unsigned long long* out32_host) {
   // debug aid: enable/disable per-phase cycle accounting of the forward kernel and read + reset the buckets
   g_profile_phases = enable != 0;
-  unsigned long long zero[16] = {0};
-  if (out16_host) {
+  unsigned long long zero[32] = {0};
+  if (out32_host) {
     CU_TRY(cudaDeviceSynchronize());
-    CU_TRY(cudaMemcpyFromSymbol(out16_host, g_phase_cycles, sizeof(zero)));
+    CU_TRY(cudaMemcpyFromSymbol(out32_host, g_phase_cycles, sizeof(zero)));
   }
   CU_TRY(cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)));
   return 0;

@@ -29,19 +29,19 @@ struct HostStructure {
   std::vector<int> csr_ptr, csr_col;
   std::vector<double> csr_val;
   bool a_unit = true;  // every non-zero of A equals 1: value streams are skipped
-  // A by columns, 32 consecutive columns per group, entries interleaved: entry t of column 32g+l sits at
-  // (csc_gptr[g] + t) * 32 + l ; padded with row = m8 (a guaranteed-zero slot of every m-vector) / value 0
+  // A by columns, 32 consecutive columns per group, group length padded to a multiple of 8.  Values: entry t of
+  // column 32g+l sits at (csc_gptr[g] + t) * 32 + l.  Row indices: chunk-major, the eight indices t = 8c..8c+7 of
+  // column 32g+l are the 16 bytes at ((csc_gptr[g]/8 + c) * 32 + l) * 8, so a warp reads one chunk of its 32
+  // columns with a single coalesced 128-bit load per lane.  Padding: row = m8 (a guaranteed-zero slot of every
+  // m-vector) / value 0
   std::vector<int> csc_gptr, csc_glen;
   std::vector<uint16_t> csc_row;
   std::vector<double> csc_val;
   // run-length forms for unit-weight A (consecutive indices collapse to start | len << 16):
   //  * rows: whole rows packed into 32-lane slots, one run per lane (rs_row = row id, 0xffff = padding lane);
-  //  * columns: per 32-column group, R = cr_gptr[g+1]-cr_gptr[g] run slots per lane (R % 4 == 0), lane-major
   std::vector<uint32_t> rs_hdr;
   std::vector<uint16_t> rs_row;
   int rs_slots = 0;
-  std::vector<int> cr_gptr;
-  std::vector<uint32_t> cr_hdr;
   // scalar envelope (first non-zero column of each row of M in internal order)
   std::vector<int> sky_first;
   int sky_size = 0;
@@ -265,6 +265,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   for (int g = 0; g < ngrp; ++g) {
     int len = 0;
     for (int k = 32 * g; k < std::min(n, 32 * g + 32); ++k) len = std::max(len, cptr[k + 1] - cptr[k]);
+    len = (len + 7) & ~7;  // whole 16-byte index chunks
     S.csc_glen[g] = len;
     S.csc_gptr[g + 1] = S.csc_gptr[g] + len;
   }
@@ -273,14 +274,15 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   for (int k = 0; k < n; ++k) {
     int g = k >> 5, l = k & 31;
     for (int t = 0; t < cptr[k + 1] - cptr[k]; ++t) {
-      size_t d = ((size_t)S.csc_gptr[g] + t) * 32 + l;
-      S.csc_row[d] = (uint16_t)crow[cptr[k] + t];
-      S.csc_val[d] = cval[cptr[k] + t];
+      // indices: chunk-major (8 per lane and chunk, one 16-byte load); values: term-major (8-byte loads)
+      size_t dr = ((((size_t)S.csc_gptr[g] >> 3) + (size_t)(t >> 3)) * 32 + l) * 8 + (size_t)(t & 7);
+      size_t dv = ((size_t)S.csc_gptr[g] + t) * 32 + l;
+      S.csc_row[dr] = (uint16_t)crow[cptr[k] + t];
+      S.csc_val[dv] = cval[cptr[k] + t];
     }
   }
 
   // ---- run-length forms of A (unit weights only) -----------------------------------------------------
-  S.cr_gptr.assign(ngrp + 1, 0);
   if (S.a_unit && n < 65535) {
     auto runs_of = [](const int* idx, int len) {
       std::vector<uint32_t> r;
@@ -328,20 +330,6 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
       S.rs_hdr = hdr;
       S.rs_row = rid;
       S.rs_slots = (int)hdr.size() / 32;
-    }
-    // columns -> lane-major run slots per 32-column group
-    std::vector<std::vector<uint32_t>> cruns(n);
-    for (int k = 0; k < n; ++k) cruns[k] = runs_of(crow.data() + cptr[k], cptr[k + 1] - cptr[k]);
-    for (int g = 0; g < ngrp; ++g) {
-      size_t R = 0;
-      for (int k = 32 * g; k < std::min(n, 32 * g + 32); ++k) R = std::max(R, cruns[k].size());
-      S.cr_gptr[g + 1] = S.cr_gptr[g] + (int)((R + 3) & ~(size_t)3);
-    }
-    S.cr_hdr.assign((size_t)S.cr_gptr[ngrp] * 32, 0u);
-    for (int k = 0; k < n; ++k) {
-      const int g = k >> 5, l = k & 31;
-      const size_t R = (size_t)(S.cr_gptr[g + 1] - S.cr_gptr[g]);
-      for (size_t r = 0; r < cruns[k].size(); ++r) S.cr_hdr[(size_t)S.cr_gptr[g] * 32 + (size_t)l * R + r] = cruns[k][r];
     }
   }
 

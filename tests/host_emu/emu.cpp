@@ -37,7 +37,16 @@ extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const doubl
   a.status = status; a.iters = iters; a.ws = ws.data(); a.ws_stride = 0;
   a.factor_in_smem = 1; a.gather_in_smem = 1;
   a.alpha0 = alpha0; a.tol = tol; a.thr = thr; a.damping = damping_fwd; a.max_iter = max_iter;
-  for (int i = 0; i < B; ++i) intopt::forward_instance(cx, P, M, a, i, ws.data(), L);
+  // cold-start factor (as the CUDA host code does): built once with the instance code path, copied in at iteration 1
+  std::vector<double> cold((size_t)S.bsize);
+  int cold_ok = 0;
+  if (!init) {
+    intopt::cold_factor_build(cx, P, M, damping_fwd, ws.data(), L, cold.data(), &cold_ok);
+    a.cold_factor = cold.data();
+    a.cold_ok = &cold_ok;
+  }
+  const bool use_cold = !init && cold_ok;
+  for (int i = 0; i < B; ++i) intopt::forward_instance(cx, P, M, a, i, ws.data(), L, use_cold, 0u);
   if (gx && gc) {
     intopt::BwdParams g{};
     g.B = B; g.mode = bwd_mode; g.nvar = nvar; g.damping = damping_bwd; g.state = state; g.c = c;
