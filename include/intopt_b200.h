@@ -123,6 +123,11 @@ int intopt_measure_fp64_peak(double* gflops_out, int repeats);
  * 16-23 sub-phases of 1, 4, 7 and 9 (names in neuripsintopt_b200/_capi.py:PHASES). */
 int intopt_debug_phase_cycles(int enable, unsigned long long* out32_host);
 
+/* Debug aid for profiles/: SM cycles per repetition of one building block of the solver (which: 0 barrier only,
+ * 1 A.v, 2 A^T.y, 3 A^T.[y1 y2], 4 assembly, 5 assembly+Cholesky, 6 solve (2 rhs), 7 solve (1 rhs), 8/10 n-loops,
+ * 9 CTA reduction) on `grid` persistent CTAs; cycles_host[grid].  Synchronises the device. */
+int intopt_debug_microbench(const IntoptProblem* p, int which, int reps, int grid, unsigned long long* cycles_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,7 @@ class IntoptInfo(ctypes.Structure):
 
 EXPORTS = ["intopt_version", "intopt_last_error", "intopt_analyze", "intopt_problem_create",
            "intopt_problem_destroy", "intopt_problem_info", "intopt_workspace_bytes", "intopt_forward",
-           "intopt_backward", "intopt_measure_fp64_peak", "intopt_debug_phase_cycles"]
+           "intopt_backward", "intopt_measure_fp64_peak", "intopt_debug_phase_cycles", "intopt_debug_microbench"]
 
 _lib = None
 
@@ -73,6 +73,7 @@ def lib():
     L.intopt_backward.argtypes = [vp, ci, ci, cd, ci, vp, vp, cll, vp, cll, vp, vp, vp, vp, csz, vp]
     L.intopt_measure_fp64_peak.argtypes = [ctypes.POINTER(cd), ci]
     L.intopt_debug_phase_cycles.argtypes = [ci, vp]
+    L.intopt_debug_microbench.argtypes = [vp, ci, ci, ci, vp]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here means the library and the header disagree
     _lib = L
@@ -119,3 +120,17 @@ def phase_cycles(enable=True, read=False):
     check(lib().intopt_debug_phase_cycles(1 if enable else 0, out.ctypes.data if read else None),
           "intopt_debug_phase_cycles")
     return dict(zip(PHASES, out[:len(PHASES)].tolist())) if read else None
+
+
+MICRO = ["barrier", "A.v (spmv_rows)", "A^T.y", "A^T.[y1 y2]", "assembly", "assembly+cholesky", "solve 2 rhs",
+         "solve 1 rhs", "n-loop smem<-2 global", "cta_sum<5>", "n-loop global rmw", "256 dependent DFMA", "256 dependent LDS",
+         "256 dependent SHFL64+DADD", "256 dependent DADD", "64 dependent L2 loads", "64 dependent rsqrt+add",
+         "64 dependent div+add", "spmv: headers only", "spmv: +run_total", "spmv: +scan only", "spmv: full copy"]
+
+
+def microbench(handle, which, reps=20, grid=1):
+    """Debug aid: median/max SM cycles per repetition of one building block on `grid` persistent CTAs."""
+    import numpy as np
+    out = np.zeros(grid, dtype=np.uint64)
+    check(lib().intopt_debug_microbench(handle, which, reps, grid, out.ctypes.data), "intopt_debug_microbench")
+    return float(np.median(out)), float(out.max())

@@ -54,7 +54,7 @@ inline void bind_problem(const HostStructure& S, ProblemDev& D, Up&& up) {
 
 // doubles of shared memory the solver needs beyond the (optional) factor and gather buffer
 inline size_t smem_fixed_doubles(const HostStructure& S) {
-  return (size_t)S_NVEC * (S.m8 + 8) + S_SCRATCH + 2 * (size_t)scan_len(S.n);
+  return (size_t)S_NVEC * (S.m8 + 8) + S_SCRATCH + (scan_in_factor(S.bsize, S.n) ? 0 : 2 * (size_t)scan_len(S.n));
 }
 
 }  // namespace intopt

@@ -86,6 +86,18 @@ namespace intopt {
 enum { ST_OK = 0, ST_MAXITER = 1, ST_INFEAS = 2, ST_BREAKDOWN = 3, ST_NONFINITE = 4 };
 constexpr int KB = 8;  // block edge, == NB of intopt_structure.hpp
 
+// The gather buffer is indexed through gpad(): one unused slot after every 32 elements, so that run starts a
+// multiple of 16 or 32 elements apart (the Energy LP: 144 = one task's variables) no longer share a bank.
+// Every gather index list built on the host (intopt_structure.hpp) is in padded coordinates.
+IO_HD int gpad(int k) { return k + (k >> 5); }
+// Store element k of a gather vector; the pad slot after every 32nd element is kept at zero (the run-length row
+// kernel sums straight across it, and the assembly's prefix sums overwrite the whole region in between).
+IO_HD void gstore(double* G, int k, double v) {
+  const int p = gpad(k);
+  G[p] = v;
+  if ((k & 31) == 31) G[p + 1] = 0.0;
+}
+
 struct ProblemDev {
   int m, n, nnz, mb, m8, mv, n_act;  // mv = m8 + 8: length of every m-vector (slot m8 is always zero)
   const int* g_csr_ptr;
@@ -259,7 +271,7 @@ IO_FORCEINLINE double dd_diff(D2 hi, D2 lo) {  // hi - lo rounded to double
   return s + (e + (hi.y - lo.y));
 }
 
-// Exclusive double-double prefix sums of d[0..n) into PP[0..n] (PP[k] = sum_{k'<k} d[k']).  Chunks of 8
+// Exclusive double-double prefix sums of d[0..n): PP[gpad(k)] = sum_{k'<k} d[k'] for k = 0..n.  Chunks of 8
 // consecutive elements per thread, chunk totals scanned in two more levels.  `tot` holds ceil(n/8) + 40 D2.
 IO_DEV void dd_prefix_scan(const CtaCtx& cx, const double* __restrict__ d, int n, D2* PP, D2* tot) {
   const int nch = (n + 7) >> 3, ngr = (nch + 31) >> 5;
@@ -270,7 +282,7 @@ IO_DEV void dd_prefix_scan(const CtaCtx& cx, const double* __restrict__ d, int n
     acc.y = 0.0;
     const int k0 = t << 3, k1 = k0 + 8 < n ? k0 + 8 : n;
     for (int k = k0; k < k1; ++k) {
-      PP[k] = acc;  // exclusive, local to the chunk
+      PP[gpad(k)] = acc;  // exclusive, local to the chunk
       acc = dd_add_d(acc, d[k]);
     }
     tot[t] = acc;
@@ -298,13 +310,13 @@ IO_DEV void dd_prefix_scan(const CtaCtx& cx, const double* __restrict__ d, int n
       tot2[gq] = acc;
       acc = dd_add(acc, v);
     }
-    PP[n] = acc;
+    PP[gpad(n)] = acc;
   }
   CTA_SYNC();
   CTA_FOR(t, nch) {
     const D2 off = dd_add(tot2[t >> 5], tot[t]);
     const int k0 = t << 3, k1 = k0 + 8 < n ? k0 + 8 : n;
-    for (int k = k0; k < k1; ++k) PP[k] = dd_add(off, PP[k]);
+    for (int k = k0; k < k1; ++k) PP[gpad(k)] = dd_add(off, PP[gpad(k)]);
   }
   CTA_SYNC();
 }
@@ -319,11 +331,12 @@ IO_DEV void dd_prefix_scan(const CtaCtx& cx, const double* __restrict__ d, int n
 IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* __restrict__ d,
                                    double* region, D2* scan_tmp, double delta, double* L, int dbg = 0) {
   const int n = P.n;
-  CTA_FOR(e, P.bsize) L[e] = 0.0;
   const int ngrp = (dbg & 1) ? 0 : (P.n_asm >> 5);
   if (P.asm_run) {
     D2* PP = reinterpret_cast<D2*>(region);
-    dd_prefix_scan(cx, d, n, PP, scan_tmp);  // (its barriers also order the zero fill)
+    dd_prefix_scan(cx, d, n, PP, scan_tmp);  // scan_tmp may alias L (scan_in_factor): the zero fill comes after
+    CTA_FOR(e, P.bsize) L[e] = 0.0;
+    CTA_SYNC();
     CTA_FOR(e, P.n_dummy) L[P.dummy_pos[e]] = 1.0;
     // Lane l of a warp owns entry 32*grp + l; its R run headers are contiguous and fetched 12 at a time with
     // three 16-byte loads that are all in flight together (one L2 round trip per group).
@@ -362,8 +375,9 @@ IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const 
     CTA_SYNC();
     return;
   }
-  CTA_FOR(k, n) region[k] = d[k];
-  if (cx.tid == 0) region[n] = 0.0;
+  CTA_FOR(e, P.bsize) L[e] = 0.0;
+  CTA_FOR(k, n) region[gpad(k)] = d[k];
+  if (cx.tid == 0) region[gpad(n)] = 0.0;
   CTA_SYNC();
   CTA_FOR(e, P.n_dummy) L[P.dummy_pos[e]] = 1.0;
   const double* g = region;
@@ -832,6 +846,19 @@ IO_FORCEINLINE double run_total(const double* gp, int len) {
   return (s0 + s1) + (s2 + s3);
 }
 
+// sum of a run of at most 16 consecutive entries (the row kernel's pieces, RS_MAXLEN): fully predicated, no loop
+IO_FORCEINLINE double run_total16(const double* gp, int len) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    if (j < len) s0 += gp[j];
+    if (j + 1 < len) s1 += gp[j + 1];
+    if (j + 2 < len) s2 += gp[j + 2];
+    if (j + 3 < len) s3 += gp[j + 3];
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
 IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* src, double* out) {
   if (P.rs_hdr) {
     // unit-weight A in run-length form: every lane sums one run of consecutive src entries, rows are whole
@@ -842,7 +869,7 @@ IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, cons
         const uint32_t h = P.rs_hdr[slot * 32 + l];
         const int row = P.rs_row[slot * 32 + l];
         if (row == 0xffff) continue;
-        const double s = run_total(src + (h & 0xffffu), (int)(h >> 16));
+        const double s = run_total16(src + (h & 0xffffu), (int)(h >> 16));
         const bool first = l == 0 || P.rs_row[slot * 32 + l - 1] != row;
         out[row] = first ? s : out[row] + s;
       }
@@ -862,7 +889,7 @@ IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, cons
         hn = P.rs_hdr[nxt * 32 + cx.lane];
         rown = P.rs_row[nxt * 32 + cx.lane];
       }
-      double s = run_total(src + (h & 0xffffu), (int)(h >> 16));
+      double s = run_total16(src + (h & 0xffffu), (int)(h >> 16));
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const double v = __shfl_up_sync(0xffffffffu, s, off);
@@ -1054,8 +1081,9 @@ struct SmemLayout {
   int* meta;  // P.meta_ints ints when the schedule is staged in shared memory
 };
 
-IO_HD int gather_len(int n) { return (n + 2) & ~1; }
+IO_HD int gather_len(int n) { return (gpad(n) + 3) & ~1; }
 IO_HD int scan_len(int n) { return ((n + 7) >> 3) + 40; }  // D2 entries of prefix-scan scratch
+IO_HD bool scan_in_factor(int bsize, int n) { return bsize >= 2 * scan_len(n); }
 
 // Carve shared memory (and, for spilled pieces, the tail of the per-CTA workspace).  ALLSMEM = factor and
 // gather buffers both live in shared memory: every pointer is then derived unconditionally from the shared
@@ -1096,8 +1124,10 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
   s.red = s.dscr + KB + KB * KB;
   s.flag = (int*)(s.red + 8 * 32);
   s.mbar = reinterpret_cast<unsigned long long*>(s.red + 8 * 32 + 2);
-  s.scan = reinterpret_cast<D2*>(s.red + 8 * 32 + 4);
-  s.meta = (int*)(s.red + 8 * 32 + 4 + 2 * scan_len(P.n));
+  // the prefix-scan scratch aliases the factor storage when it fits (the scan runs before the factor is zero-filled)
+  const int own_scan = scan_in_factor(P.bsize, P.n) ? 0 : 2 * scan_len(P.n);
+  s.scan = own_scan ? reinterpret_cast<D2*>(s.red + 8 * 32 + 4) : reinterpret_cast<D2*>(s.L);
+  s.meta = (int*)(s.red + 8 * 32 + 4 + own_scan);
 #ifndef INTOPT_HOST_EMU
   if (ALLSMEM) {
     __builtin_assume(__isShared(s.L));
@@ -1232,7 +1262,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     q[i] = 0.0;
     v[i] = 0.0;
   }
-  if (cx.tid == 0) G[n] = 0.0;
+  if (cx.tid == 0) G[gpad(n)] = 0.0;
   double tau = 1.0, kappa = 1.0;
   const long long slen = 2LL * n + m + 2;
   CTA_SYNC();
@@ -1240,7 +1270,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     const double* s0 = a.init + (long long)inst * slen;
     CTA_FOR(k, n) {
       x[k] = s0[k];
-      G[k] = s0[k];
+      gstore(G, k, s0[k]);
       t[k] = s0[n + m + k];
     }
     CTA_FOR(i, m) y[i] = s0[n + P.perm[i]];
@@ -1249,7 +1279,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
   } else {
     CTA_FOR(k, n) {
       x[k] = 1.0;
-      G[k] = 1.0;  // G mirrors x at every loop top: the residual A x gathers from shared memory
+      gstore(G, k, 1.0);  // G mirrors x at every loop top: the residual A x gathers from shared memory
       t[k] = 1.0;
     }
   }
@@ -1371,7 +1401,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
         dv[u] = D[k];
         cv[u] = c[k];
       }
-      BATCH_EACH(u, k, k0, n, NU) G[k] = dv[u] * cv[u];
+      BATCH_EACH(u, k, k0, n, NU) gstore(G, k, dv[u] * cv[u]);
     }
     if (reuse_cold) {
       solved = true;
@@ -1381,7 +1411,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     }
     PHASE_MARK(pt, 3);
     if (!solved) {  // deltas = 0 (:855-857): the iterate is unchanged, the tests run at loop top
-      CTA_FOR(k, n) G[k] = x[k];  // G must mirror x again
+      CTA_FOR(k, n) gstore(G, k, x[k]);  // G must mirror x again
       CTA_SYNC();
       continue;
     }
@@ -1401,7 +1431,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
         const double rxt = -(xv[u] * tv[u]);             // :788 with gamma = 0
         const double wk = rv[u] - (1.0 / xv[u]) * rxt;   // :801 with eta(0) = 1
         w[k] = wk;
-        G[k] = dv[u] * wk;
+        gstore(G, k, dv[u] * wk);
       }
     }
     CTA_FOR(i, m) q[i] = bs[i] + q[i];  // r = r2 + A(Dinv r1), :666 with (r1,r2) = (c,b)
@@ -1453,7 +1483,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
       bv_ = acc2[3];
       if (acc2[4] > 0.0) {  // NaN in p or q (:805-806) -> unsolved
         solved = false;
-        CTA_FOR(k, n) G[k] = x[k];
+        CTA_FOR(k, n) gstore(G, k, x[k]);
         CTA_SYNC();
         continue;
       }
@@ -1481,7 +1511,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
             const double rxt = -(xv[u] * tv[u] - gm) - ev[u];      // :788,793
             const double wk = eta * rv[u] - (1.0 / xv[u]) * rxt;  // :801
             w[k] = wk;
-            G[k] = dv[u] * wk;
+            gstore(G, k, dv[u] * wk);
           }
         }
         CTA_SYNC();
@@ -1570,7 +1600,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
             const double dtk = (1.0 / xk) * (rxt - tk * dxk);
             const double xn = xk + al * dxk;
             x[k] = xn;
-            G[k] = xn;
+            gstore(G, k, xn);
             t[k] = tk + al * dtk;
           }
         }
@@ -1616,7 +1646,7 @@ IO_DEV void cold_factor_build(const CtaCtx& cx, const ProblemDev& P, const Meta&
   const int n = P.n;
   double* D = wsi + (long long)W_D * n;
   CTA_FOR(k, n) D[k] = 1.0;
-  if (cx.tid == 0) S.G[n] = 0.0;
+  if (cx.tid == 0) S.G[gpad(n)] = 0.0;
   CTA_SYNC();
   assemble_normal_matrix(cx, P, M, D, S.G, S.scan, delta, S.L);
   const bool ok = block_cholesky(cx, P, M, S.L, S.dscr, S.flag);
@@ -1671,7 +1701,7 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
     q[i] = 0.0;
     v[i] = 0.0;
   }
-  if (cx.tid == 0) G[n] = 0.0;
+  if (cx.tid == 0) G[gpad(n)] = 0.0;
   double xt[2] = {0.0, 0.0};
   CTA_FOR(k, n) {
     const double xk = whole ? xs[k] : xs[k] / tau;  // alter saves x/tau, t/tau (ip_model_alter.py:1459-1461)
@@ -1687,7 +1717,7 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
 
   CTA_SYNC();
   assemble_normal_matrix(cx, P, M, x2, G, S.scan, a.damping, L);  // :1525-1527,1535
-  CTA_FOR(k, n) G[k] = (k < nvar) ? x2[k] * g[k] : 0.0;
+  CTA_FOR(k, n) gstore(G, k, (k < nvar) ? x2[k] * g[k] : 0.0);
   const bool ok = block_cholesky(cx, P, M, L, S.dscr, S.flag);
   if (!ok) {
     // the reference raises LinAlgError (:1546-1547); here: zero gradient + status
@@ -1708,7 +1738,7 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
     CTA_SYNC();
     return;
   }
-  CTA_FOR(k, n) G[k] = x2[k] * c[k];
+  CTA_FOR(k, n) gstore(G, k, x2[k] * c[k]);
   CTA_FOR(i, m) v[i] = tau * v[i];  // r1 g = tau A X2 g (:1529)
   CTA_SYNC();
   spmv_rows(cx, P, M, G, q);

@@ -21,6 +21,9 @@ namespace intopt {
 
 constexpr int NB = 8;           // block edge of the block-skyline factor
 constexpr int NBB = NB * NB;    // doubles per block
+// index of element k in the solver's padded gather buffer; MUST match intopt::gpad() of intopt_solver.cuh
+inline int gpad_host(int k) { return k + (k >> 5); }
+constexpr int RS_MAXLEN = 15;   // longest run piece of the run-length row kernel (<= 16, odd)
 
 struct HostStructure {
   int m = 0, n = 0, nnz = 0, mb = 0, m8 = 0;
@@ -57,7 +60,7 @@ struct HostStructure {
   int n_asm = 0;  // padded to a multiple of 32
   std::vector<int> asm_gptr, asm_glen, asm_pos;  // asm_pos < 0: padding entry
   std::vector<unsigned char> asm_diag;
-  std::vector<int> asm_k;  // index into the gather buffer; n = the zero slot
+  std::vector<int> asm_k;  // padded index (gpad) into the gather buffer; gpad(n) = the zero slot
   std::vector<uint16_t> asm_k16;  // the same as 16-bit indices when n < 65535 (then asm_k is not uploaded)
   std::vector<double> asm_w;
   bool asm_unit = true;
@@ -283,7 +286,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   }
 
   // ---- run-length forms of A (unit weights only) -----------------------------------------------------
-  if (S.a_unit && n < 65535) {
+  if (S.a_unit && gpad_host(n) < 65535) {
     auto runs_of = [](const int* idx, int len) {
       std::vector<uint32_t> r;
       int t = 0;
@@ -301,7 +304,22 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
     std::vector<uint16_t> rid;
     int used = 32;  // lanes used in the current slot (start a new slot first)
     for (int i = 0; i < m && ok; ++i) {
-      auto r = runs_of(S.csr_col.data() + S.csr_ptr[i], S.csr_ptr[i + 1] - S.csr_ptr[i]);
+      auto r0 = runs_of(S.csr_col.data() + S.csr_ptr[i], S.csr_ptr[i + 1] - S.csr_ptr[i]);
+      // long runs are cut into pieces of at most RS_MAXLEN so every lane of a slot does the same bounded amount of
+      // work (the segmented scan adds the pieces up again); the odd piece stride spreads the pieces of one run
+      // over different shared-memory banks
+      std::vector<uint32_t> r;
+      for (uint32_t h : r0) {
+        int st = (int)(h & 0xffffu), len = (int)(h >> 16);
+        while (len > 0) {
+          // padded coordinates: a piece that crosses a multiple of 32 also sums the (always zero) pad slot there
+          const int piece = std::min(len, RS_MAXLEN);
+          const int p0 = gpad_host(st), p1 = gpad_host(st + piece - 1);
+          r.push_back((uint32_t)p0 | ((uint32_t)(p1 - p0 + 1) << 16));
+          st += piece;
+          len -= piece;
+        }
+      }
       if (r.size() > 32) ok = false;
       if (used + (int)r.size() > 32) {
         while (used < 32 && !hdr.empty()) {
@@ -429,14 +447,16 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
         en.w.push_back(w);
         if (w != 1.0) S.asm_unit = false;
       }
-  const bool rle = S.asm_unit && n < 65535;
+  const bool rle = S.asm_unit && gpad_host(n) < 65535;
   if (rle)
     for (Ent& en : ents) {
       size_t t = 0;
       while (t < en.k.size()) {
         size_t len = 1;
         while (t + len < en.k.size() && en.k[t + len] == en.k[t] + (int)len && len < 65535) ++len;
-        en.runs.push_back((uint32_t)en.k[t] | ((uint32_t)len << 16));
+        // prefix-sum difference PP[gpad(a + len)] - PP[gpad(a)]: header = padded start | padded distance << 16
+        const int a = en.k[t], pa = gpad_host(a), pb = gpad_host(a + (int)len);
+        en.runs.push_back((uint32_t)pa | ((uint32_t)(pb - pa) << 16));
         t += len;
       }
       std::stable_sort(en.runs.begin(), en.runs.end(), [](uint32_t a, uint32_t b) { return (a >> 16) > (b >> 16); });
@@ -474,7 +494,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
     S.asm_rptr[g + 1] = S.asm_rptr[g] + (int)((R + 3) & ~(size_t)3);  // multiple of 4: 16-byte header loads
   }
   S.asm_padded = rle ? (long long)S.asm_rptr[nag] * 32 : (long long)S.asm_gptr[nag] * 32;
-  S.asm_k.assign((size_t)S.asm_gptr[nag] * 32, n);  // n = the zero slot of the gather buffer
+  S.asm_k.assign((size_t)S.asm_gptr[nag] * 32, gpad_host(n));  // gpad(n) = the zero slot of the gather buffer
   S.asm_w.assign((size_t)S.asm_gptr[nag] * 32, 0.0);
   S.asm_run.assign((size_t)S.asm_rptr[nag] * 32, 0u);
   for (int e = 0; e < ne; ++e) {
@@ -489,15 +509,17 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
     } else {
       for (size_t t = 0; t < en.k.size(); ++t) {
         const size_t d = ((size_t)S.asm_gptr[g] + t) * 32 + l;
-        S.asm_k[d] = en.k[t];
+        S.asm_k[d] = gpad_host(en.k[t]);
         S.asm_w[d] = en.w[t];
       }
     }
   }
-  if (!rle && n < 65535) {
+  if (!rle && gpad_host(n) < 65535) {
     S.asm_k16.resize(S.asm_k.size());
     for (size_t i = 0; i < S.asm_k.size(); ++i) S.asm_k16[i] = (uint16_t)S.asm_k[i];
   }
+  // the row lists gather from the padded buffer as well (every structure above was built from the plain indices)
+  for (int& cidx : S.csr_col) cidx = gpad_host(cidx);
   return 0;
 }
 
