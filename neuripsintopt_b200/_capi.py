@@ -125,7 +125,10 @@ def phase_cycles(enable=True, read=False):
 MICRO = ["barrier", "A.v (spmv_rows)", "A^T.y", "A^T.[y1 y2]", "assembly", "assembly+cholesky", "solve 2 rhs",
          "solve 1 rhs", "n-loop smem<-2 global", "cta_sum<5>", "n-loop global rmw", "256 dependent DFMA", "256 dependent LDS",
          "256 dependent SHFL64+DADD", "256 dependent DADD", "64 dependent L2 loads", "64 dependent rsqrt+add",
-         "64 dependent div+add", "spmv: headers only", "spmv: +run_total", "spmv: +scan only", "spmv: full copy"]
+         "64 dependent div+add", "spmv: headers only", "spmv: +run_total", "spmv: +scan only", "spmv: full copy", "10 barriers",
+         "9x(warp0 LDS+16 DFMA+STS, barrier)+barrier", "chol w/o trailing updates", "chol w/o diag factor",
+         "chol w/o panels", "chol w/o fuse", "chol skeleton only", "solve2 w/o pivots", "solve2 w/o row updates",
+         "solve2 skeleton only", "2*nsteps x (record load, barrier)", "2*nsteps x (record load, branches, barrier)"]
 
 
 def microbench(handle, which, reps=20, grid=1):
