@@ -12,7 +12,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libintopt_b200.so")
+LIB_PATH = os.environ.get("INTOPT_LIB_OVERRIDE") or os.path.join(_HERE, "lib", "libintopt_b200.so")  # override: A/B tuning only
 
 
 class IntoptOpts(ctypes.Structure):
@@ -74,8 +74,9 @@ def lib():
     L.intopt_measure_fp64_peak.argtypes = [ctypes.POINTER(cd), ci]
     L.intopt_debug_phase_cycles.argtypes = [ci, vp]
     L.intopt_debug_microbench.argtypes = [vp, ci, ci, ci, vp]
-    for name in EXPORTS:
-        getattr(L, name)  # AttributeError here means the library and the header disagree
+    if not os.environ.get("INTOPT_LIB_OVERRIDE"):
+        for name in EXPORTS:
+            getattr(L, name)  # AttributeError here means the library and the header disagree
     _lib = L
     return L
 

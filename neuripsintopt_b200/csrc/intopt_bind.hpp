@@ -7,12 +7,9 @@
 
 namespace intopt {
 
-static_assert(MAXSEG == KSEG && ST_REC == KREC, "constants of the host analysis and the kernels differ");
-
-inline int meta_ints(const HostStructure& S) {  // ints of the schedule arrays staged in shared memory (stage_meta)
-  const bool rle = !S.asm_run.empty();
-  return 2 * (int)S.st_fwd.size() + S.mb + 2 * (S.mb + 1) + 2 * (int)S.act_blk.size() + (S.rs_slots ? 0 : S.m + 1) +
-         (int)S.csc_gptr.size() + (int)(rle ? S.asm_rptr.size() : S.asm_gptr.size()) + S.mb + (int)S.seg_bord.size() + 4;
+inline int meta_ints(const HostStructure& S) {
+  return S.mb + 2 * (S.mb + 1) + (int)S.act_blk.size() + (S.m + 1) + (int)S.csc_gptr.size() +
+         2 * (int)S.asm_gptr.size();
 }
 
 template <class Up>
@@ -41,23 +38,7 @@ inline void bind_problem(const HostStructure& S, ProblemDev& D, Up&& up) {
   D.n_dummy = (int)S.dummy_pos.size();
   D.g_act_ptr = up(S.act_ptr);
   D.g_act_blk = up(S.act_blk);
-  D.g_act_off = up(S.act_off);
   D.n_act = (int)S.act_blk.size();
-  D.nseg = S.nseg;
-  D.seg_end = S.seg_end;
-  D.seg_tmax = S.seg_tmax;
-  D.nbord = (int)S.seg_bord.size();
-  for (int s = 0; s < MAXSEG; ++s) {
-    D.seg_start[s] = S.seg_start[s];
-    D.seg_len[s] = S.seg_len[s];
-  }
-  D.g_act_ns = up(S.act_ns);
-  D.g_seg_bord = up(S.seg_bord);
-  D.nsteps = S.nsteps;
-  D.n_wblk = S.n_wblk;
-  D.g_st_fwd = up(S.st_fwd);
-  D.g_st_bwd = up(S.st_bwd);
-  D.g_wblk_col = up(S.wblk_col);
   D.meta_ints = meta_ints(S);
   D.n_asm = S.n_asm;
   D.g_asm_gptr = up(S.asm_gptr);

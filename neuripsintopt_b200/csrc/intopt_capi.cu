@@ -89,7 +89,7 @@ cudaError_t upload(const std::vector<T>& h, const T** d, std::vector<void*>& all
 // Cold-start factor cache (see FwdParams::cold_factor): one entry per forward damping value seen.
 struct ColdEntry {
   double delta;
-  double* factor;  // bsize doubles of the factor + n_wblk * 64 doubles of fused look-ahead blocks
+  double* factor;  // bsize doubles
   int* ok;         // device flag: 1 if the factorisation succeeded
   cudaEvent_t ready;
   bool done;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_microbench_k
   __syncthreads();
   if (which >= 5 && which <= 7) {  // a valid factor for the factor/solve blocks
     intopt::assemble_normal_matrix(cx, P, M, D, S.G, S.scan, 1e-6, S.L);
-    if (which != 5) intopt::block_cholesky(cx, P, M, S.L, S.W, S.dscr, S.flag);
+    if (which != 5) intopt::block_cholesky(cx, P, M, S.L, S.dscr, S.flag);
     __syncthreads();
   }
   const long long t0 = clock64();
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_microbench_k
       case 4: intopt::assemble_normal_matrix(cx, P, M, D, S.G, S.scan, 1e-6, S.L); break;
       case 5:
         intopt::assemble_normal_matrix(cx, P, M, D, S.G, S.scan, 1e-6, S.L);
-        intopt::block_cholesky(cx, P, M, S.L, S.W, S.dscr, S.flag);
+        intopt::block_cholesky(cx, P, M, S.L, S.dscr, S.flag);
         break;
       case 6: {
         CTA_FOR(i, P.mv) {
@@ -264,13 +264,13 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_microbench_k
         }
         __syncthreads();
         double* const rhs2[2] = {S.q, S.v};
-        intopt::block_solve<2>(cx, P, M, S.L, S.W, rhs2);
+        intopt::block_solve<2>(cx, P, M, S.L, rhs2, S.ybuf);
       } break;
       case 7: {
         CTA_FOR(i, P.mv) S.v[i] = i < P.m ? 2.0 : 0.0;
         __syncthreads();
         double* const rhs1[1] = {S.v};
-        intopt::block_solve<1>(cx, P, M, S.L, S.W, rhs1);
+        intopt::block_solve<1>(cx, P, M, S.L, rhs1, S.ybuf);
       } break;
       case 8: CTA_FOR(k, n) intopt::gstore(S.G, k, D[k] * c[k]); break;
       case 9: {
@@ -279,63 +279,6 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_microbench_k
         sink += a5[0];
       } break;
       case 10: CTA_FOR(k, n) D[k] = D[k] * 1.0000001 + c[k] * 1e-9; break;
-      case 24: case 25: case 26: case 27: case 28: {  // Cholesky with stages switched off (numerically meaningless)
-        const int dbgs[5] = {4, 8, 16, 32, 4 | 8 | 16 | 32};
-        intopt::block_cholesky(cx, P, M, S.L, S.W, S.dscr, S.flag, nullptr, dbgs[which - 24]);
-      } break;
-      case 29: case 30: case 31: {  // 2-rhs solve with stages switched off
-        double* const rhs2[2] = {S.q, S.v};
-        intopt::block_solve<2>(cx, P, M, S.L, S.W, rhs2, which - 28);
-      } break;
-      case 32: {  // 2 x nsteps x (load one step record, barrier)
-        int acc = 0;
-        for (int rep2 = 0; rep2 < 2; ++rep2)
-          for (int st = 0; st < P.nsteps; ++st) {
-            const intopt::StepRec R = intopt::load_step(rep2 ? M.st_bwd : M.st_fwd, st);
-            acc += R.ne + R.flags + R.npriv + R.nsh + R.toff[1] + R.toff[2] + R.toff[3] + R.k[0] + R.k[1] + R.k[2] + R.k[3] +
-                   R.poff[0] + R.poff[1] + R.poff[2] + R.poff[3] + R.look[0] + R.look[1] + R.look[2] + R.look[3];
-            __syncthreads();
-          }
-        sink += acc;
-      } break;
-      case 33: {  // 2 x nsteps x (load one step record, warp-uniform branches as in block_solve, barrier)
-        int acc = 0;
-        for (int rep2 = 0; rep2 < 2; ++rep2)
-          for (int st = 0; st < P.nsteps; ++st) {
-            const intopt::StepRec R = intopt::load_step(rep2 ? M.st_bwd : M.st_fwd, st);
-            if (R.flags & 1) {
-              acc += 7;
-              __syncthreads();
-            }
-            for (int sgi = cx.warp; sgi < R.ne; sgi += cx.nwarps) acc += SEG_PICK(R.k, sgi) + SEG_PICK(R.look, sgi);
-            const int npw = (R.ne < cx.nwarps ? R.ne : cx.nwarps) * 32;
-            const int wid = cx.tid >= npw ? cx.tid - npw : cx.tid + cx.nthreads - npw;
-            const int ntask = R.npriv * 2 + R.nsh * 16;
-            for (int task = wid; task < ntask; task += cx.nthreads) {
-              const int pt = task - R.nsh * 16;
-              const int sgi = (pt >= R.toff[1] * 2) + (pt >= R.toff[2] * 2) + (pt >= R.toff[3] * 2);
-              acc += SEG_PICK(R.b, sgi) + SEG_PICK(R.c, sgi);
-            }
-            __syncthreads();
-          }
-        sink += acc;
-      } break;
-      case 22:  // nine extra barriers
-#pragma unroll
-        for (int i = 0; i < 9; ++i) __syncthreads();
-        break;
-      case 23: {  // nine (warp-0 work, barrier) pairs: 16 dependent DFMA on warp 0 only
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          if (cx.warp == 0) {
-            double z = S.G[cx.lane];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) z = fma(z, 0.999999, 1e-9);
-            S.G[cx.lane] = z;
-          }
-          __syncthreads();
-        }
-      } break;
       case 18: spmv_rows_dbg(cx, P, S.G, S.q, 0); break;
       case 19: spmv_rows_dbg(cx, P, S.G, S.q, 1); break;
       case 20: spmv_rows_dbg(cx, P, S.G, S.q, 2); break;
@@ -454,7 +397,6 @@ size_t ws_per_slot_doubles(const IntoptProblem* p) {
   size_t per = (size_t)intopt::W_NVEC * p->info.n;
   if (!p->info.factor_in_smem) per += (size_t)p->info.envelope;
   if (!p->info.gather_in_smem) per += 2 * (size_t)intopt::gather_len(p->info.n);
-  if (!intopt::w_in_gather(p->dev.n_wblk, p->info.n)) per += (size_t)p->dev.n_wblk * 64;
   return (per + 1) & ~(size_t)1;
 }
 
@@ -481,7 +423,7 @@ int cold_factor_for(const IntoptProblem* p, double delta, cudaStream_t stream, c
   e.delta = delta;
   e.done = false;
   double* ws = nullptr;
-  CU_TRY(cudaMalloc((void**)&e.factor, sizeof(double) * ((size_t)p->info.envelope + (size_t)p->dev.n_wblk * 64)));
+  CU_TRY(cudaMalloc((void**)&e.factor, sizeof(double) * (size_t)p->info.envelope));
   p->cold_allocs.push_back(e.factor);
   CU_TRY(cudaMalloc((void**)&e.ok, sizeof(int)));
   p->cold_allocs.push_back(e.ok);
@@ -525,7 +467,7 @@ int intopt_problem_create(IntoptProblem** out, int m, int n, const int* rowptr, 
   if (!out) return fail(-1, "out is NULL");
   *out = nullptr;
   intopt::HostStructure S;
-  int rc = intopt::analyze(m, n, rowptr, colidx, val, S, env_int("INTOPT_NO_SEG", 0) ? -2 : -1);
+  int rc = intopt::analyze(m, n, rowptr, colidx, val, S);
   if (rc) return fail(rc, "malformed CSR input");
   int ndev = 0;
   cudaError_t e0 = cudaGetDeviceCount(&ndev);

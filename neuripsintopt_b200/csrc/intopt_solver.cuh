@@ -85,8 +85,6 @@ namespace intopt {
 
 enum { ST_OK = 0, ST_MAXITER = 1, ST_INFEAS = 2, ST_BREAKDOWN = 3, ST_NONFINITE = 4 };
 constexpr int KB = 8;  // block edge, == NB of intopt_structure.hpp
-constexpr int KSEG = 4;  // == MAXSEG of intopt_structure.hpp (checked in intopt_bind.hpp)
-constexpr int KREC = 12 + 4 * KSEG;  // == ST_REC: ints per step record of the substitution schedule
 
 // The gather buffer is indexed through gpad(): one unused slot after every 32 elements, so that run starts a
 // multiple of 16 or 32 elements apart (the Energy LP: 144 = one task's variables) no longer share a bank.
@@ -120,17 +118,6 @@ struct ProblemDev {
   int n_dummy;
   const int* g_act_ptr;
   const int* g_act_blk;
-  const int* g_act_off;
-  // concurrent leading segments (intopt_structure.hpp): nseg == 0 disables
-  int nseg, seg_end, seg_tmax, nbord;
-  int seg_start[KSEG], seg_len[KSEG];
-  const int* g_act_ns;
-  const int* g_seg_bord;
-  // substitution schedule (intopt_structure.hpp: st_fwd / st_bwd, one KREC-int record per step)
-  int nsteps, n_wblk;
-  const int* g_st_fwd;
-  const int* g_st_bwd;
-  const int* g_wblk_col;  // column K of W slot w (n_wblk entries)
   int meta_ints;  // total ints of {fb, boff, act_ptr, act_blk, csr_ptr, csc_gptr, asm_gptr}: staged in smem if small
   int n_asm;
   const int* g_asm_gptr;
@@ -151,15 +138,10 @@ struct Meta {
   const int* boff;
   const int* act_ptr;
   const int* act_blk;
-  const int* act_off;
   const int* csr_ptr;
   const int* csc_gptr;
   const int* asm_gptr;
   const int* asm_rptr;
-  const int* act_ns;
-  const int* seg_bord;
-  const int* st_fwd;
-  const int* st_bwd;
 };
 
 // Sum N partial values over the CTA; every thread receives the totals (fixed order => deterministic).
@@ -649,597 +631,219 @@ IO_DEV void chol_update_task(const ProblemDev& P, const Meta& M, double* L, int 
   }
 }
 
-// ---- concurrent leading segments ------------------------------------------------------------------------
-// Per-thread view of step t of the segment phase: column K[s] = seg_start[s] + t of every segment that is still
-// running (na[s] == 0 and K[s] == -1 otherwise).  Everything is indexed with compile-time s (registers).
-struct SegStep {
-  int K[KSEG], a0[KSEG], na[KSEG], ns[KSEG], ld[KSEG];
-};
-IO_FORCEINLINE SegStep seg_step(const ProblemDev& P, const Meta& M, int t) {
-  SegStep g;
-#pragma unroll
-  for (int s = 0; s < KSEG; ++s) {
-    const bool on = s < P.nseg && t < P.seg_len[s];
-    const int K = on ? P.seg_start[s] + t : 0;
-    g.K[s] = on ? K : -1;
-    g.a0[s] = M.act_ptr[K];
-    g.na[s] = on ? M.act_ptr[K + 1] - g.a0[s] : 0;
-    g.ns[s] = on ? M.act_ns[K] : 0;  // active rows inside the segment (they come first in the list)
-    g.ld[s] = (g.ns[s] > 0 && M.act_blk[g.a0[s]] == K + 1) ? 1 : 0;  // block (K+1,K) exists: look-ahead pivot
-  }
-  return g;
-}
-#define SEG_PICK(arr, s) ((s) == 0 ? (arr)[0] : (s) == 1 ? (arr)[1] : (s) == 2 ? (arr)[2] : (arr)[3])
-#define SEG_PICK5(arr, s) ((s) == 0 ? (arr)[0] : (s) == 1 ? (arr)[1] : (s) == 2 ? (arr)[2] : (s) == 3 ? (arr)[3] : (arr)[4])
-#define SEG_PICK4(arr, s, f) ((s) == 0 ? (arr)[0].f : (s) == 1 ? (arr)[1].f : (s) == 2 ? (arr)[2].f : (arr)[3].f)
-
-// acc += rows 4tr..4tr+3 of L_IK times rows 4tc..4tc+3 of L_JK, transposed (one 4x4 tile of L_IK L_JK^T)
-IO_FORCEINLINE void chol_tile_acc(const Meta& M, const double* L, int I, int J, int K, int tr, int tc, double (&acc)[4][4]) {
-  const double* A = L + M.boff[I] + (K - M.fb[I]) * 64 + tr * 32;
-  const double* Bm = L + M.boff[J] + (K - M.fb[J]) * 64 + tc * 32;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    D2 av[4], bv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      av[i] = reinterpret_cast<const D2*>(A + i * KB)[c ^ bswz(4 * tr + i)];
-      bv[i] = reinterpret_cast<const D2*>(Bm + i * KB)[c ^ bswz(4 * tc + i)];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i].y, bv[j].y, fma(av[i].x, bv[j].x, acc[i][j]));
-  }
-}
-IO_FORCEINLINE void chol_tile_sub(const Meta& M, double* L, int I, int J, int tr, int tc, const double (&acc)[4][4]) {
-  double* dst = L + M.boff[I] + (J - M.fb[I]) * 64 + tr * 32;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    D2* drow = reinterpret_cast<D2*>(dst + i * KB);
-    const int sw = bswz(4 * tr + i);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      D2 t = drow[(2 * tc + h) ^ sw];
-      t.x -= acc[i][2 * h];
-      t.y -= acc[i][2 * h + 1];
-      drow[(2 * tc + h) ^ sw] = t;
-    }
-  }
-}
-
-// one panel row: row `rr` of block (I,K) times Linv_KK^T, in place
-IO_FORCEINLINE void chol_panel_row(const Meta& M, double* L, int I, int K, int rr) {
-  const double* Linv = L + M.boff[K] + (K - M.fb[K]) * 64;
-  double* blk = L + M.boff[I] + (K - M.fb[I]) * 64;
-  double cin[KB], out[KB];
-  load_row(blk, rr, cin);
-#pragma unroll
-  for (int c = 0; c < KB; ++c) {
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < KB; ++k)
-      if (k <= c) s = fma(cin[k], Linv[bidx(c, k)], s);
-    out[c] = s;
-  }
-  store_row(blk, rr, out);
-}
-
-// Segment phase of the factorisation: step t handles column seg_start[s] + t of every segment at once.  Warp s
-// factors the segment's next diagonal block (look-ahead, its update by the fresh panel block fused in) while the
-// remaining warps apply the trailing updates: targets inside a segment or in (tail row x segment column) belong to
-// one column; (tail x tail) targets sum the contributions of all running segments in fixed order (deterministic).
-IO_DEV void chol_segment_phase(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, double* scratch,
-                               int* fail_flag, int dbg) {
-  double* myscr = scratch + (cx.warp < KSEG ? cx.warp : 0) * (KB + KB * KB);
-  for (int s = cx.warp; s < P.nseg; s += cx.nwarps) {
-    const int K = P.seg_start[s];
-    diag_block_factor_invert(cx, L + M.boff[K] + (K - M.fb[K]) * 64, myscr, fail_flag);
-  }
-  CTA_SYNC();
-  const int nbp = P.nbord * (P.nbord + 1) / 2;
-  for (int t = 0; t < P.seg_tmax; ++t) {
-    const SegStep g = seg_step(P, M, t);
-    // (a) panels of every running column
-    int poff[KSEG + 1];
-    poff[0] = 0;
-#pragma unroll
-    for (int s = 0; s < KSEG; ++s) poff[s + 1] = poff[s] + g.na[s] * KB;
-    if (!(dbg & 16)) CTA_FOR(idx, poff[KSEG]) {
-      const int s = (idx >= poff[1]) + (idx >= poff[2]) + (idx >= poff[3]);
-      const int loc = idx - SEG_PICK(poff, s);
-      const int K = SEG_PICK(g.K, s);
-      chol_panel_row(M, L, M.act_blk[SEG_PICK(g.a0, s) + (loc >> 3)], K, loc & 7);
-    }
-    CTA_SYNC();
-    // (b) look-ahead pivots on the first warps, trailing updates on the others
-    int nd = 0;  // running segments come first?  not necessarily: warp s serves segment s
-#pragma unroll
-    for (int s = 0; s < KSEG; ++s)
-      if (g.ld[s]) nd = s + 1;
-    const int nded = cx.nwarps > nd ? nd : 0;  // warps dedicated to the pivots (none if the CTA is that small)
-    for (int s = cx.warp; s < nd; s += cx.nwarps) {
-      if (SEG_PICK(g.ld, s) && !(dbg & 8)) {
-        const int K = SEG_PICK(g.K, s);
-        const double* lead_panel = L + M.boff[K + 1] + (K - M.fb[K + 1]) * 64;
-        diag_block_factor_invert(cx, L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64, myscr, fail_flag, lead_panel);
-      }
-    }
-    if (cx.warp >= nded && !(dbg & 4)) {
-      const int w_tid = cx.tid - nded * cx.warpsize, w_n = cx.nthreads - nded * cx.warpsize;
-      // private targets of column K[s]: pairs (ia >= ib) of its active rows with ib inside the segment
-      int toff[KSEG + 1];
-      toff[0] = 0;
-#pragma unroll
-      for (int s = 0; s < KSEG; ++s) {
-        const int npair = g.ns[s] * (g.ns[s] + 1) / 2 + (g.na[s] - g.ns[s]) * g.ns[s];
-        toff[s + 1] = toff[s] + (npair - g.ld[s]) * 4;
-      }
-      const int ntask = toff[KSEG] + nbp * 4;
-      for (int task = w_tid; task < ntask; task += w_n) {
-        double acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-        if (task < toff[KSEG]) {
-          const int s = (task >= toff[1]) + (task >= toff[2]) + (task >= toff[3]);
-          const int loc = task - SEG_PICK(toff, s) + SEG_PICK(g.ld, s) * 4;
-          const int pi = loc >> 2, tr = (loc >> 1) & 1, tc = loc & 1;
-          const int ns = SEG_PICK(g.ns, s), a0 = SEG_PICK(g.a0, s), K = SEG_PICK(g.K, s);
-          const int ntri = ns * (ns + 1) / 2;
-          int ia, ib;
-          if (pi < ntri) {
-            ia = tri_row(pi);
-            ib = pi - ia * (ia + 1) / 2;
-          } else {
-            const int r = pi - ntri;
-            ia = ns + r / ns;
-            ib = r - (ia - ns) * ns;
-          }
-          const int I = M.act_blk[a0 + ia], J = M.act_blk[a0 + ib];
-          chol_tile_acc(M, L, I, J, K, tr, tc, acc);
-          chol_tile_sub(M, L, I, J, tr, tc, acc);
-        } else {
-          const int loc = task - toff[KSEG];
-          const int pi = loc >> 2, tr = (loc >> 1) & 1, tc = loc & 1;
-          const int ia = tri_row(pi), ib = pi - ia * (ia + 1) / 2;
-          const int I = M.seg_bord[ia], J = M.seg_bord[ib];
-          const int fI = M.fb[I], fJ = M.fb[J];
-          bool any = false;
-#pragma unroll
-          for (int s = 0; s < KSEG; ++s) {
-            const int K = g.K[s];
-            if (K >= 0 && fI <= K && fJ <= K) {
-              chol_tile_acc(M, L, I, J, K, tr, tc, acc);
-              any = true;
-            }
-          }
-          if (any) chol_tile_sub(M, L, I, J, tr, tc, acc);
-        }
-      }
-    }
-    CTA_SYNC();
-  }
-}
-
-IO_DEV void fuse_coupling_blocks(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, double* W);
-
-IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, double* W, double* scratch,
-                           int* fail_flag, PhaseTimer* pt = nullptr, int dbg = 0) {
+IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, double* scratch,
+                           int* fail_flag, PhaseTimer* pt = nullptr) {
   const int mb = P.mb;
   if (cx.tid == 0) *fail_flag = 0;
   CTA_SYNC();
-  const int K0 = P.nseg > 1 ? P.seg_end : 0;  // first column of the sequential part
-  if (P.nseg > 1) chol_segment_phase(cx, P, M, L, scratch, fail_flag, dbg);
-  if (K0 < mb) {
-    if (cx.warp == 0) diag_block_factor_invert(cx, L + M.boff[K0] + (K0 - M.fb[K0]) * 64, scratch, fail_flag);
-    CTA_SYNC();
-  }
-  if (pt) { PHASE_MARK(*pt, 11); }
+  if (cx.warp == 0) diag_block_factor_invert(cx, L + M.boff[0] + (0 - M.fb[0]) * 64, scratch, fail_flag);
+  CTA_SYNC();
   const int o_tid = cx.nwarps > 1 ? cx.tid - cx.warpsize : 0;
   const int o_n = cx.nwarps > 1 ? cx.nthreads - cx.warpsize : 1;
-  for (int K = K0; K < mb; ++K) {
+  for (int K = 0; K < mb; ++K) {
+    const double* Linv = L + M.boff[K] + (K - M.fb[K]) * 64;
     // (a) panel rows
     const int a0 = M.act_ptr[K], na = M.act_ptr[K + 1] - a0;
-    if (!(dbg & 16)) CTA_FOR(idx, na * KB) chol_panel_row(M, L, M.act_blk[a0 + (idx >> 3)], K, idx & 7);
+    CTA_FOR(idx, na * KB) {
+      const int I = M.act_blk[a0 + (idx >> 3)];
+      double* blk = L + M.boff[I] + (K - M.fb[I]) * 64;
+      double cin[KB], out[KB];
+      load_row(blk, idx & 7, cin);
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < KB; ++k)
+          if (k <= c) s = fma(cin[k], Linv[bidx(c, k)], s);
+        out[c] = s;
+      }
+      store_row(blk, idx & 7, out);
+    }
     CTA_SYNC();
-    if (pt) { PHASE_MARK(*pt, 12); }
+    if (pt) { PHASE_MARK(*pt, 11); }
     // (b) trailing update with look-ahead
     const int np = na * (na + 1) / 2;
     const int lead = (na > 0 && M.act_blk[a0] == K + 1) ? 1 : 0;  // pair 0 updates block (K+1,K+1)
     if (cx.warp == 0) {
-      if (K + 1 < mb && !(dbg & 8)) {
+      if (pt) { PHASE_MARK(*pt, 12); }
+      if (K + 1 < mb) {
         // the update of the next diagonal block by this step's panel block (K+1,K) is fused into its factorisation
         const double* lead_panel = lead ? L + M.boff[K + 1] + (K - M.fb[K + 1]) * 64 : nullptr;
         diag_block_factor_invert(cx, L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64, scratch, fail_flag, lead_panel);
       }
       if (pt) { PHASE_MARK(*pt, 13); }
     }
-    if ((cx.nwarps == 1 || cx.warp > 0) && !(dbg & 4)) {
+    if (cx.nwarps == 1 || cx.warp > 0) {
       for (int task = lead * 4 + o_tid; task < np * 4; task += o_n) chol_update_task(P, M, L, K, a0, task);
     }
     CTA_SYNC();
     if (pt) { PHASE_MARK(*pt, 14); }
   }
-  const bool ok = *fail_flag == 0;
-  if (ok && !(dbg & 32)) fuse_coupling_blocks(cx, P, M, L, W);
-  return ok;
+  return *fail_flag == 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Solve L L^T z = r in place for NR right-hand sides at once (blocked substitution; the diagonal blocks hold
-// Linv).  One barrier per step: while the CTA applies the step's update to the other rows, the pivot warp
-// first updates the rows of the NEXT pivot block and immediately multiplies them by its inverted diagonal
-// block (in place), so the next step's pivot values are ready when the barrier opens.  With concurrent
-// leading segments a step handles one column of every segment (pivot warp s serves segment s).
+// Solve L L^T z = r in place for NR right-hand sides at once (blocked substitution; the diagonal blocks
+// hold Linv).  One barrier per block step: while the CTA applies block K's update to the rows below,
+// warp 0 first updates the rows of the NEXT pivot block and immediately multiplies them by its inverted
+// diagonal block, so the next step's pivot values are ready when the barrier opens.
+// `ybuf` is 2*NR*8 doubles of scratch (double buffered, 16-byte aligned).
 // ---------------------------------------------------------------------------------------------
 template <int NR>
 IO_FORCEINLINE double* rhs_sel(double* const (&r)[NR], int q) {
   return (NR > 1 && q) ? r[NR - 1] : r[0];  // NR is 1 or 2
 }
 
-// r_blk <- Linv r_blk (or Linv^T r_blk), all NR right-hand sides, in place; executed by one full warp
+// y[idx] (idx = q*8 + i) = row i of Linv (or of Linv^T) times the 8-vector v_q
 template <int NR, bool TRANS>
-IO_FORCEINLINE void pivot_inplace(const CtaCtx& cx, const double* Linv, double* const (&r)[NR], int blk) {
-#ifdef INTOPT_HOST_EMU
-  (void)cx;
-  double tmp[NR * KB];
-  for (int idx = 0; idx < NR * KB; ++idx) {
-    const int q = idx >> 3, i = idx & 7;
-    const double* rk = rhs_sel<NR>(r, q) + blk * KB;
-    double s = 0.0;
-    for (int j = 0; j < KB; ++j) {
-      if (!TRANS && j <= i) s = fma(Linv[bidx(i, j)], rk[j], s);
-      if (TRANS && j >= i) s = fma(Linv[bidx(j, i)], rk[j], s);
-    }
-    tmp[idx] = s;
-  }
-  for (int idx = 0; idx < NR * KB; ++idx) rhs_sel<NR>(r, idx >> 3)[blk * KB + (idx & 7)] = tmp[idx];
-#else
-  const int idx = cx.lane, q = idx >> 3, i = idx & 7;
+IO_FORCEINLINE void pivot_apply(const double* Linv, double* const (&r)[NR], int blk, int idx, double* yout) {
+  const int q = idx >> 3, i = idx & 7;
+  double rk[KB];
+  load_vec8(rhs_sel<NR>(r, q) + blk * KB, rk);
   double s = 0.0;
-  if (idx < NR * KB) {
-    double rk[KB];
-    load_vec8(rhs_sel<NR>(r, q) + blk * KB, rk);
-    if (!TRANS) {
-      double li[KB];
-      load_row(Linv, i, li);
-#pragma unroll
-      for (int j = 0; j < KB; ++j)
-        if (j <= i) s = fma(li[j], rk[j], s);
-    } else {
-#pragma unroll
-      for (int j = 0; j < KB; ++j)
-        if (j >= i) s = fma(Linv[bidx(j, i)], rk[j], s);
-    }
-  }
-  __syncwarp();
-  if (idx < NR * KB) rhs_sel<NR>(r, q)[blk * KB + i] = s;
-  __syncwarp();
-#endif
-}
-
-// row rr of the block at `blk` times y_K   (forward substitution update of one row, right-hand side q)
-template <int NR>
-IO_FORCEINLINE double fwd_row_dot(const double* blk, double* const (&r)[NR], int q, int K, int rr) {
-  double row[KB], yk[KB];
-  load_row(blk, rr, row);
-  load_vec8(rhs_sel<NR>(r, q) + K * KB, yk);
-  double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-  for (int k = 0; k < KB; k += 2) {
-    s0 = fma(row[k], yk[k], s0);
-    s1 = fma(row[k + 1], yk[k + 1], s1);
-  }
-  return s0 + s1;
-}
-// r_Kc[2c..2c+1] -= (B^T z_I)[2c..2c+1] with B = block (I,Kc) at `blk`   (backward substitution update)
-template <int NR>
-IO_FORCEINLINE void bwd_chunk_update(const double* blk, double* const (&r)[NR], int q, int I, int Kc, int c) {
-  double zi[KB];
-  load_vec8(rhs_sel<NR>(r, q) + I * KB, zi);
-  double sx = 0.0, sy = 0.0, tx = 0.0, ty = 0.0;
-#pragma unroll
-  for (int i = 0; i < KB; i += 2) {
-    const D2 t2 = reinterpret_cast<const D2*>(blk + i * KB)[c ^ bswz(i)];
-    const D2 t3 = reinterpret_cast<const D2*>(blk + (i + 1) * KB)[c ^ bswz(i + 1)];
-    sx = fma(t2.x, zi[i], sx);
-    sy = fma(t2.y, zi[i], sy);
-    tx = fma(t3.x, zi[i + 1], tx);
-    ty = fma(t3.y, zi[i + 1], ty);
-  }
-  D2* dst = reinterpret_cast<D2*>(rhs_sel<NR>(r, q) + Kc * KB) + c;
-  D2 t2 = *dst;
-  t2.x -= sx + tx;
-  t2.y -= sy + ty;
-  *dst = t2;
-}
-
-// After the factorisation: for every coupling block inside a chain, Lb = L_(K+1,K), form
-//   W = Linv_(K+1) Lb  (kept in the W buffer, slot look_fwd)   and   V = Lb Linv_K  (stored in place of Lb),
-// the blocks of the fused look-ahead pivots:  y_(K+1) = Linv_(K+1) r_(K+1) - W y_K   (forward)  and
-// z_K = Linv_K^T r_K - V^T z_(K+1)  (backward).  Lb itself is not needed by the substitutions any more.
-IO_DEV void fuse_coupling_blocks(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, double* W) {
-  // one thread per (coupling block, row i): row i of W and row i of V; V is written back after a barrier because
-  // it overwrites the block every row of the same task group reads
-  const int ntask = P.n_wblk * KB;
-#ifdef INTOPT_HOST_EMU
-  (void)cx;
-  for (int w = 0; w < P.n_wblk; ++w) {  // single-threaded build: whole block at a time, same arithmetic
-    const int K = P.g_wblk_col[w];
-    double* Lb = L + M.boff[K + 1] + (K - M.fb[K + 1]) * 64;
-    const double* Linv1 = L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64;
-    const double* Linv0 = L + M.boff[K] + (K - M.fb[K]) * 64;
-    double vall[KB][KB];
-    for (int i = 0; i < KB; ++i)
-      for (int j = 0; j < KB; ++j) {
-        double wv = 0.0, vv = 0.0;
-        for (int k = 0; k < KB; ++k) {
-          if (k <= i) wv = fma(Linv1[bidx(i, k)], Lb[bidx(k, j)], wv);
-          if (j <= k) vv = fma(Lb[bidx(i, k)], Linv0[bidx(k, j)], vv);
-        }
-        W[w * 64 + bidx(i, j)] = wv;
-        vall[i][j] = vv;
-      }
-    for (int i = 0; i < KB; ++i)
-      for (int j = 0; j < KB; ++j) Lb[bidx(i, j)] = vall[i][j];
-  }
-  if (ntask >= 0) return;
-#endif
-  for (int base = 0; base < ntask; base += cx.nthreads) {
-    const int task = base + cx.tid;
-    double vrow[KB];
-    double* Lb = nullptr;
-    int i = 0;
-    if (task < ntask) {
-      const int w = task >> 3;
-      i = task & 7;
-      const int K = P.g_wblk_col[w];
-      Lb = L + M.boff[K + 1] + (K - M.fb[K + 1]) * 64;
-      const double* Linv1 = L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64;
-      const double* Linv0 = L + M.boff[K] + (K - M.fb[K]) * 64;
-      double li[KB], bi[KB], wrow[KB];
-      load_row(Linv1, i, li);
-      load_row(Lb, i, bi);
-#pragma unroll
-      for (int j = 0; j < KB; ++j) {
-        wrow[j] = 0.0;
-        vrow[j] = 0.0;
-      }
-#pragma unroll
-      for (int k = 0; k < KB; ++k) {
-        double bk[KB], ik[KB];
-        load_row(Lb, k, bk);
-        load_row(Linv0, k, ik);
-#pragma unroll
-        for (int j = 0; j < KB; ++j) {
-          if (k <= i) wrow[j] = fma(li[k], bk[j], wrow[j]);    // W = Linv_(K+1) Lb   (Linv lower triangular)
-          if (j <= k) vrow[j] = fma(bi[k], ik[j], vrow[j]);    // V = Lb Linv_K
-        }
-      }
-      store_row(W + w * 64, i, wrow);
-    }
-    CTA_SYNC();
-    if (task < ntask) store_row(Lb, i, vrow);
-    CTA_SYNC();
-  }
-}
-
-// fused forward look-ahead: r_(K+1) <- Linv_(K+1) r_(K+1) - W y_K, all NR right-hand sides, one full warp
-template <int NR>
-IO_FORCEINLINE void pivot_fused_fwd(const CtaCtx& cx, const double* Linv, const double* Wb, double* const (&r)[NR], int K) {
-#ifdef INTOPT_HOST_EMU
-  (void)cx;
-  double tmp[NR * KB];
-  for (int idx = 0; idx < NR * KB; ++idx) {
-    const int q = idx >> 3, i = idx & 7;
-    const double* rn = rhs_sel<NR>(r, q) + (K + 1) * KB;
-    const double* yk = rhs_sel<NR>(r, q) + K * KB;
-    double s1 = 0.0, s2 = 0.0;
-    for (int j = 0; j < KB; ++j) {
-      if (j <= i) s1 = fma(Linv[bidx(i, j)], rn[j], s1);
-      s2 = fma(Wb[bidx(i, j)], yk[j], s2);
-    }
-    tmp[idx] = s1 - s2;
-  }
-  for (int idx = 0; idx < NR * KB; ++idx) rhs_sel<NR>(r, idx >> 3)[(K + 1) * KB + (idx & 7)] = tmp[idx];
-#else
-  const int idx = cx.lane, q = idx >> 3, i = idx & 7;
-  double s1 = 0.0, s2 = 0.0;
-  if (idx < NR * KB) {
-    double rn[KB], yk[KB], li[KB], wi[KB];
-    load_vec8(rhs_sel<NR>(r, q) + (K + 1) * KB, rn);
-    load_vec8(rhs_sel<NR>(r, q) + K * KB, yk);
+  if (!TRANS) {
+    double li[KB];
     load_row(Linv, i, li);
-    load_row(Wb, i, wi);
-    double s1b = 0.0, s2b = 0.0;
 #pragma unroll
-    for (int j = 0; j < KB; j += 2) {
-      if (j <= i) s1 = fma(li[j], rn[j], s1);
-      if (j + 1 <= i) s1b = fma(li[j + 1], rn[j + 1], s1b);
-      s2 = fma(wi[j], yk[j], s2);
-      s2b = fma(wi[j + 1], yk[j + 1], s2b);
-    }
-    s1 += s1b;
-    s2 += s2b;
-  }
-  __syncwarp();
-  if (idx < NR * KB) rhs_sel<NR>(r, q)[(K + 1) * KB + i] = s1 - s2;
-  __syncwarp();
-#endif
-}
-// fused backward look-ahead: r_(I-1) <- Linv_(I-1)^T r_(I-1) - V^T z_I
-template <int NR>
-IO_FORCEINLINE void pivot_fused_bwd(const CtaCtx& cx, const double* Linv, const double* Vb, double* const (&r)[NR], int I) {
-#ifdef INTOPT_HOST_EMU
-  (void)cx;
-  double tmp[NR * KB];
-  for (int idx = 0; idx < NR * KB; ++idx) {
-    const int q = idx >> 3, i = idx & 7;
-    const double* rp = rhs_sel<NR>(r, q) + (I - 1) * KB;
-    const double* zi = rhs_sel<NR>(r, q) + I * KB;
-    double s1 = 0.0, s2 = 0.0;
-    for (int j = 0; j < KB; ++j) {
-      if (j >= i) s1 = fma(Linv[bidx(j, i)], rp[j], s1);
-      s2 = fma(Vb[bidx(j, i)], zi[j], s2);
-    }
-    tmp[idx] = s1 - s2;
-  }
-  for (int idx = 0; idx < NR * KB; ++idx) rhs_sel<NR>(r, idx >> 3)[(I - 1) * KB + (idx & 7)] = tmp[idx];
-#else
-  const int idx = cx.lane, q = idx >> 3, i = idx & 7;
-  double s1 = 0.0, s2 = 0.0;
-  if (idx < NR * KB) {
-    double rp[KB], zi[KB];
-    load_vec8(rhs_sel<NR>(r, q) + (I - 1) * KB, rp);
-    load_vec8(rhs_sel<NR>(r, q) + I * KB, zi);
-    double s1b = 0.0, s2b = 0.0;
+    for (int j = 0; j < KB; ++j)
+      if (j <= i) s = fma(li[j], rk[j], s);
+  } else {
 #pragma unroll
-    for (int j = 0; j < KB; j += 2) {
-      if (j >= i) s1 = fma(Linv[bidx(j, i)], rp[j], s1);
-      if (j + 1 >= i) s1b = fma(Linv[bidx(j + 1, i)], rp[j + 1], s1b);
-      s2 = fma(Vb[bidx(j, i)], zi[j], s2);
-      s2b = fma(Vb[bidx(j + 1, i)], zi[j + 1], s2b);
-    }
-    s1 += s1b;
-    s2 += s2b;
+    for (int j = 0; j < KB; ++j)
+      if (j >= i) s = fma(Linv[bidx(j, i)], rk[j], s);
   }
-  __syncwarp();
-  if (idx < NR * KB) rhs_sel<NR>(r, q)[(I - 1) * KB + i] = s1 - s2;
-  __syncwarp();
-#endif
-}
-
-// One step record of the substitution schedule in registers (see intopt_structure.hpp: ST_REC).
-struct StepRec {
-  int ne, flags, npriv, nsh;
-  int toff[KSEG];
-  int k[KSEG], b[KSEG], c[KSEG], look[KSEG], poff[KSEG];  // entry fields 0..4
-};
-IO_FORCEINLINE StepRec load_step(const int* tab, int st) {
-  const U4* rec = reinterpret_cast<const U4*>(tab + st * KREC);
-  StepRec R;
-  const U4 h0 = rec[0], h1 = rec[1], h2 = rec[2];
-  R.ne = (int)h0.x;
-  R.flags = (int)h0.y;
-  R.npriv = (int)h0.z;
-  R.nsh = (int)h0.w;
-  R.toff[0] = (int)h1.x;
-  R.toff[1] = (int)h1.y;
-  R.toff[2] = (int)h1.z;
-  R.toff[3] = (int)h1.w;
-  R.poff[0] = (int)h2.x;
-  R.poff[1] = (int)h2.y;
-  R.poff[2] = (int)h2.z;
-  R.poff[3] = (int)h2.w;
-#pragma unroll
-  for (int s = 0; s < KSEG; ++s) {
-    const U4 e0 = rec[3 + s];
-    R.k[s] = (int)e0.x;
-    R.b[s] = (int)e0.y;
-    R.c[s] = (int)e0.z;
-    R.look[s] = (int)e0.w;
-  }
-  return R;
+  yout[idx] = s;
 }
 
 template <int NR>
-IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* L, const double* W,
-                        double* const (&r)[NR], int dbg = 0) {
-  const int nsteps = P.nsteps;
-  // ================= forward: L y = r =================================================================
-  for (int st = 0; st < nsteps; ++st) {
-    const StepRec R = load_step(M.st_fwd, st);
-    if (R.flags & 1) {  // chain heads: their pivots have no look-ahead producer
-      for (int s = cx.warp; s < R.ne; s += cx.nwarps) {
-        const int K = SEG_PICK(R.k, s);
-        pivot_inplace<NR, false>(cx, L + M.boff[K] + (K - M.fb[K]) * 64, r, K);
-      }
-      CTA_SYNC();
-    }
-    if (!(dbg & 1))
-      for (int s = cx.warp; s < R.ne; s += cx.nwarps) {
-        const int K = SEG_PICK(R.k, s), look = SEG_PICK(R.look, s);
-        const double* Linv = L + SEG_PICK(R.poff, s);
-        if (look >= 0)
-          pivot_fused_fwd<NR>(cx, Linv, W + look * 64, r, K);
-        else if (look == -1)
-          pivot_inplace<NR, false>(cx, Linv, r, K + 1);
-      }
-    {
-      // every thread takes row updates; the warps that just produced a pivot come last in the task order
-      const int npw = (R.ne < cx.nwarps ? R.ne : cx.nwarps) * cx.warpsize;
-      const int wid = cx.tid >= npw ? cx.tid - npw : cx.tid + cx.nthreads - npw;
-      const int nsh = R.nsh * KB * NR;
-      const int ntask = (dbg & 2) ? 0 : R.npriv * NR + nsh;
-      for (int task = wid; task < ntask; task += cx.nthreads) {
-        if (task >= nsh) {  // a private row of one column
-          const int pt = task - nsh;
-          const int s = (pt >= R.toff[1] * NR) + (pt >= R.toff[2] * NR) + (pt >= R.toff[3] * NR);
-          const int loc = pt - SEG_PICK(R.toff, s) * NR;
-          const int nrow = SEG_PICK(R.c, s) * KB;
-          const int q = (NR > 1 && loc >= nrow) ? 1 : 0, rem = loc - q * nrow;
-          const int ai = SEG_PICK(R.b, s) + (rem >> 3), rr = rem & 7;
-          const int I = M.act_blk[ai];
-          rhs_sel<NR>(r, q)[I * KB + rr] -= fwd_row_dot<NR>(L + M.act_off[ai], r, q, SEG_PICK(R.k, s), rr);
-        } else {  // a tail row reaching into the segments: every running column, in fixed order (longest tasks first)
-          const int nrow = R.nsh * KB;
-          const int q = (NR > 1 && task >= nrow) ? 1 : 0, rem = task - q * nrow;
-          const int I = M.seg_bord[rem >> 3], rr = rem & 7, fI = M.fb[I];
-          const double* rowblk = L + M.boff[I] - fI * 64;
+IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* L, double* const (&r)[NR],
+                        double* ybuf) {
+  const int mb = P.mb;
+  const int o_tid = cx.nwarps > 1 ? cx.tid - cx.warpsize : 0;
+  const int o_n = cx.nwarps > 1 ? cx.nthreads - cx.warpsize : 1;
+  // ---- forward: L y = r --------------------------------------------------------------------------
+  if (cx.warp == 0) {
+    LANE_FOR(idx, 0, NR * KB) pivot_apply<NR, false>(L + M.boff[0] + (0 - M.fb[0]) * 64, r, 0, idx, ybuf);
+  }
+  CTA_SYNC();
+  for (int K = 0; K < mb; ++K) {
+    const double* ycur = ybuf + (K & 1) * NR * KB;
+    double* ynext = ybuf + ((K + 1) & 1) * NR * KB;
+    const int a0 = M.act_ptr[K], na = M.act_ptr[K + 1] - a0;
+    const int lead = (na > 0 && M.act_blk[a0] == K + 1) ? 1 : 0;  // the next pivot block is updated by this step
+    if (cx.warp == 0) {
+      LANE_FOR(idx, 0, NR * KB) {
+        rhs_sel<NR>(r, idx >> 3)[K * KB + (idx & 7)] = ycur[idx];  // y_K is final: store it
+        if (lead) {
+          const int q = idx >> 3, rr = idx & 7;
+          double row[KB], yk[KB];
+          load_row(L + M.boff[K + 1] + (K - M.fb[K + 1]) * 64, rr, row);
+          load_vec8(ycur + q * KB, yk);
           double sacc = 0.0;
 #pragma unroll
-          for (int s = 0; s < KSEG; ++s)
-            if (R.k[s] >= 0 && fI <= R.k[s]) sacc += fwd_row_dot<NR>(rowblk + R.k[s] * 64, r, q, R.k[s], rr);
-          rhs_sel<NR>(r, q)[I * KB + rr] -= sacc;
+          for (int k = 0; k < KB; ++k) sacc = fma(row[k], yk[k], sacc);
+          rhs_sel<NR>(r, q)[(K + 1) * KB + rr] -= sacc;
         }
       }
-    }
-    CTA_SYNC();
-  }
-  // ================= backward: L^T z = y ==============================================================
-  for (int st = nsteps - 1; st >= 0; --st) {
-    const StepRec R = load_step(M.st_bwd, st);
-    // pivots nobody produced by look-ahead: the very last block, and every segment's last block when the tail is done
-    if (R.flags & 1) {
-      if (cx.warp == 0) {
-        const int I = P.mb - 1;
-        pivot_inplace<NR, true>(cx, L + M.boff[I] + (I - M.fb[I]) * 64, r, I);
+      WARP_SYNC();
+      if (K + 1 < mb) {
+        LANE_FOR(idx, 0, NR * KB)
+        pivot_apply<NR, false>(L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64, r, K + 1, idx, ynext);
       }
-      CTA_SYNC();
     }
-    if (R.flags & 2) {
-      for (int s = cx.warp; s < P.nseg; s += cx.nwarps) {
-        const int E = P.seg_start[s] + P.seg_len[s] - 1;
-        pivot_inplace<NR, true>(cx, L + M.boff[E] + (E - M.fb[E]) * 64, r, E);
-      }
-      CTA_SYNC();
-    }
-    if (!(dbg & 1))
-      for (int s = cx.warp; s < R.ne; s += cx.nwarps) {
-        const int I = SEG_PICK(R.k, s), look = SEG_PICK(R.look, s);
-        const double* Linv = L + SEG_PICK(R.poff, s);
-        if (look >= 0)
-          pivot_fused_bwd<NR>(cx, Linv, L + look, r, I);
-        else if (look == -1)
-          pivot_inplace<NR, true>(cx, Linv, r, I - 1);
-      }
-    {
-      const int npw = (R.ne < cx.nwarps ? R.ne : cx.nwarps) * cx.warpsize;
-      const int wid = cx.tid >= npw ? cx.tid - npw : cx.tid + cx.nthreads - npw;
-      const int ntask = (dbg & 2) ? 0 : R.npriv * NR;
-      for (int task = wid; task < ntask; task += cx.nthreads) {
-        const int s = (task >= R.toff[1] * NR) + (task >= R.toff[2] * NR) + (task >= R.toff[3] * NR);
-        const int loc = task - SEG_PICK(R.toff, s) * NR;
-        const int I = SEG_PICK(R.k, s), f = SEG_PICK(R.b, s);
-        const int nkk = (I - f - (SEG_PICK(R.look, s) >= 0 ? 1 : 0)) * 4;
-        const int q = (NR > 1 && loc >= nkk) ? 1 : 0, rem = loc - q * nkk;
-        const int Kc = f + (rem >> 2);
-        bwd_chunk_update<NR>(L + SEG_PICK(R.c, s) + (Kc - f) * 64, r, q, I, Kc, rem & 3);
+    if (cx.nwarps == 1 || cx.warp > 0) {
+      const int nrest = na - lead;
+      for (int idx = o_tid; idx < nrest * KB * NR; idx += o_n) {
+        const int q = idx / (nrest * KB), rem = idx - q * (nrest * KB);
+        const int I = M.act_blk[a0 + lead + (rem >> 3)], rr = rem & 7;
+        double row[KB], yk[KB];
+        load_row(L + M.boff[I] + (K - M.fb[I]) * 64, rr, row);
+        load_vec8(ycur + q * KB, yk);
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < KB; ++k) sacc = fma(row[k], yk[k], sacc);
+        rhs_sel<NR>(r, q)[I * KB + rr] -= sacc;
       }
     }
     CTA_SYNC();
   }
+  // ---- backward: L^T z = y -----------------------------------------------------------------------
+  if (cx.warp == 0) {
+    LANE_FOR(idx, 0, NR * KB)
+    pivot_apply<NR, true>(L + M.boff[mb - 1] + (mb - 1 - M.fb[mb - 1]) * 64, r, mb - 1, idx, ybuf + ((mb - 1) & 1) * NR * KB);
+  }
+  CTA_SYNC();
+  for (int I = mb - 1; I >= 0; --I) {
+    const int f = M.fb[I];
+    const double* zcur = ybuf + (I & 1) * NR * KB;
+    double* znext = ybuf + ((I + 1) & 1) * NR * KB;  // buffer of parity (I-1)&1
+    const int lead = (I > 0 && f <= I - 1) ? 1 : 0;  // block (I, I-1) exists: row block I-1 is updated by this step
+    if (cx.warp == 0) {
+      LANE_FOR(idx, 0, NR * KB) rhs_sel<NR>(r, idx >> 3)[I * KB + (idx & 7)] = zcur[idx];  // z_I is final
+      if (lead) {
+        LANE_FOR(idx, 0, NR * 4) {  // the four 16-byte chunks (two columns each) of block (I, I-1)
+          const int q = idx >> 2, c = idx & 3;
+          const double* blk = L + M.boff[I] + (I - 1 - f) * 64;
+          double zi[KB];
+          load_vec8(zcur + q * KB, zi);
+          double sx = 0.0, sy = 0.0;
+#pragma unroll
+          for (int i = 0; i < KB; ++i) {
+            const D2 t2 = reinterpret_cast<const D2*>(blk + i * KB)[c ^ bswz(i)];
+            sx = fma(t2.x, zi[i], sx);
+            sy = fma(t2.y, zi[i], sy);
+          }
+          D2* dst = reinterpret_cast<D2*>(rhs_sel<NR>(r, q) + (I - 1) * KB) + c;
+          D2 t2 = *dst;
+          t2.x -= sx;
+          t2.y -= sy;
+          *dst = t2;
+        }
+      }
+      WARP_SYNC();
+      if (I > 0) {
+        LANE_FOR(idx, 0, NR * KB)
+        pivot_apply<NR, true>(L + M.boff[I - 1] + (I - 1 - M.fb[I - 1]) * 64, r, I - 1, idx, znext);
+      }
+    }
+    if (cx.nwarps == 1 || cx.warp > 0) {
+      const int nk = I - f - lead;  // block columns f .. I-1-lead
+      for (int idx = o_tid; idx < nk * 4 * NR; idx += o_n) {
+        const int q = idx / (nk * 4), rem = idx - q * (nk * 4);
+        const int Kc = f + (rem >> 2), c = rem & 3;
+        const double* blk = L + M.boff[I] + (Kc - f) * 64;
+        double zi[KB];
+        load_vec8(zcur + q * KB, zi);
+        double sx = 0.0, sy = 0.0;
+#pragma unroll
+        for (int i = 0; i < KB; ++i) {
+          const D2 t2 = reinterpret_cast<const D2*>(blk + i * KB)[c ^ bswz(i)];
+          sx = fma(t2.x, zi[i], sx);
+          sy = fma(t2.y, zi[i], sy);
+        }
+        D2* dst = reinterpret_cast<D2*>(rhs_sel<NR>(r, q) + Kc * KB) + c;
+        D2 t2 = *dst;
+        t2.x -= sx;
+        t2.y -= sy;
+        *dst = t2;
+      }
+    }
+    CTA_SYNC();
+  }
+}
+
+IO_FORCEINLINE double run_total(const double* gp, int len) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int j = 0;
+  for (; j + 4 <= len; j += 4) {
+    const double a0 = gp[j], a1 = gp[j + 1], a2 = gp[j + 2], a3 = gp[j + 3];
+    s0 += a0;
+    s1 += a1;
+    s2 += a2;
+    s3 += a3;
+  }
+  for (; j < len; ++j) s0 += gp[j];
+  return (s0 + s1) + (s2 + s3);
 }
 
 // sum of a run of at most 16 consecutive entries (the row kernel's pieces, RS_MAXLEN): fully predicated, no loop
@@ -1424,50 +1028,41 @@ IO_DEV Meta global_meta(const ProblemDev& P) {
   M.boff = P.g_boff;
   M.act_ptr = P.g_act_ptr;
   M.act_blk = P.g_act_blk;
-  M.act_off = P.g_act_off;
   M.csr_ptr = P.g_csr_ptr;
   M.csc_gptr = P.g_csc_gptr;
   M.asm_gptr = P.g_asm_gptr;
   M.asm_rptr = P.g_asm_rptr;
-  M.act_ns = P.g_act_ns;
-  M.seg_bord = P.g_seg_bord;
-  M.st_fwd = P.g_st_fwd;
-  M.st_bwd = P.g_st_bwd;
   return M;
 }
 
 // Copies the schedule arrays into shared memory (`dst` holds P.meta_ints ints) and returns pointers to the copies.
 IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
-  constexpr int NA = 13;
-  // (the 16-byte aligned tables come first: st_fwd / st_bwd are read with 128-bit loads)
-  // arrays of code paths this problem never takes stay in global memory (count 0): the row pointers when the
-  // run-length row kernel applies, the per-term / run-length group pointers of the assembly form not in use
-  const int cnt[NA] = {KREC * P.nsteps, KREC * P.nsteps, P.mb, P.mb + 1, P.mb + 1, P.n_act, P.rs_hdr ? 0 : P.m + 1,
-                       ((P.n + 31) >> 5) + 1, P.asm_run ? 0 : (P.n_asm >> 5) + 1, P.asm_run ? (P.n_asm >> 5) + 1 : 0,
-                       P.mb, P.nbord, P.n_act};
-  const int* src[NA] = {P.g_st_fwd, P.g_st_bwd, P.g_fb, P.g_boff, P.g_act_ptr, P.g_act_blk, P.g_csr_ptr, P.g_csc_gptr,
-                        P.g_asm_gptr, P.g_asm_rptr, P.g_act_ns, P.g_seg_bord, P.g_act_off};
-  const int* ptr[NA];
+  const int cnt[8] = {P.mb, P.mb + 1, P.mb + 1, P.n_act, P.m + 1, ((P.n + 31) >> 5) + 1, (P.n_asm >> 5) + 1,
+                      (P.n_asm >> 5) + 1};
+  const int* src[8] = {P.g_fb, P.g_boff, P.g_act_ptr, P.g_act_blk, P.g_csr_ptr, P.g_csc_gptr, P.g_asm_gptr,
+                       P.g_asm_rptr};
   int* d = dst;
-  for (int a = 0; a < NA; ++a) {
+  for (int a = 0; a < 8; ++a) {
     CTA_FOR(i, cnt[a]) d[i] = src[a][i];
-    ptr[a] = cnt[a] ? d : src[a];
     d += cnt[a];
   }
   Meta M;
-  M.st_fwd = ptr[0];
-  M.st_bwd = ptr[1];
-  M.fb = ptr[2];
-  M.boff = ptr[3];
-  M.act_ptr = ptr[4];
-  M.act_blk = ptr[5];
-  M.csr_ptr = ptr[6];
-  M.csc_gptr = ptr[7];
-  M.asm_gptr = ptr[8];
-  M.asm_rptr = ptr[9];
-  M.act_ns = ptr[10];
-  M.seg_bord = ptr[11];
-  M.act_off = ptr[12];
+  d = dst;
+  M.fb = d;
+  d += cnt[0];
+  M.boff = d;
+  d += cnt[1];
+  M.act_ptr = d;
+  d += cnt[2];
+  M.act_blk = d;
+  d += cnt[3];
+  M.csr_ptr = d;
+  d += cnt[4];
+  M.csc_gptr = d;
+  d += cnt[5];
+  M.asm_gptr = d;
+  d += cnt[6];
+  M.asm_rptr = d;
   CTA_SYNC();
   return M;
 }
@@ -1476,11 +1071,10 @@ IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
 enum { W_X = 0, W_T, W_D, W_R2, W_P, W_W, W_DX, W_DXDT, W_NVEC };
 // shared-memory m-vector slots
 enum { S_B = 0, S_Y, S_R1, S_Q, S_V, S_NVEC };
-constexpr int S_SCRATCH = KSEG * (KB + KB * KB) + 8 * 32 + 4;  // diag scratch (one per concurrent segment) + red + flag + mbarrier
+constexpr int S_SCRATCH = 4 * KB + (KB + KB * KB) + 8 * 32 + 4;  // ybuf (double buffered, 2 rhs) + diag scratch + red + flag + mbarrier
 
 struct SmemLayout {
   double *L, *G, *bs, *y, *r1, *q, *v, *ybuf, *dscr, *red;  // G: gather region of 2*gather_len(n) doubles
-  double* W;  // fused look-ahead blocks of the forward substitution: n_wblk x 64 doubles (upper half of G if they fit)
   D2* scan;  // scratch of the double-double prefix scan: scan_len(n) D2
   int* flag;
   unsigned long long* mbar;  // mbarrier of the cold-start factor prefetch (bulk async copy)
@@ -1490,8 +1084,6 @@ struct SmemLayout {
 IO_HD int gather_len(int n) { return (gpad(n) + 3) & ~1; }
 IO_HD int scan_len(int n) { return ((n + 7) >> 3) + 40; }  // D2 entries of prefix-scan scratch
 IO_HD bool scan_in_factor(int bsize, int n) { return bsize >= 2 * scan_len(n); }
-// the W blocks live in the upper half of the gather region (only the assembly's prefix sums use it) when they fit
-IO_HD bool w_in_gather(int n_wblk, int n) { return n_wblk * 64 <= gather_len(n); }
 
 // Carve shared memory (and, for spilled pieces, the tail of the per-CTA workspace).  ALLSMEM = factor and
 // gather buffers both live in shared memory: every pointer is then derived unconditionally from the shared
@@ -1521,16 +1113,15 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
       ws_tail += 2 * gather_len(P.n);
     }
   }
-  s.W = w_in_gather(P.n_wblk, P.n) ? s.G + gather_len(P.n) : ws_tail;
   s.bs = p + S_B * P.mv;
   s.y = p + S_Y * P.mv;
   s.r1 = p + S_R1 * P.mv;
   s.q = p + S_Q * P.mv;
   s.v = p + S_V * P.mv;
   p += S_NVEC * P.mv;
-  s.dscr = p;
-  s.ybuf = p;  // (unused: the substitutions work in place)
-  s.red = s.dscr + KSEG * (KB + KB * KB);
+  s.ybuf = p;
+  s.dscr = p + 4 * KB;
+  s.red = s.dscr + KB + KB * KB;
   s.flag = (int*)(s.red + 8 * 32);
   s.mbar = reinterpret_cast<unsigned long long*>(s.red + 8 * 32 + 2);
   // the prefix-scan scratch aliases the factor storage when it fits (the scan runs before the factor is zero-filled)
@@ -1578,55 +1169,41 @@ IO_FORCEINLINE void mbar_wait(unsigned long long* mbar, unsigned parity) {
 }
 #endif
 
-// Begin copying the precomputed factor `src` (P.bsize doubles followed by the P.n_wblk*64 doubles of the W blocks,
-// 16-byte aligned) into L and W.  Call after a CTA barrier that ends every earlier use of L and W.
-IO_FORCEINLINE void bulk_copy_g2s(double* dst, const double* src, uint32_t bytes, unsigned long long* mbar) {
+// Begin copying the precomputed factor `src` (P.bsize doubles, 16-byte aligned) into L.  Call after a CTA
+// barrier that ends every earlier use of L.
+IO_DEV void cold_copy_begin(const CtaCtx& cx, const ProblemDev& P, const double* src, double* L, unsigned long long* mbar,
+                            bool l_in_smem) {
+#ifdef INTOPT_HOST_EMU
+  (void)cx; (void)P; (void)src; (void)L; (void)mbar; (void)l_in_smem;
+#else
+  if (l_in_smem && cx.tid == 0) {
+    const uint32_t bytes = (uint32_t)P.bsize * 8u, bar = smem_addr_u32(mbar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to L vs the async writes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    for (uint32_t off = 0; off < bytes; off += 32768u) {
+      const uint32_t len = bytes - off < 32768u ? bytes - off : 32768u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_addr_u32(L) + off),
+                   "l"((const char*)src + off), "r"(len), "r"(bar)
+                   : "memory");
+    }
+  }
+#endif
+}
+// Complete the copy: on return every thread may read L.
+IO_DEV void cold_copy_finish(const CtaCtx& cx, const ProblemDev& P, const double* src, double* L, unsigned long long* mbar,
+                             bool l_in_smem, unsigned parity) {
 #ifndef INTOPT_HOST_EMU
-  const uint32_t bar = smem_addr_u32(mbar);
-  for (uint32_t off = 0; off < bytes; off += 32768u) {
-    const uint32_t len = bytes - off < 32768u ? bytes - off : 32768u;
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_addr_u32(dst) + off),
-                 "l"((const char*)src + off), "r"(len), "r"(bar)
-                 : "memory");
+  if (l_in_smem) {
+    mbar_wait(mbar, parity);
+    return;
   }
 #else
-  (void)dst; (void)src; (void)bytes; (void)mbar;
-#endif
-}
-IO_DEV void cold_copy_begin(const CtaCtx& cx, const ProblemDev& P, const double* src, double* L, double* W,
-                            unsigned long long* mbar, bool l_in_smem, bool w_in_smem) {
-#ifdef INTOPT_HOST_EMU
-  (void)cx; (void)P; (void)src; (void)L; (void)W; (void)mbar; (void)l_in_smem; (void)w_in_smem;
-#else
-  if ((l_in_smem || w_in_smem) && cx.tid == 0) {
-    const uint32_t lb = l_in_smem ? (uint32_t)P.bsize * 8u : 0u, wb = w_in_smem ? (uint32_t)P.n_wblk * 512u : 0u;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses vs the async writes
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(mbar)), "r"(lb + wb) : "memory");
-    if (lb) bulk_copy_g2s(L, src, lb, mbar);
-    if (wb) bulk_copy_g2s(W, src + P.bsize, wb, mbar);
-  }
-#endif
-}
-// Complete the copy: on return every thread may read L and W.
-IO_DEV void cold_copy_finish(const CtaCtx& cx, const ProblemDev& P, const double* src, double* L, double* W,
-                             unsigned long long* mbar, bool l_in_smem, bool w_in_smem, unsigned parity) {
-#ifdef INTOPT_HOST_EMU
-  (void)mbar; (void)parity;
-  l_in_smem = w_in_smem = false;
+  (void)mbar; (void)l_in_smem; (void)parity;
 #endif
   const D2* __restrict__ s2 = reinterpret_cast<const D2*>(src);
-  if (!l_in_smem) {
-    D2* d2 = reinterpret_cast<D2*>(L);
-    CTA_FOR(e, P.bsize >> 1) d2[e] = s2[e];  // bsize is a multiple of 64
-  }
-  if (!w_in_smem) {
-    D2* d2 = reinterpret_cast<D2*>(W);
-    CTA_FOR(e, P.n_wblk * 32) d2[e] = s2[(P.bsize >> 1) + e];
-  }
-#ifndef INTOPT_HOST_EMU
-  if (l_in_smem || w_in_smem) mbar_wait(mbar, parity);
-#endif
+  D2* d2 = reinterpret_cast<D2*>(L);
+  CTA_FOR(e, P.bsize >> 1) d2[e] = s2[e];  // bsize is a multiple of 64
   CTA_SYNC();
 }
 
@@ -1673,8 +1250,8 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
 
   PhaseTimer pt{a.phase_cycles, 0};
   PHASE_START(pt);
-  const bool l_in_smem = a.factor_in_smem != 0, w_in_smem = a.gather_in_smem != 0 && w_in_gather(P.n_wblk, P.n);
-  if (cold) cold_copy_begin(cx, P, a.cold_factor, L, S.W, S.mbar, l_in_smem, w_in_smem);
+  const bool l_in_smem = a.factor_in_smem != 0;
+  if (cold) cold_copy_begin(cx, P, a.cold_factor, L, S.mbar, l_in_smem);
   // ---- load b, initial point (_initialization :647-661); padded slots of m-vectors are zero ---------
   CTA_FOR(i, mv) {
     double bv = 0.0;
@@ -1721,17 +1298,20 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
       if (!(fabs(ck) < 1e300)) acc[2] += 1.0;
     }
     double accp = 0.0;  // ||b - A 1||
-    WARP_ROWS(i, m) {
-      double s = 0.0;
-      if (P.a_unit) {
-        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s += 1.0;
-      } else {
-        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s += P.csr_val[e];
-      }
-      s = warp_sum(s);
-      if (cx.lane == 0) {
-        const double e = bs[i] - s;
+    if (P.a_unit) {  // row sum of a 0/1 matrix = its entry count (exactly what summing the ones gives)
+      CTA_FOR(i, m) {
+        const double e = bs[i] - (double)(M.csr_ptr[i + 1] - M.csr_ptr[i]);
         accp = fma(e, e, accp);
+      }
+    } else {
+      WARP_ROWS(i, m) {
+        double s = 0.0;
+        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s += P.csr_val[e];
+        s = warp_sum(s);
+        if (cx.lane == 0) {
+          const double e = bs[i] - s;
+          accp = fma(e, e, accp);
+        }
       }
     }
     double red[4] = {acc[0], acc[1], acc[2], accp};
@@ -1746,7 +1326,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
   bool solved = true;
   if (nonfinite) status = ST_NONFINITE;  // the reference raises LinAlgError here (:1332-1341)
 
-  if (cold) cold_copy_finish(cx, P, a.cold_factor, L, S.W, S.mbar, l_in_smem, w_in_smem, cold_parity);
+  if (cold) cold_copy_finish(cx, P, a.cold_factor, L, S.mbar, l_in_smem, cold_parity);
   PHASE_MARK(pt, 0);
   while (status != ST_NONFINITE) {
     // ---- residuals at the current iterate (:765-770; the same r_p, r_d as _indicators :887-894) ----
@@ -1830,7 +1410,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
       solved = true;
       CTA_SYNC();
     } else {
-      solved = block_cholesky(cx, P, M, L, S.W, S.dscr, S.flag, &pt);  // (its barriers order the G writes)
+      solved = block_cholesky(cx, P, M, L, S.dscr, S.flag, &pt);  // (its barriers order the G writes)
     }
     PHASE_MARK(pt, 3);
     if (!solved) {  // deltas = 0 (:855-857): the iterate is unchanged, the tests run at loop top
@@ -1868,7 +1448,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     PHASE_MARK(pt, 4);
     {
       double* const rhs2[2] = {q, v};
-      block_solve<2>(cx, P, M, L, S.W, rhs2);
+      block_solve<2>(cx, P, M, L, rhs2, S.ybuf);
     }
     PHASE_MARK(pt, 5);
     double cp_, bq_, cu_, bv_;
@@ -1947,7 +1527,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
         PHASE_MARK(pt, 7);
         {
           double* const rhs1[1] = {v};
-          block_solve<1>(cx, P, M, L, S.W, rhs1);
+          block_solve<1>(cx, P, M, L, rhs1, S.ybuf);
         }
         PHASE_MARK(pt, 8);
         double acc3[2] = {0.0, 0.0};
@@ -2072,9 +1652,8 @@ IO_DEV void cold_factor_build(const CtaCtx& cx, const ProblemDev& P, const Meta&
   if (cx.tid == 0) S.G[gpad(n)] = 0.0;
   CTA_SYNC();
   assemble_normal_matrix(cx, P, M, D, S.G, S.scan, delta, S.L);
-  const bool ok = block_cholesky(cx, P, M, S.L, S.W, S.dscr, S.flag);
+  const bool ok = block_cholesky(cx, P, M, S.L, S.dscr, S.flag);
   CTA_FOR(e, P.bsize) out[e] = S.L[e];
-  CTA_FOR(e, P.n_wblk * 64) out[P.bsize + e] = S.W[e];
   if (cx.tid == 0) *ok_out = ok ? 1 : 0;
   CTA_SYNC();
 }
@@ -2142,7 +1721,7 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   CTA_SYNC();
   assemble_normal_matrix(cx, P, M, x2, G, S.scan, a.damping, L);  // :1525-1527,1535
   CTA_FOR(k, n) gstore(G, k, (k < nvar) ? x2[k] * g[k] : 0.0);
-  const bool ok = block_cholesky(cx, P, M, L, S.W, S.dscr, S.flag);
+  const bool ok = block_cholesky(cx, P, M, L, S.dscr, S.flag);
   if (!ok) {
     // the reference raises LinAlgError (:1546-1547); here: zero gradient + status
     CTA_FOR(k, nvar) gc[k] = 0.0;
@@ -2154,7 +1733,7 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   CTA_SYNC();
   if (!whole) {
     double* const rhs1[1] = {v};
-    block_solve<1>(cx, P, M, L, S.W, rhs1);
+    block_solve<1>(cx, P, M, L, rhs1, S.ybuf);
     at_mult<1>(cx, P, M, v, nullptr, G, nullptr);
     CTA_SYNC();
     CTA_FOR(k, nvar) gc[k] = -x2[k] * (g[k] - G[k]) / mu;
@@ -2171,7 +1750,7 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   CTA_SYNC();
   {
     double* const rhs2[2] = {q, v};
-    block_solve<2>(cx, P, M, L, S.W, rhs2);
+    block_solve<2>(cx, P, M, L, rhs2, S.ybuf);
   }
   double* ug = wsi + (long long)W_DX * n;
   double* pp = wsi + (long long)W_P * n;

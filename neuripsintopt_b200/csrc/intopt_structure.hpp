@@ -23,8 +23,6 @@ constexpr int NB = 8;           // block edge of the block-skyline factor
 constexpr int NBB = NB * NB;    // doubles per block
 // index of element k in the solver's padded gather buffer; MUST match intopt::gpad() of intopt_solver.cuh
 inline int gpad_host(int k) { return k + (k >> 5); }
-constexpr int MAXSEG = 4;        // independent leading segments factored concurrently (== intopt::MAXSEG)
-constexpr int ST_REC = 12 + 4 * MAXSEG;  // ints per step record of the substitution schedule
 constexpr int RS_MAXLEN = 15;   // longest run piece of the run-length row kernel (<= 16, odd)
 
 struct HostStructure {
@@ -56,34 +54,8 @@ struct HostStructure {
   std::vector<int> dummy_pos;  // diagonal positions of the padding rows m..m8-1 (set to 1)
   // factorisation schedule
   std::vector<int> act_ptr, act_blk;               // block rows I > K with fb[I] <= K
-  std::vector<int> act_off;                        // offset of block (I,K) in the factor, parallel to act_blk
   std::vector<int> pair_ptr, pair_dst, pair_a, pair_b;  // trailing updates of step K: dst -= a * b^T
   std::vector<unsigned char> next_diag_first;      // pair_ptr[K] is the update of block (K+1,K+1)
-  // Independent leading segments: block columns [seg_start[s], seg_start[s]+seg_len[s]) of different segments do
-  // not touch each other (block-diagonal leading part, e.g. one band per machine in the Energy LP), so step t of
-  // every segment is factored / substituted concurrently; block rows >= seg_end (the "tail": border rows coupling
-  // the segments plus whatever follows) are processed one column at a time afterwards.  nseg == 0: no segments.
-  int nseg = 0, seg_end = 0, seg_tmax = 0;
-  int seg_start[MAXSEG] = {0, 0, 0, 0}, seg_len[MAXSEG] = {0, 0, 0, 0};
-  std::vector<int> act_ns;    // per block column K: how many of its active block rows lie before seg_end
-  std::vector<int> seg_bord;  // tail block rows that reach into the segments (fb < seg_end), ascending
-  // Substitution schedule (block_solve).  Step i handles one block column of every running segment, or one tail
-  // column.  st_fwd / st_bwd hold one fixed-size record of ST_REC ints per step (all fields of a step are fetched
-  // with independent 16-byte loads):
-  //   [0] entries  [1] flags  [2] private tasks (rhs count 1)  [3] shared tail rows   [4..7] task offset of entry s
-  //   [8..11] offset of the next pivot's diagonal block (forward: K+1, backward: I-1) of entry s
-  //   then MAXSEG entries of 4 ints:
-  //     forward  {K, first private non-lead row (index into act_blk/act_off), private non-lead rows, look}
-  //     backward {I, fb[I], boff[I], look}
-  // look >= 0: the next pivot block of the chain is produced by the fused look-ahead, forward with the block
-  // W = Linv_(K+1) L_(K+1,K) kept in slot `look` of the W buffer, backward with V = L_(I,I-1) Linv_(I-1) stored in
-  // place of L_(I,I-1) at offset `look` of the factor; -1: pivot only (no coupling block); -2: nothing.
-  // forward flags bit 0: the step's own pivots are computed at its start (chain heads), bit 1: the tail rows that
-  // reach into the segments take part; backward flags bit 0: pivot of the last block first, bit 1: pivots of every
-  // segment's last block first.  Unused entries have K = -1.
-  int nsteps = 0, n_wblk = 0;
-  std::vector<int> st_fwd, st_bwd;
-  std::vector<int> wblk_col;  // column K of the coupling block (K+1,K) that owns W slot w
   // assembly gather lists, entries sorted by length (descending), 32 entries per group, interleaved like csc
   int n_asm = 0;  // padded to a multiple of 32
   std::vector<int> asm_gptr, asm_glen, asm_pos;  // asm_pos < 0: padding entry
@@ -216,8 +188,7 @@ inline std::vector<int> dense_rows_last(const std::vector<std::vector<int>>& adj
 
 }  // namespace detail
 
-// Returns 0 on success, negative on malformed input.  `force_order`: -1 = smallest block envelope, 0..2 = that
-// candidate ordering, -2 = like -1 but without the concurrent-segment schedule (tests / A-B comparisons).
+// Returns 0 on success, negative on malformed input.  `force_order`: -1 = smallest block envelope.
 inline int analyze(int m, int n, const int* rp, const int* ci, const double* val, HostStructure& S,
                    int force_order = -1) {
   if (m <= 0 || n <= 0 || !rp || !ci || !val) return -1;
@@ -412,10 +383,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
     std::vector<int> act;
     for (int I = K + 1; I < mb; ++I)
       if (S.fb[I] <= K) act.push_back(I);
-    for (int I : act) {
-      S.act_blk.push_back(I);
-      S.act_off.push_back(S.boff[I] + (K - S.fb[I]) * NBB);
-    }
+    for (int I : act) S.act_blk.push_back(I);
     S.act_ptr[K + 1] = (int)S.act_blk.size();
     // pairs (I >= J), the update of the next diagonal block first (look-ahead)
     std::vector<std::pair<int, int>> pairs;
@@ -437,123 +405,6 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
     S.pair_ptr[K + 1] = (int)S.pair_dst.size();
     S.chol_macs += (long long)pairs.size() * NB * NB * NB + (long long)act.size() * NB * 36 + 120 + 120;
     S.solve_macs += 2 * ((long long)act.size() * NBB + 36);
-  }
-
-  // ---- independent leading segments ------------------------------------------------------------------------
-  {
-    std::vector<std::pair<int, int>> segs;
-    int cur = 0, tail = mb;
-    for (int I = 0; I < mb; ++I) {
-      if (S.fb[I] < cur) {  // couples back into an earlier segment: the tail starts here
-        tail = I;
-        break;
-      }
-      if (S.fb[I] == I && I > cur) {  // decoupled from everything before it: a new segment head
-        segs.push_back({cur, I - cur});
-        cur = I;
-      }
-    }
-    if (tail > cur) segs.push_back({cur, tail - cur});
-    if ((int)segs.size() > MAXSEG) {
-      tail = segs[MAXSEG].first;
-      segs.resize(MAXSEG);
-    }
-    S.nseg = 0;
-    S.seg_end = 0;
-    S.seg_tmax = 0;
-    if (segs.size() >= 2 && force_order != -2) {
-      S.nseg = (int)segs.size();
-      S.seg_end = tail;
-      for (int sgi = 0; sgi < S.nseg; ++sgi) {
-        S.seg_start[sgi] = segs[sgi].first;
-        S.seg_len[sgi] = segs[sgi].second;
-        S.seg_tmax = std::max(S.seg_tmax, segs[sgi].second);
-      }
-      for (int I = tail; I < mb; ++I)
-        if (S.fb[I] < tail) S.seg_bord.push_back(I);
-    }
-    S.act_ns.assign(mb, 0);
-    for (int K = 0; K < mb; ++K)
-      for (int e = S.act_ptr[K]; e < S.act_ptr[K + 1]; ++e)
-        if (S.act_blk[e] < S.seg_end) S.act_ns[K]++;
-  }
-
-  // ---- substitution schedule --------------------------------------------------------------------------------
-  {
-    S.n_wblk = 0;
-    const int K0 = S.nseg > 1 ? S.seg_end : 0;
-    struct Ent {
-      int K, a0, nrow, look, next_off, f, boffI, lookb, prev_off, nk;
-    };
-    auto diag_off = [&](int K) { return S.boff[K] + (K - S.fb[K]) * NBB; };
-    auto make_entry = [&](int K, bool in_seg, bool first_of_chain, bool last_of_chain) {
-      Ent e{};
-      const int a0 = S.act_ptr[K], na = S.act_ptr[K + 1] - a0;
-      const bool coupled = na > 0 && S.act_blk[a0] == K + 1;  // block (K+1,K) is inside the envelope
-      const int lead = (!last_of_chain && coupled) ? 1 : 0;
-      e.K = K;
-      e.a0 = a0 + lead;
-      e.nrow = (in_seg ? S.act_ns[K] : na) - lead;
-      e.look = -2;
-      if (!last_of_chain) e.look = coupled ? S.n_wblk++ : -1;
-      if (e.look >= 0) S.wblk_col.push_back(K);
-      e.next_off = last_of_chain ? 0 : diag_off(K + 1);
-      // backward view of the same column (as the row I = K): the chain predecessor is K-1
-      e.f = S.fb[K];
-      e.boffI = S.boff[K];
-      e.lookb = -2;
-      int fused_b = 0;
-      if (!first_of_chain) {
-        if (e.f <= K - 1) {
-          e.lookb = S.boff[K] + (K - 1 - e.f) * NBB;
-          fused_b = 1;
-        } else {
-          e.lookb = -1;
-        }
-      }
-      e.prev_off = first_of_chain ? 0 : diag_off(K - 1);
-      e.nk = K - e.f - fused_b;
-      return e;
-    };
-    auto push_step = [&](const std::vector<Ent>& es, int fflags, int bflags) {
-      std::vector<int> fr(ST_REC, 0), br(ST_REC, 0);
-      fr[0] = br[0] = (int)es.size();
-      fr[1] = fflags;
-      br[1] = bflags;
-      int ft = 0, bt = 0;
-      for (int sgi = 0; sgi < MAXSEG; ++sgi) {
-        fr[4 + sgi] = ft;
-        br[4 + sgi] = bt;
-        int* fe = fr.data() + 12 + 4 * sgi;
-        int* be = br.data() + 12 + 4 * sgi;
-        if (sgi < (int)es.size()) {
-          const Ent& e = es[sgi];
-          fe[0] = e.K, fe[1] = e.a0, fe[2] = e.nrow, fe[3] = e.look, fr[8 + sgi] = e.next_off;
-          be[0] = e.K, be[1] = e.f, be[2] = e.boffI, be[3] = e.lookb, br[8 + sgi] = e.prev_off;
-          ft += e.nrow * NB;
-          bt += e.nk * 4;
-        } else {
-          fe[0] = be[0] = -1;
-          fe[3] = be[3] = -2;
-        }
-      }
-      fr[2] = ft;
-      br[2] = bt;
-      fr[3] = (fflags & 2) ? (int)S.seg_bord.size() : 0;
-      S.st_fwd.insert(S.st_fwd.end(), fr.begin(), fr.end());
-      S.st_bwd.insert(S.st_bwd.end(), br.begin(), br.end());
-    };
-    const bool has_tail = K0 < mb;
-    if (S.nseg > 1)
-      for (int t = 0; t < S.seg_tmax; ++t) {
-        std::vector<Ent> es;
-        for (int sgi = 0; sgi < S.nseg; ++sgi)
-          if (t < S.seg_len[sgi]) es.push_back(make_entry(S.seg_start[sgi] + t, true, t == 0, t == S.seg_len[sgi] - 1));
-        push_step(es, (t == 0 ? 1 : 0) | (S.seg_bord.empty() ? 0 : 2), t == S.seg_tmax - 1 ? 2 : 0);
-      }
-    for (int K = K0; K < mb; ++K) push_step({make_entry(K, false, K == K0, K == mb - 1)}, K == K0 ? 1 : 0, K == mb - 1 ? 1 : 0);
-    (void)has_tail;
-    S.nsteps = (int)S.st_fwd.size() / ST_REC;
   }
 
   // ---- assembly gather lists -------------------------------------------------------------------------------

@@ -26,8 +26,8 @@ extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const doubl
   intopt::bind_problem(S, P, [](const auto& v) { return v.data(); });
   std::vector<double> smem((size_t)S.bsize + 2 * intopt::gather_len(n) + intopt::smem_fixed_doubles(S) +
                            (intopt::meta_ints(S) + 1) / 2);
-  std::vector<double> ws((size_t)intopt::W_NVEC * n + (size_t)S.n_wblk * 64);
-  const intopt::SmemLayout L = intopt::carve<true>(P, smem.data(), ws.data() + (size_t)intopt::W_NVEC * n, 1, 1);
+  std::vector<double> ws((size_t)intopt::W_NVEC * n);
+  const intopt::SmemLayout L = intopt::carve<true>(P, smem.data(), nullptr, 1, 1);
   CtaCtx cx;
   cx.red = L.red;
   const intopt::Meta M = intopt::stage_meta(cx, P, L.meta);
@@ -38,7 +38,7 @@ extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const doubl
   a.factor_in_smem = 1; a.gather_in_smem = 1;
   a.alpha0 = alpha0; a.tol = tol; a.thr = thr; a.damping = damping_fwd; a.max_iter = max_iter;
   // cold-start factor (as the CUDA host code does): built once with the instance code path, copied in at iteration 1
-  std::vector<double> cold((size_t)S.bsize + (size_t)S.n_wblk * 64);
+  std::vector<double> cold((size_t)S.bsize);
   int cold_ok = 0;
   if (!init) {
     intopt::cold_factor_build(cx, P, M, damping_fwd, ws.data(), L, cold.data(), &cold_ok);
