@@ -859,7 +859,11 @@ IO_FORCEINLINE double run_total16(const double* gp, int len) {
   return (s0 + s1) + (s2 + s3);
 }
 
-IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* src, double* out) {
+// out = A src (NV = 1), or out = A src and out2 = A src2 in one pass over A (NV = 2: the index / header stream,
+// the address arithmetic and the scan bookkeeping are shared by the two products).
+template <int NV>
+IO_DEV void spmv_rows_n(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* src, const double* src2,
+                        double* out, double* out2) {
   if (P.rs_hdr) {
     // unit-weight A in run-length form: every lane sums one run of consecutive src entries, rows are whole
     // lane ranges of a slot and are combined by a segmented shuffle scan (fixed order => deterministic)
@@ -869,9 +873,13 @@ IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, cons
         const uint32_t h = P.rs_hdr[slot * 32 + l];
         const int row = P.rs_row[slot * 32 + l];
         if (row == 0xffff) continue;
-        const double s = run_total16(src + (h & 0xffffu), (int)(h >> 16));
         const bool first = l == 0 || P.rs_row[slot * 32 + l - 1] != row;
+        const double s = run_total16(src + (h & 0xffffu), (int)(h >> 16));
         out[row] = first ? s : out[row] + s;
+        if (NV == 2) {
+          const double s2 = run_total16(src2 + (h & 0xffffu), (int)(h >> 16));
+          out2[row] = first ? s2 : out2[row] + s2;
+        }
       }
 #else
     int slot = cx.warp;
@@ -890,14 +898,24 @@ IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, cons
         rown = P.rs_row[nxt * 32 + cx.lane];
       }
       double s = run_total16(src + (h & 0xffffu), (int)(h >> 16));
+      double s2 = 0.0;
+      if (NV == 2) s2 = run_total16(src2 + (h & 0xffffu), (int)(h >> 16));
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const double v = __shfl_up_sync(0xffffffffu, s, off);
         const int r = __shfl_up_sync(0xffffffffu, row, off);
-        if (cx.lane >= off && r == row) s += v;
+        const bool take = cx.lane >= off && r == row;
+        if (take) s += v;
+        if (NV == 2) {
+          const double v2 = __shfl_up_sync(0xffffffffu, s2, off);
+          if (take) s2 += v2;
+        }
       }
       const int rnext = __shfl_down_sync(0xffffffffu, row, 1);
-      if (row != 0xffff && (cx.lane == 31 || rnext != row)) out[row] = s;
+      if (row != 0xffff && (cx.lane == 31 || rnext != row)) {
+        out[row] = s;
+        if (NV == 2) out2[row] = s2;
+      }
     }
 #endif
     return;
@@ -905,7 +923,7 @@ IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, cons
   const int W = cx.warpsize;
   WARP_ROWS(i, P.m) {
     const int lo = M.csr_ptr[i], hi = M.csr_ptr[i + 1];
-    double s0 = 0.0, s1 = 0.0;
+    double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
     for (int e = lo + cx.lane; e < hi; e += 4 * W) {
       const int e1 = e + W, e2 = e + 2 * W, e3 = e + 3 * W;
       const int c0 = P.csr_col[e];
@@ -917,16 +935,37 @@ IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, cons
         if (e1 < hi) s1 += src[c1];
         if (e2 < hi) s0 += src[c2];
         if (e3 < hi) s1 += src[c3];
+        if (NV == 2) {
+          t0 += src2[c0];
+          if (e1 < hi) t1 += src2[c1];
+          if (e2 < hi) t0 += src2[c2];
+          if (e3 < hi) t1 += src2[c3];
+        }
       } else {
-        s0 = fma(P.csr_val[e], src[c0], s0);
-        if (e1 < hi) s1 = fma(P.csr_val[e1], src[c1], s1);
-        if (e2 < hi) s0 = fma(P.csr_val[e2], src[c2], s0);
-        if (e3 < hi) s1 = fma(P.csr_val[e3], src[c3], s1);
+        const double a0 = P.csr_val[e], a1 = e1 < hi ? P.csr_val[e1] : 0.0, a2 = e2 < hi ? P.csr_val[e2] : 0.0,
+                     a3 = e3 < hi ? P.csr_val[e3] : 0.0;
+        s0 = fma(a0, src[c0], s0);
+        if (e1 < hi) s1 = fma(a1, src[c1], s1);
+        if (e2 < hi) s0 = fma(a2, src[c2], s0);
+        if (e3 < hi) s1 = fma(a3, src[c3], s1);
+        if (NV == 2) {
+          t0 = fma(a0, src2[c0], t0);
+          if (e1 < hi) t1 = fma(a1, src2[c1], t1);
+          if (e2 < hi) t0 = fma(a2, src2[c2], t0);
+          if (e3 < hi) t1 = fma(a3, src2[c3], t1);
+        }
       }
     }
     const double s = warp_sum(s0 + s1);
     if (cx.lane == 0) out[i] = s;
+    if (NV == 2) {
+      const double t = warp_sum(t0 + t1);
+      if (cx.lane == 0) out2[i] = t;
+    }
   }
+}
+IO_DEV void spmv_rows(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* src, double* out) {
+  spmv_rows_n<1>(cx, P, M, src, nullptr, out, nullptr);
 }
 
 // (A^T y)_k through the interleaved column groups (lanes of a warp own 32 consecutive columns).  Row indices
@@ -1068,7 +1107,7 @@ IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
 }
 
 // workspace n-vector slots (global, per CTA)
-enum { W_X = 0, W_T, W_D, W_R2, W_P, W_W, W_DX, W_DXDT, W_NVEC };
+enum { W_X = 0, W_T, W_D, W_R2, W_P, W_W, W_DX, W_DXDT, W_ATY, W_NVEC };
 // shared-memory m-vector slots
 enum { S_B = 0, S_Y, S_R1, S_Q, S_V, S_NVEC };
 constexpr int S_SCRATCH = 4 * KB + (KB + KB * KB) + 8 * 32 + 4;  // ybuf (double buffered, 2 rhs) + diag scratch + red + flag + mbarrier
@@ -1246,6 +1285,9 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
   double* __restrict__ w = wsi + (long long)W_W * n;
   double* __restrict__ dx = wsi + (long long)W_DX * n;
   double* __restrict__ dxdt = wsi + (long long)W_DXDT * n;
+  // A^T y, carried along the iteration: y only ever changes by alpha * (v + q dtau), and A^T(v + q dtau) is what the
+  // direction was built from, so the product never has to be formed again after the starting point
+  double* __restrict__ aty = wsi + (long long)W_ATY * n;
   const double* __restrict__ c = a.c + (long long)inst * a.c_stride;
 
   PhaseTimer pt{a.phase_cycles, 0};
@@ -1276,8 +1318,11 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     CTA_FOR(i, m) y[i] = s0[n + P.perm[i]];
     tau = s0[2 * n + m];
     kappa = s0[2 * n + m + 1];
+    CTA_SYNC();
+    CTA_FOR(k, n) aty[k] = col_dot(P, M, k, y);
   } else {
     CTA_FOR(k, n) {
+      aty[k] = 0.0;  // y = 0
       x[k] = 1.0;
       gstore(G, k, 1.0);  // G mirrors x at every loop top: the residual A x gathers from shared memory
       t[k] = 1.0;
@@ -1332,16 +1377,16 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     // ---- residuals at the current iterate (:765-770; the same r_p, r_d as _indicators :887-894) ----
     double acc[3] = {0.0, 0.0, 0.0};
     CTA_BATCH_FOR(k0, n, NUC) {
-      double xv[NUC], tv[NUC], cv[NUC];
+      double xv[NUC], tv[NUC], cv[NUC], av[NUC];
       BATCH_EACH(u, k, k0, n, NUC) {
         xv[u] = x[k];
         tv[u] = t[k];
         cv[u] = c[k];
+        av[u] = aty[k];
       }
       BATCH_EACH(u, k, k0, n, NUC) {
         const double xk = xv[u], tk = tv[u], ck = cv[u];
-        const double aty = col_dot(P, M, k, y);
-        const double r = -(aty + tk - ck * tau);  // :766
+        const double r = -(av[u] + tk - ck * tau);  // :766
         const double dk = xk / tk;                // :772
         r2[k] = r;
         D[k] = dk;
@@ -1397,14 +1442,25 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     const bool reuse_cold = cold && iters == 1;  // x = t = 1: L already holds chol(A A^T + delta I)
     if (!reuse_cold) assemble_normal_matrix(cx, P, M, D, G, S.scan, a.damping, L, a.debug);
     PHASE_MARK(pt, 2);
-    // right-hand side of the (p,q) solve (:800): G = D*c
+    // right-hand sides of the (p,q) solve (:800) and of the predictor (gamma = 0, eta = 1): G = D*c and, in the
+    // upper half of the gather region (only the assembly's prefix sums use it), G2 = D*w
+    double* G2 = G + gather_len(n);
     CTA_BATCH_FOR(k0, n, NU) {
-      double dv[NU], cv[NU];
+      double dv[NU], cv[NU], xv[NU], tv[NU], rv[NU];
       BATCH_EACH(u, k, k0, n, NU) {
         dv[u] = D[k];
         cv[u] = c[k];
+        xv[u] = x[k];
+        tv[u] = t[k];
+        rv[u] = r2[k];
       }
-      BATCH_EACH(u, k, k0, n, NU) gstore(G, k, dv[u] * cv[u]);
+      BATCH_EACH(u, k, k0, n, NU) {
+        gstore(G, k, dv[u] * cv[u]);
+        const double rxt = -(xv[u] * tv[u]);             // :788 with gamma = 0
+        const double wk = rv[u] - (1.0 / xv[u]) * rxt;   // :801 with eta(0) = 1
+        w[k] = wk;
+        gstore(G2, k, dv[u] * wk);
+      }
     }
     if (reuse_cold) {
       solved = true;
@@ -1418,32 +1474,13 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
       CTA_SYNC();
       continue;
     }
-    spmv_rows(cx, P, M, G, q);
+    spmv_rows_n<2>(cx, P, M, G, G2, q, v);  // A(D c) and A(D w) in one pass over A
     CTA_SYNC();
     PHASE_MARK(pt, 18);
-    // predictor: gamma = 0, eta = 1
-    CTA_BATCH_FOR(k0, n, NU) {
-      double xv[NU], tv[NU], rv[NU], dv[NU];
-      BATCH_EACH(u, k, k0, n, NU) {
-        xv[u] = x[k];
-        tv[u] = t[k];
-        rv[u] = r2[k];
-        dv[u] = D[k];
-      }
-      BATCH_EACH(u, k, k0, n, NU) {
-        const double rxt = -(xv[u] * tv[u]);             // :788 with gamma = 0
-        const double wk = rv[u] - (1.0 / xv[u]) * rxt;   // :801 with eta(0) = 1
-        w[k] = wk;
-        gstore(G, k, dv[u] * wk);
-      }
+    CTA_FOR(i, m) {
+      q[i] = bs[i] + q[i];  // r = r2 + A(Dinv r1), :666 with (r1,r2) = (c,b)
+      v[i] = r1[i] + v[i];
     }
-    CTA_FOR(i, m) q[i] = bs[i] + q[i];  // r = r2 + A(Dinv r1), :666 with (r1,r2) = (c,b)
-    CTA_SYNC();
-    PHASE_MARK(pt, 19);
-    spmv_rows(cx, P, M, G, v);
-    CTA_SYNC();
-    PHASE_MARK(pt, 20);
-    CTA_FOR(i, m) v[i] = r1[i] + v[i];
     CTA_SYNC();
     PHASE_MARK(pt, 4);
     {
@@ -1600,11 +1637,14 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
             const double xk = xv[u], tk = tv[u];
             const double rxt = -(xk * tk - gm) - ev[u];
             const double dxk = uv[u];
-            const double dtk = (1.0 / xk) * (rxt - tk * dxk);
+            const double rx = 1.0 / xk;
+            const double dtk = rx * (rxt - tk * dxk);
             const double xn = xk + al * dxk;
             x[k] = xn;
             gstore(G, k, xn);
             t[k] = tk + al * dtk;
+            // A^T d_y = A^T v + dtau A^T q, recovered from d_x = D (A^T v - w) + D (A^T q - c) dtau with 1/D = t/x
+            aty[k] = aty[k] + al * (dxk * tk * rx + w[k] + dtau * c[k]);
           }
         }
         CTA_FOR(i, m) y[i] = y[i] + al * (v[i] + q[i] * dtau);  // d_y = v + q d_tau (:840)
@@ -1720,7 +1760,11 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
 
   CTA_SYNC();
   assemble_normal_matrix(cx, P, M, x2, G, S.scan, a.damping, L);  // :1525-1527,1535
-  CTA_FOR(k, n) gstore(G, k, (k < nvar) ? x2[k] * g[k] : 0.0);
+  double* G2 = G + gather_len(n);  // upper half of the gather region: X2 c beside X2 g, one pass over A for both
+  CTA_FOR(k, n) {
+    gstore(G, k, (k < nvar) ? x2[k] * g[k] : 0.0);
+    if (whole) gstore(G2, k, x2[k] * c[k]);
+  }
   const bool ok = block_cholesky(cx, P, M, L, S.dscr, S.flag);
   if (!ok) {
     // the reference raises LinAlgError (:1546-1547); here: zero gradient + status
@@ -1729,7 +1773,10 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
     CTA_SYNC();
     return;
   }
-  spmv_rows(cx, P, M, G, v);  // A (X2 g_hat)
+  if (whole)
+    spmv_rows_n<2>(cx, P, M, G, G2, v, q);  // A (X2 g_hat) and A (X2 c)
+  else
+    spmv_rows(cx, P, M, G, v);  // A (X2 g_hat)
   CTA_SYNC();
   if (!whole) {
     double* const rhs1[1] = {v};
@@ -1741,12 +1788,10 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
     CTA_SYNC();
     return;
   }
-  CTA_FOR(k, n) gstore(G, k, x2[k] * c[k]);
-  CTA_FOR(i, m) v[i] = tau * v[i];  // r1 g = tau A X2 g (:1529)
-  CTA_SYNC();
-  spmv_rows(cx, P, M, G, q);
-  CTA_SYNC();
-  CTA_FOR(i, m) q[i] = mu * bs[i] + q[i];  // r2 = mu b + A(X2 c) (:1530)
+  CTA_FOR(i, m) {
+    v[i] = tau * v[i];            // r1 g = tau A X2 g (:1529)
+    q[i] = mu * bs[i] + q[i];     // r2 = mu b + A(X2 c) (:1530)
+  }
   CTA_SYNC();
   {
     double* const rhs2[2] = {q, v};
