@@ -1589,30 +1589,35 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
       }
       dtau = ((eta * r3 + 1.0 / tau * rtk - (-cu_ + bv_)) / (1.0 / tau * kappa + (-cp_ + bq_)));  // :837-838
       dkappa = (rtk - kappa * dtau) / tau;                                                         // :842
+      // ratio test (:871-875): min over x/-dx and t/-dt of the decreasing components = 1 / max(-dx/x, -dt/t); the
+      // reciprocals come from 1/x (needed for d_t anyway) and 1/t = D/x, so the loop has one division instead of three
       double mn[1] = {INFINITY};
       CTA_BATCH_FOR(k0, n, NU) {
-        double xv[NU], tv[NU], uv[NU], pv[NU], ev[NU];
+        double xv[NU], tv[NU], uv[NU], pv[NU], ev[NU], dv[NU];
         BATCH_EACH(u, k, k0, n, NU) {
           xv[u] = x[k];
           tv[u] = t[k];
           uv[u] = dx[k];
           pv[u] = p[k];
+          dv[u] = D[k];
           ev[u] = pass == 1 ? dxdt[k] : 0.0;
         }
         BATCH_EACH(u, k, k0, n, NU) {
           const double xk = xv[u], tk = tv[u];
           double rxt = -(xk * tk - gm);
           if (pass == 1) rxt -= ev[u];
-          const double dxk = uv[u] + pv[u] * dtau;           // :839
-          const double dtk = (1.0 / xk) * (rxt - tk * dxk);  // :841
+          const double dxk = uv[u] + pv[u] * dtau;  // :839
+          const double rx = 1.0 / xk;
+          const double dtk = rx * (rxt - tk * dxk);  // :841
           dx[k] = dxk;
           if (pass == 0) dxdt[k] = dxk * dtk;
-          if (dxk < 0.0) mn[0] = fmin(mn[0], xk / -dxk);  // :871-875
-          if (dtk < 0.0) mn[0] = fmin(mn[0], tk / -dtk);
+          // -mn[0] tracks max(-dx/x, -dt/t) over the decreasing components (as a min of the negated values)
+          if (dxk < 0.0) mn[0] = fmin(mn[0], dxk * rx);
+          if (dtk < 0.0) mn[0] = fmin(mn[0], dtk * (dv[u] * rx));
         }
       }
       cta_min<1>(cx, mn);
-      minr = mn[0];
+      minr = mn[0] < 0.0 ? -1.0 / mn[0] : INFINITY;
       PHASE_MARK(pt, 23);
       // _get_step (:870-878) with alpha0 = 1 (:843); an empty candidate set contributes 1
       double alpha = fmin(1.0, minr);
