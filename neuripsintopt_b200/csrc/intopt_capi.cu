@@ -117,6 +117,8 @@ __device__ __forceinline__ CtaCtx make_ctx(double* red) {
   cx.warp = threadIdx.x >> 5;
   cx.nwarps = blockDim.x >> 5;
   cx.red = red;
+  cx.bar_id = 0;
+  cx.bar_n = blockDim.x;
   return cx;
 }
 

@@ -38,8 +38,19 @@ struct CtaCtx {
   int tid, nthreads, lane, warp, nwarps;
   static constexpr int warpsize = 32;
   double* red;  // 8*32 doubles of shared scratch
+  // Barrier of this execution group: id 0 = the whole CTA (__syncthreads); a warp-specialised phase runs two
+  // sub-groups side by side, each with its own named barrier (bar.sync id, threads).
+  int bar_id, bar_n;
 };
-#define CTA_SYNC() __syncthreads()
+__device__ __forceinline__ void group_barrier(const CtaCtx& cx) {
+  if (cx.bar_id == 0)
+    __syncthreads();
+  else if (cx.bar_id == 1)  // (immediate barrier ids, so that the assembler counts the barriers the kernel uses)
+    asm volatile("bar.sync 1, %0;" ::"r"(cx.bar_n) : "memory");
+  else
+    asm volatile("bar.sync 2, %0;" ::"r"(cx.bar_n) : "memory");
+}
+#define CTA_SYNC() group_barrier(cx)
 #define WARP_SYNC() __syncwarp()
 IO_FORCEINLINE double warp_sum(double v) {
 #pragma unroll
@@ -1273,6 +1284,47 @@ struct FwdParams {
   int debug;                         // debug switches for bottleneck isolation (env INTOPT_DEBUG), 0 in production
 };
 
+// Factor L (block_cholesky) and form the two products out1 = A src1, out2 = A src2 (out2 may be null: one product),
+// side by side when the CTA has at least 4 warps: the products need nothing from the factorisation.  On return
+// (after a full CTA barrier) *S.flag tells whether the factorisation succeeded.
+constexpr int RHS_WARPS = 3;
+IO_DEV void factor_and_rhs(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, const SmemLayout& S,
+                           const double* src1, const double* src2, double* out1, double* out2, PhaseTimer* pt) {
+#ifndef INTOPT_HOST_EMU
+  if (cx.nwarps >= 4 + RHS_WARPS - 1) {
+    const int ga = cx.nwarps - RHS_WARPS;
+    if (cx.warp < ga) {
+      CtaCtx ca = cx;
+      ca.nthreads = ga * 32;
+      ca.nwarps = ga;
+      ca.bar_id = 1;
+      ca.bar_n = ga * 32;
+      block_cholesky(ca, P, M, L, S.dscr, S.flag, pt);
+    } else {
+      CtaCtx cb = cx;
+      cb.tid = cx.tid - ga * 32;
+      cb.warp = cx.warp - ga;
+      cb.nthreads = RHS_WARPS * 32;
+      cb.nwarps = RHS_WARPS;
+      cb.bar_id = 2;
+      cb.bar_n = RHS_WARPS * 32;
+      if (out2)
+        spmv_rows_n<2>(cb, P, M, src1, src2, out1, out2);
+      else
+        spmv_rows_n<1>(cb, P, M, src1, nullptr, out1, nullptr);
+    }
+    __syncthreads();
+    return;
+  }
+#endif
+  block_cholesky(cx, P, M, L, S.dscr, S.flag, pt);
+  if (out2)
+    spmv_rows_n<2>(cx, P, M, src1, src2, out1, out2);
+  else
+    spmv_rows_n<1>(cx, P, M, src1, nullptr, out1, nullptr);
+  CTA_SYNC();
+}
+
 IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst, double* wsi,
                              const SmemLayout& S, bool cold = false, unsigned cold_parity = 0) {
   const int m = P.m, n = P.n, mv = P.mv;
@@ -1462,26 +1514,33 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
         gstore(G2, k, dv[u] * wk);
       }
     }
+    CTA_SYNC();  // G, G2 complete
+    // The factorisation is a dependent chain that keeps few warps busy, and the two products A(D c), A(D w) do not
+    // depend on it: with enough warps the CTA splits, the last RHS_WARPS warps form the right-hand sides while the
+    // others factor (each group on its own named barrier).
     if (reuse_cold) {
       solved = true;
+      spmv_rows_n<2>(cx, P, M, G, G2, q, v);
       CTA_SYNC();
+      CTA_FOR(i, m) {
+        q[i] = bs[i] + q[i];  // r = r2 + A(Dinv r1), :666 with (r1,r2) = (c,b)
+        v[i] = r1[i] + v[i];
+      }
     } else {
-      solved = block_cholesky(cx, P, M, L, S.dscr, S.flag, &pt);  // (its barriers order the G writes)
+      factor_and_rhs(cx, P, M, L, S, G, G2, q, v, &pt);
+      solved = *S.flag == 0;
+      CTA_FOR(i, m) {
+        q[i] = bs[i] + q[i];
+        v[i] = r1[i] + v[i];
+      }
     }
+    CTA_SYNC();
     PHASE_MARK(pt, 3);
     if (!solved) {  // deltas = 0 (:855-857): the iterate is unchanged, the tests run at loop top
       CTA_FOR(k, n) gstore(G, k, x[k]);  // G must mirror x again
       CTA_SYNC();
       continue;
     }
-    spmv_rows_n<2>(cx, P, M, G, G2, q, v);  // A(D c) and A(D w) in one pass over A
-    CTA_SYNC();
-    PHASE_MARK(pt, 18);
-    CTA_FOR(i, m) {
-      q[i] = bs[i] + q[i];  // r = r2 + A(Dinv r1), :666 with (r1,r2) = (c,b)
-      v[i] = r1[i] + v[i];
-    }
-    CTA_SYNC();
     PHASE_MARK(pt, 4);
     {
       double* const rhs2[2] = {q, v};
@@ -1770,7 +1829,9 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
     gstore(G, k, (k < nvar) ? x2[k] * g[k] : 0.0);
     if (whole) gstore(G2, k, x2[k] * c[k]);
   }
-  const bool ok = block_cholesky(cx, P, M, L, S.dscr, S.flag);
+  CTA_SYNC();  // G, G2 complete
+  factor_and_rhs(cx, P, M, L, S, G, whole ? G2 : nullptr, v, whole ? q : nullptr, nullptr);  // A (X2 g_hat) [, A (X2 c)]
+  const bool ok = *S.flag == 0;
   if (!ok) {
     // the reference raises LinAlgError (:1546-1547); here: zero gradient + status
     CTA_FOR(k, nvar) gc[k] = 0.0;
@@ -1778,11 +1839,6 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
     CTA_SYNC();
     return;
   }
-  if (whole)
-    spmv_rows_n<2>(cx, P, M, G, G2, v, q);  // A (X2 g_hat) and A (X2 c)
-  else
-    spmv_rows(cx, P, M, G, v);  // A (X2 g_hat)
-  CTA_SYNC();
   if (!whole) {
     double* const rhs1[1] = {v};
     block_solve<1>(cx, P, M, L, rhs1, S.ybuf);
