@@ -65,7 +65,16 @@ void fill_info(const intopt::HostStructure& S, IntoptInfo* info) {
   int g = 0;
   plan_smem(S, &info->factor_in_smem, &g, &info->smem_bytes);
   info->gather_in_smem = g;
-  info->threads = env_int("INTOPT_THREADS", 256);
+  // CTA size: INTOPT_THREADS overrides.  Default 256 (two LPs resident per SM for the experiment shapes); small
+  // problems take 128 threads so that four LPs share an SM; problems whose shared memory admits a single resident
+  // CTA take 512 threads (the only way to put more warps on that SM).
+  int thr = env_int("INTOPT_THREADS", 0);
+  if (thr <= 0) {
+    thr = 256;
+    if (S.m <= 64 && info->smem_bytes <= (kMaxDynSmem + 1024) / 4 - 1024) thr = 128;
+    if (info->smem_bytes > (kMaxDynSmem + 1024) / 2 - 1024) thr = 512;
+  }
+  info->threads = thr;
   info->ordering = S.ordering;
   info->scalar_envelope = S.sky_size;
   info->asm_padded = S.asm_padded;
@@ -125,7 +134,7 @@ __device__ __forceinline__ CtaCtx make_ctx(double* red) {
 // Persistent CTAs: each pulls the next LP instance from an atomic counter until the batch is exhausted,
 // so finished LPs free their SM slot without any host involvement.
 template <int TMAX, bool ALLSMEM>
-__global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_forward_kernel(const __grid_constant__ intopt::ProblemDev P,
+__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_forward_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                const __grid_constant__ intopt::FwdParams a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_inst;
@@ -150,7 +159,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_forward_kern
 
 // One CTA computes the cold-start factor chol(A A^T + delta I) with the instance code path (same CTA size).
 template <int TMAX, bool ALLSMEM>
-__global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_coldfactor_kernel(const __grid_constant__ intopt::ProblemDev P,
+__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_coldfactor_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                   double delta, double* ws, int factor_in_smem,
                                                                   int gather_in_smem, double* out, int* ok) {
   extern __shared__ __align__(16) double smem[];
@@ -161,7 +170,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_coldfactor_k
 }
 
 template <int TMAX, bool ALLSMEM>
-__global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_backward_kernel(const __grid_constant__ intopt::ProblemDev P,
+__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_backward_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                 const __grid_constant__ intopt::BwdParams a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_inst;
@@ -215,7 +224,7 @@ __device__ __forceinline__ void spmv_rows_dbg(const CtaCtx& cx, const intopt::Pr
 // Debug aid for profiles/: runs ONE building block of the solver `reps` times per CTA and reports the cycles per
 // repetition seen by thread 0 (barrier to barrier).  Not used by the product path.
 template <int TMAX, bool ALLSMEM>
-__global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_microbench_kernel(const __grid_constant__ intopt::ProblemDev P,
+__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_microbench_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                   int which, int reps, double* ws, long long ws_stride,
                                                                   int factor_in_smem, int gather_in_smem,
                                                                   unsigned long long* out) {
@@ -358,13 +367,13 @@ __global__ void __launch_bounds__(256) intopt_fp64_peak_kernel(double* out, int 
 
 __device__ unsigned long long g_phase_cycles[32];
 
-// Kernel variants: CTA size cap (192: 2 CTAs/SM x 168 registers, 256: 2 x 128, 512: 1 x 128) x whether every
+// Kernel variants: CTA size cap (128: 4 CTAs/SM x 128 registers, 192: 2 x 168, 256: 2 x 128, 512: 1 x 128) x whether every
 // buffer is in shared memory.
 #ifdef INTOPT_DEV_BUILD  // quick developer builds (INTOPT_NVCC_EXTRA=-DINTOPT_DEV_BUILD): default CTA size only
 #define INTOPT_VARIANTS(F) F(256, true) F(256, false)
 #else
 #define INTOPT_VARIANTS(F)                                                                                   \
-  F(192, true) F(192, false) F(256, true) F(256, false) F(512, true) F(512, false)
+  F(128, true) F(128, false) F(192, true) F(192, false) F(256, true) F(256, false) F(512, true) F(512, false)
 #endif
 static std::vector<const void*> all_kernels() {
   std::vector<const void*> v;
