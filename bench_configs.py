@@ -45,19 +45,11 @@ def main():
             c = torch.tensor((c0 * np.abs(1 + 0.3 * rng.standard_normal((B, n_x)))).astype(np.float32), device="cuda")
             f = IPOfunc(tt(inp["A"]), tt(bb), torch.Tensor(), torch.Tensor(), check_finite=False, **kw)
         elif name == "knapsack":
-            # one cost row per instance => B different problems; run the reference-style loop over a few of them
-            Bk = 10  # the experiment has 10 minibatches of 31 items (ModelRun.py:17,60): 10 distinct cost rows, cached
-            costs = rng.uniform(20, 1000, (Bk, n_x)).astype(np.float32)
-            c = torch.tensor(-(rng.standard_normal((Bk, n_x)) + 0.3 * rng.standard_normal((Bk, n_x))).astype(np.float32), device="cuda")
-            fs = [IPOfunc(tt(costs[i][None, :]), tt(z["budget_rhs"]), torch.Tensor(), torch.Tensor(), check_finite=False, **kw) for i in range(Bk)]
-            g = torch.ones(n_x, device="cuda")
-            def step():
-                for i in range(Bk):
-                    ci = c[i].detach().requires_grad_(True); fs[i](ci).backward(g)
-            ms = time_steps(step, max(2, args.steps // 3))
-            out.append(dict(config=name, shape="32x62 (per-instance A: one problem per instance, looped)", batch=Bk,
-                            lp_per_s=Bk / ms * 1e3, ms_per_step=ms, thr=args.thr))
-            print(json.dumps(out[-1])); continue
+            # one cost row per instance (the minibatch's cost vector is the equality row, optimizer.py:396-405): batched
+            # through the per-instance-values path, A of shape (B, 1, 31)
+            costs = rng.uniform(20, 1000, (B, 1, n_x)).astype(np.float32)
+            c = torch.tensor(-(rng.standard_normal((B, n_x)) + 0.3 * rng.standard_normal((B, n_x))).astype(np.float32), device="cuda")
+            f = IPOfunc(tt(costs), tt(z["budget_rhs"]), torch.Tensor(), torch.Tensor(), check_finite=False, **kw)
         else:
             scale = np.abs(c0).mean()
             c = torch.tensor((c0 + 0.05 * scale * rng.standard_normal((B, n_x))).astype(np.float32), device="cuda")

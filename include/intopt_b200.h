@@ -32,7 +32,13 @@
 extern "C" {
 #endif
 
-#define INTOPT_B200_VERSION 1
+#define INTOPT_B200_VERSION 2
+
+/* intopt_problem_create flag: the VALUES of A's non-zeros differ per instance (same sparsity pattern), e.g. the
+ * knapsack driver whose equality row is the minibatch's cost vector (experiments/Building Knapsack/optimizer.py:396-405).
+ * val_host then only fixes the pattern (pass any non-zero numbers); every forward/backward call must go through the
+ * *_values entry points with a_vals_dev. */
+#define INTOPT_FLAG_INSTANCE_VALUES 1
 
 typedef struct IntoptProblem IntoptProblem; /* opaque, immutable after create, one per device */
 
@@ -100,6 +106,14 @@ int intopt_forward(const IntoptProblem* p, int B, const double* c_dev, long long
                    double* xhat_dev, double* state_dev, int* status_dev, int* iters_dev,
                    void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Same with per-instance values of A: a_vals_dev is B x nnz (instance stride a_stride doubles), the values of A's
+ * non-zeros in the order of the CSR arrays given to intopt_problem_create.  NULL = the problem's own values. */
+int intopt_forward_values(const IntoptProblem* p, int B, const double* c_dev, long long c_stride,
+                          const double* b_batch_dev, long long b_stride, const double* a_vals_dev, long long a_stride,
+                          const IntoptOpts* opts, const double* init_dev,
+                          double* xhat_dev, double* state_dev, int* status_dev, int* iters_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Backward: dL/dc at the saved iterate.  mode 0 = ip_model_whole.py:1502-1560 (HSD embedding, uses the
  * un-normalised iterate), mode 1 = ip_model_alter.py:1516-1624 (log barrier, uses x/tau, t/tau).
  *   grad_x_dev   B x nvar  upstream gradient w.r.t. the leading nvar standard-form variables
@@ -111,6 +125,12 @@ int intopt_backward(const IntoptProblem* p, int B, int mode, double damping_bwd,
                     const double* b_batch_dev, long long b_stride, const double* grad_x_dev,
                     double* grad_c_dev,
                     int* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+int intopt_backward_values(const IntoptProblem* p, int B, int mode, double damping_bwd, int nvar,
+                           const double* state_dev, const double* c_dev, long long c_stride,
+                           const double* b_batch_dev, long long b_stride, const double* a_vals_dev, long long a_stride,
+                           const double* grad_x_dev, double* grad_c_dev,
+                           int* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Measured FP64 FMA throughput of the current device (GFLOP/s) with a register-resident DFMA kernel;
  * the roofline denominator MEASURED_PEAKS.json lacks.  Synchronises the device. */

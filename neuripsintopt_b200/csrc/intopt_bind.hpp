@@ -50,6 +50,11 @@ inline void bind_problem(const HostStructure& S, ProblemDev& D, Up&& up) {
   D.asm_run = S.asm_run.empty() ? nullptr : up(S.asm_run);
   D.asm_unit = S.asm_unit ? 1 : 0;
   D.asm_w = S.asm_unit ? nullptr : up(S.asm_w);
+  D.inst_values = S.inst_values ? 1 : 0;
+  D.csr_src = S.inst_values ? up(S.csr_src) : nullptr;
+  D.csc_src = S.inst_values ? up(S.csc_src) : nullptr;
+  D.asm_sa = S.inst_values ? up(S.asm_sa) : nullptr;
+  D.asm_sb = S.inst_values ? up(S.asm_sb) : nullptr;
 }
 
 // doubles of shared memory the solver needs beyond the (optional) factor and gather buffer

@@ -474,11 +474,10 @@ int intopt_analyze(int m, int n, const int* rowptr, const int* colidx, const dou
 
 int intopt_problem_create(IntoptProblem** out, int m, int n, const int* rowptr, const int* colidx,
                           const double* val, const double* b, int flags) {
-  (void)flags;
   if (!out) return fail(-1, "out is NULL");
   *out = nullptr;
   intopt::HostStructure S;
-  int rc = intopt::analyze(m, n, rowptr, colidx, val, S);
+  int rc = intopt::analyze(m, n, rowptr, colidx, val, S, -1, (flags & INTOPT_FLAG_INSTANCE_VALUES) != 0);
   if (rc) return fail(rc, "malformed CSR input");
   int ndev = 0;
   cudaError_t e0 = cudaGetDeviceCount(&ndev);
@@ -554,7 +553,17 @@ size_t intopt_workspace_bytes(const IntoptProblem* p, int B) {
 int intopt_forward(const IntoptProblem* p, int B, const double* c, long long c_stride, const double* b_batch,
                    long long b_stride, const IntoptOpts* o, const double* init, double* xhat, double* state,
                    int* status, int* iters, void* ws, size_t ws_bytes, void* stream) {
+  return intopt_forward_values(p, B, c, c_stride, b_batch, b_stride, nullptr, 0, o, init, xhat, state, status, iters, ws,
+                               ws_bytes, stream);
+}
+
+int intopt_forward_values(const IntoptProblem* p, int B, const double* c, long long c_stride, const double* b_batch,
+                          long long b_stride, const double* a_vals, long long a_stride, const IntoptOpts* o,
+                          const double* init, double* xhat, double* state, int* status, int* iters, void* ws,
+                          size_t ws_bytes, void* stream) {
   if (!p || !c || !o || !xhat || !state || !status || !iters || !ws) return fail(-1, "NULL argument");
+  if (a_vals && !p->dev.inst_values) return fail(-7, "per-instance values need a problem created with INTOPT_FLAG_INSTANCE_VALUES");
+  if (!a_vals && p->dev.inst_values) return fail(-7, "this problem was created for per-instance values: pass a_vals_dev");
   if (B <= 0) return 0;
   if (!p->b_dev && !b_batch) return fail(-3, "problem has no b and no b_batch was given");
   if (ws_bytes < intopt_workspace_bytes(p, B)) return fail(-4, "workspace too small");
@@ -566,6 +575,8 @@ int intopt_forward(const IntoptProblem* p, int B, const double* c, long long c_s
   a.b_stride = b_stride;
   a.b_problem = p->b_dev;
   a.init = init;
+  a.a_vals = a_vals;
+  a.a_stride = a_stride;
   a.xhat = xhat;
   a.state = state;
   a.status = status;
@@ -582,7 +593,7 @@ int intopt_forward(const IntoptProblem* p, int B, const double* c, long long c_s
   a.max_iter = o->max_iter;
   a.phase_cycles = nullptr;
   a.debug = env_int("INTOPT_DEBUG", 0);
-  if (!init) {
+  if (!init && !a_vals) {  // (the cold-start factor is a constant of the problem only if A is)
     int rc = cold_factor_for(p, a.damping, (cudaStream_t)stream, &a.cold_factor, &a.cold_ok);
     if (rc) return rc;
   }
@@ -605,7 +616,16 @@ int intopt_forward(const IntoptProblem* p, int B, const double* c, long long c_s
 int intopt_backward(const IntoptProblem* p, int B, int mode, double damping, int nvar, const double* state,
                     const double* c, long long c_stride, const double* b_batch, long long b_stride,
                     const double* gx, double* gc, int* status, void* ws, size_t ws_bytes, void* stream) {
+  return intopt_backward_values(p, B, mode, damping, nvar, state, c, c_stride, b_batch, b_stride, nullptr, 0, gx, gc, status,
+                                ws, ws_bytes, stream);
+}
+
+int intopt_backward_values(const IntoptProblem* p, int B, int mode, double damping, int nvar, const double* state,
+                           const double* c, long long c_stride, const double* b_batch, long long b_stride,
+                           const double* a_vals, long long a_stride, const double* gx, double* gc, int* status, void* ws,
+                           size_t ws_bytes, void* stream) {
   if (!p || !c || !state || !gx || !gc || !status || !ws) return fail(-1, "NULL argument");
+  if ((a_vals != nullptr) != (p->dev.inst_values != 0)) return fail(-7, "a_vals_dev must be given exactly for problems created with INTOPT_FLAG_INSTANCE_VALUES");
   if (B <= 0) return 0;
   if (mode != 0 && mode != 1) return fail(-5, "mode must be 0 (whole) or 1 (alter)");
   if (nvar < 0 || nvar > p->info.n) return fail(-6, "nvar out of range");
@@ -623,6 +643,8 @@ int intopt_backward(const IntoptProblem* p, int B, int mode, double damping, int
   a.b_stride = b_stride;
   a.b_problem = p->b_dev;
   a.gx = gx;
+  a.a_vals = a_vals;
+  a.a_stride = a_stride;
   a.gc = gc;
   a.status = status;
   a.counter = (int*)ws;

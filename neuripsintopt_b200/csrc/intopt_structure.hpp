@@ -32,6 +32,12 @@ struct HostStructure {
   std::vector<int> csr_ptr, csr_col;
   std::vector<double> csr_val;
   bool a_unit = true;  // every non-zero of A equals 1: value streams are skipped
+  // Per-instance values (same pattern, different numbers per LP: the knapsack cost row): position in the CALLER's
+  // CSR value array of every stored copy of an entry of A; -1 marks padding.  Built only when requested.
+  bool inst_values = false;
+  std::vector<int> csr_src;           // parallel to csr_col / csr_val
+  std::vector<int> csc_src;           // parallel to csc_val
+  std::vector<int> asm_sa, asm_sb;    // parallel to asm_k / asm_w: the term's weight is val[sa] * val[sb]
   // A by columns, 32 consecutive columns per group, group length padded to a multiple of 8.  Values: entry t of
   // column 32g+l sits at (csc_gptr[g] + t) * 32 + l.  Row indices: chunk-major, the eight indices t = 8c..8c+7 of
   // column 32g+l are the 16 bytes at ((csc_gptr[g]/8 + c) * 32 + l) * 8, so a warp reads one chunk of its 32
@@ -190,7 +196,7 @@ inline std::vector<int> dense_rows_last(const std::vector<std::vector<int>>& adj
 
 // Returns 0 on success, negative on malformed input.  `force_order`: -1 = smallest block envelope.
 inline int analyze(int m, int n, const int* rp, const int* ci, const double* val, HostStructure& S,
-                   int force_order = -1) {
+                   int force_order = -1, bool inst_values = false) {
   if (m <= 0 || n <= 0 || !rp || !ci || !val) return -1;
   if (rp[0] != 0) return -2;
   for (int i = 0; i < m; ++i)
@@ -200,6 +206,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
     if (ci[e] < 0 || ci[e] >= n) return -3;
   if (m + 2 * NB >= 65535) return -4;  // row indices travel as uint16
   S = HostStructure();
+  S.inst_values = inst_values;
   S.m = m;
   S.n = n;
   S.nnz = nnz;
@@ -233,6 +240,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   S.csr_ptr.assign(m + 1, 0);
   S.csr_col.resize(nnz);
   S.csr_val.resize(nnz);
+  S.csr_src.resize(nnz);
   for (int i = 0; i < m; ++i) S.csr_ptr[i + 1] = S.csr_ptr[i] + (rp[S.perm[i] + 1] - rp[S.perm[i]]);
   for (int i = 0; i < m; ++i) {
     int src = rp[S.perm[i]], dst = S.csr_ptr[i], len = rp[S.perm[i] + 1] - src;
@@ -242,14 +250,15 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
     for (int t = 0; t < len; ++t) {
       S.csr_col[dst + t] = ci[src + idx[t]];
       S.csr_val[dst + t] = val[src + idx[t]];
+      S.csr_src[dst + t] = src + idx[t];
     }
   }
-  S.a_unit = true;
+  S.a_unit = !inst_values;  // per-instance values always take the weighted code paths
   for (double v : S.csr_val)
     if (v != 1.0) S.a_unit = false;
 
   // ---- A by columns: plain CSC first, then the interleaved groups ------------------------------------
-  std::vector<int> cptr(n + 1, 0), crow(nnz);
+  std::vector<int> cptr(n + 1, 0), crow(nnz), csrc(nnz);
   std::vector<double> cval(nnz);
   for (int e = 0; e < nnz; ++e) cptr[S.csr_col[e] + 1]++;
   for (int k = 0; k < n; ++k) cptr[k + 1] += cptr[k];
@@ -260,6 +269,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
         int k = S.csr_col[e], d = fill[k]++;
         crow[d] = i;  // ascending in i
         cval[d] = S.csr_val[e];
+        csrc[d] = S.csr_src[e];
       }
   }
   const int ngrp = (n + 31) / 32;
@@ -274,6 +284,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   }
   S.csc_row.assign((size_t)S.csc_gptr[ngrp] * 32, (uint16_t)S.m8);
   S.csc_val.assign((size_t)S.csc_gptr[ngrp] * 32, 0.0);
+  if (inst_values) S.csc_src.assign((size_t)S.csc_gptr[ngrp] * 32, -1);
   for (int k = 0; k < n; ++k) {
     int g = k >> 5, l = k & 31;
     for (int t = 0; t < cptr[k + 1] - cptr[k]; ++t) {
@@ -282,6 +293,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
       size_t dv = ((size_t)S.csc_gptr[g] + t) * 32 + l;
       S.csc_row[dr] = (uint16_t)crow[cptr[k] + t];
       S.csc_val[dv] = cval[cptr[k] + t];
+      if (inst_values) S.csc_src[dv] = csrc[cptr[k] + t];
     }
   }
 
@@ -418,7 +430,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   struct Ent {
     int pos;
     unsigned char diag;
-    std::vector<int> k;
+    std::vector<int> k, sa, sb;
     std::vector<double> w;
     std::vector<uint32_t> runs;  // start | len << 16, longest first
   };
@@ -433,7 +445,7 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
         const int pos = pos_of(i, j);
         if (present[pos] || i == j) {
           id_of[pos] = (int)ents.size();
-          ents.push_back({pos, (unsigned char)(i == j), {}, {}, {}});
+          ents.push_back({pos, (unsigned char)(i == j), {}, {}, {}, {}, {}});
         }
       }
   }
@@ -445,7 +457,11 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
         const double w = cval[a] * cval[b2];
         en.k.push_back(k);
         en.w.push_back(w);
-        if (w != 1.0) S.asm_unit = false;
+        if (inst_values) {
+          en.sa.push_back(csrc[a]);
+          en.sb.push_back(csrc[b2]);
+        }
+        if (w != 1.0 || inst_values) S.asm_unit = false;
       }
   const bool rle = S.asm_unit && gpad_host(n) < 65535;
   if (rle)
@@ -496,6 +512,10 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   S.asm_padded = rle ? (long long)S.asm_rptr[nag] * 32 : (long long)S.asm_gptr[nag] * 32;
   S.asm_k.assign((size_t)S.asm_gptr[nag] * 32, gpad_host(n));  // gpad(n) = the zero slot of the gather buffer
   S.asm_w.assign((size_t)S.asm_gptr[nag] * 32, 0.0);
+  if (inst_values) {
+    S.asm_sa.assign((size_t)S.asm_gptr[nag] * 32, -1);
+    S.asm_sb.assign((size_t)S.asm_gptr[nag] * 32, -1);
+  }
   S.asm_run.assign((size_t)S.asm_rptr[nag] * 32, 0u);
   for (int e = 0; e < ne; ++e) {
     const Ent& en = ents[order[e]];
@@ -511,6 +531,10 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
         const size_t d = ((size_t)S.asm_gptr[g] + t) * 32 + l;
         S.asm_k[d] = gpad_host(en.k[t]);
         S.asm_w[d] = en.w[t];
+        if (inst_values) {
+          S.asm_sa[d] = en.sa[t];
+          S.asm_sb[d] = en.sb[t];
+        }
       }
     }
   }

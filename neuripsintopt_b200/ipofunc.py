@@ -66,12 +66,16 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_TAG0 = 1024.0  # tags of the pattern matrix that stands in for a batch of equality matrices (per-instance A)
+
+
 class DeviceProblem:
     """A StandardForm plus its device-resident IntoptProblem handle and index tensors (one per device)."""
 
-    def __init__(self, sf, device):
+    def __init__(self, sf, device, inst_values=False):
         self.sf = sf
         self.device = device
+        self.inst_values = inst_values
         L = _capi.lib()
         A = sf.A
         rp = np.ascontiguousarray(A.indptr, dtype=np.int32)
@@ -80,7 +84,8 @@ class DeviceProblem:
         self.handle = ctypes.c_void_p()
         with torch.cuda.device(device):
             _capi.check(L.intopt_problem_create(ctypes.byref(self.handle), sf.m, sf.n, rp.ctypes.data,
-                                                ci.ctypes.data, val.ctypes.data, None, 0),
+                                                ci.ctypes.data, val.ctypes.data, None,
+                                                _capi.FLAG_INSTANCE_VALUES if inst_values else 0),
                         "intopt_problem_create")
         info = _capi.IntoptInfo()
         _capi.check(L.intopt_problem_info(self.handle, ctypes.byref(info)), "intopt_problem_info")
@@ -99,6 +104,19 @@ class DeviceProblem:
         self.x_flip = t(sf.x_flip_ub, torch.float64) if np.isfinite(sf.x_flip_ub).any() else None
         self.free_cols = t(sf.free_cols, torch.long) if (sf.free_cols >= 0).any() else None
         self._ws = {}
+        if inst_values:
+            # standard-form entry e of instance i = val_const[e] + val_sign[e] * A_i.flat[val_src[e]]: the entries
+            # built from the tagged matrix (|value| >= _TAG0) are copies of user entries, the rest are constants
+            tagged = np.abs(val) >= _TAG0 - 0.5
+            src = np.where(tagged, np.rint(np.abs(val)) - _TAG0, 0).astype(np.int64)
+            self.val_src = t(sf.tag_flatpos[src], torch.long)
+            self.val_sign = t(np.where(tagged, np.sign(val), 0.0), torch.float64)
+            self.val_const = t(np.where(tagged, 0.0, val), torch.float64)
+            self.nnz = int(val.size)
+
+    def instance_values(self, A_flat):
+        """(B, nnz) fp64 values of the standard-form A for the user matrices A_flat (B, n_eq * n_x) on the device."""
+        return (self.val_const + self.val_sign * A_flat[:, self.val_src]).contiguous()
 
     def __del__(self):
         try:
@@ -145,8 +163,24 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
     max_iter_ = 1000 if max_iter is None else int(max_iter)
     damping_fwd = 1e-6 if variant == "whole" else float(damping)  # :774 | ip_model_alter.py:775
     mode = 0 if variant == "whole" else 1
+    # Additive: A of shape (B, n_eq, n_x) = one equality matrix per instance with a common sparsity pattern (the
+    # knapsack driver builds a fresh IPOfunc per minibatch because its equality row is the minibatch's cost vector,
+    # experiments/Building Knapsack/optimizer.py:396-405).  The structure is analysed once on a tagged pattern
+    # matrix; the numbers travel to the kernels per instance.
+    a_batched = A_np is not None and A_np.ndim == 3
+    A_all = None
+    tag_flatpos = None
+    if a_batched:
+        A_all = np.ascontiguousarray(A_np, dtype=np.float64)
+        pattern = (A_all != 0).any(axis=0)
+        tag_flatpos = np.flatnonzero(pattern)
+        if tag_flatpos.size == 0:
+            raise ValueError("the batch of equality matrices is identically zero")
+        A_np = np.zeros(pattern.shape, dtype=np.float64)
+        A_np.flat[tag_flatpos] = _TAG0 + np.arange(tag_flatpos.size)
     n_x = (A_np if A_np is not None else G_np).shape[1]
     b_batched = b_np is not None and b_np.ndim == 2
+    a_dev_cache = {}
     structure_key = _digest(A_np, G_np, h_np) + repr([tuple(bd) for bd in bounds])
     zero_cols = _problem.zero_columns(A_np, G_np, n_x)
     state = {"events": [], "time_ms": 0.0, "last": []}
@@ -161,7 +195,11 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                 sf = _problem.build_standard_form(
                     n_x, A_np, None, G_np, h_np, bounds,
                     None if not zero_cols.size else np.asarray(sign_key, dtype=np.float64))
-                hit = DeviceProblem(sf, device)
+                if a_batched:
+                    if sf.fixed_idx.size:
+                        raise NotImplementedError("per-instance A with variables fixed by presolve (singleton rows)")
+                    sf.tag_flatpos = tag_flatpos
+                hit = DeviceProblem(sf, device, inst_values=a_batched)
             except _problem.PresolveComplete as done:
                 hit = done
             _PROBLEM_CACHE[key] = hit
@@ -217,6 +255,14 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
             b_stride = sf.m
             if b_std.shape[0] != Bg:
                 raise ValueError("b has %d instances but c has %d" % (b_std.shape[0], Bg))
+        a_vals = None
+        if a_batched:
+            if str(device) not in a_dev_cache:
+                a_dev_cache[str(device)] = torch.as_tensor(A_all.reshape(A_all.shape[0], -1), device=device)
+            A_flat = a_dev_cache[str(device)]
+            if sel is None and A_flat.shape[0] != Bg:
+                raise ValueError("A has %d instances but c has %d" % (A_flat.shape[0], Bg))
+            a_vals = dp.instance_values(A_flat if sel is None else A_flat[sel])
         xhat = torch.empty(Bg, sf.n, dtype=torch.float64, device=device)
         st = torch.empty(Bg, 2 * sf.n + sf.m + 2, dtype=torch.float64, device=device)
         status = torch.empty(Bg, dtype=torch.int32, device=device)
@@ -225,9 +271,10 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
         init = pack_init(dp, Bg, device)
         opts = _capi.IntoptOpts(alpha0, tol, thr_, damping_fwd, max_iter_, 0)
         stream = torch.cuda.current_stream(device).cuda_stream
-        _capi.check(L.intopt_forward(dp.handle, Bg, _ptr(c_std), sf.n, _ptr(b_std), b_stride, ctypes.byref(opts),
-                                     _ptr(init), _ptr(xhat), _ptr(st), _ptr(status), _ptr(iters), _ptr(ws),
-                                     ws.numel() * 8, ctypes.c_void_p(stream)), "intopt_forward")
+        _capi.check(L.intopt_forward_values(dp.handle, Bg, _ptr(c_std), sf.n, _ptr(b_std), b_stride, _ptr(a_vals),
+                                            dp.nnz if a_batched else 0, ctypes.byref(opts), _ptr(init), _ptr(xhat),
+                                            _ptr(st), _ptr(status), _ptr(iters), _ptr(ws), ws.numel() * 8,
+                                            ctypes.c_void_p(stream)), "intopt_forward")
         # _postprocess (:1241-1285): undo substitutions, re-insert fixed variables
         xk = xhat[:, :sf.nvar]
         if dp.free_cols is not None:
@@ -247,7 +294,7 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
         if bad.any():  # presolve-infeasible instances return the presolve x (zeros) upstream (:1483-1488)
             badsel = bad if sel is None or bad.size == 1 else bad[sel.cpu().numpy()]
             x_user[torch.as_tensor(np.broadcast_to(badsel, (Bg,)).copy(), device=device)] = 0.0
-        return x_user, (c_std, b_std, b_stride, st, status, iters)
+        return x_user, (c_std, b_std, b_stride, st, status, iters, a_vals)
 
     class IPOfunc_cls(torch.autograd.Function):
         @staticmethod
@@ -325,7 +372,7 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                         grad = torch.zeros(B, n_x, dtype=torch.float64, device=device)
                     continue
                 sf = dp.sf
-                c_std, b_std, b_stride, st, status, iters = pack
+                c_std, b_std, b_stride, st, status, iters, a_vals = pack
                 gg = g2 if sel is None else g2[sel]
                 gk = (gg if dp.identity_vars else gg[:, dp.var_index]).contiguous()  # del_x[var_index] (:1518)
                 Bg = gk.shape[0]
@@ -333,9 +380,10 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                 bstat = torch.empty(Bg, dtype=torch.int32, device=device)
                 ws = dp.workspace(Bg)
                 stream = torch.cuda.current_stream(device).cuda_stream
-                _capi.check(L.intopt_backward(dp.handle, Bg, mode, float(damping), sf.nvar, _ptr(st), _ptr(c_std),
-                                              sf.n, _ptr(b_std), b_stride, _ptr(gk), _ptr(gc), _ptr(bstat),
-                                              _ptr(ws), ws.numel() * 8, ctypes.c_void_p(stream)),
+                _capi.check(L.intopt_backward_values(dp.handle, Bg, mode, float(damping), sf.nvar, _ptr(st),
+                                                     _ptr(c_std), sf.n, _ptr(b_std), b_stride, _ptr(a_vals),
+                                                     dp.nnz if a_vals is not None else 0, _ptr(gk), _ptr(gc),
+                                                     _ptr(bstat), _ptr(ws), ws.numel() * 8, ctypes.c_void_p(stream)),
                             "intopt_backward")
                 if dp.identity_vars:
                     gfull = gc

@@ -23,7 +23,7 @@ def build():
 
 
 def solve(A, b, c, g=None, b_batch=None, alpha0=0.9995, tol=1e-8, thr=0.0, max_iter=1000, damping_fwd=1e-6,
-          mode=0, damping_bwd=1e-2, nvar=None, force_order=-1, init=None):
+          mode=0, damping_bwd=1e-2, nvar=None, force_order=-1, init=None, a_vals=None):
     lib = ctypes.CDLL(build())
     A = sp.csr_matrix(A)
     A.sort_indices()
@@ -46,12 +46,13 @@ def solve(A, b, c, g=None, b_batch=None, alpha0=0.9995, tol=1e-8, thr=0.0, max_i
     gx = None if g is None else np.ascontiguousarray(np.atleast_2d(g), dtype=np.float64)
     gc = None if g is None else np.zeros((B, nvar))
     ini = None if init is None else np.ascontiguousarray(init, dtype=np.float64)
+    av = None if a_vals is None else np.ascontiguousarray(a_vals, dtype=np.float64)  # B x nnz, CSR order of A
     env = ctypes.c_int(0)
     rc = lib.emu_solve(ctypes.c_int(m), ctypes.c_int(n), dp(rp), dp(ci), dp(val), dp(bb), ctypes.c_int(force_order),
                        ctypes.c_int(B), dp(c), ctypes.c_longlong(c_stride), dp(bbatch), ctypes.c_double(alpha0),
                        ctypes.c_double(tol), ctypes.c_double(thr), ctypes.c_double(damping_fwd),
                        ctypes.c_int(max_iter), dp(ini), dp(xhat), dp(state), dp(status), dp(iters),
                        ctypes.c_int(mode), ctypes.c_double(damping_bwd), ctypes.c_int(nvar), dp(gx), dp(gc),
-                       dp(bstatus), ctypes.byref(env))
+                       dp(bstatus), ctypes.byref(env), dp(av))
     assert rc == 0, rc
     return dict(xhat=xhat, state=state, status=status, iters=iters, gc=gc, bstatus=bstatus, envelope=env.value)

@@ -112,6 +112,16 @@ def test_knapsack_per_instance_A():
         _check_case("knapsack", z, case, None, lambda i: GU.problem_inputs("knapsack", z, i))
 
 
+def test_knapsack_batched_per_instance_A():
+    """One launch for a batch of knapsack LPs whose equality row (the cost vector) differs per instance: A of shape
+    (B, 1, 31), same pattern, per-instance values through intopt_forward_values / intopt_backward_values."""
+    z = GU.load("knapsack")
+    for case in GU.cases(z):
+        k = len(case["c"])
+        batched = dict(A=np.stack([z["costs"][i][None, :] for i in range(k)]), b=z["budget_rhs"], G=None, h=None)
+        _check_case("knapsack", z, case, batched, lambda i: GU.problem_inputs("knapsack", z, i))
+
+
 def test_one_dimensional_c_and_dtype():
     from neuripsintopt_b200.ip_model_whole import IPOfunc
     z = GU.load("dense_m16")

@@ -57,3 +57,41 @@ def test_breakdown_is_reported_not_hidden():
     A = np.array([[1.0, 1.0, 1.0]])
     e = emu_py.solve(A, np.array([1.0]), np.array([1.0, np.nan, 2.0]))
     assert e["status"][0] == 4
+
+
+def test_emulated_per_instance_values_knapsack():
+    """Per-instance values of A (same pattern): the knapsack driver's equality row is the minibatch's cost vector
+    (experiments/Building Knapsack/optimizer.py:396-405); every instance is checked against its own oracle solve."""
+    import scipy.sparse as sp
+    z = GU.load("knapsack")
+    case = GU.cases(z)[0]
+    kw = case["kw"]
+    B = min(4, case["c"].shape[0], z["costs"].shape[0])
+    sfs, refs = [], []
+    for i in range(B):
+        inp = GU.problem_inputs("knapsack", z, i)
+        r = O.ipofunc(case["c"][i], case["g"][i], variant="whole", bounds=kw["bounds"], thr=kw["thr"],
+                      max_iter=kw["max_iter"], damping=kw["damping"], **inp)
+        refs.append(r)
+        sfs.append(r["sf"])
+    A0 = sp.csr_matrix(sfs[0]["A"])
+    A0.sort_indices()
+    vals = []
+    for s in sfs:  # same pattern, different numbers
+        Ai = sp.csr_matrix(s["A"])
+        Ai.sort_indices()
+        assert np.array_equal(Ai.indptr, A0.indptr) and np.array_equal(Ai.indices, A0.indices)
+        vals.append(Ai.data)
+    cc = np.stack([s["c"] for s in sfs])
+    gg = np.stack([case["g"][i].astype(np.float64)[sfs[i]["var_index"]] for i in range(B)])
+    e = emu_py.solve(sfs[0]["A"], sfs[0]["b"], cc, g=gg, thr=kw["thr"], max_iter=kw["max_iter"], damping_fwd=1e-6,
+                     mode=0, damping_bwd=kw["damping"], nvar=sfs[0]["nvar"], a_vals=np.stack(vals))
+    for i in range(B):
+        r = refs[i]
+        xh = r["state"]["x"] / r["state"]["tau"]
+        assert np.abs(e["xhat"][i] - xh).max() / max(1.0, np.abs(xh).max()) < 1e-6
+        assert int(e["iters"][i]) == r["iters"]
+        m, n = sfs[i]["A"].shape
+        st = GU.split_state(e["state"][i], m, n)
+        dc = O.backward_whole(sfs[i]["A"], sfs[i]["b"], sfs[i]["c"], st, gg[i], kw["damping"], sfs[i]["nvar"])
+        assert np.linalg.norm(e["gc"][i] - dc) / np.linalg.norm(dc) < 1e-6
