@@ -51,6 +51,8 @@ inline void bind_problem(const HostStructure& S, ProblemDev& D, Up&& up) {
   D.asm_unit = S.asm_unit ? 1 : 0;
   D.asm_w = S.asm_unit ? nullptr : up(S.asm_w);
   D.inst_values = S.inst_values ? 1 : 0;
+  D.n_csc_pad = (int)S.csc_val.size();
+  D.n_asm_pad = (int)S.asm_w.size();
   D.csr_src = S.inst_values ? up(S.csr_src) : nullptr;
   D.csc_src = S.inst_values ? up(S.csc_src) : nullptr;
   D.asm_sa = S.inst_values ? up(S.asm_sa) : nullptr;

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   const intopt::SmemLayout S =
       intopt::carve<ALLSMEM>(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
-  const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
   const bool cold = a.cold_factor != nullptr && a.init == nullptr && *a.cold_ok != 0;  // launch-uniform
   if (cold && a.factor_in_smem && threadIdx.x == 0) intopt::mbar_init(S.mbar, 1);
   unsigned served = 0;  // instances this CTA has run = completed phases of the prefetch mbarrier
@@ -178,7 +179,8 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   const intopt::SmemLayout S =
       intopt::carve<ALLSMEM>(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
-  const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
     __syncthreads();
@@ -404,10 +406,15 @@ static const void* pick_cold_kernel(int threads, bool allsmem) {
 
 namespace {
 bool g_profile_phases = false;
+size_t vals_ws_doubles(const IntoptProblem* p) {
+  return (size_t)p->dev.nnz + (size_t)p->dev.n_csc_pad + (size_t)p->dev.n_asm_pad;
+}
 size_t ws_per_slot_doubles(const IntoptProblem* p) {
   size_t per = (size_t)intopt::W_NVEC * p->info.n;
   if (!p->info.factor_in_smem) per += (size_t)p->info.envelope;
   if (!p->info.gather_in_smem) per += 2 * (size_t)intopt::gather_len(p->info.n);
+  per = (per + 1) & ~(size_t)1;
+  if (p->dev.inst_values) per += vals_ws_doubles(p);  // this instance's copies of the value streams of A
   return (per + 1) & ~(size_t)1;
 }
 
@@ -586,6 +593,9 @@ int intopt_forward_values(const IntoptProblem* p, int B, const double* c, long l
   a.factor_in_smem = p->info.factor_in_smem;
   a.gather_in_smem = p->info.gather_in_smem;
   a.ws_stride = (long long)ws_per_slot_doubles(p);
+  // the value streams sit at the end of every slot
+  a.vals_ws = a.ws + (a.ws_stride - (long long)((vals_ws_doubles(p) + 1) & ~(size_t)1));
+  a.vals_ws_stride = a.ws_stride;
   a.alpha0 = o->alpha0;
   a.tol = o->tol;
   a.thr = o->thr;
@@ -652,6 +662,9 @@ int intopt_backward_values(const IntoptProblem* p, int B, int mode, double dampi
   a.factor_in_smem = p->info.factor_in_smem;
   a.gather_in_smem = p->info.gather_in_smem;
   a.ws_stride = (long long)ws_per_slot_doubles(p);
+  // the value streams sit at the end of every slot
+  a.vals_ws = a.ws + (a.ws_stride - (long long)((vals_ws_doubles(p) + 1) & ~(size_t)1));
+  a.vals_ws_stride = a.ws_stride;
   const int grid = std::min(B, p->slots);
   CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
   {

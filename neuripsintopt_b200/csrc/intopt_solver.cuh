@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #ifdef INTOPT_HOST_EMU
+inline int blockIdx_x() { return 0; }
 #define IO_DEV inline
 #define IO_HD inline
 #define IO_FORCEINLINE inline
@@ -31,6 +32,7 @@ struct CtaCtx {
 IO_DEV double warp_sum(double v) { return v; }
 IO_DEV double warp_min(double v) { return v; }
 #else
+__device__ __forceinline__ int blockIdx_x() { return (int)blockIdx.x; }
 #define IO_DEV __device__ __forceinline__
 #define IO_HD __host__ __device__ inline
 #define IO_FORCEINLINE __device__ __forceinline__
@@ -141,7 +143,7 @@ struct ProblemDev {
   const double* asm_w;  // null if asm_unit
   // per-instance values of A (same pattern): positions in the caller's CSR value array, -1 = padding (see
   // intopt_structure.hpp); null unless the problem was created for it
-  int inst_values;
+  int inst_values, n_csc_pad, n_asm_pad;  // (padded lengths of csc_val / asm_w)
   const int* csr_src;
   const int* csc_src;
   const int* asm_sa;
@@ -160,7 +162,11 @@ struct Meta {
   const int* csc_gptr;
   const int* asm_gptr;
   const int* asm_rptr;
-  const double* av;  // this instance's values of A (caller's CSR order), or null: the problem's own values
+  // value streams of A (by rows, by column groups, assembly weights): the problem's own, or this instance's copies
+  // in the CTA's workspace when the values differ per instance (materialize_instance_values)
+  const double* csr_val;
+  const double* csc_val;
+  const double* asm_w;
 };
 
 // Sum N partial values over the CTA; every thread receives the totals (fixed order => deterministic).
@@ -252,26 +258,6 @@ IO_FORCEINLINE double gather_sum_weighted(const IT* __restrict__ kk, const doubl
     s1 = fma(w[3], g[k[3]], s1);
   }
   for (; t < len; ++t) s0 = fma(ww[t * 32], g[kk[t * 32]], s0);
-  return s0 + s1;
-}
-
-// per-instance values: the weight of a term is the product of two entries of this instance's A
-template <class IT>
-IO_FORCEINLINE double gather_sum_inst(const IT* __restrict__ kk, const int* __restrict__ sa, const int* __restrict__ sb,
-                                      const double* __restrict__ av, const double* g, int len) {
-  double s0 = 0.0, s1 = 0.0;
-  int t = 0;
-  for (; t + 2 <= len; t += 2) {
-    const int k0 = kk[t * 32], k1 = kk[(t + 1) * 32];
-    const int a0 = sa[t * 32], b0 = sb[t * 32], a1 = sa[(t + 1) * 32], b1 = sb[(t + 1) * 32];
-    const double w0 = a0 >= 0 ? av[a0] * av[b0] : 0.0, w1 = a1 >= 0 ? av[a1] * av[b1] : 0.0;
-    s0 = fma(w0, g[k0], s0);
-    s1 = fma(w1, g[k1], s1);
-  }
-  for (; t < len; ++t) {
-    const int a0 = sa[t * 32];
-    s0 = fma(a0 >= 0 ? av[a0] * av[sb[t * 32]] : 0.0, g[kk[t * 32]], s0);
-  }
   return s0 + s1;
 }
 
@@ -426,15 +412,12 @@ IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const 
       const int e = grp * 32 + l;
       const size_t base = (size_t)g0 * 32 + l;
       double s;
-      if (M.av) {
-        s = P.asm_k16 ? gather_sum_inst(P.asm_k16 + base, P.asm_sa + base, P.asm_sb + base, M.av, g, len)
-                      : gather_sum_inst(P.asm_k + base, P.asm_sa + base, P.asm_sb + base, M.av, g, len);
-      } else if (P.asm_k16) {
+      if (P.asm_k16) {
         s = P.asm_unit ? gather_sum_unit(P.asm_k16 + base, g, len)
-                       : gather_sum_weighted(P.asm_k16 + base, P.asm_w + base, g, len);
+                       : gather_sum_weighted(P.asm_k16 + base, M.asm_w + base, g, len);
       } else {
         s = P.asm_unit ? gather_sum_unit(P.asm_k + base, g, len)
-                       : gather_sum_weighted(P.asm_k + base, P.asm_w + base, g, len);
+                       : gather_sum_weighted(P.asm_k + base, M.asm_w + base, g, len);
       }
       const int pos = P.asm_pos[e];
       if (pos >= 0) L[pos] = P.asm_diag[e] ? s + delta : s;
@@ -984,18 +967,8 @@ IO_DEV void spmv_rows_n(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
           if (e3 < hi) t1 += src2[c3];
         }
       } else {
-        double a0, a1, a2, a3;
-        if (M.av) {
-          a0 = M.av[P.csr_src[e]];
-          a1 = e1 < hi ? M.av[P.csr_src[e1]] : 0.0;
-          a2 = e2 < hi ? M.av[P.csr_src[e2]] : 0.0;
-          a3 = e3 < hi ? M.av[P.csr_src[e3]] : 0.0;
-        } else {
-          a0 = P.csr_val[e];
-          a1 = e1 < hi ? P.csr_val[e1] : 0.0;
-          a2 = e2 < hi ? P.csr_val[e2] : 0.0;
-          a3 = e3 < hi ? P.csr_val[e3] : 0.0;
-        }
+        const double a0 = M.csr_val[e], a1 = e1 < hi ? M.csr_val[e1] : 0.0, a2 = e2 < hi ? M.csr_val[e2] : 0.0,
+                     a3 = e3 < hi ? M.csr_val[e3] : 0.0;
         s0 = fma(a0, src[c0], s0);
         if (e1 < hi) s1 = fma(a1, src[c1], s1);
         if (e2 < hi) s0 = fma(a2, src[c2], s0);
@@ -1066,22 +1039,13 @@ IO_FORCEINLINE void col_dot_n(const ProblemDev& P, const Meta& M, int k, const d
           }
         }
     } else {
-      const double* __restrict__ vv = P.csc_val + (size_t)(g0 + t0) * 32 + l;
+      const double* __restrict__ vv = M.csc_val + (size_t)(g0 + t0) * 32 + l;
 #pragma unroll
       for (int c = 0; c < NC; ++c)
         if (t0 + 8 * c < len) {
           double wv[8];
-          if (M.av) {
-            const int* __restrict__ ss = P.csc_src + (size_t)(g0 + t0) * 32 + l;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int src = ss[(8 * c + j) * 32];
-              wv[j] = src >= 0 ? M.av[src] : 0.0;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) wv[j] = vv[(8 * c + j) * 32];
-          }
+          for (int j = 0; j < 8; ++j) wv[j] = vv[(8 * c + j) * 32];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int i0 = IDX_LO(q[c], j), i1 = IDX_HI(q[c], j);
@@ -1132,7 +1096,9 @@ IO_DEV Meta global_meta(const ProblemDev& P) {
   M.csc_gptr = P.g_csc_gptr;
   M.asm_gptr = P.g_asm_gptr;
   M.asm_rptr = P.g_asm_rptr;
-  M.av = nullptr;
+  M.csr_val = P.csr_val;
+  M.csc_val = P.csc_val;
+  M.asm_w = P.asm_w;
   return M;
 }
 
@@ -1164,9 +1130,36 @@ IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
   M.asm_gptr = d;
   d += cnt[6];
   M.asm_rptr = d;
-  M.av = nullptr;
+  M.csr_val = P.csr_val;
+  M.csc_val = P.csc_val;
+  M.asm_w = P.asm_w;
   CTA_SYNC();
   return M;
+}
+
+// Per-instance values of A: the three value streams the kernels read (by rows, by column groups, assembly weights)
+// then live in the CTA's workspace (`buf` = nnz + n_csc_pad + n_asm_pad doubles, laid out like the problem's own);
+// instance_value_streams points the schedule at them once per CTA, fill_instance_values copies one instance's
+// numbers (av, in the caller's CSR order) in.
+IO_DEV void instance_value_streams(const ProblemDev& P, Meta& M, double* buf) {
+  M.csr_val = buf;
+  M.csc_val = buf + P.nnz;
+  M.asm_w = buf + P.nnz + P.n_csc_pad;
+}
+IO_DEV void fill_instance_values(const CtaCtx& cx, const ProblemDev& P, const double* av, double* buf) {
+  double* cv = buf;
+  double* sv = cv + P.nnz;
+  double* wv = sv + P.n_csc_pad;
+  CTA_FOR(e, P.nnz) cv[e] = av[P.csr_src[e]];
+  CTA_FOR(i, P.n_csc_pad) {
+    const int src = P.csc_src[i];
+    sv[i] = src >= 0 ? av[src] : 0.0;
+  }
+  CTA_FOR(i, P.n_asm_pad) {
+    const int sa = P.asm_sa[i];
+    wv[i] = sa >= 0 ? av[sa] * av[P.asm_sb[i]] : 0.0;
+  }
+  CTA_SYNC();
 }
 
 // workspace n-vector slots (global, per CTA)
@@ -1319,6 +1312,8 @@ struct FwdParams {
   const double* init;       // B x (2n+m+2) or null
   const double* a_vals;     // per-instance values of A, B x nnz (caller's CSR order), or null
   long long a_stride;
+  double* vals_ws;          // per CTA slot: nnz + n_csc_pad + n_asm_pad doubles (only with a_vals)
+  long long vals_ws_stride;
   double* xhat;
   double* state;
   int* status;
@@ -1379,10 +1374,10 @@ IO_DEV void factor_and_rhs(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
   CTA_SYNC();
 }
 
-IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M0, const FwdParams& a, int inst, double* wsi,
+IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst, double* wsi,
                              const SmemLayout& S, bool cold = false, unsigned cold_parity = 0) {
-  Meta M = M0;
-  M.av = a.a_vals ? a.a_vals + (long long)inst * a.a_stride : nullptr;
+  if (a.a_vals)  // (M already points at the CTA's value streams, see instance_value_streams)
+    fill_instance_values(cx, P, a.a_vals + (long long)inst * a.a_stride, a.vals_ws + (long long)blockIdx_x() * a.vals_ws_stride);
   const int m = P.m, n = P.n, mv = P.mv;
   double *L = S.L, *G = S.G, *bs = S.bs, *y = S.y, *r1 = S.r1, *q = S.q, *v = S.v;
   double* __restrict__ x = wsi + (long long)W_X * n;
@@ -1459,11 +1454,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     } else {
       WARP_ROWS(i, m) {
         double s = 0.0;
-        if (M.av) {
-          LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s += M.av[P.csr_src[e]];
-        } else {
-          LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s += P.csr_val[e];
-        }
+        LANE_FOR(e, M.csr_ptr[i], M.csr_ptr[i + 1]) s += M.csr_val[e];
         s = warp_sum(s);
         if (cx.lane == 0) {
           const double e = bs[i] - s;
@@ -1834,6 +1825,8 @@ struct BwdParams {
   const double* gx;  // B x nvar
   const double* a_vals;  // per-instance values of A or null
   long long a_stride;
+  double* vals_ws;
+  long long vals_ws_stride;
   double* gc;        // B x nvar
   int* status;
   double* ws;
@@ -1847,10 +1840,10 @@ struct BwdParams {
 //          s = (x.g + c.ug - b.w)/(b.q - c.p + mu/tau^2), dc = ug + p s        (ip_model_whole.py:1515-1556)
 //   alter: dc = -X2 (g - A^T M^-1 A (X2 g)) / mu  with x,t normalised by tau   (ip_model_alter.py:1524-1620)
 // with M = A diag(x^2) A^T + damping I in both.
-IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M0, const BwdParams& a, int inst, double* wsi,
+IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const BwdParams& a, int inst, double* wsi,
                               const SmemLayout& S) {
-  Meta M = M0;
-  M.av = a.a_vals ? a.a_vals + (long long)inst * a.a_stride : nullptr;
+  if (a.a_vals)
+    fill_instance_values(cx, P, a.a_vals + (long long)inst * a.a_stride, a.vals_ws + (long long)blockIdx_x() * a.vals_ws_stride);
   const int m = P.m, n = P.n, nvar = a.nvar, mv = P.mv;
   double *L = S.L, *G = S.G, *bs = S.bs, *q = S.q, *v = S.v;
   double* x2 = wsi + (long long)W_D * n;

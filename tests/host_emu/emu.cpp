@@ -30,11 +30,13 @@ extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const doubl
   const intopt::SmemLayout L = intopt::carve<true>(P, smem.data(), nullptr, 1, 1);
   CtaCtx cx;
   cx.red = L.red;
-  const intopt::Meta M = intopt::stage_meta(cx, P, L.meta);
+  intopt::Meta M = intopt::stage_meta(cx, P, L.meta);
   intopt::FwdParams a{};
   a.B = B; a.c = c; a.c_stride = c_stride; a.b_batch = b_batch; a.b_stride = m;
   a.b_problem = b ? bperm.data() : nullptr; a.init = init; a.xhat = xhat; a.state = state;
-  a.a_vals = a_vals; a.a_stride = rp[m];
+  std::vector<double> vws((size_t)rp[m] + S.csc_val.size() + S.asm_w.size() + 2);
+  a.a_vals = a_vals; a.a_stride = rp[m]; a.vals_ws = vws.data(); a.vals_ws_stride = 0;
+  if (a_vals) intopt::instance_value_streams(P, M, vws.data());
   a.status = status; a.iters = iters; a.ws = ws.data(); a.ws_stride = 0;
   a.factor_in_smem = 1; a.gather_in_smem = 1;
   a.alpha0 = alpha0; a.tol = tol; a.thr = thr; a.damping = damping_fwd; a.max_iter = max_iter;
@@ -53,7 +55,7 @@ extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const doubl
     g.B = B; g.mode = bwd_mode; g.nvar = nvar; g.damping = damping_bwd; g.state = state; g.c = c;
     g.c_stride = c_stride; g.b_batch = b_batch; g.b_stride = m; g.b_problem = b ? bperm.data() : nullptr;
     g.gx = gx; g.gc = gc; g.status = bstatus; g.ws = ws.data(); g.ws_stride = 0;
-    g.a_vals = a_vals; g.a_stride = rp[m];
+    g.a_vals = a_vals; g.a_stride = rp[m]; g.vals_ws = vws.data(); g.vals_ws_stride = 0;
     g.factor_in_smem = 1; g.gather_in_smem = 1;
     for (int i = 0; i < B; ++i) intopt::backward_instance(cx, P, M, g, i, ws.data(), L);
   }
