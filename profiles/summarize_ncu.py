@@ -29,7 +29,10 @@ keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_active",
+        "sm__icc_request_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__warps_active.avg.per_cycle_active"]
 for which in ("fwd", "bwd"):
     rep = os.path.join(go, "prof_%s_%s.ncu-rep" % (which, tag))
     if not os.path.exists(rep): continue
