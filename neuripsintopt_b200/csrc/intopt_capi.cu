@@ -372,7 +372,7 @@ __device__ unsigned long long g_phase_cycles[32];
 // Kernel variants: CTA size cap (128: 4 CTAs/SM x 128 registers, 192: 2 x 168, 256: 2 x 128, 512: 1 x 128) x whether every
 // buffer is in shared memory.
 #ifdef INTOPT_DEV_BUILD  // quick developer builds (INTOPT_NVCC_EXTRA=-DINTOPT_DEV_BUILD): default CTA size only
-#define INTOPT_VARIANTS(F) F(256, true) F(256, false)
+#define INTOPT_VARIANTS(F) F(128, true) F(128, false) F(256, true) F(256, false) F(512, true) F(512, false)
 #else
 #define INTOPT_VARIANTS(F)                                                                                   \
   F(128, true) F(128, false) F(192, true) F(192, false) F(256, true) F(256, false) F(512, true) F(512, false)

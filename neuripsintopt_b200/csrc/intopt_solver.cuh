@@ -1498,6 +1498,22 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
         acc[2] = fma(r, r, acc[2]);
       }
     }
+    if (iters > 0 && a.thr > 0.0) {
+      // Early stop (:1408): with thr > 0 the loop usually ends because mu <= thr, which makes `go` false whatever the
+      // residuals are.  If moreover tau is not tiny, both infeasibility tests (:1409-1413) are false without looking
+      // at the residuals either, so the primal residual (a product with A) need not be formed on the way out.  mu comes
+      // from the same fixed-order reduction as below: the decision is bit-identical to the full test sequence.
+      double xt1[1] = {acc[0]};
+      cta_sum<1>(cx, xt1);
+      const double mu_e = (xt1[0] + tau * kappa) / (double)(n + 1);
+      if (!(tau < a.tol * fmax(1.0, kappa)) && !(mu_e > a.thr)) {
+        if (a.max_iter < iters)
+          status = ST_MAXITER;
+        else if (!solved)
+          status = ST_BREAKDOWN;
+        break;
+      }
+    }
     double accm[2] = {0.0, 0.0};
     PHASE_MARK(pt, 16);
     spmv_rows(cx, P, M, G, r1);  // A x (G mirrors x)

@@ -122,6 +122,26 @@ def test_knapsack_batched_per_instance_A():
         _check_case("knapsack", z, case, batched, lambda i: GU.problem_inputs("knapsack", z, i))
 
 
+def test_cold_start_factor_cache_is_bit_identical(monkeypatch):
+    """Iteration 1 of a cold-started LP uses chol(A A^T + delta I) computed once per problem and streamed in by bulk
+    async copies; the claim is that this changes no bit of the result (same code computes the cached factor)."""
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = GU.load("energy_load1")
+    case = GU.cases(z)[0]
+    inp = GU.problem_inputs("energy_load1", z, 0)
+    f = IPOfunc(_tt(inp["A"]), _tt(inp["b"]), _tt(inp["G"]), _tt(inp["h"]), **case["kw"])
+    c = torch.tensor(np.repeat(case["c"], 40, axis=0), dtype=torch.float64, device="cuda")  # > one wave of CTA slots
+    outs = []
+    for no_cold in ("0", "1"):
+        monkeypatch.setenv("INTOPT_NO_COLD", no_cold)
+        cc = c.clone().requires_grad_(True)
+        x = f(cc)
+        x.sum().backward()
+        torch.cuda.synchronize()
+        outs.append((x.detach().clone(), cc.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_one_dimensional_c_and_dtype():
     from neuripsintopt_b200.ip_model_whole import IPOfunc
     z = GU.load("dense_m16")
