@@ -209,7 +209,7 @@ __device__ __forceinline__ void spmv_rows_dbg(const CtaCtx& cx, const intopt::Pr
       hn = P.rs_hdr[nxt * 32 + cx.lane];
       rown = P.rs_row[nxt * 32 + cx.lane];
     }
-    double s = (flags & 1) ? intopt::run_total16(src + (h & 0xffffu), (int)(h >> 16)) : src[h & 0xffffu];
+    double s = (flags & 1) ? intopt::run_total16(src + intopt::rs_start(h), intopt::rs_len(h), intopt::rs_rot(h)) : src[h & 0xffffu];
     if (flags & 2) {
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {

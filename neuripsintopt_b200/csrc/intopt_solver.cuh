@@ -871,18 +871,26 @@ IO_FORCEINLINE double run_total(const double* gp, int len) {
   return (s0 + s1) + (s2 + s3);
 }
 
-// sum of a run of at most 16 consecutive entries (the row kernel's pieces, RS_MAXLEN): fully predicated, no loop
-IO_FORCEINLINE double run_total16(const double* gp, int len) {
+// Sum of a run of at most 16 consecutive entries (the row kernel's pieces, RS_MAXLEN): fully predicated, no loop.
+// The 16 offsets are visited in an order rotated by `rot` (chosen on the host per lane so that start + rot == lane
+// mod 16): at every step the 32 lanes of a warp then touch 16 different 8-byte bank pairs, two lanes each - the
+// conflict-free pattern - wherever the runs start.
+IO_FORCEINLINE double run_total16(const double* gp, int len, int rot) {
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
-    if (j < len) s0 += gp[j];
-    if (j + 1 < len) s1 += gp[j + 1];
-    if (j + 2 < len) s2 += gp[j + 2];
-    if (j + 3 < len) s3 += gp[j + 3];
+    const int o0 = (j + rot) & 15, o1 = (j + 1 + rot) & 15, o2 = (j + 2 + rot) & 15, o3 = (j + 3 + rot) & 15;
+    if (o0 < len) s0 += gp[o0];
+    if (o1 < len) s1 += gp[o1];
+    if (o2 < len) s2 += gp[o2];
+    if (o3 < len) s3 += gp[o3];
   }
   return (s0 + s1) + (s2 + s3);
 }
+// header of a run piece: start | len << 16 | rot << 24
+IO_FORCEINLINE int rs_start(uint32_t h) { return (int)(h & 0xffffu); }
+IO_FORCEINLINE int rs_len(uint32_t h) { return (int)((h >> 16) & 0xffu); }
+IO_FORCEINLINE int rs_rot(uint32_t h) { return (int)(h >> 24); }
 
 // out = A src (NV = 1), or out = A src and out2 = A src2 in one pass over A (NV = 2: the index / header stream,
 // the address arithmetic and the scan bookkeeping are shared by the two products).
@@ -899,10 +907,10 @@ IO_DEV void spmv_rows_n(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
         const int row = P.rs_row[slot * 32 + l];
         if (row == 0xffff) continue;
         const bool first = l == 0 || P.rs_row[slot * 32 + l - 1] != row;
-        const double s = run_total16(src + (h & 0xffffu), (int)(h >> 16));
+        const double s = run_total16(src + rs_start(h), rs_len(h), rs_rot(h));
         out[row] = first ? s : out[row] + s;
         if (NV == 2) {
-          const double s2 = run_total16(src2 + (h & 0xffffu), (int)(h >> 16));
+          const double s2 = run_total16(src2 + rs_start(h), rs_len(h), rs_rot(h));
           out2[row] = first ? s2 : out2[row] + s2;
         }
       }
@@ -922,9 +930,9 @@ IO_DEV void spmv_rows_n(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
         hn = P.rs_hdr[nxt * 32 + cx.lane];
         rown = P.rs_row[nxt * 32 + cx.lane];
       }
-      double s = run_total16(src + (h & 0xffffu), (int)(h >> 16));
+      double s = run_total16(src + rs_start(h), rs_len(h), rs_rot(h));
       double s2 = 0.0;
-      if (NV == 2) s2 = run_total16(src2 + (h & 0xffffu), (int)(h >> 16));
+      if (NV == 2) s2 = run_total16(src2 + rs_start(h), rs_len(h), rs_rot(h));
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const double v = __shfl_up_sync(0xffffffffu, s, off);

@@ -356,6 +356,11 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
       hdr.push_back(0u);
       rid.push_back(0xffff);
     }
+    // rotation of every lane's visiting order: (start + rot) mod 16 == lane mod 16 (see run_total16)
+    for (size_t i = 0; i < hdr.size(); ++i) {
+      const int st = (int)(hdr[i] & 0xffffu), lane = (int)(i & 31);
+      hdr[i] |= (uint32_t)(((lane - st) % 16 + 16) % 16) << 24;
+    }
     if (ok) {
       S.rs_hdr = hdr;
       S.rs_row = rid;
