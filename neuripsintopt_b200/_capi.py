@@ -137,6 +137,10 @@ MICRO = ["barrier", "A.v (spmv_rows)", "A^T.y", "A^T.[y1 y2]", "assembly", "asse
          "solve2 skeleton only", "2*nsteps x (record load, barrier)", "2*nsteps x (record load, branches, barrier)"]
 
 
+MICRO += ["-"] * (35 - len(MICRO))
+MICRO[34] = "assembly: scan + zero fill only"
+
+
 def microbench(handle, which, reps=20, grid=1):
     """Debug aid: median/max SM cycles per repetition of one building block on `grid` persistent CTAs."""
     import numpy as np

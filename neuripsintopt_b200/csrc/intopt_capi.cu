@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
       case 19: spmv_rows_dbg(cx, P, S.G, S.q, 1); break;
       case 20: spmv_rows_dbg(cx, P, S.G, S.q, 2); break;
       case 21: spmv_rows_dbg(cx, P, S.G, S.q, 3); break;
+      case 34: intopt::assemble_normal_matrix(cx, P, M, D, S.G, S.scan, 1e-6, S.L, 1); break;  // prefix scan + zero fill only
       case 11: {  // dependent DFMA chain, 256 long
         double z = S.G[cx.tid & 7];
 #pragma unroll 16

@@ -346,6 +346,29 @@ IO_DEV void dd_prefix_scan(const CtaCtx& cx, const double* __restrict__ d, int n
   CTA_SYNC();
 }
 
+// 4*NQ run headers of one matrix entry (NQ 16-byte loads in flight together): every run adds the difference of two
+// double-double prefix sums; padding headers (len 0) contribute exactly 0
+template <int NQ>
+IO_FORCEINLINE void asm_run_batch(const uint32_t* __restrict__ hp, const D2* PP, double& s0, double& s1) {
+  uint32_t h[4 * NQ];
+#pragma unroll
+  for (int c = 0; c < NQ; ++c) {
+    const U4 q = *reinterpret_cast<const U4*>(hp + 4 * c);
+    h[4 * c] = q.x;
+    h[4 * c + 1] = q.y;
+    h[4 * c + 2] = q.z;
+    h[4 * c + 3] = q.w;
+  }
+#pragma unroll
+  for (int u = 0; u < 4 * NQ; u += 2) {
+    const int a0 = (int)(h[u] & 0xffffu), a1 = (int)(h[u + 1] & 0xffffu);
+    const D2 lo0 = PP[a0], hi0 = PP[a0 + (int)(h[u] >> 16)];
+    const D2 lo1 = PP[a1], hi1 = PP[a1 + (int)(h[u + 1] >> 16)];
+    s0 += dd_diff(hi0, lo0);
+    s1 += dd_diff(hi1, lo1);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: M = A diag(d) A^T + delta I, assembled entry by entry into the block skyline L.
 // `d` is the (global) weight vector, `region` the shared gather region of 2*gather_len(n) doubles.
@@ -363,34 +386,26 @@ IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const 
     CTA_FOR(e, P.bsize) L[e] = 0.0;
     CTA_SYNC();
     CTA_FOR(e, P.n_dummy) L[P.dummy_pos[e]] = 1.0;
-    // Lane l of a warp owns entry 32*grp + l; its R run headers are contiguous and fetched 12 at a time with
-    // three 16-byte loads that are all in flight together (one L2 round trip per group).
+    // Lane l of a warp owns entry 32*grp + l; its R run headers (R % 4 == 0, the same for the whole group: entries are
+    // sorted by run count) are contiguous and fetched with up to three 16-byte loads that are all in flight
+    // together; groups of 4 / 8 headers take the shorter batches, so padding headers cost nothing beyond the
+    // rounding of R to a multiple of four.
     WARP_ROWS(grp, ngrp) {
       const int r0 = M.asm_rptr[grp], R = M.asm_rptr[grp + 1] - r0;
       LANE_FOR(l, 0, 32) {
         const uint32_t* __restrict__ hp = P.asm_run + (size_t)r0 * 32 + (size_t)l * R;
         double s0 = 0.0, s1 = 0.0;
-        for (int rb = 0; rb < R; rb += 12) {
-          uint32_t h[12];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            if (rb + 4 * c < R) {
-              const U4 q = *reinterpret_cast<const U4*>(hp + rb + 4 * c);
-              h[4 * c] = q.x;
-              h[4 * c + 1] = q.y;
-              h[4 * c + 2] = q.z;
-              h[4 * c + 3] = q.w;
-            } else {
-              h[4 * c] = h[4 * c + 1] = h[4 * c + 2] = h[4 * c + 3] = 0u;
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 12; u += 2) {  // padding headers (len 0) contribute exactly 0
-            const int a0 = (int)(h[u] & 0xffffu), a1 = (int)(h[u + 1] & 0xffffu);
-            const D2 lo0 = PP[a0], hi0 = PP[a0 + (int)(h[u] >> 16)];
-            const D2 lo1 = PP[a1], hi1 = PP[a1 + (int)(h[u + 1] >> 16)];
-            s0 += dd_diff(hi0, lo0);
-            s1 += dd_diff(hi1, lo1);
+        for (int rb = 0; rb < R;) {
+          const int left = R - rb;
+          if (left >= 12) {
+            asm_run_batch<3>(hp + rb, PP, s0, s1);
+            rb += 12;
+          } else if (left >= 8) {
+            asm_run_batch<2>(hp + rb, PP, s0, s1);
+            rb += 8;
+          } else {
+            asm_run_batch<1>(hp + rb, PP, s0, s1);
+            rb += 4;
           }
         }
         const int e = grp * 32 + l, pos = P.asm_pos[e];
@@ -1344,7 +1359,7 @@ struct FwdParams {
 // Factor L (block_cholesky) and form the two products out1 = A src1, out2 = A src2 (out2 may be null: one product),
 // side by side when the CTA has at least 4 warps: the products need nothing from the factorisation.  On return
 // (after a full CTA barrier) *S.flag tells whether the factorisation succeeded.
-constexpr int RHS_WARPS = 3;
+constexpr int RHS_WARPS = 2;
 IO_DEV void factor_and_rhs(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, const SmemLayout& S,
                            const double* src1, const double* src2, double* out1, double* out2, PhaseTimer* pt) {
 #ifndef INTOPT_HOST_EMU

@@ -491,6 +491,9 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
     if (rle) {
       const auto &ra = ents[a].runs, &rb = ents[b].runs;
+      // a run costs two gathers whatever its length (prefix sums), so the work of a lane is its run COUNT: groups
+      // of equal count first (no padding slots inside a group), then the old tie-break by run lengths
+      if (((ra.size() + 3) >> 2) != ((rb.size() + 3) >> 2)) return ra.size() > rb.size();
       const size_t c = std::min(ra.size(), rb.size());
       for (size_t u = 0; u < c; ++u)
         if ((ra[u] >> 16) != (rb[u] >> 16)) return (ra[u] >> 16) > (rb[u] >> 16);
