@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   __shared__ int s_inst;
   double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
   const intopt::SmemLayout S =
-      intopt::carve<ALLSMEM>(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
+      intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
   intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
                                                                   double delta, double* ws, int factor_in_smem,
                                                                   int gather_in_smem, double* out, int* ok) {
   extern __shared__ __align__(16) double smem[];
-  const intopt::SmemLayout S = intopt::carve<ALLSMEM>(P, smem, ws + (long long)intopt::W_NVEC * P.n, factor_in_smem, gather_in_smem);
+  const intopt::SmemLayout S = intopt::carve<ALLSMEM>(P, smem, ws + intopt::ws_nvec_doubles(P.n), factor_in_smem, gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
   const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   intopt::cold_factor_build(cx, P, M, delta, ws, S, out, ok);
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   __shared__ int s_inst;
   double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
   const intopt::SmemLayout S =
-      intopt::carve<ALLSMEM>(P, smem, wsi + (long long)intopt::W_NVEC * P.n, a.factor_in_smem, a.gather_in_smem);
+      intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
   intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
                                                                   unsigned long long* out) {
   extern __shared__ __align__(16) double smem[];
   double* wsi = ws + (long long)blockIdx.x * ws_stride;
-  const intopt::SmemLayout S = intopt::carve<ALLSMEM>(P, smem, wsi + (long long)intopt::W_NVEC * P.n, factor_in_smem, gather_in_smem);
+  const intopt::SmemLayout S = intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), factor_in_smem, gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
   const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   const int n = P.n;
@@ -411,7 +411,7 @@ size_t vals_ws_doubles(const IntoptProblem* p) {
   return (size_t)p->dev.nnz + (size_t)p->dev.n_csc_pad + (size_t)p->dev.n_asm_pad;
 }
 size_t ws_per_slot_doubles(const IntoptProblem* p) {
-  size_t per = (size_t)intopt::W_NVEC * p->info.n;
+  size_t per = (size_t)intopt::ws_nvec_doubles(p->info.n);
   if (!p->info.factor_in_smem) per += (size_t)p->info.envelope;
   if (!p->info.gather_in_smem) per += 2 * (size_t)intopt::gather_len(p->info.n);
   per = (per + 1) & ~(size_t)1;

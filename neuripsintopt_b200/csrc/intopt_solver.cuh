@@ -1187,6 +1187,9 @@ IO_DEV void fill_instance_values(const CtaCtx& cx, const ProblemDev& P, const do
 
 // workspace n-vector slots (global, per CTA)
 enum { W_X = 0, W_T, W_D, W_R2, W_P, W_W, W_DX, W_DXDT, W_ATY, W_NVEC };
+// doubles of the n-vector block of a workspace slot; even, so that whatever follows (a spilled factor / gather
+// region, read with 16-byte accesses) stays 16-byte aligned
+IO_HD long long ws_nvec_doubles(int n) { return ((long long)W_NVEC * n + 1) & ~1LL; }
 // shared-memory m-vector slots
 enum { S_B = 0, S_Y, S_R1, S_Q, S_V, S_NVEC };
 constexpr int S_SCRATCH = 4 * KB + (KB + KB * KB) + 8 * 32 + 4;  // ybuf (double buffered, 2 rhs) + diag scratch + red + flag + mbarrier

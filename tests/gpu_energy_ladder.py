@@ -1,0 +1,46 @@
+"""Diagnostic (not a test): SURVEY §8(d) config 4 - larger Energy-scheduling instances synthesised in the ICON format
+((machines, tasks) ladder): parity of two instances against the oracle and throughput."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from neuripsintopt_b200.data import icon
+from neuripsintopt_b200.ip_model_whole import IPOfunc
+from neuripsintopt_b200 import ipofunc as _ipo
+from oracle import hsd_numpy as O
+
+ladder = [(3, 10), (5, 20), (8, 30)]
+sel = [int(a) for a in sys.argv[1:]] or [0, 1]
+for li in sel:
+    M_, T_ = ladder[li]
+    par = icon.load1_day01() if li == 0 else icon.synthesize(M_, T_, q=30, seed=0)
+    A, b, G, h, F = icon.make_matrix_intopt(**par)
+    B = 128
+    rng = np.random.default_rng(0)
+    P = rng.uniform(20.0, 120.0, (B, F.shape[1]))
+    c = np.asarray((F @ P.T).T, dtype=np.float32)
+    g = np.asarray(c / F.shape[0], dtype=np.float32)
+    tt = lambda Mx: torch.as_tensor(Mx.toarray() if hasattr(Mx, "toarray") else Mx, dtype=torch.float32)
+    t0 = time.time()
+    f = IPOfunc(tt(A), tt(b), tt(G), tt(h), bounds=[(0.0, None)], thr=0.1, damping=1e-6, check_finite=False)
+    ct = torch.tensor(c, device="cuda", requires_grad=True)
+    gt = torch.tensor(g, device="cuda")
+    x = f(ct); x.backward(gt); torch.cuda.synchronize()
+    t_first = time.time() - t0
+    status, iters = IPOfunc.status()
+    info = [v.info for v in _ipo._PROBLEM_CACHE.values() if hasattr(v, "info")][-1]
+    ex = eg = 0.0
+    Ad, Gd = A.toarray(), G.toarray()
+    for i in range(2):
+        r = O.ipofunc(c[i], g[i], A=Ad, b=b, G=Gd, h=h, bounds=[(0.0, None)], thr=0.1, damping=1e-6)
+        ex = max(ex, float(np.abs(x[i].detach().double().cpu().numpy() - r["x"]).max() / max(1.0, np.abs(r["x"]).max())))
+        eg = max(eg, float(np.linalg.norm(ct.grad[i].double().cpu().numpy() - r["grad"]) / np.linalg.norm(r["grad"])))
+        assert int(iters[i]) == r["iters"], (int(iters[i]), r["iters"])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        cc = ct.detach().requires_grad_(True); f(cc).backward(gt)
+    e1.record(); e1.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print("(M,T)=(%d,%d): std form %dx%d nnz %d | x_rel %.1e grad_rel %.1e iters %.2f bad %d | B=%d %.0f LP/s (%.2f ms/step) | smem %d B factor_in_smem %d gather_in_smem %d ctas/sm %d threads %d envelope %d | setup+first %.1f s" % (
+        M_, T_, info["m"], info["n"], info["nnz"], ex, eg, float(iters.float().mean()), int((status != 0).sum()), B, B / ms * 1e3, ms,
+        info["smem_bytes"], info["factor_in_smem"], info["gather_in_smem"], info["ctas_per_sm"], info["threads"], info["envelope"], t_first), flush=True)

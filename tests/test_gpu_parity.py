@@ -142,6 +142,28 @@ def test_cold_start_factor_cache_is_bit_identical(monkeypatch):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
+def test_larger_energy_instance_spilled_buffers():
+    """a synthesised (5 machines, 20 tasks) ICON instance - standard form 297 x 5037, odd n,
+    gather buffers spilled to the workspace (one LP fills an SM, 512 threads).  Guards the 16-byte alignment of the
+    spilled regions (an odd number of n-vectors times an odd n once misaligned them)."""
+    from neuripsintopt_b200.data import icon
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    par = icon.synthesize(5, 20, q=30, seed=0)
+    A, b, G, h, F = icon.make_matrix_intopt(**par)
+    rng = np.random.default_rng(0)
+    Bn = 3
+    c = np.asarray((F @ rng.uniform(20.0, 120.0, (Bn, F.shape[1])).T).T, dtype=np.float32)
+    g = (c / F.shape[0]).astype(np.float32)
+    Ad, Gd = A.toarray(), G.toarray()
+    kw = dict(bounds=[(0.0, None)], thr=0.1, damping=1e-6)
+    xs, gs, status, iters, _ = _run_gpu("whole", kw, dict(A=Ad, b=b, G=Gd, h=h), c, g)
+    assert (status == 0).all()
+    for i in range(2):
+        r = O.ipofunc(c[i], g[i], A=Ad, b=b, G=Gd, h=h, variant="whole", **kw)
+        assert iters[i] == r["iters"]
+        assert _relinf(xs[i], r["x"]) < X_TOL and _rel2(gs[i], r["grad"]) < G_TOL
+
+
 def test_one_dimensional_c_and_dtype():
     from neuripsintopt_b200.ip_model_whole import IPOfunc
     z = GU.load("dense_m16")
