@@ -45,8 +45,8 @@ def synthetic_costs(F, B, seed):
     rng = np.random.default_rng(seed)
     P_true = rng.uniform(20.0, 120.0, (B, 48))
     P_pred = P_true * np.abs(1.0 + 0.2 * rng.standard_normal((B, 48)))
-    c = np.asarray((F @ P_pred.T).T, dtype=np.float32)
-    g = np.asarray((F @ P_true.T).T / F.shape[0], dtype=np.float32)
+    c = np.ascontiguousarray((F @ P_pred.T).T, dtype=np.float32)  # row-major (B, n), like a predictor's output
+    g = np.ascontiguousarray((F @ P_true.T).T / F.shape[0], dtype=np.float32)
     return c, g
 
 

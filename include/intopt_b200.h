@@ -132,6 +132,15 @@ int intopt_backward_values(const IntoptProblem* p, int B, int mode, double dampi
                            const double* grad_x_dev, double* grad_c_dev,
                            int* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Host-glue helper (one launch on `stream`): dst[b][j] = idx[j] >= 0 ? scale[j] * src[b][idx[j]] : constv[j] for
+ * b < B, j < n_out, with float <-> double conversion (src_is_f32 / dst_is_f32; idx NULL = identity, scale NULL = 1,
+ * constv NULL = 0; strides in elements, src_stride 0 = one shared row).  Maps the user's cost vectors to the standard
+ * form (ip_model_whole.py:1380 _get_Abc's c), the solution back (_postprocess :1241-1285, fixed variables
+ * re-inserted) and the gradient both ways (:1518, :1559-1560) without a chain of cast / fill / index kernels. */
+int intopt_gather_convert(const void* src_dev, int src_is_f32, long long src_stride, int B, int n_out,
+                          const int* idx_dev, const double* scale_dev, const double* constv_dev, void* dst_dev,
+                          int dst_is_f32, long long dst_stride, void* stream);
+
 /* Measured FP64 FMA throughput of the current device (GFLOP/s) with a register-resident DFMA kernel;
  * the roofline denominator MEASURED_PEAKS.json lacks.  Synchronises the device. */
 int intopt_measure_fp64_peak(double* gflops_out, int repeats);

@@ -34,7 +34,8 @@ class IntoptInfo(ctypes.Structure):
 
 EXPORTS = ["intopt_version", "intopt_last_error", "intopt_analyze", "intopt_problem_create",
            "intopt_problem_destroy", "intopt_problem_info", "intopt_workspace_bytes", "intopt_forward",
-           "intopt_backward", "intopt_forward_values", "intopt_backward_values", "intopt_measure_fp64_peak",
+           "intopt_backward", "intopt_forward_values", "intopt_backward_values", "intopt_gather_convert",
+           "intopt_measure_fp64_peak",
            "intopt_debug_phase_cycles", "intopt_debug_microbench"]
 FLAG_INSTANCE_VALUES = 1
 
@@ -76,6 +77,7 @@ def lib():
     L.intopt_forward_values.argtypes = [vp, ci, vp, cll, vp, cll, vp, cll, ctypes.POINTER(IntoptOpts), vp, vp, vp, vp, vp,
                                         vp, csz, vp]
     L.intopt_backward_values.argtypes = [vp, ci, ci, cd, ci, vp, vp, cll, vp, cll, vp, cll, vp, vp, vp, vp, csz, vp]
+    L.intopt_gather_convert.argtypes = [vp, ci, cll, ci, ci, vp, vp, vp, vp, ci, cll, vp]
     L.intopt_measure_fp64_peak.argtypes = [ctypes.POINTER(cd), ci]
     L.intopt_debug_phase_cycles.argtypes = [ci, vp]
     L.intopt_debug_microbench.argtypes = [vp, ci, ci, ci, vp]

@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -345,6 +346,30 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   }
   const long long t1 = clock64();
   if (cx.tid == 0) out[blockIdx.x] = (unsigned long long)((t1 - t0) / (reps > 0 ? reps : 1)) + (sink == 12345.0 ? 1 : 0);
+}
+
+// Host-glue helper: dst[b, j] = idx[j] >= 0 ? scale[j] * src[b, idx[j]] : constv[j]   (scale NULL = 1, constv NULL = 0),
+// converting between float and double on the way.  One launch replaces the cast + zero-fill + index / index_put
+// chains that map the user's cost / gradient vectors to the standard form and the solution back.
+template <class TS, class TD>
+__global__ void __launch_bounds__(256) intopt_gather_convert_kernel(const TS* __restrict__ src, long long src_stride, int B,
+                                                                    int n_out, const int* __restrict__ idx,
+                                                                    const double* __restrict__ scale,
+                                                                    const double* __restrict__ constv, TD* __restrict__ dst,
+                                                                    long long dst_stride) {
+  const long long total = (long long)B * n_out;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / n_out), j = (int)(e - (long long)b * n_out);
+    const int k = idx ? idx[j] : j;
+    double v;
+    if (k >= 0) {
+      v = (double)src[(long long)b * src_stride + k];
+      if (scale) v *= scale[j];
+    } else {
+      v = constv ? constv[j] : 0.0;
+    }
+    dst[(long long)b * dst_stride + j] = (TD)v;
+  }
 }
 
 // Register-resident DFMA chains: the measured FP64 roofline denominator.
@@ -711,6 +736,27 @@ int intopt_debug_microbench(const IntoptProblem* p, int which, int reps, int gri
   CU_TRY(cudaMemcpy(cycles_host, out, sizeof(unsigned long long) * (size_t)grid, cudaMemcpyDeviceToHost));
   cudaFree(ws);
   cudaFree(out);
+  return 0;
+}
+
+int intopt_gather_convert(const void* src, int src_is_f32, long long src_stride, int B, int n_out, const int* idx,
+                          const double* scale, const double* constv, void* dst, int dst_is_f32, long long dst_stride,
+                          void* stream) {
+  if (!src || !dst || B < 0 || n_out < 0) return fail(-1, "bad argument");
+  const long long total = (long long)B * n_out;
+  if (total == 0) return 0;
+  const int threads = 256;
+  const int blocks = (int)std::min<long long>((total + threads - 1) / threads, 148LL * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_is_f32 && dst_is_f32)
+    intopt_gather_convert_kernel<float, float><<<blocks, threads, 0, st>>>((const float*)src, src_stride, B, n_out, idx, scale, constv, (float*)dst, dst_stride);
+  else if (src_is_f32)
+    intopt_gather_convert_kernel<float, double><<<blocks, threads, 0, st>>>((const float*)src, src_stride, B, n_out, idx, scale, constv, (double*)dst, dst_stride);
+  else if (dst_is_f32)
+    intopt_gather_convert_kernel<double, float><<<blocks, threads, 0, st>>>((const double*)src, src_stride, B, n_out, idx, scale, constv, (float*)dst, dst_stride);
+  else
+    intopt_gather_convert_kernel<double, double><<<blocks, threads, 0, st>>>((const double*)src, src_stride, B, n_out, idx, scale, constv, (double*)dst, dst_stride);
+  CU_TRY(cudaGetLastError());
   return 0;
 }
 

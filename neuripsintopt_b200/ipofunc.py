@@ -66,6 +66,17 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def _gather_convert(src, src_stride, B, n_out, idx, scale, constv, dst, stream):
+    """dst[b, j] = idx[j] >= 0 ? scale[j] * src[b, idx[j]] : constv[j] in one launch (float <-> double on the way)."""
+    _capi.check(_capi.lib().intopt_gather_convert(
+        _ptr(src), 1 if src.dtype == torch.float32 else 0, src_stride, B, n_out, _ptr(idx), _ptr(scale), _ptr(constv),
+        _ptr(dst), 1 if dst.dtype == torch.float32 else 0, dst.stride(0), ctypes.c_void_p(stream)), "intopt_gather_convert")
+
+
+def _glue_ok(t):
+    return t.dtype in (torch.float32, torch.float64) and t.dim() == 2 and t.stride(1) == 1
+
+
 _TAG0 = 1024.0  # tags of the pattern matrix that stands in for a batch of equality matrices (per-instance A)
 
 
@@ -104,6 +115,15 @@ class DeviceProblem:
         self.x_flip = t(sf.x_flip_ub, torch.float64) if np.isfinite(sf.x_flip_ub).any() else None
         self.free_cols = t(sf.free_cols, torch.long) if (sf.free_cols >= 0).any() else None
         self._ws = {}
+        # maps of the fused host glue (intopt_gather_convert): standard-form column j takes c_sign_full[j] * c[c_src_full[j]]
+        # (-1: slack / split column, cost 0); user variable i takes xhat[x_src[i]] or, if fixed by presolve, its value
+        self.c_src_full = t(sf.c_src, torch.int32)
+        self.c_sign_full = t(sf.c_sign, torch.float64)
+        x_src = np.full(sf.n_x, -1, dtype=np.int32)
+        x_src[sf.var_index] = np.arange(sf.nvar, dtype=np.int32)
+        self.x_src = t(x_src, torch.int32)
+        self.var_index32 = t(sf.var_index, torch.int32)
+        self.simple_post = self.x_shift is None and self.x_flip is None and self.free_cols is None
         if inst_values:
             # standard-form entry e of instance i = val_const[e] + val_sign[e] * A_i.flat[val_src[e]]: the entries
             # built from the tagged matrix (|value| >= _TAG0) are copies of user entries, the rest are constants
@@ -235,17 +255,23 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
             buf[:, lo:hi] = v.to(device=device, dtype=torch.float64).reshape(-1, hi - lo)
         return buf
 
-    def solve_group(dp, c2, sel):
-        """c2: (Bg, n_x) fp64 on device.  Returns x_user (Bg, n_x) fp64 and the tensors backward needs."""
+    def solve_group(dp, c2, sel, out_dtype):
+        """c2: (Bg, n_x) costs on device (float or double).  Returns x_user (Bg, n_x) and the tensors backward needs."""
         sf = dp.sf
         L = _capi.lib()
         Bg = c2.shape[0]
         device = c2.device
-        c_std = torch.zeros(Bg, sf.n, dtype=torch.float64, device=device)
-        if dp.c_plain:
-            c_std[:, :sf.nvar] = c2 if dp.identity_vars else c2[:, dp.c_src]
+        stream = torch.cuda.current_stream(device).cuda_stream
+        if _glue_ok(c2):  # one launch: cast, sign, scatter into the standard-form columns, zero cost on the slacks
+            c_std = torch.empty(Bg, sf.n, dtype=torch.float64, device=device)
+            _gather_convert(c2, c2.stride(0), Bg, sf.n, dp.c_src_full, dp.c_sign_full, None, c_std, stream)
         else:
-            c_std[:, dp.c_cols] = c2[:, dp.c_src] * dp.c_sign
+            c2 = c2.double()
+            c_std = torch.zeros(Bg, sf.n, dtype=torch.float64, device=device)
+            if dp.c_plain:
+                c_std[:, :sf.nvar] = c2 if dp.identity_vars else c2[:, dp.c_src]
+            else:
+                c_std[:, dp.c_cols] = c2[:, dp.c_src] * dp.c_sign
         b_all, bad, fixed_all = b_on_device(dp, device)
         if b_all.shape[0] == 1:
             b_std, b_stride, fixed = b_all, 0, fixed_all
@@ -270,12 +296,23 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
         ws = dp.workspace(Bg)
         init = pack_init(dp, Bg, device)
         opts = _capi.IntoptOpts(alpha0, tol, thr_, damping_fwd, max_iter_, 0)
-        stream = torch.cuda.current_stream(device).cuda_stream
         _capi.check(L.intopt_forward_values(dp.handle, Bg, _ptr(c_std), sf.n, _ptr(b_std), b_stride, _ptr(a_vals),
                                             dp.nnz if a_batched else 0, ctypes.byref(opts), _ptr(init), _ptr(xhat),
                                             _ptr(st), _ptr(status), _ptr(iters), _ptr(ws), ws.numel() * 8,
                                             ctypes.c_void_p(stream)), "intopt_forward")
         # _postprocess (:1241-1285): undo substitutions, re-insert fixed variables
+        if dp.simple_post and fixed.shape[0] == 1 and not bad.any():
+            # the drivers' case (lb = 0, no upper-bound flips, no free variables, fixed values shared by the batch): one
+            # launch writes x in the caller's dtype
+            x_user = torch.empty(Bg, n_x, dtype=out_dtype, device=device)
+            xkey = ("xconst", id(dp), str(device))
+            if xkey not in b_cache:  # values of the presolve-fixed variables in user positions (constant per problem)
+                xc = torch.zeros(n_x, dtype=torch.float64, device=device)
+                if sf.fixed_idx.size:
+                    xc[dp.fixed_idx] = fixed[0]
+                b_cache[xkey] = xc
+            _gather_convert(xhat, sf.n, Bg, n_x, dp.x_src, None, b_cache[xkey], x_user, stream)
+            return x_user, (c_std, b_std, b_stride, st, status, iters, a_vals)
         xk = xhat[:, :sf.nvar]
         if dp.free_cols is not None:
             neg = torch.where(dp.free_cols >= 0, xhat[:, dp.free_cols.clamp(min=0)], torch.zeros_like(xk))
@@ -306,7 +343,9 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
             ev1 = torch.cuda.Event(enable_timing=True)
             ev0.record()
             squeeze = c.dim() == 1
-            c2 = c.detach().reshape(-1, c.shape[-1]).double()
+            c2 = c.detach().reshape(-1, c.shape[-1])  # (kept in the caller's dtype: the pack kernel converts)
+            if c2.dtype not in (torch.float32, torch.float64):
+                c2 = c2.double()
             if c2.shape[1] != n_x:
                 raise ValueError("c must have %d entries per instance" % n_x)
             if check_finite and not bool(torch.isfinite(c2).all()):
@@ -335,9 +374,13 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                     # decided in presolve: upstream returns presolve's x and saves nothing (:1483-1488);
                     # the gradient of such instances is zero here
                     xg = torch.as_tensor(dp.x, dtype=torch.float64, device=device).expand(cg.shape[0], -1)
+                    if single:
+                        xg = xg.to(c.dtype)
                     saved.append((None, sel, None))
                 else:
-                    xg, pack = solve_group(dp, cg.contiguous(), sel)
+                    # (an expanded shared c keeps its stride 0: the pack kernel reads the one row for every instance)
+                    xg, pack = solve_group(dp, cg if (single and cg.stride(1) == 1) else cg.contiguous(), sel,
+                                           c.dtype if (single and c.dtype in (torch.float32, torch.float64)) else torch.float64)
                     saved.append((dp, sel, pack))
                 if single:
                     x_out = xg
@@ -361,7 +404,9 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
             L = _capi.lib()
             device = del_x.device
             B = ctx.B
-            g2 = del_x.detach().reshape(-1, n_x).double()
+            g2 = del_x.detach().reshape(-1, n_x)
+            if g2.dtype not in (torch.float32, torch.float64):
+                g2 = g2.double()
             if g2.shape[0] != B:
                 g2 = g2.expand(B, -1)
             single = len(ctx.saved) == 1
@@ -374,18 +419,29 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                 sf = dp.sf
                 c_std, b_std, b_stride, st, status, iters, a_vals = pack
                 gg = g2 if sel is None else g2[sel]
-                gk = (gg if dp.identity_vars else gg[:, dp.var_index]).contiguous()  # del_x[var_index] (:1518)
-                Bg = gk.shape[0]
+                if gg.stride(1) != 1 and gg.stride(0) != 0:
+                    gg = gg.contiguous()
+                Bg = gg.shape[0]
+                stream = torch.cuda.current_stream(device).cuda_stream
+                fast = sel is None and gg.stride(1) == 1 and ctx.in_dtype in (torch.float32, torch.float64)
+                if fast:  # del_x[var_index] (:1518) as doubles, one launch
+                    gk = torch.empty(Bg, sf.nvar, dtype=torch.float64, device=device)
+                    _gather_convert(gg, gg.stride(0), Bg, sf.nvar, dp.var_index32, None, None, gk, stream)
+                else:
+                    gk = (gg if dp.identity_vars else gg[:, dp.var_index]).double().contiguous()
                 gc = torch.empty(Bg, sf.nvar, dtype=torch.float64, device=device)
                 bstat = torch.empty(Bg, dtype=torch.int32, device=device)
                 ws = dp.workspace(Bg)
-                stream = torch.cuda.current_stream(device).cuda_stream
                 _capi.check(L.intopt_backward_values(dp.handle, Bg, mode, float(damping), sf.nvar, _ptr(st),
                                                      _ptr(c_std), sf.n, _ptr(b_std), b_stride, _ptr(a_vals),
                                                      dp.nnz if a_vals is not None else 0, _ptr(gk), _ptr(gc),
                                                      _ptr(bstat), _ptr(ws), ws.numel() * 8, ctypes.c_void_p(stream)),
                             "intopt_backward")
-                if dp.identity_vars:
+                if fast and single and not (len(ctx.in_shape) == 1 and B > 1):
+                    # c_grad[var_index] = dc, zeros elsewhere (:1559-1560), in the caller's dtype: one launch
+                    gfull = torch.empty(Bg, n_x, dtype=ctx.in_dtype, device=device)
+                    _gather_convert(gc, sf.nvar, Bg, n_x, dp.x_src, None, None, gfull, stream)
+                elif dp.identity_vars:
                     gfull = gc
                 else:
                     gfull = torch.zeros(Bg, n_x, dtype=torch.float64, device=device)
