@@ -395,9 +395,9 @@ def run_gpu(args):
                             NSETS, NSETS * 2 * c_dev.numel() * 4 / 1e6), parallelism="dp%d" % world),
             e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int(c_host.numel() * 4 + g_host.numel() * 4),
                      d2h_bytes_per_step=int(x_host.numel() * 4 + gc_host.numel() * 4)),
-            # per step: intopt_forward_kernel + intopt_backward_kernel + four intopt_gather_convert_kernel launches
-            # (cost -> standard form, solution back, upstream gradient in, dL/dc back)
-            gpu_launches=6 * K,
+            # per step: intopt_forward_kernel + intopt_backward_kernel (the mapping between the caller's float32 user
+            # layout and the standard form runs inside them)
+            gpu_launches=2 * K,
             roofline=dict(bound="fp64", kernel="intopt_forward_kernel", achieved=ach_fwd, peak=fp64_peak,
                           unit="TFLOP/s", frac=ach_fwd / fp64_peak,
                           # DRAM bytes of one forward launch from the committed `ncu --set full` capture of this

@@ -132,6 +132,39 @@ int intopt_backward_values(const IntoptProblem* p, int B, int mode, double dampi
                            const double* grad_x_dev, double* grad_c_dev,
                            int* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Optional mapping between the caller's own layout / precision and the standard form, applied INSIDE the solver kernels
+ * (no separate pack / unpack launches).  Any of the two halves may be off (in_dev / out_dev NULL).
+ *   input : standard-form entry j = in_scale[j] * in[inst][in_idx[j]]  (in_idx[j] < 0: 0; in_scale NULL: 1).  Forward: the
+ *           user's cost vectors (length of in_idx = n); backward: the upstream gradient (length nvar).  The packed rows are
+ *           written to c_dev / grad_x_dev, which are then outputs (the packed c is what the backward call wants as c_dev).
+ *   output: user entry i (< n_out) = std[out_idx[i]], or out_const[i] where out_idx[i] < 0 (out_const NULL: 0).  Forward:
+ *           x with the presolve-fixed variables re-inserted (_postprocess, ip_model_whole.py:1241-1285; xhat_dev may then
+ *           be NULL); backward: c_grad[var_index] = dc, zeros elsewhere (:1559-1560). */
+typedef struct IntoptUserMap {
+  const void* in_dev;
+  int in_is_f32;
+  long long in_stride;      /* elements between instances, 0 = one shared row */
+  const int* in_idx_dev;
+  const double* in_scale_dev;
+  void* out_dev;
+  int out_is_f32;
+  long long out_stride;
+  int n_out;
+  const int* out_idx_dev;
+  const double* out_const_dev;
+} IntoptUserMap;
+
+int intopt_forward_mapped(const IntoptProblem* p, int B, double* c_dev, long long c_stride,
+                          const double* b_batch_dev, long long b_stride, const double* a_vals_dev, long long a_stride,
+                          const IntoptOpts* opts, const double* init_dev, const IntoptUserMap* map,
+                          double* xhat_dev, double* state_dev, int* status_dev, int* iters_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+int intopt_backward_mapped(const IntoptProblem* p, int B, int mode, double damping_bwd, int nvar,
+                           const double* state_dev, const double* c_dev, long long c_stride,
+                           const double* b_batch_dev, long long b_stride, const double* a_vals_dev, long long a_stride,
+                           const IntoptUserMap* map, double* grad_x_dev, double* grad_c_dev,
+                           int* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Host-glue helper (one launch on `stream`): dst[b][j] = idx[j] >= 0 ? scale[j] * src[b][idx[j]] : constv[j] for
  * b < B, j < n_out, with float <-> double conversion (src_is_f32 / dst_is_f32; idx NULL = identity, scale NULL = 1,
  * constv NULL = 0; strides in elements, src_stride 0 = one shared row).  Maps the user's cost vectors to the standard

@@ -20,6 +20,13 @@ class IntoptOpts(ctypes.Structure):
                 ("damping_fwd", ctypes.c_double), ("max_iter", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
+class IntoptUserMap(ctypes.Structure):
+    _fields_ = [("in_dev", ctypes.c_void_p), ("in_is_f32", ctypes.c_int), ("in_stride", ctypes.c_longlong),
+                ("in_idx_dev", ctypes.c_void_p), ("in_scale_dev", ctypes.c_void_p), ("out_dev", ctypes.c_void_p),
+                ("out_is_f32", ctypes.c_int), ("out_stride", ctypes.c_longlong), ("n_out", ctypes.c_int),
+                ("out_idx_dev", ctypes.c_void_p), ("out_const_dev", ctypes.c_void_p)]
+
+
 class IntoptInfo(ctypes.Structure):
     _fields_ = [("m", ctypes.c_int), ("n", ctypes.c_int), ("nnz", ctypes.c_int), ("envelope", ctypes.c_int),
                 ("dense_lower", ctypes.c_int), ("asm_terms", ctypes.c_longlong), ("chol_macs", ctypes.c_longlong),
@@ -34,7 +41,8 @@ class IntoptInfo(ctypes.Structure):
 
 EXPORTS = ["intopt_version", "intopt_last_error", "intopt_analyze", "intopt_problem_create",
            "intopt_problem_destroy", "intopt_problem_info", "intopt_workspace_bytes", "intopt_forward",
-           "intopt_backward", "intopt_forward_values", "intopt_backward_values", "intopt_gather_convert",
+           "intopt_backward", "intopt_forward_values", "intopt_backward_values", "intopt_forward_mapped",
+           "intopt_backward_mapped", "intopt_gather_convert",
            "intopt_measure_fp64_peak",
            "intopt_debug_phase_cycles", "intopt_debug_microbench"]
 FLAG_INSTANCE_VALUES = 1
@@ -78,6 +86,10 @@ def lib():
                                         vp, csz, vp]
     L.intopt_backward_values.argtypes = [vp, ci, ci, cd, ci, vp, vp, cll, vp, cll, vp, cll, vp, vp, vp, vp, csz, vp]
     L.intopt_gather_convert.argtypes = [vp, ci, cll, ci, ci, vp, vp, vp, vp, ci, cll, vp]
+    um = ctypes.POINTER(IntoptUserMap)
+    L.intopt_forward_mapped.argtypes = [vp, ci, vp, cll, vp, cll, vp, cll, ctypes.POINTER(IntoptOpts), vp, um, vp, vp, vp, vp,
+                                        vp, csz, vp]
+    L.intopt_backward_mapped.argtypes = [vp, ci, ci, cd, ci, vp, vp, cll, vp, cll, vp, cll, um, vp, vp, vp, vp, csz, vp]
     L.intopt_measure_fp64_peak.argtypes = [ctypes.POINTER(cd), ci]
     L.intopt_debug_phase_cycles.argtypes = [ci, vp]
     L.intopt_debug_microbench.argtypes = [vp, ci, ci, ci, vp]

@@ -594,7 +594,34 @@ int intopt_forward_values(const IntoptProblem* p, int B, const double* c, long l
                           long long b_stride, const double* a_vals, long long a_stride, const IntoptOpts* o,
                           const double* init, double* xhat, double* state, int* status, int* iters, void* ws,
                           size_t ws_bytes, void* stream) {
-  if (!p || !c || !o || !xhat || !state || !status || !iters || !ws) return fail(-1, "NULL argument");
+  return intopt_forward_mapped(p, B, const_cast<double*>(c), c_stride, b_batch, b_stride, a_vals, a_stride, o, init, nullptr,
+                               xhat, state, status, iters, ws, ws_bytes, stream);
+}
+
+static void fill_user_map(intopt::UserMap& u, const IntoptUserMap* m) {
+  u = intopt::UserMap{};
+  if (!m) return;
+  u.in = m->in_dev;
+  u.in_f32 = m->in_is_f32;
+  u.in_stride = m->in_stride;
+  u.in_idx = m->in_idx_dev;
+  u.in_scale = m->in_scale_dev;
+  u.out = m->out_dev;
+  u.out_f32 = m->out_is_f32;
+  u.out_stride = m->out_stride;
+  u.n_out = m->n_out;
+  u.out_idx = m->out_idx_dev;
+  u.out_const = m->out_const_dev;
+}
+
+int intopt_forward_mapped(const IntoptProblem* p, int B, double* c, long long c_stride, const double* b_batch,
+                          long long b_stride, const double* a_vals, long long a_stride, const IntoptOpts* o,
+                          const double* init, const IntoptUserMap* um, double* xhat, double* state, int* status,
+                          int* iters, void* ws, size_t ws_bytes, void* stream) {
+  if (!p || !c || !o || !state || !status || !iters || !ws) return fail(-1, "NULL argument");
+  if (!xhat && !(um && um->out_dev)) return fail(-1, "neither xhat_dev nor a mapped output was given");
+  if (um && um->in_dev && (!um->in_idx_dev || c_stride < p->info.n)) return fail(-8, "mapped input needs in_idx_dev and one writable c row per instance");
+  if (um && um->out_dev && !um->out_idx_dev) return fail(-8, "mapped output needs out_idx_dev");
   if (a_vals && !p->dev.inst_values) return fail(-7, "per-instance values need a problem created with INTOPT_FLAG_INSTANCE_VALUES");
   if (!a_vals && p->dev.inst_values) return fail(-7, "this problem was created for per-instance values: pass a_vals_dev");
   if (B <= 0) return 0;
@@ -608,6 +635,7 @@ int intopt_forward_values(const IntoptProblem* p, int B, const double* c, long l
   a.b_stride = b_stride;
   a.b_problem = p->b_dev;
   a.init = init;
+  fill_user_map(a.um, um);
   a.a_vals = a_vals;
   a.a_stride = a_stride;
   a.xhat = xhat;
@@ -660,7 +688,16 @@ int intopt_backward_values(const IntoptProblem* p, int B, int mode, double dampi
                            const double* c, long long c_stride, const double* b_batch, long long b_stride,
                            const double* a_vals, long long a_stride, const double* gx, double* gc, int* status, void* ws,
                            size_t ws_bytes, void* stream) {
+  return intopt_backward_mapped(p, B, mode, damping, nvar, state, c, c_stride, b_batch, b_stride, a_vals, a_stride, nullptr,
+                                const_cast<double*>(gx), gc, status, ws, ws_bytes, stream);
+}
+
+int intopt_backward_mapped(const IntoptProblem* p, int B, int mode, double damping, int nvar, const double* state,
+                           const double* c, long long c_stride, const double* b_batch, long long b_stride,
+                           const double* a_vals, long long a_stride, const IntoptUserMap* um, double* gx, double* gc,
+                           int* status, void* ws, size_t ws_bytes, void* stream) {
   if (!p || !c || !state || !gx || !gc || !status || !ws) return fail(-1, "NULL argument");
+  if (um && ((um->in_dev && !um->in_idx_dev) || (um->out_dev && !um->out_idx_dev))) return fail(-8, "mapped input / output needs its index array");
   if ((a_vals != nullptr) != (p->dev.inst_values != 0)) return fail(-7, "a_vals_dev must be given exactly for problems created with INTOPT_FLAG_INSTANCE_VALUES");
   if (B <= 0) return 0;
   if (mode != 0 && mode != 1) return fail(-5, "mode must be 0 (whole) or 1 (alter)");
@@ -679,6 +716,7 @@ int intopt_backward_values(const IntoptProblem* p, int B, int mode, double dampi
   a.b_stride = b_stride;
   a.b_problem = p->b_dev;
   a.gx = gx;
+  fill_user_map(a.um, um);
   a.a_vals = a_vals;
   a.a_stride = a_stride;
   a.gc = gc;

@@ -1328,6 +1328,38 @@ IO_DEV void cold_copy_finish(const CtaCtx& cx, const ProblemDev& P, const double
   CTA_SYNC();
 }
 
+// Optional mapping between the caller's own layout / precision and the standard form, applied inside the solver
+// kernels (saves the separate pack / unpack launches of the host glue).  `in == nullptr` / `out == nullptr`: off.
+//   input  : standard-form entry j (< n_in) = in_scale[j] * in[inst][in_idx[j]]   (in_idx[j] < 0: 0; in_scale null: 1)
+//            forward: the cost vector c, backward: the upstream gradient; the packed row is written to the kernel's
+//            regular input buffer (c / grad_x), which must then be writable
+//   output : user entry i (< n_out) = std[out_idx[i]], or out_const[i] where out_idx[i] < 0 (out_const null: 0)
+//            forward: x = x_hat with the presolve-fixed variables re-inserted, backward: dL/dc
+struct UserMap {
+  const void* in;
+  int in_f32;
+  long long in_stride;
+  const int* in_idx;
+  const double* in_scale;
+  void* out;
+  int out_f32;
+  long long out_stride;
+  int n_out;
+  const int* out_idx;
+  const double* out_const;
+};
+IO_FORCEINLINE double um_load(const UserMap& u, long long inst, int k) {
+  const long long o = inst * u.in_stride + k;
+  return u.in_f32 ? (double)reinterpret_cast<const float*>(u.in)[o] : reinterpret_cast<const double*>(u.in)[o];
+}
+IO_FORCEINLINE void um_store(const UserMap& u, long long inst, int i, double v) {
+  const long long o = inst * u.out_stride + i;
+  if (u.out_f32)
+    reinterpret_cast<float*>(u.out)[o] = (float)v;
+  else
+    reinterpret_cast<double*>(u.out)[o] = v;
+}
+
 struct FwdParams {
   int B;
   const double* c;
@@ -1336,6 +1368,7 @@ struct FwdParams {
   long long b_stride;
   const double* b_problem;  // internal row order or null
   const double* init;       // B x (2n+m+2) or null
+  UserMap um;               // optional user-layout input / output (see UserMap)
   const double* a_vals;     // per-instance values of A, B x nnz (caller's CSR order), or null
   long long a_stride;
   double* vals_ws;          // per CTA slot: nnz + n_csc_pad + n_asm_pad doubles (only with a_vals)
@@ -1421,6 +1454,14 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
 
   PhaseTimer pt{a.phase_cycles, 0};
   PHASE_START(pt);
+  if (a.um.in) {  // the caller's cost vector -> this instance's standard-form row (kept for the backward)
+    double* cw = const_cast<double*>(a.c) + (long long)inst * a.c_stride;
+    CTA_FOR(k, n) {
+      const int src = a.um.in_idx[k];
+      cw[k] = src >= 0 ? (a.um.in_scale ? a.um.in_scale[k] : 1.0) * um_load(a.um, inst, src) : 0.0;
+    }
+    CTA_SYNC();
+  }
   const bool l_in_smem = a.factor_in_smem != 0;
   if (cold) cold_copy_begin(cx, P, a.cold_factor, L, S.mbar, l_in_smem);
   // ---- load b, initial point (_initialization :647-661); padded slots of m-vectors are zero ---------
@@ -1815,7 +1856,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
 
   // ---- epilogue (:1441-1447): x_hat = x / tau, save the iterate ------------------------------------
   double* st = a.state + (long long)inst * slen;
-  double* xh = a.xhat + (long long)inst * n;
+  double* xh = a.xhat ? a.xhat + (long long)inst * n : nullptr;
   CTA_BATCH_FOR(k0, n, NU) {
     double xv[NU], tv[NU];
     BATCH_EACH(u, k, k0, n, NU) {
@@ -1823,9 +1864,15 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
       tv[u] = t[k];
     }
     BATCH_EACH(u, k, k0, n, NU) {
-      xh[k] = xv[u] / tau;
+      if (xh) xh[k] = xv[u] / tau;
       st[k] = xv[u];
       st[n + m + k] = tv[u];
+    }
+  }
+  if (a.um.out) {  // x in the caller's layout and precision, presolve-fixed variables re-inserted (_postprocess :1241-1285)
+    CTA_FOR(i, a.um.n_out) {
+      const int k = a.um.out_idx[i];
+      um_store(a.um, inst, i, k >= 0 ? x[k] / tau : (a.um.out_const ? a.um.out_const[i] : 0.0));
     }
   }
   CTA_FOR(i, m) st[n + P.perm[i]] = y[i];
@@ -1865,6 +1912,7 @@ struct BwdParams {
   long long b_stride;
   const double* b_problem;
   const double* gx;  // B x nvar
+  UserMap um;        // optional user-layout input / output (see UserMap)
   const double* a_vals;  // per-instance values of A or null
   long long a_stride;
   double* vals_ws;
@@ -1876,6 +1924,16 @@ struct BwdParams {
   int* counter;
   int factor_in_smem, gather_in_smem;
 };
+
+// c_grad[var_index] = dc, zeros elsewhere (:1559-1560), in the caller's layout and precision (after a CTA barrier
+// that completes gc)
+IO_DEV void backward_unpack(const CtaCtx& cx, const BwdParams& a, int inst, const double* gc) {
+  if (!a.um.out) return;
+  CTA_FOR(i, a.um.n_out) {
+    const int k = a.um.out_idx[i];
+    um_store(a.um, inst, i, k >= 0 ? gc[k] : 0.0);
+  }
+}
 
 // K5: dL/dc at the saved iterate, VJP form:
 //   whole: w = M^-1 (tau A(X2 g)), ug = X2 (A^T w - tau g)/mu, q = M^-1 (mu b + A(X2 c)), p = X2 (A^T q - c)/mu,
@@ -1894,6 +1952,11 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   const double* __restrict__ c = a.c + (long long)inst * a.c_stride;
   const double* __restrict__ g = a.gx + (long long)inst * nvar;
   double* gc = a.gc + (long long)inst * nvar;
+  if (a.um.in) {  // the caller's upstream gradient -> del_x[var_index] (:1518)
+    double* gw = const_cast<double*>(a.gx) + (long long)inst * nvar;
+    CTA_FOR(k, nvar) gw[k] = um_load(a.um, inst, a.um.in_idx[k]);
+    CTA_SYNC();
+  }
   const double* xs = st;
   const double* ts = st + n + m;
   const double tau = st[2 * n + m], kappa = st[2 * n + m + 1];
@@ -1936,6 +1999,7 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
     CTA_FOR(k, nvar) gc[k] = 0.0;
     if (cx.tid == 0) a.status[inst] = ST_BREAKDOWN;
     CTA_SYNC();
+    backward_unpack(cx, a, inst, gc);
     return;
   }
   if (!whole) {
@@ -1946,6 +2010,7 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
     CTA_FOR(k, nvar) gc[k] = -x2[k] * (g[k] - G[k]) / mu;
     if (cx.tid == 0) a.status[inst] = ST_OK;
     CTA_SYNC();
+    backward_unpack(cx, a, inst, gc);
     return;
   }
   CTA_FOR(i, m) {
@@ -1981,6 +2046,7 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   CTA_FOR(k, nvar) gc[k] = ug[k] + pp[k] * s;                                      // :1554-1556
   if (cx.tid == 0) a.status[inst] = ST_OK;
   CTA_SYNC();
+  backward_unpack(cx, a, inst, gc);
 }
 
 }  // namespace intopt

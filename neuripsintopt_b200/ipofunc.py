@@ -262,9 +262,12 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
         Bg = c2.shape[0]
         device = c2.device
         stream = torch.cuda.current_stream(device).cuda_stream
-        if _glue_ok(c2):  # one launch: cast, sign, scatter into the standard-form columns, zero cost on the slacks
-            c_std = torch.empty(Bg, sf.n, dtype=torch.float64, device=device)
-            _gather_convert(c2, c2.stride(0), Bg, sf.n, dp.c_src_full, dp.c_sign_full, None, c_std, stream)
+        um = _capi.IntoptUserMap()  # all-null: no mapping inside the kernel
+        map_in = _glue_ok(c2)
+        if map_in:  # the kernel reads the caller's c itself: cast, sign, scatter into the standard-form columns
+            c_std = torch.empty(Bg, sf.n, dtype=torch.float64, device=device)  # (filled by the kernel, kept for backward)
+            um.in_dev, um.in_is_f32, um.in_stride = c2.data_ptr(), int(c2.dtype == torch.float32), c2.stride(0)
+            um.in_idx_dev, um.in_scale_dev = dp.c_src_full.data_ptr(), dp.c_sign_full.data_ptr()
         else:
             c2 = c2.double()
             c_std = torch.zeros(Bg, sf.n, dtype=torch.float64, device=device)
@@ -289,21 +292,11 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
             if sel is None and A_flat.shape[0] != Bg:
                 raise ValueError("A has %d instances but c has %d" % (A_flat.shape[0], Bg))
             a_vals = dp.instance_values(A_flat if sel is None else A_flat[sel])
-        xhat = torch.empty(Bg, sf.n, dtype=torch.float64, device=device)
-        st = torch.empty(Bg, 2 * sf.n + sf.m + 2, dtype=torch.float64, device=device)
-        status = torch.empty(Bg, dtype=torch.int32, device=device)
-        iters = torch.empty(Bg, dtype=torch.int32, device=device)
-        ws = dp.workspace(Bg)
-        init = pack_init(dp, Bg, device)
-        opts = _capi.IntoptOpts(alpha0, tol, thr_, damping_fwd, max_iter_, 0)
-        _capi.check(L.intopt_forward_values(dp.handle, Bg, _ptr(c_std), sf.n, _ptr(b_std), b_stride, _ptr(a_vals),
-                                            dp.nnz if a_batched else 0, ctypes.byref(opts), _ptr(init), _ptr(xhat),
-                                            _ptr(st), _ptr(status), _ptr(iters), _ptr(ws), ws.numel() * 8,
-                                            ctypes.c_void_p(stream)), "intopt_forward")
-        # _postprocess (:1241-1285): undo substitutions, re-insert fixed variables
-        if dp.simple_post and fixed.shape[0] == 1 and not bad.any():
-            # the drivers' case (lb = 0, no upper-bound flips, no free variables, fixed values shared by the batch): one
-            # launch writes x in the caller's dtype
+        map_out = dp.simple_post and fixed.shape[0] == 1 and not bad.any()
+        x_user = None
+        if map_out:
+            # the drivers' case (lb = 0, no upper-bound flips, no free variables, fixed values shared by the batch): the
+            # kernel writes x in the caller's layout and dtype, fixed variables re-inserted (_postprocess :1241-1285)
             x_user = torch.empty(Bg, n_x, dtype=out_dtype, device=device)
             xkey = ("xconst", id(dp), str(device))
             if xkey not in b_cache:  # values of the presolve-fixed variables in user positions (constant per problem)
@@ -311,8 +304,22 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                 if sf.fixed_idx.size:
                     xc[dp.fixed_idx] = fixed[0]
                 b_cache[xkey] = xc
-            _gather_convert(xhat, sf.n, Bg, n_x, dp.x_src, None, b_cache[xkey], x_user, stream)
+            um.out_dev, um.out_is_f32, um.out_stride, um.n_out = x_user.data_ptr(), int(out_dtype == torch.float32), n_x, n_x
+            um.out_idx_dev, um.out_const_dev = dp.x_src.data_ptr(), b_cache[xkey].data_ptr()
+        xhat = None if map_out else torch.empty(Bg, sf.n, dtype=torch.float64, device=device)
+        st = torch.empty(Bg, 2 * sf.n + sf.m + 2, dtype=torch.float64, device=device)
+        status = torch.empty(Bg, dtype=torch.int32, device=device)
+        iters = torch.empty(Bg, dtype=torch.int32, device=device)
+        ws = dp.workspace(Bg)
+        init = pack_init(dp, Bg, device)
+        opts = _capi.IntoptOpts(alpha0, tol, thr_, damping_fwd, max_iter_, 0)
+        _capi.check(L.intopt_forward_mapped(dp.handle, Bg, _ptr(c_std), sf.n, _ptr(b_std), b_stride, _ptr(a_vals),
+                                            dp.nnz if a_batched else 0, ctypes.byref(opts), _ptr(init), ctypes.byref(um),
+                                            _ptr(xhat), _ptr(st), _ptr(status), _ptr(iters), _ptr(ws), ws.numel() * 8,
+                                            ctypes.c_void_p(stream)), "intopt_forward")
+        if map_out:
             return x_user, (c_std, b_std, b_stride, st, status, iters, a_vals)
+        # _postprocess (:1241-1285): undo substitutions, re-insert fixed variables
         xk = xhat[:, :sf.nvar]
         if dp.free_cols is not None:
             neg = torch.where(dp.free_cols >= 0, xhat[:, dp.free_cols.clamp(min=0)], torch.zeros_like(xk))
@@ -424,23 +431,31 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                 Bg = gg.shape[0]
                 stream = torch.cuda.current_stream(device).cuda_stream
                 fast = sel is None and gg.stride(1) == 1 and ctx.in_dtype in (torch.float32, torch.float64)
-                if fast:  # del_x[var_index] (:1518) as doubles, one launch
+                um = _capi.IntoptUserMap()
+                if fast:  # the kernel gathers del_x[var_index] (:1518) itself, as doubles
                     gk = torch.empty(Bg, sf.nvar, dtype=torch.float64, device=device)
-                    _gather_convert(gg, gg.stride(0), Bg, sf.nvar, dp.var_index32, None, None, gk, stream)
+                    um.in_dev, um.in_is_f32, um.in_stride = gg.data_ptr(), int(gg.dtype == torch.float32), gg.stride(0)
+                    um.in_idx_dev = dp.var_index32.data_ptr()
                 else:
                     gk = (gg if dp.identity_vars else gg[:, dp.var_index]).double().contiguous()
+                fast_out = fast and single and not (len(ctx.in_shape) == 1 and B > 1)
+                gfull = None
+                if fast_out:  # ... and writes c_grad[var_index] = dc, zeros elsewhere (:1559-1560), in the caller's dtype
+                    gfull = torch.empty(Bg, n_x, dtype=ctx.in_dtype, device=device)
+                    um.out_dev, um.out_is_f32, um.out_stride, um.n_out = (gfull.data_ptr(), int(ctx.in_dtype == torch.float32),
+                                                                           n_x, n_x)
+                    um.out_idx_dev = dp.x_src.data_ptr()
                 gc = torch.empty(Bg, sf.nvar, dtype=torch.float64, device=device)
                 bstat = torch.empty(Bg, dtype=torch.int32, device=device)
                 ws = dp.workspace(Bg)
-                _capi.check(L.intopt_backward_values(dp.handle, Bg, mode, float(damping), sf.nvar, _ptr(st),
+                _capi.check(L.intopt_backward_mapped(dp.handle, Bg, mode, float(damping), sf.nvar, _ptr(st),
                                                      _ptr(c_std), sf.n, _ptr(b_std), b_stride, _ptr(a_vals),
-                                                     dp.nnz if a_vals is not None else 0, _ptr(gk), _ptr(gc),
-                                                     _ptr(bstat), _ptr(ws), ws.numel() * 8, ctypes.c_void_p(stream)),
+                                                     dp.nnz if a_vals is not None else 0, ctypes.byref(um), _ptr(gk),
+                                                     _ptr(gc), _ptr(bstat), _ptr(ws), ws.numel() * 8,
+                                                     ctypes.c_void_p(stream)),
                             "intopt_backward")
-                if fast and single and not (len(ctx.in_shape) == 1 and B > 1):
-                    # c_grad[var_index] = dc, zeros elsewhere (:1559-1560), in the caller's dtype: one launch
-                    gfull = torch.empty(Bg, n_x, dtype=ctx.in_dtype, device=device)
-                    _gather_convert(gc, sf.nvar, Bg, n_x, dp.x_src, None, None, gfull, stream)
+                if fast_out:
+                    pass
                 elif dp.identity_vars:
                     gfull = gc
                 else:

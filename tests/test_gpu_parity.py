@@ -164,6 +164,24 @@ def test_larger_energy_instance_spilled_buffers():
         assert _relinf(xs[i], r["x"]) < X_TOL and _rel2(gs[i], r["grad"]) < G_TOL
 
 
+def test_gather_convert_helper():
+    """intopt_gather_convert (the stand-alone layout/precision helper of the C ABI) against the torch ops it replaces."""
+    from neuripsintopt_b200 import ipofunc as I
+    g = torch.Generator(device="cuda").manual_seed(0)
+    src = torch.randn(7, 13, device="cuda", generator=g)
+    idx = torch.tensor([3, -1, 0, 12, 5, -1, 7, 7, 1], dtype=torch.int32, device="cuda")
+    scale = torch.linspace(-2, 2, 9, dtype=torch.float64, device="cuda")
+    const = torch.arange(9, dtype=torch.float64, device="cuda") * 0.5
+    dst = torch.empty(7, 9, dtype=torch.float64, device="cuda")
+    I._gather_convert(src, src.stride(0), 7, 9, idx, scale, const, dst, torch.cuda.current_stream().cuda_stream)
+    ref = torch.where(idx >= 0, src.double()[:, idx.clamp(min=0).long()] * scale, const.expand(7, -1))
+    assert torch.equal(dst, ref)
+    dst32 = torch.empty(7, 9, dtype=torch.float32, device="cuda")
+    I._gather_convert(src.double(), 13, 7, 9, idx, None, None, dst32, torch.cuda.current_stream().cuda_stream)
+    ref32 = torch.where(idx >= 0, src[:, idx.clamp(min=0).long()], torch.zeros(7, 9, device="cuda"))
+    assert torch.equal(dst32, ref32)
+
+
 def test_one_dimensional_c_and_dtype():
     from neuripsintopt_b200.ip_model_whole import IPOfunc
     z = GU.load("dense_m16")
