@@ -1583,7 +1583,12 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     }
     double accm[2] = {0.0, 0.0};
     PHASE_MARK(pt, 16);
-    spmv_rows(cx, P, M, G, r1);  // A x (G mirrors x)
+    if (iters == 0 && !a.init && P.a_unit) {
+      // cold start of a 0/1 matrix: x = 1, so A x is the entry count of every row (exactly what the product returns)
+      CTA_FOR(i, m) r1[i] = (double)(M.csr_ptr[i + 1] - M.csr_ptr[i]);
+    } else {
+      spmv_rows(cx, P, M, G, r1);  // A x (G mirrors x)
+    }
     CTA_SYNC();
     PHASE_MARK(pt, 17);
     CTA_FOR(i, m) {
