@@ -311,6 +311,49 @@ def test_batched_energy_learner_gradient_matches_oracle():
     assert np.isfinite(loss0)
 
 
+def test_batched_shortest_path_and_knapsack_learners():
+    """The batched counterparts of the other two reference training loops (neuripsintopt_b200/learners.py): the LP
+    layer they build must reproduce the oracle's x and dL/dc instance by instance."""
+    from neuripsintopt_b200.learners import IntoptKnapsackLearner, IntoptShortestPathLearner, make_fc
+    # --- shortest path: shared predicted costs, a batch of (source, destination) right-hand sides
+    z = GU.load("twitter_sp")
+    case = GU.cases(z)[0]
+    Afull = GU.dense(z, "Afull")
+    A_rr = np.delete(Afull, z["removed_rows"], axis=0)
+    lrn = IntoptShortestPathLearner(A_rr, Afull.shape[0], z["removed_rows"], make_fc(2, 4), thr=0.1, max_iter=100,
+                                    damping=1e-2, lr=0.1)
+    pairs = [tuple(int(v) for v in p) for p in z["train_pairs"][:3]]
+    np.testing.assert_array_equal(lrn.rhs(pairs), z["b_rr"][:3].astype(np.float32))
+    c = torch.tensor(case["c"][0], dtype=torch.float32, device="cuda", requires_grad=True)
+    y = torch.tensor(z["c_true"], dtype=torch.float32, device="cuda")
+    x = lrn.solve(c, pairs)
+    (y * x).mean(dim=1).sum().backward()
+    want = np.zeros(c.shape[0])
+    for i in range(3):
+        r = O.ipofunc(case["c"][0], (z["c_true"] / c.shape[0]).astype(np.float32), A=A_rr, b=z["b_rr"][i],
+                      bounds=[(0.0, None)], thr=0.1, max_iter=100, damping=1e-2)
+        assert _relinf(x[i].detach().double().cpu().numpy(), r["x"]) < X_TOL
+        want += r["grad"]
+    assert _rel2(c.grad.double().cpu().numpy(), want) < G_TOL
+    # --- knapsack: one cost row per minibatch
+    zk = GU.load("knapsack")
+    ck = GU.cases(zk)[0]
+    K = 3
+    costs = zk["costs"][:K]
+    budget = float(zk["budget_rhs"][0]) / costs.shape[1]
+    kl = IntoptKnapsackLearner(torch.nn.Linear(2, 2), budget=budget, thr=ck["kw"]["thr"], damping=ck["kw"]["damping"],
+                               max_iter=ck["kw"]["max_iter"], lr=0.01)
+    prices = torch.tensor(-ck["c"][:K], dtype=torch.float32, device="cuda", requires_grad=True)  # the layer gets -prices
+    yk = torch.tensor(ck["g"][:K], dtype=torch.float32, device="cuda")
+    xk = kl.solve(prices, costs)
+    (xk * yk).sum().backward()
+    for i in range(K):
+        r = O.ipofunc(ck["c"][i], ck["g"][i], variant="whole", bounds=ck["kw"]["bounds"], thr=ck["kw"]["thr"],
+                      max_iter=ck["kw"]["max_iter"], damping=ck["kw"]["damping"], **GU.problem_inputs("knapsack", zk, i))
+        assert _relinf(xk[i].detach().double().cpu().numpy(), r["x"]) < X_TOL
+        assert _rel2(-prices.grad[i].double().cpu().numpy(), r["grad"]) < G_TOL  # d/dprice = -d/dc
+
+
 def test_full_size_batch_properties():
     """BASELINE size (B=1024 Energy LPs): size-independent checks — all status words 0, every instance stops
     after the same 2 iterations as the reference, primal residual small relative to the cold start, and
