@@ -164,6 +164,28 @@ def test_larger_energy_instance_spilled_buffers():
         assert _relinf(xs[i], r["x"]) < X_TOL and _rel2(gs[i], r["grad"]) < G_TOL
 
 
+def test_non_contiguous_inputs_take_the_same_path_results():
+    """The kernels read the caller's c / upstream gradient in place when they are row-major; column-major (or
+    otherwise strided) inputs go through a copy first.  Both must give identical results."""
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = GU.load("energy_load1")
+    case = GU.cases(z)[0]
+    inp = GU.problem_inputs("energy_load1", z, 0)
+    f = IPOfunc(_tt(inp["A"]), _tt(inp["b"]), _tt(inp["G"]), _tt(inp["h"]), **case["kw"])
+    c_rm = torch.tensor(np.ascontiguousarray(case["c"]), dtype=torch.float32, device="cuda")
+    g_rm = torch.tensor(np.ascontiguousarray(case["g"]), dtype=torch.float32, device="cuda")
+    c_cm = c_rm.t().contiguous().t()  # same values, column-major strides
+    g_cm = g_rm.t().contiguous().t()
+    assert not c_cm.is_contiguous() and not g_cm.is_contiguous()
+    outs = []
+    for cc, gg in ((c_rm, g_rm), (c_cm, g_cm)):
+        ct = cc.clone().requires_grad_(True) if cc.is_contiguous() else cc.detach().requires_grad_(True)
+        x = f(ct)
+        x.backward(gg)
+        outs.append((x.detach().clone(), ct.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_gather_convert_helper():
     """intopt_gather_convert (the stand-alone layout/precision helper of the C ABI) against the torch ops it replaces."""
     from neuripsintopt_b200 import ipofunc as I
