@@ -24,6 +24,7 @@ import hashlib
 from collections import OrderedDict
 
 import numpy as np
+import scipy.sparse as sp
 import torch
 from scipy.linalg import LinAlgError
 
@@ -80,63 +81,31 @@ def _glue_ok(t):
 _TAG0 = 1024.0  # tags of the pattern matrix that stands in for a batch of equality matrices (per-instance A)
 
 
-class DeviceProblem:
-    """A StandardForm plus its device-resident IntoptProblem handle and index tensors (one per device)."""
+class _DeviceHandle:
+    """An IntoptProblem handle on one device and its workspace."""
 
-    def __init__(self, sf, device, inst_values=False):
-        self.sf = sf
+    handle = None
+
+    def _create(self, A, device, inst_values):
+        """A: scipy CSR (m x n).  Returns its value array in the order the handle (and per-instance values) use."""
         self.device = device
         self.inst_values = inst_values
         L = _capi.lib()
-        A = sf.A
         rp = np.ascontiguousarray(A.indptr, dtype=np.int32)
         ci = np.ascontiguousarray(A.indices, dtype=np.int32)
         val = np.ascontiguousarray(A.data, dtype=np.float64)
         self.handle = ctypes.c_void_p()
         with torch.cuda.device(device):
-            _capi.check(L.intopt_problem_create(ctypes.byref(self.handle), sf.m, sf.n, rp.ctypes.data,
+            _capi.check(L.intopt_problem_create(ctypes.byref(self.handle), A.shape[0], A.shape[1], rp.ctypes.data,
                                                 ci.ctypes.data, val.ctypes.data, None,
                                                 _capi.FLAG_INSTANCE_VALUES if inst_values else 0),
                         "intopt_problem_create")
         info = _capi.IntoptInfo()
         _capi.check(L.intopt_problem_info(self.handle, ctypes.byref(info)), "intopt_problem_info")
         self.info = info.as_dict()
-        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=device)
-        kept = sf.c_src >= 0
-        cols = np.nonzero(kept)[0]
-        self.c_cols = t(cols, torch.long)                 # standard-form columns fed by user costs
-        self.c_src = t(sf.c_src[kept], torch.long)
-        self.c_sign = t(sf.c_sign[kept], torch.float64)
-        self.identity_vars = bool(sf.nvar == sf.n_x and sf.fixed_idx.size == 0)
-        self.c_plain = bool((sf.c_sign[kept] == 1).all() and cols.size == sf.nvar)
-        self.var_index = t(sf.var_index, torch.long)
-        self.fixed_idx = t(sf.fixed_idx, torch.long)
-        self.x_shift = t(sf.x_shift, torch.float64) if np.any(sf.x_shift != 0) else None
-        self.x_flip = t(sf.x_flip_ub, torch.float64) if np.isfinite(sf.x_flip_ub).any() else None
-        self.free_cols = t(sf.free_cols, torch.long) if (sf.free_cols >= 0).any() else None
+        self.nnz = int(val.size)
         self._ws = {}
-        # maps of the fused host glue (intopt_gather_convert): standard-form column j takes c_sign_full[j] * c[c_src_full[j]]
-        # (-1: slack / split column, cost 0); user variable i takes xhat[x_src[i]] or, if fixed by presolve, its value
-        self.c_src_full = t(sf.c_src, torch.int32)
-        self.c_sign_full = t(sf.c_sign, torch.float64)
-        x_src = np.full(sf.n_x, -1, dtype=np.int32)
-        x_src[sf.var_index] = np.arange(sf.nvar, dtype=np.int32)
-        self.x_src = t(x_src, torch.int32)
-        self.var_index32 = t(sf.var_index, torch.int32)
-        self.simple_post = self.x_shift is None and self.x_flip is None and self.free_cols is None
-        if inst_values:
-            # standard-form entry e of instance i = val_const[e] + val_sign[e] * A_i.flat[val_src[e]]: the entries
-            # built from the tagged matrix (|value| >= _TAG0) are copies of user entries, the rest are constants
-            tagged = np.abs(val) >= _TAG0 - 0.5
-            src = np.where(tagged, np.rint(np.abs(val)) - _TAG0, 0).astype(np.int64)
-            self.val_src = t(sf.tag_flatpos[src], torch.long)
-            self.val_sign = t(np.where(tagged, np.sign(val), 0.0), torch.float64)
-            self.val_const = t(np.where(tagged, 0.0, val), torch.float64)
-            self.nnz = int(val.size)
-
-    def instance_values(self, A_flat):
-        """(B, nnz) fp64 values of the standard-form A for the user matrices A_flat (B, n_eq * n_x) on the device."""
-        return (self.val_const + self.val_sign * A_flat[:, self.val_src]).contiguous()
+        return val
 
     def __del__(self):
         try:
@@ -155,6 +124,83 @@ class DeviceProblem:
         return ws
 
 
+class SlicedProblem(_DeviceHandle):
+    """The sub-problem the reference's backward sees for `method` 2 / 3 (saved-tensor slices,
+    ip_model_whole.py:1467-1482): the rows of the standard form that state upper bounds are dropped (they come first,
+    :471-482), and for method 2 so are all columns beyond the presolved variables (slack and split columns)."""
+
+    def __init__(self, dp, method):
+        sf = dp.sf
+        self.r0 = int(sf.meta["n_bound_rows"])
+        self.nc = int(sf.nvar if method == 2 else sf.n)
+        A = sp.csr_matrix(sf.A)
+        tagged = sp.csr_matrix((np.arange(1, A.nnz + 1, dtype=np.float64), A.indices, A.indptr), shape=A.shape)
+        sub = tagged[self.r0:, :self.nc].tocsr()
+        sub.sort_indices()
+        self.entry = (sub.data - 1).astype(np.int64)   # entry e of the slice = entry self.entry[e] of the full matrix
+        sub.data = np.asarray(A.data, dtype=np.float64)[self.entry]
+        self.m, self.n = sub.shape
+        self.trivial = self.r0 == 0 and self.nc == sf.n
+        if not self.trivial:
+            self._create(sub, dp.device, dp.inst_values)
+            self.entry_dev = torch.as_tensor(self.entry, dtype=torch.long, device=dp.device)
+
+    def slices(self, sf, c_std, b_std, st, a_vals):
+        """(c, b, state, values) of the slice, contiguous."""
+        n, m, r0, nc = sf.n, sf.m, self.r0, self.nc
+        st_s = torch.cat([st[:, :nc], st[:, n + r0:n + m], st[:, n + m:n + m + nc], st[:, 2 * n + m:]], dim=1)
+        return (c_std[:, :nc].contiguous(), b_std[:, r0:].contiguous(), st_s,
+                None if a_vals is None else a_vals[:, self.entry_dev].contiguous())
+
+
+class DeviceProblem(_DeviceHandle):
+    """A StandardForm plus its device-resident IntoptProblem handle and index tensors (one per device)."""
+
+    def __init__(self, sf, device, inst_values=False):
+        self.sf = sf
+        val = self._create(sf.A, device, inst_values)
+        self._sliced = {}
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=device)
+        kept = sf.c_src >= 0
+        cols = np.nonzero(kept)[0]
+        self.c_cols = t(cols, torch.long)                 # standard-form columns fed by user costs
+        self.c_src = t(sf.c_src[kept], torch.long)
+        self.c_sign = t(sf.c_sign[kept], torch.float64)
+        self.identity_vars = bool(sf.nvar == sf.n_x and sf.fixed_idx.size == 0)
+        self.c_plain = bool((sf.c_sign[kept] == 1).all() and cols.size == sf.nvar)
+        self.var_index = t(sf.var_index, torch.long)
+        self.fixed_idx = t(sf.fixed_idx, torch.long)
+        self.x_shift = t(sf.x_shift, torch.float64) if np.any(sf.x_shift != 0) else None
+        self.x_flip = t(sf.x_flip_ub, torch.float64) if np.isfinite(sf.x_flip_ub).any() else None
+        self.free_cols = t(sf.free_cols, torch.long) if (sf.free_cols >= 0).any() else None
+        # maps of the fused host glue (intopt_gather_convert): standard-form column j takes c_sign_full[j] * c[c_src_full[j]]
+        # (-1: slack / split column, cost 0); user variable i takes xhat[x_src[i]] or, if fixed by presolve, its value
+        self.c_src_full = t(sf.c_src, torch.int32)
+        self.c_sign_full = t(sf.c_sign, torch.float64)
+        x_src = np.full(sf.n_x, -1, dtype=np.int32)
+        x_src[sf.var_index] = np.arange(sf.nvar, dtype=np.int32)
+        self.x_src = t(x_src, torch.int32)
+        self.var_index32 = t(sf.var_index, torch.int32)
+        self.simple_post = self.x_shift is None and self.x_flip is None and self.free_cols is None
+        if inst_values:
+            # standard-form entry e of instance i = val_const[e] + val_sign[e] * A_i.flat[val_src[e]]: the entries
+            # built from the tagged matrix (|value| >= _TAG0) are copies of user entries, the rest are constants
+            tagged = np.abs(val) >= _TAG0 - 0.5
+            src = np.where(tagged, np.rint(np.abs(val)) - _TAG0, 0).astype(np.int64)
+            self.val_src = t(sf.tag_flatpos[src], torch.long)
+            self.val_sign = t(np.where(tagged, np.sign(val), 0.0), torch.float64)
+            self.val_const = t(np.where(tagged, 0.0, val), torch.float64)
+
+    def sliced(self, method):
+        if method not in self._sliced:
+            self._sliced[method] = SlicedProblem(self, method)
+        return self._sliced[method]
+
+    def instance_values(self, A_flat):
+        """(B, nnz) fp64 values of the standard-form A for the user matrices A_flat (B, n_eq * n_x) on the device."""
+        return (self.val_const + self.val_sign * A_flat[:, self.val_src]).contiguous()
+
+
 def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.1, pc=True, tol=1e-8,
                  max_iter=1000, init_val=None, method=1, mu0=None, smoothing=False, bounds=None, thr=None,
                  new_grad=True, presolve=True, A_eq_rr=True, damping=1e-2, check_finite=True):
@@ -169,8 +215,8 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
         raise ValueError(variant)
     if not pc:
         raise NotImplementedError("pc=False (plain path-following) is not used by any reference driver")
-    if method != 1:
-        raise NotImplementedError("method 2/3 (sliced saved tensors, ip_model_whole.py:1467-1482) not implemented")
+    if method not in (1, 2, 3):
+        raise ValueError("method must be 1 (full), 2 (rows and columns sliced) or 3 (rows sliced), :1459-1482")
     if not presolve:
         raise NotImplementedError("presolve=False is not used by any reference driver")
     A_np, b_np, G_np, h_np = _to_numpy(A), _to_numpy(b), _to_numpy(G), _to_numpy(h)
@@ -362,6 +408,9 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                 B = b_np.shape[0]
                 c2 = c2.expand(B, -1)
                 squeeze = False
+            if B == 0:  # nothing to solve: no launch, empty result, empty gradient
+                ctx.saved, ctx.in_shape, ctx.B, ctx.in_dtype = [], c.shape, 0, c.dtype
+                return torch.empty_like(c2, dtype=c.dtype)
             # group by the sign pattern of c on unconstrained columns (presolve zero-column rule, :995-1016)
             if zero_cols.size:
                 signs = torch.sign(c2[:, torch.as_tensor(zero_cols, device=device)]).to(torch.int8).cpu().numpy()
@@ -411,6 +460,8 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
             L = _capi.lib()
             device = del_x.device
             B = ctx.B
+            if B == 0:
+                return torch.zeros(ctx.in_shape, dtype=ctx.in_dtype, device=device)
             g2 = del_x.detach().reshape(-1, n_x)
             if g2.dtype not in (torch.float32, torch.float64):
                 g2 = g2.double()
@@ -431,6 +482,13 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                 Bg = gg.shape[0]
                 stream = torch.cuda.current_stream(device).cuda_stream
                 fast = sel is None and gg.stride(1) == 1 and ctx.in_dtype in (torch.float32, torch.float64)
+                prob, n_std = dp, sf.n
+                if method != 1:
+                    sub = dp.sliced(method)
+                    if not sub.trivial:  # the backward of methods 2 / 3 is the same kernel on the sliced problem
+                        prob, n_std = sub, sub.n
+                        c_std, b_std, st, a_vals = sub.slices(sf, c_std, b_std, st, a_vals)
+                        b_stride = sub.m if b_stride else 0
                 um = _capi.IntoptUserMap()
                 if fast:  # the kernel gathers del_x[var_index] (:1518) itself, as doubles
                     gk = torch.empty(Bg, sf.nvar, dtype=torch.float64, device=device)
@@ -447,10 +505,10 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                     um.out_idx_dev = dp.x_src.data_ptr()
                 gc = torch.empty(Bg, sf.nvar, dtype=torch.float64, device=device)
                 bstat = torch.empty(Bg, dtype=torch.int32, device=device)
-                ws = dp.workspace(Bg)
-                _capi.check(L.intopt_backward_mapped(dp.handle, Bg, mode, float(damping), sf.nvar, _ptr(st),
-                                                     _ptr(c_std), sf.n, _ptr(b_std), b_stride, _ptr(a_vals),
-                                                     dp.nnz if a_vals is not None else 0, ctypes.byref(um), _ptr(gk),
+                ws = prob.workspace(Bg)
+                _capi.check(L.intopt_backward_mapped(prob.handle, Bg, mode, float(damping), sf.nvar, _ptr(st),
+                                                     _ptr(c_std), n_std, _ptr(b_std), b_stride, _ptr(a_vals),
+                                                     prob.nnz if a_vals is not None else 0, ctypes.byref(um), _ptr(gk),
                                                      _ptr(gc), _ptr(bstat), _ptr(ws), ws.numel() * 8,
                                                      ctypes.c_void_p(stream)),
                             "intopt_backward")

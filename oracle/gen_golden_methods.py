@@ -1,0 +1,32 @@
+"""TEST INFRASTRUCTURE — writes tests/golden/methods.npz: dL/dc of the UNTOUCHED reference (through
+oracle/ref_shim.py) for `method` = 1, 2, 3 (the saved-tensor slices of ip_model_whole.py:1467-1482 /
+ip_model_alter.py:1482-1496), both variants, on instance 0 of the knapsack and Energy fixtures.
+Run here (needs /root/reference):  python -m oracle.gen_golden_methods"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from oracle import ref_shim  # noqa: E402
+from tests import golden_util as GU  # noqa: E402
+
+
+def main():
+    out = {}
+    for name in ("knapsack", "energy_load1"):
+        z = GU.load(name)
+        inp = GU.problem_inputs(name, z, 0)
+        case = GU.cases(z)[0]
+        for variant in ("whole", "alter"):
+            for method in (1, 2, 3):
+                kw = dict(case["kw"], method=method)
+                x, grad, cap = ref_shim.run_ipofunc(variant, case["c"][0], case["g"][0], **inp, **kw)
+                out["%s_%s_m%d_grad" % (name, variant, method)] = grad.astype(np.float32)
+                out["%s_%s_m%d_x" % (name, variant, method)] = x.astype(np.float32)
+    np.savez_compressed(os.path.join(GU.GOLDEN, "methods.npz"), **out)
+    print("wrote", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

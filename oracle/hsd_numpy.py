@@ -194,7 +194,7 @@ def standard_form(c, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=None, to
     lb_shift = lbs[~lb_none]
     c0 += float(np.sum(lb_shift * c_std[i_shift]))
     b = b - (A[:, i_shift] * lb_shift).sum(axis=1)
-    out.update(A=A, b=b, c=c_std, c0=c0, nvar=n, m_ub=m_ub, n_free=i_free.size,
+    out.update(A=A, b=b, c=c_std, c0=c0, nvar=n, m_ub=m_ub, n_free=i_free.size, n_bound_rows=nb,
                lb0=(lb_mod[0] if n and np.isfinite(lb_mod[0]) else 0.0))
     return out
 
@@ -432,7 +432,7 @@ def backward_alter_asref(A, b, c, st, g, damping, nvar=None, f=np.float32):
 
 def ipofunc(c, g=None, A=None, b=None, G=None, h=None, bounds=None, variant="whole",
             alpha0=0.9995, tol=1e-8, thr=None, max_iter=1000, damping=1e-2, asref=False,
-            init=None):
+            init=None, method=1):
     """fp64 oracle of `IPOfunc(A,b,G,h,...)(c)` followed by `(x*g).sum().backward()`.
 
     Inputs are rounded to float32 first, like the torch tensors the drivers pass
@@ -457,7 +457,16 @@ def ipofunc(c, g=None, A=None, b=None, G=None, h=None, bounds=None, variant="who
             fn = backward_whole_asref if asref else backward_whole
         else:
             fn = backward_alter_asref if asref else backward_alter
-        dc = fn(sf["A"], sf["b"], sf["c"], st, gk, damping, sf["nvar"])
+        A_s, b_s, c_s, st_s = sf["A"], sf["b"], sf["c"], st
+        if method in (2, 3):
+            # saved-tensor slices (ip_model_whole.py:1467-1482): the backward sees only the last n_ub + n_eq rows
+            # (the rows that state upper bounds are dropped) and, for method 2, only the first n_x_afterpre
+            # columns (slack and split columns dropped)
+            r0 = sf["n_bound_rows"]
+            nc = sf["nvar"] if method == 2 else sf["A"].shape[1]
+            A_s, b_s, c_s = sf["A"][r0:, :nc], sf["b"][r0:], sf["c"][:nc]
+            st_s = dict(st, x=st["x"][:nc], t=st["t"][:nc], y=st["y"][r0:])
+        dc = fn(A_s, b_s, c_s, st_s, gk, damping, sf["nvar"])
         grad = np.zeros(n_x)
         grad[sf["var_index"]] = dc
     return dict(x=x, grad=grad, iters=st["iters"], status=st["status"], state=st, sf=sf)

@@ -241,6 +241,99 @@ def test_error_conventions():
     assert status.cpu().tolist() == [0, 4]
 
 
+_EDGE = {
+    # x0 + x1 = -1 has no point with x >= 0; min -x0 on the ray x0 = x1 = x2 is unbounded; the third is a plain
+    # feasible LP that is cut off by max_iter (the reference runs max_iter + 1 iterations, ip_model_whole.py:1414)
+    "infeasible": (np.array([[1., 1., 0.], [0., 1., 1.]]), np.array([-1., 2.]), np.array([1., 2., 0.5]), 1000, 2),
+    "unbounded": (np.array([[1., -1., 0.], [0., 1., -1.]]), np.array([0., 0.]), np.array([-1., 0., 0.]), 1000, 2),
+    "iteration_cap": (np.array([[1., 1., 1., 0.], [1., -1., 0., 1.]]), np.array([4., 1.]),
+                      np.array([-1., -2., 0., 0.]), 3, 1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_EDGE))
+def test_infeasible_unbounded_and_capped_runs_end_like_the_reference(name):
+    """The reference returns its last iterate silently in all three cases (:1408-1423); the kernels must stop at
+    the same iteration with the same iterate, and say why in the status word (2 = infeasibility/unboundedness
+    indicators, 1 = iteration cap)."""
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    A, b, c, max_iter, want = _EDGE[name]
+    r = O.ipofunc(c.astype(np.float32), np.ones_like(c), A=A, b=b, bounds=[(0.0, None)], thr=0.0,
+                  max_iter=max_iter, damping=1e-2)
+    assert r["status"] == want
+    f = IPOfunc(_tt(A), _tt(b), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)], thr=0.0, max_iter=max_iter)
+    ct = torch.tensor(np.stack([c, c]), dtype=torch.float64, device="cuda", requires_grad=True)
+    x = f(ct)
+    x.sum().backward()
+    status, iters = IPOfunc.status()
+    assert status.cpu().tolist() == [want, want] and iters.cpu().tolist() == [r["iters"]] * 2
+    assert _relinf(x[0].detach().cpu().numpy(), r["x"]) < X_TOL
+    assert torch.equal(x[0], x[1]) and torch.isfinite(ct.grad).all()
+
+
+def test_empty_batch():
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = GU.load("dense_m16")
+    case = GU.cases(z)[0]
+    f = IPOfunc(_tt(z["A"]), _tt(z["b"]), torch.Tensor(), torch.Tensor(), **case["kw"])
+    c0 = torch.zeros((0, case["c"].shape[1]), device="cuda", requires_grad=True)
+    x0 = f(c0)
+    assert x0.shape == c0.shape
+    x0.sum().backward()
+    assert c0.grad.shape == c0.shape
+
+
+@pytest.mark.parametrize("name", ["knapsack", "energy_load1"])
+@pytest.mark.parametrize("variant", ["whole", "alter"])
+def test_saved_tensor_slices_method_2_and_3(name, variant):
+    """`method` 2 / 3 change what the backward sees (ip_model_whole.py:1467-1482): bound rows dropped, and for
+    method 2 the slack columns too.  dL/dc against the oracle on the same slices (1e-5) and against the
+    reference's own float32 gradients (tests/golden/methods.npz, from oracle/gen_golden_methods.py)."""
+    z = GU.load(name)
+    ref = GU.load("methods")
+    inp = GU.problem_inputs(name, z, 0)
+    case = GU.cases(z)[0]
+    mod = _module(variant)
+    grads = {}
+    for method in (1, 2, 3):
+        kw = dict(case["kw"], method=method)
+        f = mod.IPOfunc(_tt(inp["A"]), _tt(inp["b"]), _tt(inp["G"]), _tt(inp["h"]), **kw)
+        ct = torch.tensor(case["c"][:2], dtype=torch.float32, device="cuda", requires_grad=True)
+        x = f(ct)
+        (x * torch.tensor(case["g"][:2], dtype=torch.float32, device="cuda")).sum().backward()
+        got = ct.grad.double().cpu().numpy()
+        for i in range(2):
+            r = O.ipofunc(case["c"][i], case["g"][i], variant=variant, bounds=kw.get("bounds"), thr=kw.get("thr"),
+                          max_iter=kw.get("max_iter") or 1000, damping=kw["damping"], method=method, **inp)
+            assert _relinf(x[i].detach().double().cpu().numpy(), r["x"]) < X_TOL
+            assert _rel2(got[i], r["grad"]) < G_TOL, (name, variant, method, i, _rel2(got[i], r["grad"]))
+        gref = ref["%s_%s_m%d_grad" % (name, variant, method)].astype(np.float64)
+        assert _rel2(got[0], gref) < 1e-3, (name, variant, method, _rel2(got[0], gref))   # float32 reference
+        grads[method] = got[0]
+    # the slices matter: method 2 differs from method 1 on both problems (slack columns exist)
+    assert _rel2(grads[2], grads[1]) > 1e-2
+    if name == "energy_load1":  # no finite upper bounds: no rows to drop, method 3 is method 1
+        assert np.array_equal(grads[3], grads[1])
+
+
+def test_method_2_with_per_instance_A():
+    """Knapsack minibatches through the per-instance-values path with sliced backward == one call per matrix."""
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = GU.load("knapsack")
+    case = GU.cases(z)[0]
+    kw = dict(case["kw"], method=2)
+    k = min(3, len(case["c"]))
+    A3 = np.stack([GU.problem_inputs("knapsack", z, i)["A"] for i in range(k)])
+    b = GU.problem_inputs("knapsack", z, 0)["b"]
+    ct = torch.tensor(case["c"][:k], dtype=torch.float32, device="cuda", requires_grad=True)
+    x = IPOfunc(_tt(A3), _tt(b), torch.Tensor(), torch.Tensor(), **kw)(ct)
+    (x * torch.tensor(case["g"][:k], dtype=torch.float32, device="cuda")).sum().backward()
+    for i in range(k):
+        r = O.ipofunc(case["c"][i], case["g"][i], bounds=kw["bounds"], thr=kw["thr"], max_iter=kw["max_iter"],
+                      damping=kw["damping"], method=2, A=A3[i], b=b)
+        assert _rel2(ct.grad[i].double().cpu().numpy(), r["grad"]) < G_TOL
+
+
 def test_batch_position_independence():
     """Instances are independent: the same LP gives bitwise identical results wherever it sits in a batch
     (this is what makes 1-GPU and N-GPU shards agree exactly)."""

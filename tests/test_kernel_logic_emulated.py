@@ -95,3 +95,21 @@ def test_emulated_per_instance_values_knapsack():
         st = GU.split_state(e["state"][i], m, n)
         dc = O.backward_whole(sfs[i]["A"], sfs[i]["b"], sfs[i]["c"], st, gg[i], kw["damping"], sfs[i]["nvar"])
         assert np.linalg.norm(e["gc"][i] - dc) / np.linalg.norm(dc) < 1e-6
+
+
+@pytest.mark.parametrize("max_iter", [1000, 3])
+def test_emulated_infeasible_unbounded_and_capped_runs(max_iter):
+    """Same stopping iteration, status word and last iterate as the oracle for an infeasible LP, an unbounded LP
+    and a run cut off by max_iter (which executes max_iter + 1 iterations, ip_model_whole.py:1414)."""
+    cases = [(np.array([[1., 1., 0.], [0., 1., 1.]]), np.array([-1., 2.]), np.array([1., 2., 0.5])),
+             (np.array([[1., -1., 0.], [0., 1., -1.]]), np.array([0., 0.]), np.array([-1., 0., 0.])),
+             (np.array([[1., 1., 1., 0.], [1., -1., 0., 1.]]), np.array([4., 1.]), np.array([-1., -2., 0., 0.]))]
+    seen = set()
+    for A, b, c in cases:
+        r = O.forward(A, b, c, thr=0.0, max_iter=max_iter)
+        e = emu_py.solve(A, b, c, thr=0.0, max_iter=max_iter)
+        assert e["iters"][0] == r["iters"] and e["status"][0] == r["status"]
+        xo = r["x"] / r["tau"]
+        assert np.abs(e["xhat"][0] - xo).max() <= 1e-9 * max(1.0, np.abs(xo).max())
+        seen.add(int(r["status"]))
+    assert seen == ({0, 2} if max_iter == 1000 else {1, 2})
