@@ -75,7 +75,10 @@ int intopt_version(void);
 const char* intopt_last_error(void);
 
 /* Host-only structure analysis of a standard-form A (CSR, m x n).  Fills `info` and, if non-NULL,
- * row_perm_host[m] (internal row i = original row row_perm_host[i]).  Needs no GPU. */
+ * row_perm_host[m] (internal row i = original row row_perm_host[i]).  Needs no GPU.
+ * Returns 0, -1..-4 for malformed input (NULL / non-monotone rowptr / column out of range / m too large for the
+ * 16-bit row indices), -5 when the problem is too large for the gather-list assembly (asm_terms > 2^28: large dense
+ * matrices, m >~ 600 at n = 2m); intopt_problem_create returns the same codes. */
 int intopt_analyze(int m, int n, const int* rowptr_host, const int* colidx_host, const double* val_host,
                    IntoptInfo* info, int* row_perm_host);
 

@@ -499,6 +499,7 @@ int intopt_analyze(int m, int n, const int* rowptr, const int* colidx, const dou
   if (!info) return fail(-1, "info is NULL");
   intopt::HostStructure S;
   int rc = intopt::analyze(m, n, rowptr, colidx, val, S);
+  if (rc == -5) return fail(rc, "problem too large for the gather-list assembly (sum over columns of nnz*(nnz+1)/2 > 2^28)");
   if (rc) return fail(rc, "malformed CSR input");
   fill_info(S, info);
   if (row_perm) std::memcpy(row_perm, S.perm.data(), sizeof(int) * m);
@@ -511,6 +512,7 @@ int intopt_problem_create(IntoptProblem** out, int m, int n, const int* rowptr, 
   *out = nullptr;
   intopt::HostStructure S;
   int rc = intopt::analyze(m, n, rowptr, colidx, val, S, -1, (flags & INTOPT_FLAG_INSTANCE_VALUES) != 0);
+  if (rc == -5) return fail(rc, "problem too large for the gather-list assembly (sum over columns of nnz*(nnz+1)/2 > 2^28)");
   if (rc) return fail(rc, "malformed CSR input");
   int ndev = 0;
   cudaError_t e0 = cudaGetDeviceCount(&ndev);

@@ -195,6 +195,8 @@ inline std::vector<int> dense_rows_last(const std::vector<std::vector<int>>& adj
 }  // namespace detail
 
 // Returns 0 on success, negative on malformed input.  `force_order`: -1 = smallest block envelope.
+constexpr long long kMaxAssemblyTerms = 1LL << 28;  // 268 M pair terms (dense 512 x 1024 has 134 M)
+
 inline int analyze(int m, int n, const int* rp, const int* ci, const double* val, HostStructure& S,
                    int force_order = -1, bool inst_values = false) {
   if (m <= 0 || n <= 0 || !rp || !ci || !val) return -1;
@@ -205,6 +207,15 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
   for (int e = 0; e < nnz; ++e)
     if (ci[e] < 0 || ci[e] >= n) return -3;
   if (m + 2 * NB >= 65535) return -4;  // row indices travel as uint16
+  {
+    // The normal matrix is formed from gather lists with one term per pair of entries in a column: refuse problems
+    // whose lists would not fit (large dense matrices) instead of exhausting host and device memory.
+    std::vector<int> cnt(n, 0);
+    for (int e = 0; e < nnz; ++e) cnt[ci[e]]++;
+    long long terms = 0;
+    for (int k = 0; k < n; ++k) terms += (long long)cnt[k] * (cnt[k] + 1) / 2;
+    if (terms > kMaxAssemblyTerms) return -5;
+  }
   S = HostStructure();
   S.inst_values = inst_values;
   S.m = m;

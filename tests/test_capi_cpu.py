@@ -59,6 +59,17 @@ def test_malformed_input_is_rejected(lib):
     assert rc != 0 and lib.intopt_last_error()
 
 
+def test_oversized_dense_problem_is_refused_before_allocating(lib):
+    """Dense 1024 x 2048 would need 1.07e9 gather-list terms: refused (-5) by the column-count check, in milliseconds."""
+    m, n = 1024, 2048
+    rp = (np.arange(m + 1, dtype=np.int64) * n).astype(np.int32)
+    ci = np.tile(np.arange(n, dtype=np.int32), m)
+    val = np.ones(m * n)
+    info = _capi.IntoptInfo()
+    rc = lib.intopt_analyze(m, n, rp.ctypes.data, ci.ctypes.data, val.ctypes.data, ctypes.byref(info), None)
+    assert rc == -5 and b"too large" in lib.intopt_last_error()
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_gpu_means_loud_failure(lib):
     A = sp.csr_matrix(np.array([[1.0, 1.0, 0.0], [0.0, 1.0, 1.0]]))
