@@ -31,9 +31,11 @@ def main():
     from neuripsintopt_b200.ip_model_whole import IPOfunc
     from neuripsintopt_b200 import ipofunc as _ipo
     tt = lambda v: torch.Tensor() if v is None else torch.as_tensor(np.asarray(v), dtype=torch.float32)
+    from neuripsintopt_b200 import _capi
     rng = np.random.default_rng(0)
     B = args.batch
     out = []
+    peak = _capi.measure_fp64_peak(5) * 1e-3  # TFLOP/s, DFMA micro-kernel on this device (as in bench.py)
     for name in ("energy_load1", "twitter_sp", "dense_m16", "dense_m64", "knapsack"):
         z = GU.load(name); case = GU.cases(z)[0]; kw = dict(case["kw"]); kw["thr"] = args.thr
         inp = GU.problem_inputs(name, z, 0)
@@ -61,8 +63,17 @@ def main():
         status, iters = IPOfunc.status()
         ms = time_steps(step, args.steps)
         info = [v.info for v in _ipo._PROBLEM_CACHE.values() if hasattr(v, "info")][-1]
+        # algorithmic flops per LP: F_it = 2S + m^3/3 + 6m^2 + 20 nnz + 30 n per iteration,
+        # F_bw = 2S + m^3/3 + 4m^2 + 12 nnz + 20 n for the (whole) backward
+        m_, n_, nnz_, S_ = info["m"], info["n"], info["nnz"], info["asm_terms"]
+        f_it = 2 * S_ + m_ ** 3 / 3 + 6 * m_ ** 2 + 20 * nnz_ + 30 * n_
+        f_bw = 2 * S_ + m_ ** 3 / 3 + 4 * m_ ** 2 + 12 * nnz_ + 20 * n_
+        flops = float(iters.float().sum()) * f_it + B * f_bw
+        tf = flops / (ms * 1e-3) / 1e12
         out.append(dict(config=name, shape="%dx%d nnz %d" % (info["m"], info["n"], info["nnz"]), batch=B,
                         lp_per_s=B / ms * 1e3, ms_per_step=ms, thr=args.thr, mean_iters=float(iters.float().mean()),
+                        roofline=dict(bound="fp64", achieved=tf, peak=peak, unit="TFLOP/s", frac=tf / peak,
+                                      flops_per_iter=f_it, flops_backward=f_bw),
                         bad_status=int((status != 0).sum()), smem_bytes=info["smem_bytes"], ctas_per_sm=info["ctas_per_sm"],
                         envelope=info["envelope"]))
         print(json.dumps(out[-1]))
