@@ -217,8 +217,6 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
         raise NotImplementedError("pc=False (plain path-following) is not used by any reference driver")
     if method not in (1, 2, 3):
         raise ValueError("method must be 1 (full), 2 (rows and columns sliced) or 3 (rows sliced), :1459-1482")
-    if not presolve:
-        raise NotImplementedError("presolve=False is not used by any reference driver")
     A_np, b_np, G_np, h_np = _to_numpy(A), _to_numpy(b), _to_numpy(G), _to_numpy(h)
     assert (A_np is not None or G_np is not None) and (b_np is not None or h_np is not None)  # :1209
     if A_np is not None and b_np is None:
@@ -247,8 +245,8 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
     n_x = (A_np if A_np is not None else G_np).shape[1]
     b_batched = b_np is not None and b_np.ndim == 2
     a_dev_cache = {}
-    structure_key = _digest(A_np, G_np, h_np) + repr([tuple(bd) for bd in bounds])
-    zero_cols = _problem.zero_columns(A_np, G_np, n_x)
+    structure_key = _digest(A_np, G_np, h_np) + repr([tuple(bd) for bd in bounds]) + ("" if presolve else "|raw")
+    zero_cols = _problem.zero_columns(A_np, G_np, n_x) if presolve else np.zeros(0, dtype=np.int64)
     state = {"events": [], "time_ms": 0.0, "last": []}
     b_cache = {}
 
@@ -260,7 +258,7 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
             try:
                 sf = _problem.build_standard_form(
                     n_x, A_np, None, G_np, h_np, bounds,
-                    None if not zero_cols.size else np.asarray(sign_key, dtype=np.float64))
+                    None if not zero_cols.size else np.asarray(sign_key, dtype=np.float64), presolve=bool(presolve))
                 if a_batched:
                     if sf.fixed_idx.size:
                         raise NotImplementedError("per-instance A with variables fixed by presolve (singleton rows)")

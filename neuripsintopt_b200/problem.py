@@ -163,12 +163,15 @@ def zero_columns(A_eq, A_ub, n_x):
     return np.nonzero(nnz == 0)[0]
 
 
-def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=None, zero_col_sign=None):
+def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=None, zero_col_sign=None,
+                        presolve=True):
     """Presolve + standard form for every cost vector whose sign pattern on the zero columns is
     `zero_col_sign` (array over `zero_columns(...)`, entries -1/0/+1; ignored if there are none).
 
     `b_eq` may be None (per-instance right-hand sides are supplied later through `b_std`).
     Raises PresolveComplete when presolve decides the problem independently of `c`'s values.
+    `presolve=False` (ip_model_whole.py:1352): no row / column is removed and no variable fixed; the standard form
+    is `_get_Abc` of the inputs as given.
     """
     A_eq = _as_matrix(A_eq, n_x, "A_eq")
     A_ub = _as_matrix(A_ub, n_x, "A_ub")
@@ -188,17 +191,19 @@ def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=
 
     # -- zero rows (:957-991) ---------------------------------------------------------------------
     eq_nnz = np.diff(A_eq.indptr)
+    ub_nnz = np.diff(A_ub.indptr)
+    if not presolve:
+        eq_nnz, ub_nnz = np.ones(n_eq, dtype=np.int64), np.ones(n_ubr, dtype=np.int64)  # every row is kept
     zero_rows_eq = np.nonzero(eq_nnz == 0)[0]
     if zero_rows_eq.size and b_eq_v is not None and (np.abs(b_eq_v[zero_rows_eq]) > TOL).any():
         raise PresolveComplete(2, x_pre)
     eq_keep = np.nonzero(eq_nnz != 0)[0]
-    ub_nnz = np.diff(A_ub.indptr)
     if ((ub_nnz == 0) & (b_ub_v < -TOL)).any():
         raise PresolveComplete(2, x_pre)
     ub_keep = np.nonzero(ub_nnz != 0)[0]
 
     # -- zero columns (:995-1016): depends on sign(c) ------------------------------------------------
-    zc = zero_columns(A_eq, A_ub, n_x)
+    zc = zero_columns(A_eq, A_ub, n_x) if presolve else np.zeros(0, dtype=np.int64)
     if zc.size:
         sgn = np.zeros(zc.size) if zero_col_sign is None else np.asarray(zero_col_sign, dtype=np.float64)
         neg, pos = zc[sgn < 0], zc[sgn > 0]
@@ -211,7 +216,7 @@ def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=
 
     # -- singleton equality rows fix a variable (:1020-1041) ---------------------------------------
     A_eq_k = A_eq[eq_keep]
-    sing_local = np.nonzero(np.diff(A_eq_k.indptr) == 1)[0]
+    sing_local = np.nonzero(np.diff(A_eq_k.indptr) == 1)[0] if presolve else np.zeros(0, dtype=np.int64)
     s_rows = eq_keep[sing_local]
     s_cols = A_eq_k.indices[A_eq_k.indptr[sing_local]] if sing_local.size else np.zeros(0, dtype=np.int64)
     s_coef = A_eq_k.data[A_eq_k.indptr[sing_local]] if sing_local.size else np.zeros(0)
@@ -231,7 +236,7 @@ def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=
 
     # -- singleton inequality rows tighten bounds (:1048-1072) -------------------------------------
     A_ub_k = A_ub[ub_keep]
-    sing_ub = np.nonzero(np.diff(A_ub_k.indptr) == 1)[0]
+    sing_ub = np.nonzero(np.diff(A_ub_k.indptr) == 1)[0] if presolve else np.zeros(0, dtype=np.int64)
     for loc in sing_ub:
         col = A_ub_k.indices[A_ub_k.indptr[loc]]
         a = A_ub_k.data[A_ub_k.indptr[loc]]
@@ -252,7 +257,7 @@ def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=
         ub_keep = ub_keep[mask]
 
     # -- fixed variables (:1075-1110) ---------------------------------------------------------------
-    i_f = np.abs(lb - ub) < TOL
+    i_f = (np.abs(lb - ub) < TOL) if presolve else np.zeros(n_x, dtype=bool)
     for col in fixed_by_row:  # fixed whatever b_eq turns out to be
         i_f[col] = True
     A_eq2, A_ub2 = A_eq[eq_keep], A_ub[ub_keep]
@@ -285,7 +290,7 @@ def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=
     lb_k, ub_k = lb[var_index], ub[var_index]
     nvar = var_index.size
 
-    if A_eq3.nnz == 0 and A_ub3.nnz == 0:
+    if presolve and A_eq3.nnz == 0 and A_ub3.nnz == 0:
         # no non-trivial constraints left (:1113-1144): the answer depends on c only through its sign;
         # callers handle this rare case through the exception (x is filled where it is c-independent).
         raise PresolveComplete(0, x_pre)

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE — writes tests/golden/methods.npz: dL/dc of the UNTOUCHED reference (through
 oracle/ref_shim.py) for `method` = 1, 2, 3 (the saved-tensor slices of ip_model_whole.py:1467-1482 /
-ip_model_alter.py:1482-1496), both variants, on instance 0 of the knapsack and Energy fixtures.
+ip_model_alter.py:1482-1496), both variants, on instance 0 of the knapsack and Energy fixtures, and for
+`presolve=False` on the Energy instance.
 Run here (needs /root/reference):  python -m oracle.gen_golden_methods"""
 import os
 import sys
@@ -24,6 +25,15 @@ def main():
                 x, grad, cap = ref_shim.run_ipofunc(variant, case["c"][0], case["g"][0], **inp, **kw)
                 out["%s_%s_m%d_grad" % (name, variant, method)] = grad.astype(np.float32)
                 out["%s_%s_m%d_x" % (name, variant, method)] = x.astype(np.float32)
+    # presolve=False (ip_model_whole.py:1352): x and dL/dc of the reference on the Energy LP (174 x 1584 standard form)
+    z = GU.load("energy_load1")
+    inp = GU.problem_inputs("energy_load1", z, 0)
+    case = GU.cases(z)[0]
+    for variant in ("whole", "alter"):
+        x, grad, cap = ref_shim.run_ipofunc(variant, case["c"][0], case["g"][0], **inp, **dict(case["kw"], presolve=False))
+        out["energy_load1_%s_nopresolve_grad" % variant] = grad.astype(np.float32)
+        out["energy_load1_%s_nopresolve_x" % variant] = x.astype(np.float32)
+        out["energy_load1_%s_nopresolve_iters" % variant] = np.int32(cap["iters"])
     np.savez_compressed(os.path.join(GU.GOLDEN, "methods.npz"), **out)
     print("wrote", len(out), "arrays")
 

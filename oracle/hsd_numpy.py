@@ -56,7 +56,7 @@ def _broadcast_bounds(bounds, n_x):
     return lb, ub
 
 
-def standard_form(c, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=None, tol=1e-9):
+def standard_form(c, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=None, tol=1e-9, presolve=True):
     """Restates forward()'s host prep, ip_model_whole.py:1317-1383.
 
     Returns a dict with the standard-form `A (m×n), b (m), c (n)` of
@@ -78,59 +78,62 @@ def standard_form(c, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=None, to
 
     # ---- _presolve (:918-1161), single pass, rule order preserved -----------------------
     x_pre = np.zeros(n_x)
-    zr = (A_eq != 0).sum(axis=1) == 0  # :957
-    if zr.any():
-        if (zr & (np.abs(b_eq) > tol)).any():
-            return dict(out, complete=True, status=2, x=x_pre)
-        A_eq, b_eq = A_eq[~zr], b_eq[~zr]
-    zr = (A_ub != 0).sum(axis=1) == 0  # :977
-    if zr.any():
-        if (zr & (b_ub < -tol)).any():
-            return dict(out, complete=True, status=2, x=x_pre)
-        A_ub, b_ub = A_ub[~zr], b_ub[~zr]
-    Aall = np.vstack((A_eq, A_ub))  # :995
-    if Aall.shape[0] > 0:
-        zc = (Aall != 0).sum(axis=0) == 0
-        neg, pos = zc & (c < 0), zc & (c > 0)
-        x_pre[neg] = ub[neg]
-        x_pre[pos] = lb[pos]
-        if np.isinf(x_pre).any():
-            return dict(out, complete=True, status=3, x=x_pre)
-        lb[neg] = ub[neg]
-        ub[pos] = lb[pos]
-    sr = (A_eq != 0).sum(axis=1) == 1  # :1020
-    if sr.any():
-        for row in np.where(sr)[0]:
-            col = np.nonzero(A_eq[row])[0][0]
-            val = b_eq[row] / A_eq[row, col]
-            if not (lb[col] - tol <= val <= ub[col] + tol):
-                return dict(out, complete=True, status=2, x=x_pre)
-            lb[col] = val
-            ub[col] = val
-        A_eq, b_eq = A_eq[~sr], b_eq[~sr]
-    sr = (A_ub != 0).sum(axis=1) == 1  # :1048
-    if sr.any():
-        for row in np.where(sr)[0]:
-            col = np.nonzero(A_ub[row])[0][0]
-            val = b_ub[row] / A_ub[row, col]
-            if A_ub[row, col] > 0:
-                if val < lb[col] - tol:
-                    return dict(out, complete=True, status=2, x=x_pre)
-                if val < ub[col]:
-                    ub[col] = val
-            else:
-                if val > ub[col] + tol:
-                    return dict(out, complete=True, status=2, x=x_pre)
-                if val > lb[col]:
-                    lb[col] = val
-        A_ub, b_ub = A_ub[~sr], b_ub[~sr]
-    i_f = np.abs(lb - ub) < tol  # :1075
+    i_f = np.zeros(n_x, dtype=bool)  # presolve=False (:1352): nothing removed, nothing fixed
     i_nf = ~i_f
-    if i_f.all():  # :1079
-        residual = b_eq - A_eq.dot(lb)
-        slack = b_ub - A_ub.dot(lb)
-        if (A_ub.size > 0 and (slack < 0).any()) or (A_eq.size > 0 and not np.allclose(residual, 0)):
-            return dict(out, complete=True, status=2, x=x_pre)
+    if presolve:
+        zr = (A_eq != 0).sum(axis=1) == 0  # :957
+        if zr.any():
+            if (zr & (np.abs(b_eq) > tol)).any():
+                return dict(out, complete=True, status=2, x=x_pre)
+            A_eq, b_eq = A_eq[~zr], b_eq[~zr]
+        zr = (A_ub != 0).sum(axis=1) == 0  # :977
+        if zr.any():
+            if (zr & (b_ub < -tol)).any():
+                return dict(out, complete=True, status=2, x=x_pre)
+            A_ub, b_ub = A_ub[~zr], b_ub[~zr]
+        Aall = np.vstack((A_eq, A_ub))  # :995
+        if Aall.shape[0] > 0:
+            zc = (Aall != 0).sum(axis=0) == 0
+            neg, pos = zc & (c < 0), zc & (c > 0)
+            x_pre[neg] = ub[neg]
+            x_pre[pos] = lb[pos]
+            if np.isinf(x_pre).any():
+                return dict(out, complete=True, status=3, x=x_pre)
+            lb[neg] = ub[neg]
+            ub[pos] = lb[pos]
+        sr = (A_eq != 0).sum(axis=1) == 1  # :1020
+        if sr.any():
+            for row in np.where(sr)[0]:
+                col = np.nonzero(A_eq[row])[0][0]
+                val = b_eq[row] / A_eq[row, col]
+                if not (lb[col] - tol <= val <= ub[col] + tol):
+                    return dict(out, complete=True, status=2, x=x_pre)
+                lb[col] = val
+                ub[col] = val
+            A_eq, b_eq = A_eq[~sr], b_eq[~sr]
+        sr = (A_ub != 0).sum(axis=1) == 1  # :1048
+        if sr.any():
+            for row in np.where(sr)[0]:
+                col = np.nonzero(A_ub[row])[0][0]
+                val = b_ub[row] / A_ub[row, col]
+                if A_ub[row, col] > 0:
+                    if val < lb[col] - tol:
+                        return dict(out, complete=True, status=2, x=x_pre)
+                    if val < ub[col]:
+                        ub[col] = val
+                else:
+                    if val > ub[col] + tol:
+                        return dict(out, complete=True, status=2, x=x_pre)
+                    if val > lb[col]:
+                        lb[col] = val
+            A_ub, b_ub = A_ub[~sr], b_ub[~sr]
+        i_f = np.abs(lb - ub) < tol  # :1075
+        i_nf = ~i_f
+        if i_f.all():  # :1079
+            residual = b_eq - A_eq.dot(lb)
+            slack = b_ub - A_ub.dot(lb)
+            if (A_ub.size > 0 and (slack < 0).any()) or (A_eq.size > 0 and not np.allclose(residual, 0)):
+                return dict(out, complete=True, status=2, x=x_pre)
     fixed_idx = np.zeros(0, dtype=np.int64)
     fixed_val = np.zeros(0)
     c0 = 0.0
@@ -148,7 +151,7 @@ def standard_form(c, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=None, to
         lb_mod, ub_mod = lb[i_nf], ub[i_nf]
     out.update(fixed_idx=fixed_idx, fixed_val=fixed_val,
                var_index=np.setdiff1d(np.arange(n_x), fixed_idx))
-    if A_eq.size == 0 and A_ub.size == 0:  # :1113-1144 trivial problem
+    if presolve and A_eq.size == 0 and A_ub.size == 0:  # :1113-1144 trivial problem
         x = x_pre.copy()
         status = 0
         if c.size and (((c < 0) & (ub_mod == np.inf)).any() or ((c > 0) & (lb_mod == -np.inf)).any()):
@@ -432,7 +435,7 @@ def backward_alter_asref(A, b, c, st, g, damping, nvar=None, f=np.float32):
 
 def ipofunc(c, g=None, A=None, b=None, G=None, h=None, bounds=None, variant="whole",
             alpha0=0.9995, tol=1e-8, thr=None, max_iter=1000, damping=1e-2, asref=False,
-            init=None, method=1):
+            init=None, method=1, presolve=True):
     """fp64 oracle of `IPOfunc(A,b,G,h,...)(c)` followed by `(x*g).sum().backward()`.
 
     Inputs are rounded to float32 first, like the torch tensors the drivers pass
@@ -443,7 +446,7 @@ def ipofunc(c, g=None, A=None, b=None, G=None, h=None, bounds=None, variant="who
         bounds = [(0.0, None)] if variant == "whole" else [(0.0, 1.0)]
     thr = 0.0 if thr is None else thr
     max_iter = 1000 if max_iter is None else max_iter
-    sf = standard_form(c, f32(A), f32(b), f32(G), f32(h), bounds)
+    sf = standard_form(c, f32(A), f32(b), f32(G), f32(h), bounds, presolve=presolve)
     n_x = sf["n_x"]
     if sf["complete"]:
         return dict(x=sf["x"], grad=np.zeros(n_x), iters=0, status=sf["status"], state=None, sf=sf)

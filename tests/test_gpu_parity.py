@@ -316,6 +316,27 @@ def test_saved_tensor_slices_method_2_and_3(name, variant):
         assert np.array_equal(grads[3], grads[1])
 
 
+@pytest.mark.parametrize("variant", ["whole", "alter"])
+def test_presolve_false(variant):
+    """`presolve=False` (ip_model_whole.py:1352): the kernels see the un-reduced 174 x 1584 Energy standard form
+    (two singleton rows and the variables they fix stay in).  Against the oracle (1e-6 / 1e-5) and the reference's
+    own float32 output (tests/golden/methods.npz)."""
+    z, ref = GU.load("energy_load1"), GU.load("methods")
+    inp = GU.problem_inputs("energy_load1", z, 0)
+    case = GU.cases(z)[0]
+    kw = dict(case["kw"], presolve=False)
+    xs, gs, status, iters, _ = _run_gpu(variant, kw, inp, case["c"][:2], case["g"][:2])
+    assert status.tolist() == [0, 0]
+    for i in range(2):
+        r = O.ipofunc(case["c"][i], case["g"][i], variant=variant, bounds=kw.get("bounds"), thr=kw.get("thr"),
+                      max_iter=kw.get("max_iter") or 1000, damping=kw["damping"], presolve=False, **inp)
+        assert r["sf"]["A"].shape == (174, 1584) and iters[i] == r["iters"]
+        assert _relinf(xs[i], r["x"]) < X_TOL and _rel2(gs[i], r["grad"]) < G_TOL
+    assert iters[0] == int(ref["energy_load1_%s_nopresolve_iters" % variant])
+    assert _relinf(xs[0], ref["energy_load1_%s_nopresolve_x" % variant].astype(np.float64)) < 5e-6
+    assert _rel2(gs[0], ref["energy_load1_%s_nopresolve_grad" % variant].astype(np.float64)) < 1e-3
+
+
 def test_method_2_with_per_instance_A():
     """Knapsack minibatches through the per-instance-values path with sliced backward == one call per matrix."""
     from neuripsintopt_b200.ip_model_whole import IPOfunc

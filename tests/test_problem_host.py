@@ -91,6 +91,47 @@ def test_random_lps_match_oracle_restatement(seed):
     np.testing.assert_allclose(sf.fixed_const, ref["fixed_val"], atol=1e-15)
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_presolve_false_keeps_everything(seed):
+    """`presolve=False` (ip_model_whole.py:1352): the same LPs as above, with a zero row, a zero column, singleton
+    rows and a fixed variable left in place — standard form equal to the oracle restatement (itself checked
+    against the reference's `_get_Abc` output for presolve=False on the Energy / knapsack / dense fixtures)."""
+    rng = np.random.default_rng(seed)
+    n, me, mu = 9, 4, 4
+    A = rng.integers(-2, 3, (me, n)).astype(float)
+    A[0] = 0
+    A[0, 2] = 2.0
+    A[3] = 0                # zero row (rhs 0)
+    G = rng.integers(-2, 3, (mu, n)).astype(float)
+    G[1] = 0
+    G[1, 4] = -1.0
+    A[:, 7] = 0
+    G[:, 7] = 0             # zero column
+    b = np.append(rng.uniform(0.5, 2.0, me - 1), 0.0)
+    h = rng.uniform(1.0, 3.0, mu)
+    bounds = [(0, None), (0, 2.0), (0, 3), (None, 5.0), (-1.0, None), (None, None), (2.0, 2.0), (0, None), (None, None)]
+    c = rng.standard_normal(n)
+    ref = O.standard_form(c, A, b, G, h, bounds, presolve=False)
+    sf = PR.build_standard_form(n, A, b, G, h, bounds, None, presolve=False)
+    assert ref["A"].shape[0] == me + mu + 3 and sf.fixed_idx.size == 0 and sf.nvar == n  # 3 finite upper bounds
+    np.testing.assert_allclose(sf.A.toarray(), ref["A"], atol=0)
+    np.testing.assert_allclose(sf.b, ref["b"], atol=1e-14)
+    c_std = np.where(sf.c_src >= 0, c[np.maximum(sf.c_src, 0)] * sf.c_sign, 0.0)
+    np.testing.assert_allclose(c_std, ref["c"], atol=0)
+
+
+def test_presolve_false_on_energy_fixture():
+    z = GU.load("energy_load1")
+    inp = GU.problem_inputs("energy_load1", z, 0)
+    sf = PR.build_standard_form(1440, f32(inp["A"]), f32(inp["b"]), f32(inp["G"]), f32(inp["h"]), [(0.0, None)], None,
+                                presolve=False)
+    assert sf.A.shape == (174, 1584)      # what the reference builds with presolve=False (172 x 1582 with presolve)
+    ref = O.standard_form(np.ones(1440), f32(inp["A"]), f32(inp["b"]), f32(inp["G"]), f32(inp["h"]), [(0.0, None)],
+                          presolve=False)
+    np.testing.assert_array_equal(sf.A.toarray(), ref["A"])
+    np.testing.assert_array_equal(sf.b, ref["b"])
+
+
 def test_presolve_outcomes():
     with pytest.raises(PR.PresolveComplete) as e:  # zero row, non-zero rhs (:957-970)
         PR.build_standard_form(3, np.array([[0.0, 0, 0], [1, 1, 1]]), np.array([1.0, 1.0]))
