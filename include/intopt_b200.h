@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define INTOPT_B200_VERSION 2
+#define INTOPT_B200_VERSION 3
 
 /* intopt_problem_create flag: the VALUES of A's non-zeros differ per instance (same sparsity pattern), e.g. the
  * knapsack driver whose equality row is the minibatch's cost vector (experiments/Building Knapsack/optimizer.py:396-405).
@@ -49,7 +49,9 @@ typedef struct IntoptOpts {
   double thr;         /* early stop: loop ends when mu <= thr (:1408); thr=None -> 0 (:1319) */
   double damping_fwd; /* diagonal damping of A.diag(x/t).A^T: 1e-6 in whole (:774), `damping` in alter */
   int max_iter;       /* up to max_iter+1 iterations run (:1414) */
-  int reserved;
+  int plain;          /* 0: Mehrotra predictor-corrector (pc=True, every reference driver); 1: pc=False — one direction
+                         per iteration with centring gamma = beta * mean(x.t) (:1392-1394, :846-847) */
+  double beta;        /* only read when plain = 1; default 0.1 (:1287) */
 } IntoptOpts;
 
 /* Static facts about a problem after structure analysis (host side, no GPU needed to read). */

@@ -17,7 +17,8 @@ LIB_PATH = os.environ.get("INTOPT_LIB_OVERRIDE") or os.path.join(_HERE, "lib", "
 
 class IntoptOpts(ctypes.Structure):
     _fields_ = [("alpha0", ctypes.c_double), ("tol", ctypes.c_double), ("thr", ctypes.c_double),
-                ("damping_fwd", ctypes.c_double), ("max_iter", ctypes.c_int), ("reserved", ctypes.c_int)]
+                ("damping_fwd", ctypes.c_double), ("max_iter", ctypes.c_int), ("plain", ctypes.c_int),
+                ("beta", ctypes.c_double)]
 
 
 class IntoptUserMap(ctypes.Structure):

@@ -134,7 +134,9 @@ __device__ __forceinline__ CtaCtx make_ctx(double* red) {
 
 // Persistent CTAs: each pulls the next LP instance from an atomic counter until the batch is exhausted,
 // so finished LPs free their SM slot without any host involvement.
-template <int TMAX, bool ALLSMEM>
+// PLAIN: pc=False upstream (one direction per iteration) — its own instantiation, so that the predictor-corrector kernels
+// are compiled exactly as if the option did not exist.
+template <int TMAX, bool ALLSMEM, bool PLAIN = false>
 __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_forward_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                const __grid_constant__ intopt::FwdParams a) {
   extern __shared__ __align__(16) double smem[];
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
     const int inst = s_inst;
     __syncthreads();
     if (inst >= a.B) break;
-    intopt::forward_instance(cx, P, M, a, inst, wsi, S, cold, served & 1u);
+    intopt::forward_instance_t<PLAIN>(cx, P, M, a, inst, wsi, S, cold, served & 1u);
     ++served;
   }
 }
@@ -407,6 +409,7 @@ static std::vector<const void*> all_kernels() {
   std::vector<const void*> v;
 #define ADD_(T, A)                                          \
   v.push_back((const void*)intopt_forward_kernel<T, A>);    \
+  v.push_back((const void*)intopt_forward_kernel<T, A, true>); \
   v.push_back((const void*)intopt_backward_kernel<T, A>);   \
   v.push_back((const void*)intopt_coldfactor_kernel<T, A>); \
   v.push_back((const void*)intopt_microbench_kernel<T, A>);
@@ -414,10 +417,11 @@ static std::vector<const void*> all_kernels() {
 #undef ADD_
   return v;
 }
-static const void* pick_kernel(bool forward, int threads, bool allsmem) {
+static const void* pick_kernel(bool forward, int threads, bool allsmem, bool plain = false) {
 #define PICK_(T, A)                                                                                        \
   if (threads <= T && allsmem == A)                                                                        \
-    return forward ? (const void*)intopt_forward_kernel<T, A> : (const void*)intopt_backward_kernel<T, A>;
+    return forward ? (plain ? (const void*)intopt_forward_kernel<T, A, true> : (const void*)intopt_forward_kernel<T, A>) \
+                   : (const void*)intopt_backward_kernel<T, A>;
   INTOPT_VARIANTS(PICK_)
 #undef PICK_
   return nullptr;
@@ -657,6 +661,8 @@ int intopt_forward_mapped(const IntoptProblem* p, int B, double* c, long long c_
   a.thr = o->thr;
   a.damping = o->damping_fwd;
   a.max_iter = o->max_iter;
+  a.plain = o->plain != 0;
+  a.beta = o->beta;
   a.phase_cycles = nullptr;
   a.debug = env_int("INTOPT_DEBUG", 0);
   if (!init && !a_vals) {  // (the cold-start factor is a constant of the problem only if A is)
@@ -672,7 +678,7 @@ int intopt_forward_mapped(const IntoptProblem* p, int B, double* c, long long c_
   CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
   {
     void* args[2] = {(void*)&p->dev, (void*)&a};
-    CU_TRY(cudaLaunchKernel(pick_kernel(true, p->info.threads, a.factor_in_smem && a.gather_in_smem), dim3(grid),
+    CU_TRY(cudaLaunchKernel(pick_kernel(true, p->info.threads, a.factor_in_smem && a.gather_in_smem, a.plain != 0), dim3(grid),
                             dim3(p->info.threads), args, (size_t)p->info.smem_bytes, (cudaStream_t)stream));
   }
   CU_TRY(cudaGetLastError());

@@ -1388,6 +1388,8 @@ struct FwdParams {
   const int* cold_ok;
   double alpha0, tol, thr, damping;
   int max_iter;
+  int plain;    // 1: pc=False upstream — one pass per iteration with centring gamma = beta * mean(x t) (:1392)
+  double beta;
   unsigned long long* phase_cycles;  // null unless profiling
   int debug;                         // debug switches for bottleneck isolation (env INTOPT_DEBUG), 0 in production
 };
@@ -1433,8 +1435,12 @@ IO_DEV void factor_and_rhs(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
   CTA_SYNC();
 }
 
-IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst, double* wsi,
-                             const SmemLayout& S, bool cold = false, unsigned cold_parity = 0) {
+// PLAIN = false: Mehrotra predictor-corrector (pc=True upstream, every reference driver).  PLAIN = true: pc=False.  A
+// template parameter, and one kernel per value, rather than a run-time switch: the run-time version cost the
+// predictor-corrector path 0.45 %, both instantiations inside one kernel 3.8 % (register allocation).
+template <bool PLAIN>
+IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst, double* wsi,
+                               const SmemLayout& S, bool cold = false, unsigned cold_parity = 0) {
   if (a.a_vals)  // (M already points at the CTA's value streams, see instance_value_streams)
     fill_instance_values(cx, P, a.a_vals + (long long)inst * a.a_stride, a.vals_ws + (long long)blockIdx_x() * a.vals_ws_stride);
   const int m = P.m, n = P.n, mv = P.mv;
@@ -1627,6 +1633,11 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
     }
     ++iters;
     const double r3 = -(-cx_ + by_ - kappa);  // :767
+    // pass-0 centring (:1392-1394): 0 with the predictor-corrector, beta * mean(x t) without; x*t - 0 and 1*r are exact,
+    // so the predictor-corrector path computes the same bits as before
+    const double gamma0 = PLAIN ? a.beta * (xt_ / (double)n) : 0.0;
+    const double eta0 = 1.0 - gamma0;
+    const double gm0 = gamma0 * mu;
     PHASE_MARK(pt, 1);
 
     // ---- M = A D A^T + delta I, factor (:772-777) ------------------------------------------------
@@ -1647,8 +1658,14 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
       }
       BATCH_EACH(u, k, k0, n, NU) {
         gstore(G, k, dv[u] * cv[u]);
-        const double rxt = -(xv[u] * tv[u]);             // :788 with gamma = 0
-        const double wk = rv[u] - (1.0 / xv[u]) * rxt;   // :801 with eta(0) = 1
+        double wk;
+        if (!PLAIN) {
+          const double rxt = -(xv[u] * tv[u]);      // :788 with gamma = 0
+          wk = rv[u] - (1.0 / xv[u]) * rxt;         // :801 with eta(0) = 1
+        } else {
+          const double rxt = -(xv[u] * tv[u] - gm0);
+          wk = eta0 * rv[u] - (1.0 / xv[u]) * rxt;
+        }
         w[k] = wk;
         gstore(G2, k, dv[u] * wk);
       }
@@ -1663,14 +1680,14 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
       CTA_SYNC();
       CTA_FOR(i, m) {
         q[i] = bs[i] + q[i];  // r = r2 + A(Dinv r1), :666 with (r1,r2) = (c,b)
-        v[i] = r1[i] + v[i];
+        v[i] = (PLAIN ? eta0 * r1[i] : r1[i]) + v[i];  // :785,666
       }
     } else {
       factor_and_rhs(cx, P, M, L, S, G, G2, q, v, &pt);
       solved = *S.flag == 0;
       CTA_FOR(i, m) {
         q[i] = bs[i] + q[i];
-        v[i] = r1[i] + v[i];
+        v[i] = (PLAIN ? eta0 * r1[i] : r1[i]) + v[i];  // :785,666
       }
     }
     CTA_SYNC();
@@ -1729,8 +1746,8 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
 
     PHASE_MARK(pt, 6);
     // ---- predictor (pass 0) and corrector (pass 1) (:783-847) ---------------------------------------
-    double gamma = 0.0, dtau = 0.0, dkappa = 0.0, minr = 0.0;
-    for (int pass = 0; pass < 2; ++pass) {
+    double gamma = gamma0, dtau = 0.0, dkappa = 0.0, minr = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {  // (:846-847: without the corrector the first direction is the step)
       const double eta = 1.0 - gamma;
       const double gm = gamma * mu;
       double rtk = -(tau * kappa - gm);     // :789
@@ -1823,7 +1840,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
       if (dkappa < 0.0) alpha = fmin(alpha, kappa / -dkappa);
       const double oma = 1.0 - alpha;
       gamma = oma * oma * fmin(0.1, oma);  // :844
-      if (pass == 1) {
+      if (pass == 1 || PLAIN) {
         // ---- step (:1402-1403).  alpha0*min(x/-dx) == min(alpha0*x/-dx) bit for bit
         double al = fmin(1.0, a.alpha0 * minr);
         if (dtau < 0.0) al = fmin(al, a.alpha0 * tau / -dtau);  // evaluation order of :874,876
@@ -1834,7 +1851,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
             xv[u] = x[k];
             tv[u] = t[k];
             uv[u] = dx[k];
-            ev[u] = dxdt[k];
+            ev[u] = pass == 1 ? dxdt[k] : 0.0;  // Mehrotra term of the corrector only (:793)
           }
           BATCH_EACH(u, k, k0, n, NU) {
             const double xk = xv[u], tk = tv[u];
@@ -1854,6 +1871,7 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
         tau = tau + al * dtau;
         kappa = kappa + al * dkappa;
         CTA_SYNC();
+        break;
       }
     }
     PHASE_MARK(pt, 9);
@@ -1890,6 +1908,16 @@ IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& 
   CTA_SYNC();
   PHASE_MARK(pt, 10);
 }
+
+#ifdef INTOPT_HOST_EMU  // (the CUDA kernels pick the instantiation at launch: one kernel per value of PLAIN)
+IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst, double* wsi,
+                             const SmemLayout& S, bool cold = false, unsigned cold_parity = 0) {
+  if (a.plain)
+    forward_instance_t<true>(cx, P, M, a, inst, wsi, S, cold, cold_parity);
+  else
+    forward_instance_t<false>(cx, P, M, a, inst, wsi, S, cold, cold_parity);
+}
+#endif
 
 // The factor every cold-started instance uses at its first iteration: chol(A A^T + delta I) in the block-skyline
 // layout, computed by exactly the code path an instance would run (D = x/t = 1), hence bit-identical to it.

@@ -206,15 +206,13 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                  new_grad=True, presolve=True, A_eq_rr=True, damping=1e-2, check_finite=True):
     """Shared implementation behind ip_model_whole.IPOfunc / ip_model_alter.IPOfunc.
 
-    Unused upstream keywords are accepted and ignored exactly as upstream does: `beta` (only if pc=False),
-    `mu0`, `new_grad`, `A_eq_rr` are never read, `smoothing` is only logged (ip_model_whole.py:1339).
+    `pc=False` runs one direction per iteration with centring `beta * mean(x t)` (:1392-1394).  Unused upstream
+    keywords are accepted and ignored exactly as upstream does: `mu0`, `new_grad`, `A_eq_rr` are never read, `smoothing` is only logged (ip_model_whole.py:1339).
     `check_finite` (additive): True reproduces upstream's LinAlgError on non-finite `c` (:1332-1341) at the
     price of one device->host sync per call; False leaves it to the per-instance status word (4).
     """
     if variant not in ("whole", "alter"):
         raise ValueError(variant)
-    if not pc:
-        raise NotImplementedError("pc=False (plain path-following) is not used by any reference driver")
     if method not in (1, 2, 3):
         raise ValueError("method must be 1 (full), 2 (rows and columns sliced) or 3 (rows sliced), :1459-1482")
     A_np, b_np, G_np, h_np = _to_numpy(A), _to_numpy(b), _to_numpy(G), _to_numpy(h)
@@ -356,7 +354,7 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
         iters = torch.empty(Bg, dtype=torch.int32, device=device)
         ws = dp.workspace(Bg)
         init = pack_init(dp, Bg, device)
-        opts = _capi.IntoptOpts(alpha0, tol, thr_, damping_fwd, max_iter_, 0)
+        opts = _capi.IntoptOpts(alpha0, tol, thr_, damping_fwd, max_iter_, 0 if pc else 1, float(beta))
         _capi.check(L.intopt_forward_mapped(dp.handle, Bg, _ptr(c_std), sf.n, _ptr(b_std), b_stride, _ptr(a_vals),
                                             dp.nnz if a_batched else 0, ctypes.byref(opts), _ptr(init), ctypes.byref(um),
                                             _ptr(xhat), _ptr(st), _ptr(status), _ptr(iters), _ptr(ws), ws.numel() * 8,

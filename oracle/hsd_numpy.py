@@ -231,7 +231,7 @@ STATUS_OK, STATUS_MAXITER, STATUS_INFEAS, STATUS_BREAKDOWN, STATUS_NONFINITE = 0
 
 
 def forward(A, b, c, alpha0=0.9995, tol=1e-8, thr=0.0, max_iter=1000, damping_fwd=1e-6,
-            init=None, trace=None):
+            init=None, trace=None, pc=True, beta=0.1):
     """One LP: returns dict(x,y,t,tau,kappa,iters,status,mu).  `A` dense (m×n) fp64.
 
     Follows the loop at ip_model_whole.py:1385-1423 with `_get_delta` (:761-859, pc=True),
@@ -290,10 +290,10 @@ def forward(A, b, c, alpha0=0.9995, tol=1e-8, thr=0.0, max_iter=1000, damping_fw
             if not (np.isfinite(p).all() and np.isfinite(q).all()):
                 solved = False
         if solved:
-            gamma = 0.0
+            gamma = 0.0 if pc else beta * np.mean(t * x)  # :1392
             dx = dt = None
             dtau = dkappa = 0.0
-            for i in (0, 1):  # :783
+            for i in ((0, 1) if pc else (0,)):  # :783, :846-847
                 eta = 1.0 - gamma
                 rxt = -(x * t - gamma * mu)  # :788
                 rtk = -(tau * kappa - gamma * mu)  # :789
@@ -435,7 +435,7 @@ def backward_alter_asref(A, b, c, st, g, damping, nvar=None, f=np.float32):
 
 def ipofunc(c, g=None, A=None, b=None, G=None, h=None, bounds=None, variant="whole",
             alpha0=0.9995, tol=1e-8, thr=None, max_iter=1000, damping=1e-2, asref=False,
-            init=None, method=1, presolve=True):
+            init=None, method=1, presolve=True, pc=True, beta=0.1):
     """fp64 oracle of `IPOfunc(A,b,G,h,...)(c)` followed by `(x*g).sum().backward()`.
 
     Inputs are rounded to float32 first, like the torch tensors the drivers pass
@@ -451,7 +451,7 @@ def ipofunc(c, g=None, A=None, b=None, G=None, h=None, bounds=None, variant="who
     if sf["complete"]:
         return dict(x=sf["x"], grad=np.zeros(n_x), iters=0, status=sf["status"], state=None, sf=sf)
     dfwd = 1e-6 if variant == "whole" else damping
-    st = forward(sf["A"], sf["b"], sf["c"], alpha0, tol, thr, max_iter, dfwd, init)
+    st = forward(sf["A"], sf["b"], sf["c"], alpha0, tol, thr, max_iter, dfwd, init, pc=pc, beta=beta)
     x = postprocess(st["x"] / st["tau"], sf)
     grad = None
     if g is not None:

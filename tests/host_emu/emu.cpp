@@ -12,7 +12,7 @@ extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const doubl
                          double alpha0, double tol, double thr, double damping_fwd, int max_iter,
                          const double* init, double* xhat, double* state, int* status, int* iters,
                          int bwd_mode, double damping_bwd, int nvar, const double* gx, double* gc,
-                         int* bstatus, int* envelope_out, const double* a_vals) {
+                         int* bstatus, int* envelope_out, const double* a_vals, int plain, double beta) {
   intopt::HostStructure S;
   int rc = intopt::analyze(m, n, rp, ci, val, S, force_order, a_vals != nullptr);
   if (rc) return rc;
@@ -40,6 +40,7 @@ extern "C" int emu_solve(int m, int n, const int* rp, const int* ci, const doubl
   a.status = status; a.iters = iters; a.ws = ws.data(); a.ws_stride = 0;
   a.factor_in_smem = 1; a.gather_in_smem = 1;
   a.alpha0 = alpha0; a.tol = tol; a.thr = thr; a.damping = damping_fwd; a.max_iter = max_iter;
+  a.plain = plain; a.beta = beta;
   // cold-start factor (as the CUDA host code does): built once with the instance code path, copied in at iteration 1
   std::vector<double> cold((size_t)S.bsize);
   int cold_ok = 0;

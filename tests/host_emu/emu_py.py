@@ -23,7 +23,7 @@ def build():
 
 
 def solve(A, b, c, g=None, b_batch=None, alpha0=0.9995, tol=1e-8, thr=0.0, max_iter=1000, damping_fwd=1e-6,
-          mode=0, damping_bwd=1e-2, nvar=None, force_order=-1, init=None, a_vals=None):
+          mode=0, damping_bwd=1e-2, nvar=None, force_order=-1, init=None, a_vals=None, plain=0, beta=0.1):
     lib = ctypes.CDLL(build())
     A = sp.csr_matrix(A)
     A.sort_indices()
@@ -53,6 +53,6 @@ def solve(A, b, c, g=None, b_batch=None, alpha0=0.9995, tol=1e-8, thr=0.0, max_i
                        ctypes.c_double(tol), ctypes.c_double(thr), ctypes.c_double(damping_fwd),
                        ctypes.c_int(max_iter), dp(ini), dp(xhat), dp(state), dp(status), dp(iters),
                        ctypes.c_int(mode), ctypes.c_double(damping_bwd), ctypes.c_int(nvar), dp(gx), dp(gc),
-                       dp(bstatus), ctypes.byref(env), dp(av))
+                       dp(bstatus), ctypes.byref(env), dp(av), ctypes.c_int(plain), ctypes.c_double(beta))
     assert rc == 0, rc
     return dict(xhat=xhat, state=state, status=status, iters=iters, gc=gc, bstatus=bstatus, envelope=env.value)

@@ -28,7 +28,7 @@ def test_exports_match_header(lib):
     assert declared == set(_capi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.intopt_version() == 2
+    assert lib.intopt_version() == 3
 
 
 def test_structure_analysis_on_reference_shapes(lib):

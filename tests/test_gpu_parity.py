@@ -337,6 +337,22 @@ def test_presolve_false(variant):
     assert _rel2(gs[0], ref["energy_load1_%s_nopresolve_grad" % variant].astype(np.float64)) < 1e-3
 
 
+@pytest.mark.parametrize("name", ["knapsack", "energy_load1"])
+def test_pc_false(name):
+    """pc=False (ip_model_whole.py:1392-1394, :846-847) against the oracle and the reference's float32 output."""
+    z, ref = GU.load(name), GU.load("methods")
+    inp = GU.problem_inputs(name, z, 0)
+    case = GU.cases(z)[0]
+    kw = dict(case["kw"], pc=False)
+    xs, gs, status, iters, _ = _run_gpu("whole", kw, inp, case["c"][:1], case["g"][:1])
+    r = O.ipofunc(case["c"][0], case["g"][0], bounds=kw.get("bounds"), thr=kw.get("thr"),
+                  max_iter=kw.get("max_iter") or 1000, damping=kw["damping"], pc=False, **inp)
+    assert status.tolist() == [0] and iters[0] == r["iters"] == int(ref[name + "_whole_plain_iters"])
+    assert _relinf(xs[0], r["x"]) < X_TOL and _rel2(gs[0], r["grad"]) < G_TOL
+    assert _relinf(xs[0], ref[name + "_whole_plain_x"].astype(np.float64)) < 5e-6
+    assert _rel2(gs[0], ref[name + "_whole_plain_grad"].astype(np.float64)) < 1e-3
+
+
 def test_method_2_with_per_instance_A():
     """Knapsack minibatches through the per-instance-values path with sliced backward == one call per matrix."""
     from neuripsintopt_b200.ip_model_whole import IPOfunc

@@ -113,3 +113,25 @@ def test_emulated_infeasible_unbounded_and_capped_runs(max_iter):
         assert np.abs(e["xhat"][0] - xo).max() <= 1e-9 * max(1.0, np.abs(xo).max())
         seen.add(int(r["status"]))
     assert seen == ({0, 2} if max_iter == 1000 else {1, 2})
+
+
+@pytest.mark.parametrize("name", ["knapsack", "energy_load1", "dense_m16"])
+@pytest.mark.parametrize("thr", [0.1, 0.0])
+def test_emulated_plain_path_following(name, thr):
+    """pc=False (IntoptOpts.plain = 1): same iteration count and iterate as the oracle, early-stopped and converged."""
+    z = GU.load(name)
+    inp = GU.problem_inputs(name, z, 0)
+    case = GU.cases(z)[0]
+    kw = case["kw"]
+    mi = kw.get("max_iter") or 1000
+    r = O.ipofunc(case["c"][0], case["g"][0], bounds=kw.get("bounds"), thr=thr, max_iter=mi, damping=kw["damping"],
+                  pc=False, **inp)
+    sf = r["sf"]
+    g = case["g"][0].astype(np.float64)[sf["var_index"]]
+    e = emu_py.solve(sf["A"], sf["b"], sf["c"], g=g, thr=thr, max_iter=mi, damping_bwd=kw["damping"], nvar=sf["nvar"],
+                     plain=1, beta=0.1)
+    assert e["iters"][0] == r["iters"] and e["status"][0] == 0
+    xo = r["state"]["x"] / r["state"]["tau"]
+    assert np.abs(e["xhat"][0] - xo).max() <= 1e-6 * max(1.0, np.abs(xo).max())
+    if thr > 0:
+        assert np.linalg.norm(e["gc"][0] - r["grad"][sf["var_index"]]) <= 1e-5 * np.linalg.norm(r["grad"])
