@@ -401,9 +401,9 @@ def run_gpu(args):
             roofline=dict(bound="fp64", kernel="intopt_forward_kernel", achieved=ach_fwd, peak=fp64_peak,
                           unit="TFLOP/s", frac=ach_fwd / fp64_peak,
                           # DRAM bytes of one forward launch from the committed `ncu --set full` capture of this
-                          # default configuration (profiles/r01_s7_ncu_summary.txt: 14.4 MB read + 104.2 MB written for
+                          # default configuration (profiles/r01_final_ncu_summary.txt: 14.3 MB read + 105.6 MB written for
                           # 2368 LPs = float32 c in, packed c + saved iterate + float32 x out); null for other configurations
-                          traffic=(118.6e6 if (B == 2368 and args.thr == 0.1) else None),
+                          traffic=(119.9e6 if (B == 2368 and args.thr == 0.1) else None),
                           peak_source="DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
                           flops_per_iter=f_it, flops_backward=f_bw,
                           backward=dict(kernel="intopt_backward_kernel", achieved=ach_bwd, frac=ach_bwd / fp64_peak),
