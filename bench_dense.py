@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Dense LP sweep (BASELINE.json configs[4]): batched IPOfunc forward+backward on synthetic
+feasible-and-bounded dense LPs (m x 2m) through the lock-step dense path, roofline fraction against the MEASURED
+FP64 tensor-core (DMMA) peak, parity of the first instances against the CPU oracle.  One JSON line per shape.
+
+    python bench_dense.py [--shapes 256x512,1024x256,...]  (m x batch)  [--thr 0.1] [--steps 3]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+
+def gen(m, B):
+    rng = np.random.default_rng(m)
+    n = 2 * m
+    A = rng.standard_normal((m, n)).astype(np.float32)
+    x0 = rng.uniform(0.1, 1.0, n)
+    b = (A.astype(np.float64) @ x0).astype(np.float32)
+    y0 = rng.standard_normal((B, m))
+    s0 = rng.uniform(0.1, 1.0, (B, n))
+    c = (y0 @ A.astype(np.float64) + s0).astype(np.float32)
+    return A, b, c
+
+
+def contract_flops(m, n, iters_sum, B):
+    """F_it = 2S + m^3/3 + 6 m^2 + 20 nnz + 30 n, F_bw = 2S + m^3/3 + 4 m^2 + 12 nnz + 20 n (whole)."""
+    S = n * m * (m + 1) / 2.0
+    nnz = m * n
+    f_it = 2 * S + m ** 3 / 3.0 + 6 * m * m + 20 * nnz + 30 * n
+    f_bw = 2 * S + m ** 3 / 3.0 + 4 * m * m + 12 * nnz + 20 * n
+    return iters_sum * f_it + B * f_bw
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shapes", default="256x1024,512x512,1024x256")
+    ap.add_argument("--thr", type=float, default=0.1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--parity", type=int, default=1)
+    args = ap.parse_args()
+    from neuripsintopt_b200 import _capi, ipofunc
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    from oracle import hsd_numpy as O  # checker only
+
+    dmma = _capi.measure_dmma_peak(5) * 1e-3
+    dfma = _capi.measure_fp64_peak(5) * 1e-3
+    thr = args.thr if args.thr > 0 else None
+    for shape in args.shapes.split(","):
+        m, B = (int(v) for v in shape.split("x"))
+        n = 2 * m
+        A, b, c = gen(m, B)
+        ipofunc.clear_cache()
+        t0 = time.time()
+        f = IPOfunc(torch.tensor(A), torch.tensor(b), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)], thr=thr,
+                    damping=1e-6, check_finite=False)
+        ct = torch.tensor(c, device="cuda", requires_grad=True)
+        g = torch.ones_like(ct)
+        x = f(ct)
+        x.backward(g)
+        torch.cuda.synchronize()
+        t_first = time.time() - t0
+        status, iters = IPOfunc.status()
+        info = [v.info for v in ipofunc._PROBLEM_CACHE.values() if hasattr(v, "info")][-1]
+        ex = eg = None
+        if args.parity:
+            ex = eg = 0.0
+            for i in range(args.parity):
+                r = O.ipofunc(c[i], np.ones(n, np.float32), A=A, b=b, bounds=[(0.0, None)], thr=thr, damping=1e-6)
+                xi = x[i].detach().double().cpu().numpy()
+                ex = max(ex, float(np.abs(xi - r["x"]).max() / max(1.0, np.abs(r["x"]).max())))
+                eg = max(eg, float(np.linalg.norm(ct.grad[i].double().cpu().numpy() - r["grad"]) / np.linalg.norm(r["grad"])))
+                if thr:
+                    assert int(iters[i]) == r["iters"], (int(iters[i]), r["iters"])
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tf = tb = 0.0
+        for _ in range(args.steps):
+            cc = ct.detach().requires_grad_(True)
+            ev[0].record()
+            xx = f(cc)
+            ev[1].record()
+            xx.backward(g)
+            ev[2].record()
+            ev[2].synchronize()
+            tf += ev[0].elapsed_time(ev[1])
+            tb += ev[1].elapsed_time(ev[2])
+        tf /= args.steps
+        tb /= args.steps
+        ms = tf + tb
+        fl = contract_flops(m, n, float(iters.sum()), B)
+        tfl = fl / (ms * 1e-3) * 1e-12
+        print(json.dumps({
+            "config": "dense m=%d n=%d" % (m, n), "batch": B, "thr": args.thr, "path": info["path"],
+            "lp_per_s": round(B / ms * 1e3, 1), "ms_fwd": round(tf, 3), "ms_bwd": round(tb, 3),
+            "iters_mean": round(float(iters.float().mean()), 2), "bad_status": int((status != 0).sum()),
+            "contract_gflop": round(fl * 1e-9, 2), "achieved_tflops": round(tfl, 3),
+            "dmma_peak_tflops": round(dmma, 2), "dfma_peak_tflops": round(dfma, 2),
+            "roofline_frac_dmma": round(tfl / dmma, 4), "roofline_frac_dfma": round(tfl / dfma, 4),
+            "x_rel_vs_oracle": ex, "grad_rel_vs_oracle": eg, "first_call_s": round(t_first, 2)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

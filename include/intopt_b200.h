@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define INTOPT_B200_VERSION 3
+#define INTOPT_B200_VERSION 4
 
 /* intopt_problem_create flag: the VALUES of A's non-zeros differ per instance (same sparsity pattern), e.g. the
  * knapsack driver whose equality row is the minibatch's cost vector (experiments/Building Knapsack/optimizer.py:396-405).
@@ -68,7 +68,8 @@ typedef struct IntoptInfo {
   int gather_in_smem;     /* 1 if the n-vector gather buffer lives in shared memory */
   int ctas_per_sm;        /* resident CTAs per SM (set by intopt_problem_create, 0 from intopt_analyze) */
   int scalar_envelope;    /* doubles a scalar skyline would need (for comparison) */
-  int reserved;
+  int path;               /* 0: persistent-CTA path (one CTA owns one LP, factor in shared memory);
+                             1: lock-step dense path (batch-wide DMMA kernels, factor tiled through HBM) */
   long long asm_padded;   /* gather-list slots incl. padding of the warp-interleaved layout */
   long long solve_macs;   /* MACs of one blocked L L^T solve */
 } IntoptInfo;
@@ -79,8 +80,9 @@ const char* intopt_last_error(void);
 /* Host-only structure analysis of a standard-form A (CSR, m x n).  Fills `info` and, if non-NULL,
  * row_perm_host[m] (internal row i = original row row_perm_host[i]).  Needs no GPU.
  * Returns 0, -1..-4 for malformed input (NULL / non-monotone rowptr / column out of range / m too large for the
- * 16-bit row indices), -5 when the problem is too large for the gather-list assembly (asm_terms > 2^28: large dense
- * matrices, m >~ 600 at n = 2m); intopt_problem_create returns the same codes. */
+ * 16-bit row indices), -5 when a SPARSE problem is too large for the gather-list assembly (asm_terms > 2^28);
+ * intopt_problem_create returns the same codes.  Dense problems (nnz >= m n / 4) with m >= 192 take the lock-step dense
+ * path (info.path = 1, m <= 4096) and are not subject to that limit. */
 int intopt_analyze(int m, int n, const int* rowptr_host, const int* colidx_host, const double* val_host,
                    IntoptInfo* info, int* row_perm_host);
 
@@ -179,21 +181,20 @@ int intopt_gather_convert(const void* src_dev, int src_is_f32, long long src_str
                           const int* idx_dev, const double* scale_dev, const double* constv_dev, void* dst_dev,
                           int dst_is_f32, long long dst_stride, void* stream);
 
+/* Lock-step dense path only (IntoptInfo.path == 1): z_b = (A diag(d_b) A^T + delta I)^-1 rhs_b for B instances — the
+ * normal-matrix assembly (:772-775), tiled Cholesky (:742) and blocked substitution (:745) kernels as a stand-alone
+ * primitive.  d_dev: B x n, rhs_dev: B x m (in: right-hand sides, out: solutions), fail_dev: int32[B] (non-positive
+ * pivot) or NULL; workspace as for intopt_forward. */
+int intopt_dense_normal_solve(const IntoptProblem* p, int B, const double* d_dev, double delta, double* rhs_dev,
+                              int* fail_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Measured FP64 tensor-core (DMMA m8n8k4) throughput of the current device (GFLOP/s), register-resident chains:
+ * the roofline denominator of the dense path.  Synchronises the device. */
+int intopt_measure_dmma_peak(double* gflops_out, int repeats);
+
 /* Measured FP64 FMA throughput of the current device (GFLOP/s) with a register-resident DFMA kernel;
  * the roofline denominator MEASURED_PEAKS.json lacks.  Synchronises the device. */
 int intopt_measure_fp64_peak(double* gflops_out, int repeats);
-
-/* Debug aid for profiles/: enable (1) / disable (0) per-phase SM-cycle accounting of the forward kernel;
- * if out32_host is non-NULL the 32 cycle buckets are copied out (after a device sync) and reset.
- * Buckets: 0 setup, 1 residuals+tests, 2 assembly, 3 Cholesky, 4 rhs/spmv, 5 solve(2 rhs), 6 p/u loop,
- * 7 corrector rhs, 8 solve(1 rhs), 9 direction/ratio/update loops, 10 epilogue, 11-14 Cholesky sub-phases,
- * 16-23 sub-phases of 1, 4, 7 and 9 (names in neuripsintopt_b200/_capi.py:PHASES). */
-int intopt_debug_phase_cycles(int enable, unsigned long long* out32_host);
-
-/* Debug aid for profiles/: SM cycles per repetition of one building block of the solver (which: 0 barrier only,
- * 1 A.v, 2 A^T.y, 3 A^T.[y1 y2], 4 assembly, 5 assembly+Cholesky, 6 solve (2 rhs), 7 solve (1 rhs), 8/10 n-loops,
- * 9 CTA reduction) on `grid` persistent CTAs; cycles_host[grid].  Synchronises the device. */
-int intopt_debug_microbench(const IntoptProblem* p, int which, int reps, int grid, unsigned long long* cycles_host);
 
 #ifdef __cplusplus
 }

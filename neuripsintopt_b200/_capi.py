@@ -33,7 +33,7 @@ class IntoptInfo(ctypes.Structure):
                 ("dense_lower", ctypes.c_int), ("asm_terms", ctypes.c_longlong), ("chol_macs", ctypes.c_longlong),
                 ("smem_bytes", ctypes.c_int), ("factor_in_smem", ctypes.c_int), ("threads", ctypes.c_int),
                 ("ordering", ctypes.c_int), ("gather_in_smem", ctypes.c_int), ("ctas_per_sm", ctypes.c_int),
-                ("scalar_envelope", ctypes.c_int), ("reserved", ctypes.c_int), ("asm_padded", ctypes.c_longlong),
+                ("scalar_envelope", ctypes.c_int), ("path", ctypes.c_int), ("asm_padded", ctypes.c_longlong),
                 ("solve_macs", ctypes.c_longlong)]
 
     def as_dict(self):
@@ -44,17 +44,20 @@ EXPORTS = ["intopt_version", "intopt_last_error", "intopt_analyze", "intopt_prob
            "intopt_problem_destroy", "intopt_problem_info", "intopt_workspace_bytes", "intopt_forward",
            "intopt_backward", "intopt_forward_values", "intopt_backward_values", "intopt_forward_mapped",
            "intopt_backward_mapped", "intopt_gather_convert",
-           "intopt_measure_fp64_peak",
-           "intopt_debug_phase_cycles", "intopt_debug_microbench"]
+           "intopt_dense_normal_solve", "intopt_measure_dmma_peak", "intopt_measure_fp64_peak"]
+# only in the profiling build (csrc/build.sh profile -> lib/libintopt_b200_profile.so, include/intopt_b200_profile.h)
+PROFILE_EXPORTS = ["intopt_debug_phase_cycles", "intopt_debug_microbench"]
+PROFILE_LIB_PATH = os.path.join(_HERE, "lib", "libintopt_b200_profile.so")
 FLAG_INSTANCE_VALUES = 1
 
 _lib = None
 
 
-def build(verbose=False):
-    """Compile libintopt_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+def build(verbose=False, profile=False):
+    """Compile libintopt_b200.so for sm_100a with nvcc (cross-compiles without a GPU).  `profile=True` builds the
+    separate profiling library instead (phase-cycle probes + micro-benchmarks; never loaded by the product path)."""
     script = os.path.join(_HERE, "csrc", "build.sh")
-    out = subprocess.run(["bash", script], capture_output=True, text=True)
+    out = subprocess.run(["bash", script] + (["profile"] if profile else []), capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("nvcc build of libintopt_b200.so failed:\n" + out.stdout + out.stderr)
     if verbose:
@@ -92,11 +95,13 @@ def lib():
                                         vp, csz, vp]
     L.intopt_backward_mapped.argtypes = [vp, ci, ci, cd, ci, vp, vp, cll, vp, cll, vp, cll, um, vp, vp, vp, vp, csz, vp]
     L.intopt_measure_fp64_peak.argtypes = [ctypes.POINTER(cd), ci]
-    L.intopt_debug_phase_cycles.argtypes = [ci, vp]
-    L.intopt_debug_microbench.argtypes = [vp, ci, ci, ci, vp]
-    if not os.environ.get("INTOPT_LIB_OVERRIDE"):
-        for name in EXPORTS:
-            getattr(L, name)  # AttributeError here means the library and the header disagree
+    L.intopt_measure_dmma_peak.argtypes = [ctypes.POINTER(cd), ci]
+    L.intopt_dense_normal_solve.argtypes = [vp, ci, vp, cd, vp, vp, vp, csz, vp]
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError here means the library and the header disagree
+    if hasattr(L, "intopt_debug_phase_cycles"):  # profiling build loaded through INTOPT_LIB_OVERRIDE
+        L.intopt_debug_phase_cycles.argtypes = [ci, vp]
+        L.intopt_debug_microbench.argtypes = [vp, ci, ci, ci, vp]
     _lib = L
     return L
 
@@ -122,6 +127,13 @@ def analyze(csr):
     return info.as_dict(), perm
 
 
+def measure_dmma_peak(repeats=5):
+    """FP64 tensor-core (DMMA) throughput of the current device in GFLOP/s (roofline denominator of the dense path)."""
+    out = ctypes.c_double(0.0)
+    check(lib().intopt_measure_dmma_peak(ctypes.byref(out), repeats), "intopt_measure_dmma_peak")
+    return out.value
+
+
 def measure_fp64_peak(repeats=5):
     out = ctypes.c_double(0.0)
     check(lib().intopt_measure_fp64_peak(ctypes.byref(out), repeats), "intopt_measure_fp64_peak")
@@ -134,8 +146,15 @@ PHASES = ["setup", "residuals+tests", "assembly", "cholesky", "rhs/spmv", "solve
           "rhs:spmv(v)", "corr:n-loop", "corr:spmv(v)", "dir:n-loop+min"]
 
 
+def _need_profile_lib():
+    if not hasattr(lib(), "intopt_debug_phase_cycles"):
+        raise RuntimeError("profiling entry points live in libintopt_b200_profile.so: build it with "
+                           "`bash neuripsintopt_b200/csrc/build.sh profile` and set INTOPT_LIB_OVERRIDE=%s" % PROFILE_LIB_PATH)
+
+
 def phase_cycles(enable=True, read=False):
     """Debug aid: toggle per-phase cycle accounting of the forward kernel; optionally read + reset the buckets."""
+    _need_profile_lib()
     import numpy as np
     out = np.zeros(32, dtype=np.uint64)
     check(lib().intopt_debug_phase_cycles(1 if enable else 0, out.ctypes.data if read else None),
@@ -159,6 +178,7 @@ MICRO[34] = "assembly: scan + zero fill only"
 def microbench(handle, which, reps=20, grid=1):
     """Debug aid: median/max SM cycles per repetition of one building block on `grid` persistent CTAs."""
     import numpy as np
+    _need_profile_lib()
     out = np.zeros(grid, dtype=np.uint64)
     check(lib().intopt_debug_microbench(handle, which, reps, grid, out.ctypes.data), "intopt_debug_microbench")
     return float(np.median(out)), float(out.max())

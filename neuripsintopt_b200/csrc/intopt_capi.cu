@@ -12,6 +12,8 @@
 
 #include "../../include/intopt_b200.h"
 #include "intopt_bind.hpp"
+#include "intopt_kernels.cuh"
+#include "intopt_internal.hpp"
 
 namespace {
 
@@ -29,7 +31,6 @@ int fail(int code, const std::string& msg) {
 
 constexpr int kMaxThreads = 512;
 constexpr int kMaxDynSmem = 232448 - 256;  // 227 KB opt-in per CTA on sm_100, minus the kernels' static smem
-constexpr size_t kCounterBytes = 256;
 
 int env_int(const char* name, int dflt) {
   const char* v = std::getenv(name);
@@ -37,7 +38,6 @@ int env_int(const char* name, int dflt) {
 }
 
 // Decide what lives in shared memory.  Preference: factor + gather buffer; then factor only; then neither.
-constexpr int kMaxMetaInts = 4096;  // schedule arrays up to 16 KB are staged in shared memory
 
 void plan_smem(const intopt::HostStructure& S, int* factor_in_smem, int* gather_in_smem, int* smem_bytes) {
   const int mi = intopt::meta_ints(S);
@@ -82,6 +82,32 @@ void fill_info(const intopt::HostStructure& S, IntoptInfo* info) {
   info->solve_macs = S.solve_macs;
 }
 
+// The lock-step dense path keeps no block-skyline structure: its "envelope" is the padded square it factors in place.
+void fill_info_dense(int m, int n, int nnz, IntoptInfo* info) {
+  std::memset(info, 0, sizeof(*info));
+  const long long m64 = (m + 63) & ~63;
+  info->m = m;
+  info->n = n;
+  info->nnz = nnz;
+  info->envelope = (int)std::min<long long>(m64 * m64, 2147483647LL);
+  info->dense_lower = (int)((long long)m * (m + 1) / 2);
+  info->asm_terms = (long long)n * m * (m + 1) / 2;
+  info->chol_macs = (long long)m * m * m / 6;
+  info->solve_macs = (long long)m * m;
+  info->threads = 512;
+  info->path = 1;
+}
+
+int check_csr(int m, int n, const int* rp, const int* ci, const double* val) {
+  if (m <= 0 || n <= 0 || !rp || !ci || !val) return -1;
+  if (rp[0] != 0) return -2;
+  for (int i = 0; i < m; ++i)
+    if (rp[i + 1] < rp[i]) return -2;
+  for (int e = 0; e < rp[m]; ++e)
+    if (ci[e] < 0 || ci[e] >= n) return -3;
+  return 0;
+}
+
 template <class T>
 cudaError_t upload(const std::vector<T>& h, const T** d, std::vector<void*>& allocs) {
   *d = nullptr;
@@ -95,260 +121,6 @@ cudaError_t upload(const std::vector<T>& h, const T** d, std::vector<void*>& all
 }
 
 }  // namespace
-
-// Cold-start factor cache (see FwdParams::cold_factor): one entry per forward damping value seen.
-struct ColdEntry {
-  double delta;
-  double* factor;  // bsize doubles
-  int* ok;         // device flag: 1 if the factorisation succeeded
-  cudaEvent_t ready;
-  bool done;
-};
-
-struct IntoptProblem {
-  intopt::ProblemDev dev{};
-  IntoptInfo info{};
-  const double* b_dev = nullptr;
-  int device = 0;
-  int sms = 0;
-  int slots = 0;  // persistent CTAs per launch
-  std::vector<void*> allocs;
-  // lazily filled, guarded by `mu`; the problem data itself is immutable after create
-  mutable std::mutex mu;
-  mutable std::vector<ColdEntry> cold;
-  mutable std::vector<void*> cold_allocs;
-};
-
-__device__ __forceinline__ CtaCtx make_ctx(double* red) {
-  CtaCtx cx;
-  cx.tid = threadIdx.x;
-  cx.nthreads = blockDim.x;
-  cx.lane = threadIdx.x & 31;
-  cx.warp = threadIdx.x >> 5;
-  cx.nwarps = blockDim.x >> 5;
-  cx.red = red;
-  cx.bar_id = 0;
-  cx.bar_n = blockDim.x;
-  return cx;
-}
-
-// Persistent CTAs: each pulls the next LP instance from an atomic counter until the batch is exhausted,
-// so finished LPs free their SM slot without any host involvement.
-// PLAIN: pc=False upstream (one direction per iteration) — its own instantiation, so that the predictor-corrector kernels
-// are compiled exactly as if the option did not exist.
-template <int TMAX, bool ALLSMEM, bool PLAIN = false>
-__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_forward_kernel(const __grid_constant__ intopt::ProblemDev P,
-                                                               const __grid_constant__ intopt::FwdParams a) {
-  extern __shared__ __align__(16) double smem[];
-  __shared__ int s_inst;
-  double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
-  const intopt::SmemLayout S =
-      intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
-  const CtaCtx cx = make_ctx(S.red);
-  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
-  if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
-  const bool cold = a.cold_factor != nullptr && a.init == nullptr && *a.cold_ok != 0;  // launch-uniform
-  if (cold && a.factor_in_smem && threadIdx.x == 0) intopt::mbar_init(S.mbar, 1);
-  unsigned served = 0;  // instances this CTA has run = completed phases of the prefetch mbarrier
-  for (;;) {
-    if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
-    __syncthreads();
-    const int inst = s_inst;
-    __syncthreads();
-    if (inst >= a.B) break;
-    intopt::forward_instance_t<PLAIN>(cx, P, M, a, inst, wsi, S, cold, served & 1u);
-    ++served;
-  }
-}
-
-// One CTA computes the cold-start factor chol(A A^T + delta I) with the instance code path (same CTA size).
-template <int TMAX, bool ALLSMEM>
-__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_coldfactor_kernel(const __grid_constant__ intopt::ProblemDev P,
-                                                                  double delta, double* ws, int factor_in_smem,
-                                                                  int gather_in_smem, double* out, int* ok) {
-  extern __shared__ __align__(16) double smem[];
-  const intopt::SmemLayout S = intopt::carve<ALLSMEM>(P, smem, ws + intopt::ws_nvec_doubles(P.n), factor_in_smem, gather_in_smem);
-  const CtaCtx cx = make_ctx(S.red);
-  const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
-  intopt::cold_factor_build(cx, P, M, delta, ws, S, out, ok);
-}
-
-template <int TMAX, bool ALLSMEM>
-__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_backward_kernel(const __grid_constant__ intopt::ProblemDev P,
-                                                                const __grid_constant__ intopt::BwdParams a) {
-  extern __shared__ __align__(16) double smem[];
-  __shared__ int s_inst;
-  double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
-  const intopt::SmemLayout S =
-      intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
-  const CtaCtx cx = make_ctx(S.red);
-  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
-  if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
-  for (;;) {
-    if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
-    __syncthreads();
-    const int inst = s_inst;
-    __syncthreads();
-    if (inst >= a.B) break;
-    intopt::backward_instance(cx, P, M, a, inst, wsi, S);
-  }
-}
-
-// experimental copy of intopt::spmv_rows (run-length path) with switchable stages, for the micro-benchmark only
-__device__ __forceinline__ void spmv_rows_dbg(const CtaCtx& cx, const intopt::ProblemDev& P, const double* src, double* out,
-                                              int flags) {
-  int slot = cx.warp;
-  uint32_t hn = 0u;
-  int rown = 0xffff;
-  if (slot < P.rs_slots) {
-    hn = P.rs_hdr[slot * 32 + cx.lane];
-    rown = P.rs_row[slot * 32 + cx.lane];
-  }
-  for (; slot < P.rs_slots; slot += cx.nwarps) {
-    const uint32_t h = hn;
-    const int row = rown;
-    const int nxt = slot + cx.nwarps;
-    if (nxt < P.rs_slots) {
-      hn = P.rs_hdr[nxt * 32 + cx.lane];
-      rown = P.rs_row[nxt * 32 + cx.lane];
-    }
-    double s = (flags & 1) ? intopt::run_total16(src + intopt::rs_start(h), intopt::rs_len(h), intopt::rs_rot(h)) : src[h & 0xffffu];
-    if (flags & 2) {
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const double v = __shfl_up_sync(0xffffffffu, s, off);
-        const int r = __shfl_up_sync(0xffffffffu, row, off);
-        if (cx.lane >= off && r == row) s += v;
-      }
-    }
-    const int rnext = __shfl_down_sync(0xffffffffu, row, 1);
-    if (row != 0xffff && (cx.lane == 31 || rnext != row)) out[row] = s;
-  }
-}
-
-// Debug aid for profiles/: runs ONE building block of the solver `reps` times per CTA and reports the cycles per
-// repetition seen by thread 0 (barrier to barrier).  Not used by the product path.
-template <int TMAX, bool ALLSMEM>
-__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_microbench_kernel(const __grid_constant__ intopt::ProblemDev P,
-                                                                  int which, int reps, double* ws, long long ws_stride,
-                                                                  int factor_in_smem, int gather_in_smem,
-                                                                  unsigned long long* out) {
-  extern __shared__ __align__(16) double smem[];
-  double* wsi = ws + (long long)blockIdx.x * ws_stride;
-  const intopt::SmemLayout S = intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), factor_in_smem, gather_in_smem);
-  const CtaCtx cx = make_ctx(S.red);
-  const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
-  const int n = P.n;
-  double* D = wsi + (long long)intopt::W_D * n;
-  double* c = wsi + (long long)intopt::W_P * n;
-  CTA_FOR(k, n) {
-    D[k] = 1.0 + 1e-3 * (k % 7);
-    c[k] = 0.5 + (k % 5);
-    intopt::gstore(S.G, k, 1.0 + 0.01 * (k % 3));
-  }
-  CTA_FOR(i, P.mv) {
-    S.q[i] = i < P.m ? 1.0 + 0.1 * (i % 4) : 0.0;
-    S.v[i] = i < P.m ? 2.0 - 0.1 * (i % 3) : 0.0;
-    S.y[i] = 0.0;
-    S.r1[i] = 0.0;
-    S.bs[i] = 0.0;
-  }
-  if (cx.tid == 0) S.G[intopt::gpad(n)] = 0.0;
-  __syncthreads();
-  if (which >= 5 && which <= 7) {  // a valid factor for the factor/solve blocks
-    intopt::assemble_normal_matrix(cx, P, M, D, S.G, S.scan, 1e-6, S.L);
-    if (which != 5) intopt::block_cholesky(cx, P, M, S.L, S.dscr, S.flag);
-    __syncthreads();
-  }
-  const long long t0 = clock64();
-  double sink = 0.0;
-  for (int r = 0; r < reps; ++r) {
-    switch (which) {
-      case 0: break;
-      case 1: intopt::spmv_rows(cx, P, M, S.G, S.q); break;
-      case 2: intopt::at_mult<1>(cx, P, M, S.q, nullptr, S.G, nullptr); break;
-      case 3: intopt::at_mult<2>(cx, P, M, S.q, S.v, S.G, S.G + intopt::gather_len(n)); break;
-      case 4: intopt::assemble_normal_matrix(cx, P, M, D, S.G, S.scan, 1e-6, S.L); break;
-      case 5:
-        intopt::assemble_normal_matrix(cx, P, M, D, S.G, S.scan, 1e-6, S.L);
-        intopt::block_cholesky(cx, P, M, S.L, S.dscr, S.flag);
-        break;
-      case 6: {
-        CTA_FOR(i, P.mv) {
-          S.q[i] = i < P.m ? 1.0 : 0.0;
-          S.v[i] = i < P.m ? 2.0 : 0.0;
-        }
-        __syncthreads();
-        double* const rhs2[2] = {S.q, S.v};
-        intopt::block_solve<2>(cx, P, M, S.L, rhs2, S.ybuf);
-      } break;
-      case 7: {
-        CTA_FOR(i, P.mv) S.v[i] = i < P.m ? 2.0 : 0.0;
-        __syncthreads();
-        double* const rhs1[1] = {S.v};
-        intopt::block_solve<1>(cx, P, M, S.L, rhs1, S.ybuf);
-      } break;
-      case 8: CTA_FOR(k, n) intopt::gstore(S.G, k, D[k] * c[k]); break;
-      case 9: {
-        double a5[5] = {1.0, 2.0, 3.0, 4.0, 5.0};
-        intopt::cta_sum<5>(cx, a5);
-        sink += a5[0];
-      } break;
-      case 10: CTA_FOR(k, n) D[k] = D[k] * 1.0000001 + c[k] * 1e-9; break;
-      case 18: spmv_rows_dbg(cx, P, S.G, S.q, 0); break;
-      case 19: spmv_rows_dbg(cx, P, S.G, S.q, 1); break;
-      case 20: spmv_rows_dbg(cx, P, S.G, S.q, 2); break;
-      case 21: spmv_rows_dbg(cx, P, S.G, S.q, 3); break;
-      case 34: intopt::assemble_normal_matrix(cx, P, M, D, S.G, S.scan, 1e-6, S.L, 1); break;  // prefix scan + zero fill only
-      case 11: {  // dependent DFMA chain, 256 long
-        double z = S.G[cx.tid & 7];
-#pragma unroll 16
-        for (int i = 0; i < 256; ++i) z = fma(z, 0.999999, 1e-9);
-        sink += z;
-      } break;
-      case 12: {  // dependent shared-memory load chain, 256 long (pointer chasing through S.meta-like ints)
-        int idx = cx.tid & 31;
-        const double* gp = S.G;
-#pragma unroll 16
-        for (int i = 0; i < 256; ++i) idx = (int)gp[idx] + (idx & 1);
-        sink += idx;
-      } break;
-      case 13: {  // dependent 64-bit shuffle chain, 256 long
-        double z = S.G[cx.tid & 7];
-#pragma unroll 16
-        for (int i = 0; i < 256; ++i) z = __shfl_xor_sync(0xffffffffu, z, 1) + 1.0;
-        sink += z;
-      } break;
-      case 14: {  // dependent DADD chain, 256 long
-        double z = S.G[cx.tid & 7];
-#pragma unroll 16
-        for (int i = 0; i < 256; ++i) z = z + 1.25;
-        sink += z;
-      } break;
-      case 15: {  // dependent global (L2) load chain, 64 long
-        int idx = cx.tid;
-#pragma unroll 8
-        for (int i = 0; i < 64; ++i) idx = (int)D[idx] + (idx & 1) + cx.tid - 1;
-        sink += idx;
-      } break;
-      case 16: {  // rsqrt chain 64 long
-        double z = S.G[cx.tid & 7] + 2.0;
-#pragma unroll 8
-        for (int i = 0; i < 64; ++i) z = rsqrt(z) + 1.5;
-        sink += z;
-      } break;
-      case 17: {  // division chain 64 long
-        double z = S.G[cx.tid & 7] + 2.0;
-#pragma unroll 8
-        for (int i = 0; i < 64; ++i) z = 3.0 / z + 1.5;
-        sink += z;
-      } break;
-    }
-    __syncthreads();
-  }
-  const long long t1 = clock64();
-  if (cx.tid == 0) out[blockIdx.x] = (unsigned long long)((t1 - t0) / (reps > 0 ? reps : 1)) + (sink == 12345.0 ? 1 : 0);
-}
 
 // Host-glue helper: dst[b, j] = idx[j] >= 0 ? scale[j] * src[b, idx[j]] : constv[j]   (scale NULL = 1, constv NULL = 0),
 // converting between float and double on the way.  One launch replaces the cast + zero-fill + index / index_put
@@ -395,59 +167,19 @@ __global__ void __launch_bounds__(256) intopt_fp64_peak_kernel(double* out, int 
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
-__device__ unsigned long long g_phase_cycles[32];
-
-// Kernel variants: CTA size cap (128: 4 CTAs/SM x 128 registers, 192: 2 x 168, 256: 2 x 128, 512: 1 x 128) x whether every
-// buffer is in shared memory.
-#ifdef INTOPT_DEV_BUILD  // quick developer builds (INTOPT_NVCC_EXTRA=-DINTOPT_DEV_BUILD): default CTA size only
-#define INTOPT_VARIANTS(F) F(128, true) F(128, false) F(256, true) F(256, false) F(512, true) F(512, false)
-#else
-#define INTOPT_VARIANTS(F)                                                                                   \
-  F(128, true) F(128, false) F(192, true) F(192, false) F(256, true) F(256, false) F(512, true) F(512, false)
-#endif
 static std::vector<const void*> all_kernels() {
   std::vector<const void*> v;
-#define ADD_(T, A)                                          \
-  v.push_back((const void*)intopt_forward_kernel<T, A>);    \
-  v.push_back((const void*)intopt_forward_kernel<T, A, true>); \
-  v.push_back((const void*)intopt_backward_kernel<T, A>);   \
-  v.push_back((const void*)intopt_coldfactor_kernel<T, A>); \
-  v.push_back((const void*)intopt_microbench_kernel<T, A>);
-  INTOPT_VARIANTS(ADD_)
-#undef ADD_
+  intopt_k::list_forward(v);
+  intopt_k::list_forward_plain(v);
+  intopt_k::list_backward(v);
   return v;
 }
 static const void* pick_kernel(bool forward, int threads, bool allsmem, bool plain = false) {
-#define PICK_(T, A)                                                                                        \
-  if (threads <= T && allsmem == A)                                                                        \
-    return forward ? (plain ? (const void*)intopt_forward_kernel<T, A, true> : (const void*)intopt_forward_kernel<T, A>) \
-                   : (const void*)intopt_backward_kernel<T, A>;
-  INTOPT_VARIANTS(PICK_)
-#undef PICK_
-  return nullptr;
+  return forward ? intopt_k::pick_forward(threads, allsmem, plain) : intopt_k::pick_backward(threads, allsmem);
 }
-static const void* pick_cold_kernel(int threads, bool allsmem) {
-#define PICKC_(T, A) \
-  if (threads <= T && allsmem == A) return (const void*)intopt_coldfactor_kernel<T, A>;
-  INTOPT_VARIANTS(PICKC_)
-#undef PICKC_
-  return nullptr;
-}
+static const void* pick_cold_kernel(int threads, bool allsmem) { return intopt_k::pick_cold(threads, allsmem); }
 
 namespace {
-bool g_profile_phases = false;
-size_t vals_ws_doubles(const IntoptProblem* p) {
-  return (size_t)p->dev.nnz + (size_t)p->dev.n_csc_pad + (size_t)p->dev.n_asm_pad;
-}
-size_t ws_per_slot_doubles(const IntoptProblem* p) {
-  size_t per = (size_t)intopt::ws_nvec_doubles(p->info.n);
-  if (!p->info.factor_in_smem) per += (size_t)p->info.envelope;
-  if (!p->info.gather_in_smem) per += 2 * (size_t)intopt::gather_len(p->info.n);
-  per = (per + 1) & ~(size_t)1;
-  if (p->dev.inst_values) per += vals_ws_doubles(p);  // this instance's copies of the value streams of A
-  return (per + 1) & ~(size_t)1;
-}
-
 // Returns the cold-start factor for `delta` (computing it on `stream` the first time) or nulls if unavailable.
 int cold_factor_for(const IntoptProblem* p, double delta, cudaStream_t stream, const double** factor, const int** ok) {
   *factor = nullptr;
@@ -501,6 +233,13 @@ const char* intopt_last_error(void) { return g_err.c_str(); }
 int intopt_analyze(int m, int n, const int* rowptr, const int* colidx, const double* val, IntoptInfo* info,
                    int* row_perm) {
   if (!info) return fail(-1, "info is NULL");
+  if (int rc0 = check_csr(m, n, rowptr, colidx, val)) return fail(rc0, "malformed CSR input");
+  if (intopt_dense::wanted(m, n, rowptr[m], 0)) {
+    fill_info_dense(m, n, rowptr[m], info);
+    if (row_perm)
+      for (int i = 0; i < m; ++i) row_perm[i] = i;
+    return 0;
+  }
   intopt::HostStructure S;
   int rc = intopt::analyze(m, n, rowptr, colidx, val, S);
   if (rc == -5) return fail(rc, "problem too large for the gather-list assembly (sum over columns of nnz*(nnz+1)/2 > 2^28)");
@@ -514,6 +253,27 @@ int intopt_problem_create(IntoptProblem** out, int m, int n, const int* rowptr, 
                           const double* val, const double* b, int flags) {
   if (!out) return fail(-1, "out is NULL");
   *out = nullptr;
+  if (int rc0 = check_csr(m, n, rowptr, colidx, val)) return fail(rc0, "malformed CSR input");
+  if (intopt_dense::wanted(m, n, rowptr[m], flags)) {
+    int ndev0 = 0;
+    if (cudaGetDeviceCount(&ndev0) != cudaSuccess || ndev0 <= 0)
+      return fail(-10, "no CUDA device: intopt_b200 has no CPU fallback");
+    IntoptProblem* p = new (std::nothrow) IntoptProblem();
+    if (!p) return fail(-2, "out of host memory");
+    fill_info_dense(m, n, rowptr[m], &p->info);
+    std::string msg;
+    int rcd = intopt_dense::create(&p->dense, m, n, rowptr, colidx, val, b, &msg);
+    if (rcd) {
+      delete p;
+      return fail(rcd, msg);
+    }
+    CU_TRY(cudaGetDevice(&p->device));
+    CU_TRY(cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, p->device));
+    p->info.ctas_per_sm = 1;
+    p->has_b = b != nullptr;
+    *out = p;
+    return 0;
+  }
   intopt::HostStructure S;
   int rc = intopt::analyze(m, n, rowptr, colidx, val, S, -1, (flags & INTOPT_FLAG_INSTANCE_VALUES) != 0);
   if (rc == -5) return fail(rc, "problem too large for the gather-list assembly (sum over columns of nnz*(nnz+1)/2 > 2^28)");
@@ -568,6 +328,7 @@ int intopt_problem_create(IntoptProblem** out, int m, int n, const int* rowptr, 
 
 int intopt_problem_destroy(IntoptProblem* p) {
   if (!p) return 0;
+  intopt_dense::destroy(p->dense);
   for (void* a : p->allocs)
     if (a) cudaFree(a);
   for (void* a : p->cold_allocs)
@@ -585,6 +346,7 @@ int intopt_problem_info(const IntoptProblem* p, IntoptInfo* info) {
 
 size_t intopt_workspace_bytes(const IntoptProblem* p, int B) {
   if (!p || B <= 0) return 0;
+  if (p->dense) return intopt_dense::workspace_bytes(p->dense, B);
   const size_t slots = (size_t)std::min(B, p->slots);
   return kCounterBytes + ws_per_slot_doubles(p) * sizeof(double) * slots;
 }
@@ -631,6 +393,15 @@ int intopt_forward_mapped(const IntoptProblem* p, int B, double* c, long long c_
   if (a_vals && !p->dev.inst_values) return fail(-7, "per-instance values need a problem created with INTOPT_FLAG_INSTANCE_VALUES");
   if (!a_vals && p->dev.inst_values) return fail(-7, "this problem was created for per-instance values: pass a_vals_dev");
   if (B <= 0) return 0;
+  if (p->dense) {
+    if (!p->has_b && !b_batch) return fail(-3, "problem has no b and no b_batch was given");
+    intopt::UserMap umap;
+    fill_user_map(umap, um);
+    std::string msg;
+    const int rc = intopt_dense::forward(p->dense, B, c, c_stride, b_batch, b_stride, o, init, umap, xhat, state, status,
+                                         iters, ws, ws_bytes, (cudaStream_t)stream, &msg);
+    return rc ? fail(rc, msg) : 0;
+  }
   if (!p->b_dev && !b_batch) return fail(-3, "problem has no b and no b_batch was given");
   if (ws_bytes < intopt_workspace_bytes(p, B)) return fail(-4, "workspace too small");
   intopt::FwdParams a{};
@@ -663,16 +434,13 @@ int intopt_forward_mapped(const IntoptProblem* p, int B, double* c, long long c_
   a.max_iter = o->max_iter;
   a.plain = o->plain != 0;
   a.beta = o->beta;
-  a.phase_cycles = nullptr;
+#ifdef INTOPT_PROFILE
+  a.phase_cycles = intopt_profile_phase_buckets();  // null unless intopt_debug_phase_cycles(1, ...) switched it on
   a.debug = env_int("INTOPT_DEBUG", 0);
+#endif
   if (!init && !a_vals) {  // (the cold-start factor is a constant of the problem only if A is)
     int rc = cold_factor_for(p, a.damping, (cudaStream_t)stream, &a.cold_factor, &a.cold_ok);
     if (rc) return rc;
-  }
-  if (g_profile_phases) {
-    void* sym = nullptr;
-    CU_TRY(cudaGetSymbolAddress(&sym, g_phase_cycles));
-    a.phase_cycles = (unsigned long long*)sym;
   }
   const int grid = std::min(B, p->slots);
   CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
@@ -710,6 +478,15 @@ int intopt_backward_mapped(const IntoptProblem* p, int B, int mode, double dampi
   if (B <= 0) return 0;
   if (mode != 0 && mode != 1) return fail(-5, "mode must be 0 (whole) or 1 (alter)");
   if (nvar < 0 || nvar > p->info.n) return fail(-6, "nvar out of range");
+  if (p->dense) {
+    if (mode == 0 && !p->has_b && !b_batch) return fail(-3, "problem has no b and no b_batch was given");
+    intopt::UserMap umap;
+    fill_user_map(umap, um);
+    std::string msg;
+    const int rc = intopt_dense::backward(p->dense, B, mode, damping, nvar, state, c, c_stride, b_batch, b_stride, umap, gx,
+                                          gc, status, ws, ws_bytes, (cudaStream_t)stream, &msg);
+    return rc ? fail(rc, msg) : 0;
+  }
   if (mode == 0 && !p->b_dev && !b_batch) return fail(-3, "problem has no b and no b_batch was given");
   if (ws_bytes < intopt_workspace_bytes(p, B)) return fail(-4, "workspace too small");
   intopt::BwdParams a{};
@@ -748,43 +525,6 @@ int intopt_backward_mapped(const IntoptProblem* p, int B, int mode, double dampi
   return 0;
 }
 
-int intopt_debug_phase_cycles(int enable, unsigned long long* out32_host) {
-  // debug aid: enable/disable per-phase cycle accounting of the forward kernel and read + reset the buckets
-  g_profile_phases = enable != 0;
-  unsigned long long zero[32] = {0};
-  if (out32_host) {
-    CU_TRY(cudaDeviceSynchronize());
-    CU_TRY(cudaMemcpyFromSymbol(out32_host, g_phase_cycles, sizeof(zero)));
-  }
-  CU_TRY(cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)));
-  return 0;
-}
-
-int intopt_debug_microbench(const IntoptProblem* p, int which, int reps, int grid, unsigned long long* cycles_host) {
-  // debug aid: cycles per repetition of one solver building block, per CTA (see intopt_microbench_kernel)
-  if (!p || !cycles_host || grid <= 0) return fail(-1, "bad argument");
-  grid = std::min(grid, p->slots);
-  double* ws = nullptr;
-  unsigned long long* out = nullptr;
-  const size_t per = ws_per_slot_doubles(p);
-  CU_TRY(cudaMalloc((void**)&ws, sizeof(double) * per * (size_t)grid));
-  CU_TRY(cudaMalloc((void**)&out, sizeof(unsigned long long) * (size_t)grid));
-  int fis = p->info.factor_in_smem, gis = p->info.gather_in_smem;
-  long long stride = (long long)per;
-  const void* k = nullptr;
-#define PICKM_(T, A) \
-  if (!k && p->info.threads <= T && (fis && gis) == A) k = (const void*)intopt_microbench_kernel<T, A>;
-  INTOPT_VARIANTS(PICKM_)
-#undef PICKM_
-  void* args[8] = {(void*)&p->dev, (void*)&which, (void*)&reps, (void*)&ws, (void*)&stride, (void*)&fis, (void*)&gis, (void*)&out};
-  CU_TRY(cudaLaunchKernel(k, dim3(grid), dim3(p->info.threads), args, (size_t)p->info.smem_bytes, 0));
-  CU_TRY(cudaDeviceSynchronize());
-  CU_TRY(cudaMemcpy(cycles_host, out, sizeof(unsigned long long) * (size_t)grid, cudaMemcpyDeviceToHost));
-  cudaFree(ws);
-  cudaFree(out);
-  return 0;
-}
-
 int intopt_gather_convert(const void* src, int src_is_f32, long long src_stride, int B, int n_out, const int* idx,
                           const double* scale, const double* constv, void* dst, int dst_is_f32, long long dst_stride,
                           void* stream) {
@@ -804,6 +544,22 @@ int intopt_gather_convert(const void* src, int src_is_f32, long long src_stride,
     intopt_gather_convert_kernel<double, double><<<blocks, threads, 0, st>>>((const double*)src, src_stride, B, n_out, idx, scale, constv, (double*)dst, dst_stride);
   CU_TRY(cudaGetLastError());
   return 0;
+}
+
+int intopt_dense_normal_solve(const IntoptProblem* p, int B, const double* d, double delta, double* rhs, int* fail_flags,
+                              void* ws, size_t ws_bytes, void* stream) {
+  if (!p || !d || !rhs || !ws) return fail(-1, "NULL argument");
+  if (!p->dense) return fail(-13, "this problem runs on the persistent-CTA path (IntoptInfo.path == 0)");
+  if (B <= 0) return 0;
+  std::string msg;
+  const int rc = intopt_dense::normal_solve(p->dense, B, d, delta, rhs, fail_flags, ws, ws_bytes, (cudaStream_t)stream, &msg);
+  return rc ? fail(rc, msg) : 0;
+}
+
+int intopt_measure_dmma_peak(double* gflops_out, int repeats) {
+  if (!gflops_out) return fail(-1, "NULL argument");
+  const int rc = intopt_dense::measure_dmma_peak(gflops_out, repeats);
+  return rc ? fail(rc, "DMMA peak measurement failed") : 0;
 }
 
 int intopt_measure_fp64_peak(double* gflops_out, int repeats) {

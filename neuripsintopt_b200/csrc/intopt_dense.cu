@@ -1,0 +1,486 @@
+// Lock-step dense path: host side (problem data, workspace layout, the iteration schedule).  Device code and the
+// description of the design: intopt_dense.cuh.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "intopt_dense.cuh"
+#include "intopt_internal.hpp"
+
+struct IntoptDense {
+  int m = 0, n = 0, m64 = 0, n64 = 0, sms = 0;
+  double* A = nullptr;       // m64 x n64, zero padded
+  double* At = nullptr;      // n64 x m64
+  double* rowsum = nullptr;  // A 1
+  double* b = nullptr;       // m or null
+  std::vector<void*> allocs;
+  // completion signalling of the iteration loop (one forward call at a time per handle)
+  mutable std::mutex mu;
+  int* h_nactive = nullptr;  // pinned
+  cudaEvent_t ev = nullptr;
+  size_t ws_budget = 0;
+};
+
+namespace {
+
+#define DN_TRY(expr)                                                                          \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      if (err) *err = std::string(#expr) + ": " + cudaGetErrorString(e_);                     \
+      return -100 - (int)e_;                                                                  \
+    }                                                                                         \
+  } while (0)
+
+int up64(int v) { return (v + 63) & ~63; }
+int up128(int v) { return (v + 127) & ~127; }
+
+// Workspace of a chunk of Bc instances (doubles unless noted).
+struct Layout {
+  int Bc, Bp;
+  size_t X, T, Y, AX, ATY, R2, D, W, P, DX, DXDT, G, RHS, ATQV, SC, M, Linv, ints, total;  // offsets in bytes
+};
+size_t per_instance_bytes(int m64, int n64) {
+  return ((size_t)12 * n64 + 4 * (size_t)n64 + 5 * (size_t)m64 + dn::SC_N + (size_t)m64 * m64 + (size_t)m64 * dn::NB) * 8 + 16;
+}
+Layout make_layout(const IntoptDense* d, int Bc) {
+  Layout L{};
+  L.Bc = Bc;
+  L.Bp = up128(Bc);
+  const size_t nv = (size_t)L.Bp * d->n64 * 8, mv = (size_t)L.Bp * d->m64 * 8;
+  size_t o = 256;  // [0,256): n_active counter
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o += (bytes + 255) & ~(size_t)255;
+    return at;
+  };
+  L.X = take(nv);
+  L.T = take(nv);
+  L.Y = take(mv);
+  L.AX = take(mv);
+  L.ATY = take(nv);
+  L.R2 = take(nv);
+  L.D = take(nv);
+  L.W = take(nv);
+  L.P = take(nv);
+  L.DX = take(nv);
+  L.DXDT = take(nv);
+  L.G = take(2 * nv);
+  L.RHS = take(2 * mv);
+  L.ATQV = take(2 * nv);
+  L.SC = take((size_t)L.Bp * dn::SC_N * 8);
+  L.M = take((size_t)Bc * d->m64 * d->m64 * 8);
+  L.Linv = take((size_t)Bc * d->m64 * dn::NB * 8);
+  L.ints = take((size_t)L.Bp * 2 * sizeof(int));
+  L.total = o;
+  return L;
+}
+int chunk_size(const IntoptDense* d, int B) {
+  const size_t per = per_instance_bytes(d->m64, d->n64) + 2 * 128 * 20 * (size_t)d->n64 / 128;  // (+ row padding slack)
+  const size_t cap = std::max<size_t>(1, d->ws_budget / per);
+  return (int)std::min<size_t>((size_t)B, cap);
+}
+dn::DenseState bind_state(const IntoptDense* d, const Layout& L, char* ws) {
+  dn::DenseState s{};
+  s.B = L.Bc;
+  s.Bp = L.Bp;
+  s.m = d->m;
+  s.n = d->n;
+  s.m64 = d->m64;
+  s.n64 = d->n64;
+  auto at = [&](size_t off) { return reinterpret_cast<double*>(ws + off); };
+  s.X = at(L.X);
+  s.T = at(L.T);
+  s.Y = at(L.Y);
+  s.AX = at(L.AX);
+  s.ATY = at(L.ATY);
+  s.R2 = at(L.R2);
+  s.D = at(L.D);
+  s.W = at(L.W);
+  s.P = at(L.P);
+  s.DX = at(L.DX);
+  s.DXDT = at(L.DXDT);
+  s.G = at(L.G);
+  s.RHS = at(L.RHS);
+  s.ATQV = at(L.ATQV);
+  s.SC = at(L.SC);
+  s.M = at(L.M);
+  s.Linv = at(L.Linv);
+  s.active = reinterpret_cast<int*>(ws + L.ints);
+  s.fail = s.active + L.Bp;
+  s.n_active = reinterpret_cast<int*>(ws);
+  s.rowsum = d->rowsum;
+  return s;
+}
+
+constexpr int kGemmSmem = dn::GemmProd::SMEM_DOUBLES * 8;
+constexpr int kSyrk128Smem = dn::SyrkCfg<128, 512>::G::SMEM_DOUBLES * 8;
+constexpr int kSyrk64Smem = dn::SyrkCfg<64, 128>::G::SMEM_DOUBLES * 8;
+constexpr int kCholSmem = dn::CHOL_SMEM_DOUBLES * 8;
+int solve_smem(int nr, int m64) { return (nr * m64 + nr * dn::NB + 16 * nr * dn::NB) * 8; }
+
+std::once_flag g_attr_once;
+cudaError_t g_attr_err = cudaSuccess;
+void set_attrs() {
+  auto set = [&](const void* k, int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess && g_attr_err == cudaSuccess) g_attr_err = e;
+  };
+  set((const void*)dn::dense_gemm_kernel, kGemmSmem);
+  set((const void*)dn::dense_syrk_kernel<128, 512>, kSyrk128Smem);
+  set((const void*)dn::dense_syrk_kernel<64, 128>, kSyrk64Smem);
+  set((const void*)dn::dense_chol_col_kernel, kCholSmem);
+  set((const void*)dn::dense_chol_trsm_kernel, kCholSmem);
+  set((const void*)dn::dense_solve_kernel<1>, solve_smem(1, 4096));
+  set((const void*)dn::dense_solve_kernel<2>, solve_smem(2, 4096));
+}
+
+// Out(rows x N) = In(rows x K) W(N x K)^T
+void gemm(const double* In, long long ld_in, int rows, const double* W, long long ld_w, int N, int K, double* Out,
+          long long ld_out, cudaStream_t st) {
+  dim3 grid(N / 64, rows / 128);
+  dn::dense_gemm_kernel<<<grid, 256, kGemmSmem, st>>>(In, ld_in, W, ld_w, K, Out, ld_out);
+}
+
+// M_b = A diag(D_b) A^T + delta I for the active instances, then its tiled Cholesky factorisation (in place) with the
+// inverses of the diagonal blocks.
+void assemble_and_factor(const IntoptDense* d, const dn::DenseState& s, int Bc, double delta, cudaStream_t st) {
+  if (d->m64 % 128 == 0) {
+    const int T = d->m64 / 128;
+    dn::dense_syrk_kernel<128, 512><<<dim3(T * (T + 1) / 2, Bc), 512, kSyrk128Smem, st>>>(d->A, d->n64, d->m, d->m64, s.D,
+                                                                                      d->n64, delta, s.M, s.active);
+  } else {
+    const int T = d->m64 / 64;
+    dn::dense_syrk_kernel<64, 128><<<dim3(T * (T + 1) / 2, Bc), 128, kSyrk64Smem, st>>>(d->A, d->n64, d->m, d->m64, s.D,
+                                                                                    d->n64, delta, s.M, s.active);
+  }
+  const int nb = d->m64 / dn::NB;
+  for (int k = 0; k < nb; ++k) {
+    dn::dense_chol_col_kernel<<<dim3(nb - k, Bc), 256, kCholSmem, st>>>(s.M, d->m64, k, s.Linv, s.fail, s.active);
+    if (k + 1 < nb)
+      dn::dense_chol_trsm_kernel<<<dim3(nb - k - 1, Bc), 256, kCholSmem, st>>>(s.M, d->m64, k, s.Linv, s.active);
+  }
+}
+
+template <int NR>
+void solve(const IntoptDense* d, const dn::DenseState& s, int Bc, dn::SolveArgs a, cudaStream_t st) {
+  a.M = s.M;
+  a.Linv = s.Linv;
+  a.m = d->m;
+  a.m64 = d->m64;
+  a.ld = d->m64;
+  a.active = s.active;
+  a.skip = s.fail;
+  dn::dense_solve_kernel<NR><<<Bc, 256, solve_smem(NR, d->m64), st>>>(a);
+}
+
+__global__ void pad_rows_kernel(const double* src, long long src_stride, int len, double* dst, long long dst_stride,
+                                int dst_len, double fill) {
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < dst_len; k += blockDim.x)
+    dst[(long long)b * dst_stride + k] = k < len ? src[(long long)b * src_stride + k] : fill;
+}
+__global__ void unpad_rows_kernel(const double* src, long long src_stride, int len, double* dst, long long dst_stride) {
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < len; k += blockDim.x) dst[(long long)b * dst_stride + k] = src[(long long)b * src_stride + k];
+}
+__global__ void set_flags_kernel(int* active, int* fail, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    active[i] = 1;
+    fail[i] = 0;
+  }
+}
+
+}  // namespace
+
+namespace intopt_dense {
+
+bool wanted(int m, int n, long long nnz, int flags) {
+  const char* v = std::getenv("INTOPT_PATH");
+  if (flags & INTOPT_FLAG_INSTANCE_VALUES) return false;  // per-instance values of A: persistent-CTA path only
+  if (m > 4096 || n > 16384) return false;
+  if (v && !std::strcmp(v, "dense")) return true;
+  if (v && !std::strcmp(v, "cta")) return false;
+  // dense problems whose factor is too large to share an SM's shared memory between resident LPs
+  return m >= 192 && (double)nnz >= 0.25 * (double)m * (double)n;
+}
+
+int create(IntoptDense** out, int m, int n, const int* rowptr, const int* colidx, const double* val, const double* b,
+           std::string* err) {
+  *out = nullptr;
+  IntoptDense* d = new IntoptDense();
+  d->m = m;
+  d->n = n;
+  d->m64 = up64(m);
+  d->n64 = up64(n);
+  std::vector<double> A((size_t)d->m64 * d->n64, 0.0), At((size_t)d->n64 * d->m64, 0.0), rs(m, 0.0);
+  for (int i = 0; i < m; ++i) {
+    double s = 0.0;
+    for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+      A[(size_t)i * d->n64 + colidx[e]] = val[e];
+      At[(size_t)colidx[e] * d->m64 + i] = val[e];
+      s += val[e];
+    }
+    rs[i] = s;
+  }
+  auto upl = [&](const std::vector<double>& h, double** dev) -> cudaError_t {
+    cudaError_t e = cudaMalloc((void**)dev, h.size() * sizeof(double));
+    if (e != cudaSuccess) return e;
+    d->allocs.push_back(*dev);
+    return cudaMemcpy(*dev, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  cudaError_t e = upl(A, &d->A);
+  if (e == cudaSuccess) e = upl(At, &d->At);
+  if (e == cudaSuccess) e = upl(rs, &d->rowsum);
+  if (e == cudaSuccess && b) {
+    std::vector<double> bv(b, b + m);
+    e = upl(bv, &d->b);
+  }
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&d->h_nactive, 64, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev, cudaEventDisableTiming);
+  int dev = 0;
+  if (e == cudaSuccess) e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess) {
+    std::call_once(g_attr_once, set_attrs);
+    e = g_attr_err;
+  }
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("dense path set-up: ") + cudaGetErrorString(e);
+    destroy(d);
+    return -100 - (int)e;
+  }
+  const char* gb = std::getenv("INTOPT_DENSE_WS_GB");
+  d->ws_budget = (size_t)((gb && *gb ? std::atof(gb) : 32.0) * (double)(1ull << 30));
+  *out = d;
+  return 0;
+}
+
+void destroy(IntoptDense* d) {
+  if (!d) return;
+  for (void* a : d->allocs) cudaFree(a);
+  if (d->h_nactive) cudaFreeHost(d->h_nactive);
+  if (d->ev) cudaEventDestroy(d->ev);
+  delete d;
+}
+
+size_t workspace_bytes(const IntoptDense* d, int B) {
+  if (B <= 0) return 0;
+  return make_layout(d, chunk_size(d, B)).total;
+}
+
+int forward(const IntoptDense* d, int B, double* c, long long c_stride, const double* b_batch, long long b_stride,
+            const IntoptOpts* o, const double* init, const intopt::UserMap& um, double* xhat, double* state, int* status,
+            int* iters, void* ws, size_t ws_bytes, cudaStream_t st, std::string* err) {
+  const int Bc0 = chunk_size(d, B);
+  const Layout L0 = make_layout(d, Bc0);
+  if (ws_bytes < L0.total) {
+    if (err) *err = "workspace too small";
+    return -4;
+  }
+  std::lock_guard<std::mutex> lock(d->mu);
+  for (int b0 = 0; b0 < B; b0 += Bc0) {
+    const int Bc = std::min(Bc0, B - b0);
+    const Layout L = make_layout(d, Bc);
+    dn::DenseFwdArgs a{};
+    a.s = bind_state(d, L, (char*)ws);
+    a.inst0 = b0;
+    a.c = c;
+    a.c_stride = c_stride;
+    a.b_batch = b_batch;
+    a.b_stride = b_stride;
+    a.b_problem = d->b;
+    a.init = init;
+    a.um = um;
+    a.xhat = xhat;
+    a.state = state;
+    a.status = status;
+    a.iters = iters;
+    a.alpha0 = o->alpha0;
+    a.tol = o->tol;
+    a.thr = o->thr;
+    a.damping = o->damping_fwd;
+    a.beta = o->beta;
+    a.max_iter = o->max_iter;
+    a.plain = o->plain != 0;
+    const dn::DenseState& s = a.s;
+    const int Bp = L.Bp, m64 = d->m64, n64 = d->n64;
+    dn::dense_init_kernel<<<Bc, 256, 0, st>>>(a);
+    for (long long it = 0;; ++it) {
+      DN_TRY(cudaMemsetAsync(s.n_active, 0, sizeof(int), st));
+      gemm(s.X, n64, Bp, d->A, n64, m64, n64, s.AX, m64, st);   // A x
+      gemm(s.Y, m64, Bp, d->At, m64, n64, m64, s.ATY, n64, st);  // A^T y
+      dn::dense_resid_kernel<<<Bc, 256, 0, st>>>(a);
+      DN_TRY(cudaMemcpyAsync(d->h_nactive, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      DN_TRY(cudaEventRecord(d->ev, st));
+      gemm(s.G, n64, 2 * Bp, d->A, n64, m64, n64, s.RHS, m64, st);  // [A(D c) ; A(D w)]
+      assemble_and_factor(d, s, Bc, a.damping, st);
+      {
+        dn::SolveArgs sa{};
+        sa.rhs[0] = s.RHS;
+        sa.rhs[1] = s.RHS + (size_t)Bp * m64;
+        sa.add[0] = b_batch ? b_batch + (long long)b0 * b_stride : d->b;  // q: r = b + A(D c)   (:666 with (c,b))
+        sa.add_stride[0] = b_batch ? b_stride : 0;
+        sa.add[1] = s.AX;  // v: r = eta r1 + A(D w)                                              (:785,666)
+        sa.add_stride[1] = m64;
+        sa.cadd[1] = s.SC + dn::SC_ETA;
+        sa.coef_stride = dn::SC_N;
+        solve<2>(d, s, Bc, sa, st);
+      }
+      gemm(s.RHS, m64, 2 * Bp, d->At, m64, n64, m64, s.ATQV, n64, st);  // [A^T q ; A^T v]
+      dn::dense_predict_kernel<<<Bc, 256, 0, st>>>(a);
+      if (!a.plain) {
+        gemm(s.G, n64, Bp, d->A, n64, m64, n64, s.RHS + (size_t)Bp * m64, m64, st);  // A(D w')
+        {
+          dn::SolveArgs sa{};
+          sa.rhs[0] = s.RHS + (size_t)Bp * m64;
+          sa.add[0] = s.AX;
+          sa.add_stride[0] = m64;
+          sa.cadd[0] = s.SC + dn::SC_ETA;
+          sa.coef_stride = dn::SC_N;
+          solve<1>(d, s, Bc, sa, st);
+        }
+        gemm(s.RHS + (size_t)Bp * m64, m64, Bp, d->At, m64, n64, m64, s.ATQV + (size_t)Bp * n64, n64, st);  // A^T v'
+        dn::dense_step_kernel<<<Bc, 256, 0, st>>>(a);
+      }
+      DN_TRY(cudaEventSynchronize(d->ev));  // how many instances entered this iteration (they all left: stop)
+      if (*d->h_nactive == 0) break;
+      if (it > (long long)o->max_iter + 2) break;
+    }
+    dn::dense_epilogue_kernel<<<Bc, 256, 0, st>>>(a);
+    DN_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+int backward(const IntoptDense* d, int B, int mode, double damping, int nvar, const double* state, const double* c,
+             long long c_stride, const double* b_batch, long long b_stride, const intopt::UserMap& um, double* gx,
+             double* gc, int* status, void* ws, size_t ws_bytes, cudaStream_t st, std::string* err) {
+  const int Bc0 = chunk_size(d, B);
+  const Layout L0 = make_layout(d, Bc0);
+  if (ws_bytes < L0.total) {
+    if (err) *err = "workspace too small";
+    return -4;
+  }
+  for (int b0 = 0; b0 < B; b0 += Bc0) {
+    const int Bc = std::min(Bc0, B - b0);
+    const Layout L = make_layout(d, Bc);
+    dn::DenseBwdArgs a{};
+    a.s = bind_state(d, L, (char*)ws);
+    a.inst0 = b0;
+    a.mode = mode;
+    a.nvar = nvar;
+    a.damping = damping;
+    a.state = state;
+    a.c = c;
+    a.c_stride = c_stride;
+    a.b_batch = b_batch;
+    a.b_stride = b_stride;
+    a.b_problem = d->b;
+    a.gx = gx;
+    a.um = um;
+    a.gc = gc;
+    a.status = status;
+    const dn::DenseState& s = a.s;
+    const int Bp = L.Bp, m64 = d->m64, n64 = d->n64;
+    dn::dense_bwd_prep_kernel<<<Bc, 256, 0, st>>>(a);
+    const bool whole = mode == 0;
+    if (whole)
+      gemm(s.G, n64, 2 * Bp, d->A, n64, m64, n64, s.RHS, m64, st);  // [A(X2 c) ; A(X2 g)]
+    else
+      gemm(s.G + (size_t)Bp * n64, n64, Bp, d->A, n64, m64, n64, s.RHS + (size_t)Bp * m64, m64, st);  // A(X2 g)
+    assemble_and_factor(d, s, Bc, damping, st);  // :1525-1527,1535
+    if (whole) {
+      dn::SolveArgs sa{};
+      sa.rhs[0] = s.RHS;  // q: mu b + A(X2 c)  (:1530)
+      sa.rhs[1] = s.RHS + (size_t)Bp * m64;  // v: tau A(X2 g) (:1529)
+      sa.add[0] = b_batch ? b_batch + (long long)b0 * b_stride : d->b;
+      sa.add_stride[0] = b_batch ? b_stride : 0;
+      sa.cadd[0] = s.SC + dn::SB_MU;
+      sa.csrc[1] = s.SC + dn::SB_TAU;
+      sa.coef_stride = dn::SC_N;
+      solve<2>(d, s, Bc, sa, st);
+      gemm(s.RHS, m64, 2 * Bp, d->At, m64, n64, m64, s.ATQV, n64, st);
+    } else {
+      dn::SolveArgs sa{};
+      sa.rhs[0] = s.RHS + (size_t)Bp * m64;
+      sa.coef_stride = dn::SC_N;
+      solve<1>(d, s, Bc, sa, st);
+      gemm(s.RHS + (size_t)Bp * m64, m64, Bp, d->At, m64, n64, m64, s.ATQV + (size_t)Bp * n64, n64, st);
+    }
+    dn::dense_bwd_final_kernel<<<Bc, 256, 0, st>>>(a);
+    DN_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+// z_b = (A diag(d_b) A^T + delta I)^-1 rhs_b for B instances: the assembly, factorisation and solve kernels of the
+// dense path as a stand-alone primitive (rhs: B x m in/out, dvec: B x n, fail: int32[B] out or null).
+int normal_solve(const IntoptDense* d, int B, const double* dvec, double delta, double* rhs, int* fail, void* ws,
+                 size_t ws_bytes, cudaStream_t st, std::string* err) {
+  const int Bc0 = chunk_size(d, B);
+  if (ws_bytes < make_layout(d, Bc0).total) {
+    if (err) *err = "workspace too small";
+    return -4;
+  }
+  for (int b0 = 0; b0 < B; b0 += Bc0) {
+    const int Bc = std::min(Bc0, B - b0);
+    const Layout L = make_layout(d, Bc);
+    const dn::DenseState s = bind_state(d, L, (char*)ws);
+    pad_rows_kernel<<<Bc, 256, 0, st>>>(dvec + (long long)b0 * d->n, d->n, d->n, s.D, d->n64, d->n64, 0.0);
+    pad_rows_kernel<<<Bc, 256, 0, st>>>(rhs + (long long)b0 * d->m, d->m, d->m, s.RHS, d->m64, d->m64, 0.0);
+    set_flags_kernel<<<(L.Bp + 255) / 256, 256, 0, st>>>(s.active, s.fail, L.Bp);
+    assemble_and_factor(d, s, Bc, delta, st);
+    dn::SolveArgs sa{};
+    sa.rhs[0] = s.RHS;
+    sa.coef_stride = dn::SC_N;
+    sa.M = s.M;
+    sa.Linv = s.Linv;
+    sa.m = d->m;
+    sa.m64 = d->m64;
+    sa.ld = d->m64;
+    sa.active = s.active;
+    sa.skip = nullptr;
+    dn::dense_solve_kernel<1><<<Bc, 256, solve_smem(1, d->m64), st>>>(sa);
+    unpad_rows_kernel<<<Bc, 256, 0, st>>>(s.RHS, d->m64, d->m, rhs + (long long)b0 * d->m, d->m);
+    if (fail) DN_TRY(cudaMemcpyAsync(fail + b0, s.fail, sizeof(int) * Bc, cudaMemcpyDeviceToDevice, st));
+    DN_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+int measure_dmma_peak(double* gflops_out, int repeats) {
+  std::string* err = nullptr;
+  int dev = 0, sms = 0;
+  DN_TRY(cudaGetDevice(&dev));
+  DN_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, threads = 256, iters = 2048;
+  double* out = nullptr;
+  DN_TRY(cudaMalloc((void**)&out, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  DN_TRY(cudaEventCreate(&e0));
+  DN_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int r = 0; r < (repeats > 0 ? repeats : 5) + 2; ++r) {
+    DN_TRY(cudaEventRecord(e0));
+    dn::dense_dmma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0 + r);
+    DN_TRY(cudaEventRecord(e1));
+    DN_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    DN_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 512.0 * 8.0 * iters * (double)blocks * (threads / 32);  // 2*8*8*4 per DMMA per warp
+    const double gf = flops / (ms * 1e-3) * 1e-9;
+    if (r >= 2 && gf > best) best = gf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *gflops_out = best;
+  return 0;
+}
+
+}  // namespace intopt_dense

@@ -1,0 +1,105 @@
+// Kernel templates of the persistent-CTA solver path (one CTA owns one LP for the whole IPM loop) and the
+// table of instantiations.  Each intopt_inst_*.cu compiles one family of instantiations (so the families build
+// in parallel) and exports pickers; intopt_capi.cu launches through them.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "intopt_solver.cuh"
+
+constexpr int kMaxMetaInts = 4096;  // schedule arrays up to 16 KB are staged in shared memory
+
+__device__ __forceinline__ CtaCtx make_ctx(double* red) {
+  CtaCtx cx;
+  cx.tid = threadIdx.x;
+  cx.nthreads = blockDim.x;
+  cx.lane = threadIdx.x & 31;
+  cx.warp = threadIdx.x >> 5;
+  cx.nwarps = blockDim.x >> 5;
+  cx.red = red;
+  cx.bar_id = 0;
+  cx.bar_n = blockDim.x;
+  return cx;
+}
+
+// Persistent CTAs: each pulls the next LP instance from an atomic counter until the batch is exhausted,
+// so finished LPs free their SM slot without any host involvement.
+// PLAIN: pc=False upstream (one direction per iteration) — its own instantiation, so that the predictor-corrector kernels
+// are compiled exactly as if the option did not exist.
+template <int TMAX, bool ALLSMEM, bool PLAIN = false>
+__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_forward_kernel(const __grid_constant__ intopt::ProblemDev P,
+                                                               const __grid_constant__ intopt::FwdParams a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_inst;
+  double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
+  const intopt::SmemLayout S =
+      intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
+  const CtaCtx cx = make_ctx(S.red);
+  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
+  const bool cold = a.cold_factor != nullptr && a.init == nullptr && *a.cold_ok != 0;  // launch-uniform
+  if (cold && a.factor_in_smem && threadIdx.x == 0) intopt::mbar_init(S.mbar, 1);
+  unsigned served = 0;  // instances this CTA has run = completed phases of the prefetch mbarrier
+  for (;;) {
+    if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int inst = s_inst;
+    __syncthreads();
+    if (inst >= a.B) break;
+    intopt::forward_instance_t<PLAIN>(cx, P, M, a, inst, wsi, S, cold, served & 1u);
+    ++served;
+  }
+}
+
+// One CTA computes the cold-start factor chol(A A^T + delta I) with the instance code path (same CTA size).
+template <int TMAX, bool ALLSMEM>
+__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_coldfactor_kernel(const __grid_constant__ intopt::ProblemDev P,
+                                                                  double delta, double* ws, int factor_in_smem,
+                                                                  int gather_in_smem, double* out, int* ok) {
+  extern __shared__ __align__(16) double smem[];
+  const intopt::SmemLayout S = intopt::carve<ALLSMEM>(P, smem, ws + intopt::ws_nvec_doubles(P.n), factor_in_smem, gather_in_smem);
+  const CtaCtx cx = make_ctx(S.red);
+  const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  intopt::cold_factor_build(cx, P, M, delta, ws, S, out, ok);
+}
+
+template <int TMAX, bool ALLSMEM>
+__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_backward_kernel(const __grid_constant__ intopt::ProblemDev P,
+                                                                const __grid_constant__ intopt::BwdParams a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_inst;
+  double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
+  const intopt::SmemLayout S =
+      intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
+  const CtaCtx cx = make_ctx(S.red);
+  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
+  for (;;) {
+    if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int inst = s_inst;
+    __syncthreads();
+    if (inst >= a.B) break;
+    intopt::backward_instance(cx, P, M, a, inst, wsi, S);
+  }
+}
+
+
+// Kernel variants: CTA size cap (128: 4 CTAs/SM x 128 registers, 256: 2 x 128, 512: 1 x 128; 192: 2 x 168 only in
+// profiling builds) x whether every buffer is in shared memory.
+#ifdef INTOPT_PROFILE
+#define INTOPT_VARIANTS(F)                                                                                   \
+  F(128, true) F(128, false) F(192, true) F(192, false) F(256, true) F(256, false) F(512, true) F(512, false)
+#else
+#define INTOPT_VARIANTS(F) F(128, true) F(128, false) F(256, true) F(256, false) F(512, true) F(512, false)
+#endif
+
+namespace intopt_k {
+const void* pick_forward(int threads, bool allsmem, bool plain);
+const void* pick_backward(int threads, bool allsmem);
+const void* pick_cold(int threads, bool allsmem);
+void list_forward(std::vector<const void*>& v);
+void list_forward_plain(std::vector<const void*>& v);
+void list_backward(std::vector<const void*>& v);
+}  // namespace intopt_k

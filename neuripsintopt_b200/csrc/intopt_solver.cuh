@@ -379,7 +379,12 @@ IO_FORCEINLINE void asm_run_batch(const uint32_t* __restrict__ hp, const D2* PP,
 IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* __restrict__ d,
                                    double* region, D2* scan_tmp, double delta, double* L, int dbg = 0) {
   const int n = P.n;
+#ifdef INTOPT_PROFILE
   const int ngrp = (dbg & 1) ? 0 : (P.n_asm >> 5);
+#else
+  (void)dbg;
+  const int ngrp = P.n_asm >> 5;
+#endif
   if (P.asm_run) {
     D2* PP = reinterpret_cast<D2*>(region);
     dd_prefix_scan(cx, d, n, PP, scan_tmp);  // scan_tmp may alias L (scan_in_factor): the zero fill comes after
@@ -447,7 +452,7 @@ struct PhaseTimer {
   unsigned long long* buckets;
   long long last;
 };
-#ifdef INTOPT_HOST_EMU
+#if defined(INTOPT_HOST_EMU) || !defined(INTOPT_PROFILE)  // the product build carries no probes
 #define PHASE_MARK(pt, k) ((void)0)
 #define PHASE_START(pt) ((void)0)
 #else
@@ -1390,8 +1395,10 @@ struct FwdParams {
   int max_iter;
   int plain;    // 1: pc=False upstream — one pass per iteration with centring gamma = beta * mean(x t) (:1392)
   double beta;
-  unsigned long long* phase_cycles;  // null unless profiling
-  int debug;                         // debug switches for bottleneck isolation (env INTOPT_DEBUG), 0 in production
+#ifdef INTOPT_PROFILE
+  unsigned long long* phase_cycles;  // null unless switched on (profiling build only)
+  int debug;                         // switches for bottleneck isolation (env INTOPT_DEBUG)
+#endif
 };
 
 // Factor L (block_cholesky) and form the two products out1 = A src1, out2 = A src2 (out2 may be null: one product),
@@ -1458,7 +1465,11 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
   double* __restrict__ aty = wsi + (long long)W_ATY * n;
   const double* __restrict__ c = a.c + (long long)inst * a.c_stride;
 
+#ifdef INTOPT_PROFILE
   PhaseTimer pt{a.phase_cycles, 0};
+#else
+  PhaseTimer pt{nullptr, 0};
+#endif
   PHASE_START(pt);
   if (a.um.in) {  // the caller's cost vector -> this instance's standard-form row (kept for the backward)
     double* cw = const_cast<double*>(a.c) + (long long)inst * a.c_stride;
@@ -1642,7 +1653,13 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
 
     // ---- M = A D A^T + delta I, factor (:772-777) ------------------------------------------------
     const bool reuse_cold = cold && iters == 1;  // x = t = 1: L already holds chol(A A^T + delta I)
-    if (!reuse_cold) assemble_normal_matrix(cx, P, M, D, G, S.scan, a.damping, L, a.debug);
+    if (!reuse_cold) {
+#ifdef INTOPT_PROFILE
+      assemble_normal_matrix(cx, P, M, D, G, S.scan, a.damping, L, a.debug);
+#else
+      assemble_normal_matrix(cx, P, M, D, G, S.scan, a.damping, L);
+#endif
+    }
     PHASE_MARK(pt, 2);
     // right-hand sides of the (p,q) solve (:800) and of the predictor (gamma = 0, eta = 1): G = D*c and, in the
     // upper half of the gather region (only the assembly's prefix sums use it), G2 = D*w

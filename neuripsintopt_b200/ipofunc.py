@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes
 import hashlib
+import weakref
 from collections import OrderedDict
 
 import numpy as np
@@ -76,6 +77,11 @@ def _gather_convert(src, src_stride, B, n_out, idx, scale, constv, dst, stream):
 
 def _glue_ok(t):
     return t.dtype in (torch.float32, torch.float64) and t.dim() == 2 and t.stride(1) == 1
+
+
+class _Token:
+    """Weak-referenceable identity of one IPOfunc closure."""
+    __slots__ = ("__weakref__",)
 
 
 _TAG0 = 1024.0  # tags of the pattern matrix that stands in for a batch of equality matrices (per-instance A)
@@ -160,6 +166,7 @@ class DeviceProblem(_DeviceHandle):
         self.sf = sf
         val = self._create(sf.A, device, inst_values)
         self._sliced = {}
+        self.per_closure = weakref.WeakKeyDictionary()  # IPOfunc closure token -> its right-hand-side tensors
         t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=device)
         kept = sf.c_src >= 0
         cols = np.nonzero(kept)[0]
@@ -246,7 +253,7 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
     structure_key = _digest(A_np, G_np, h_np) + repr([tuple(bd) for bd in bounds]) + ("" if presolve else "|raw")
     zero_cols = _problem.zero_columns(A_np, G_np, n_x) if presolve else np.zeros(0, dtype=np.int64)
     state = {"events": [], "time_ms": 0.0, "last": []}
-    b_cache = {}
+    closure_id = _Token()  # key of this closure's b-dependent tensors inside a (shared, cached) DeviceProblem
 
     def get_problem(device, sign_key):
         """Cached DeviceProblem (or the PresolveComplete outcome) for this structure on `device`."""
@@ -260,6 +267,9 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                 if a_batched:
                     if sf.fixed_idx.size:
                         raise NotImplementedError("per-instance A with variables fixed by presolve (singleton rows)")
+                    if np.any(sf.x_shift != 0) or np.isfinite(sf.x_flip_ub).any():
+                        # the shift term of b (b - A lb, ip_model_whole.py:1096-1097) would be formed from the pattern tags
+                        raise NotImplementedError("per-instance A with non-zero lower bounds or upper-only bounds")
                     sf.tag_flatpos = tag_flatpos
                 hit = DeviceProblem(sf, device, inst_values=a_batched)
             except _problem.PresolveComplete as done:
@@ -273,7 +283,8 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
 
     def b_on_device(dp, device):
         """Standard-form right-hand side(s) (1 or B rows, fp64) and the per-instance infeasibility mask."""
-        key = (id(dp), str(device))
+        b_cache = dp.per_closure.setdefault(closure_id, {})  # lives and dies with the DeviceProblem (no id() reuse)
+        key = "b"
         if key not in b_cache:
             sf = dp.sf
             bs = np.atleast_2d(sf.b_std(b_np) if sf.n_eq_user else sf.b_const)
@@ -340,7 +351,8 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
             # the drivers' case (lb = 0, no upper-bound flips, no free variables, fixed values shared by the batch): the
             # kernel writes x in the caller's layout and dtype, fixed variables re-inserted (_postprocess :1241-1285)
             x_user = torch.empty(Bg, n_x, dtype=out_dtype, device=device)
-            xkey = ("xconst", id(dp), str(device))
+            b_cache = dp.per_closure.setdefault(closure_id, {})
+            xkey = "xconst"
             if xkey not in b_cache:  # values of the presolve-fixed variables in user positions (constant per problem)
                 xc = torch.zeros(n_x, dtype=torch.float64, device=device)
                 if sf.fixed_idx.size:
@@ -355,6 +367,7 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
         ws = dp.workspace(Bg)
         init = pack_init(dp, Bg, device)
         opts = _capi.IntoptOpts(alpha0, tol, thr_, damping_fwd, max_iter_, 0 if pc else 1, float(beta))
+        # (solve_group runs under torch.cuda.device(c.device): the library launches on the CURRENT device)
         _capi.check(L.intopt_forward_mapped(dp.handle, Bg, _ptr(c_std), sf.n, _ptr(b_std), b_stride, _ptr(a_vals),
                                             dp.nnz if a_batched else 0, ctypes.byref(opts), _ptr(init), ctypes.byref(um),
                                             _ptr(xhat), _ptr(st), _ptr(status), _ptr(iters), _ptr(ws), ws.numel() * 8,
@@ -382,15 +395,40 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
             x_user[torch.as_tensor(np.broadcast_to(badsel, (Bg,)).copy(), device=device)] = 0.0
         return x_user, (c_std, b_std, b_stride, st, status, iters, a_vals)
 
+    def _tick():
+        """Start a timed region for Runtime(): folds the pairs that have completed into the total first, so the list
+        of pending CUDA events stays short however long one IPOfunc lives."""
+        ev = state["events"]
+        while ev and ev[0][1].query():
+            e0, e1 = ev.pop(0)
+            state["time_ms"] += e0.elapsed_time(e1)
+        if len(ev) >= 256:  # never let it grow: wait for the oldest pair
+            e0, e1 = ev.pop(0)
+            e1.synchronize()
+            state["time_ms"] += e0.elapsed_time(e1)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return e0
+
+    def _tock(e0):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        state["events"].append((e0, e1))
+
     class IPOfunc_cls(torch.autograd.Function):
         @staticmethod
         def forward(ctx, c):
             if not isinstance(c, torch.Tensor) or not c.is_cuda:
                 raise RuntimeError("IPOfunc (B200): c must be a CUDA tensor; there is no CPU fallback")
+            # every launch below (kernels, the lazily built cold-start factor, the timing events) goes to c's device,
+            # whatever the caller's current device is
+            with torch.cuda.device(c.device):
+                return IPOfunc_cls._forward(ctx, c)
+
+        @staticmethod
+        def _forward(ctx, c):
             device = c.device
-            ev0 = torch.cuda.Event(enable_timing=True)
-            ev1 = torch.cuda.Event(enable_timing=True)
-            ev0.record()
+            ev0 = _tick()
             squeeze = c.dim() == 1
             c2 = c.detach().reshape(-1, c.shape[-1])  # (kept in the caller's dtype: the pack kernel converts)
             if c2.dtype not in (torch.float32, torch.float64):
@@ -400,12 +438,15 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
             if check_finite and not bool(torch.isfinite(c2).all()):
                 raise LinAlgError("c contains inf, nan, or None")  # :1332-1341
             B = c2.shape[0]
+            ctx.c_shared = False
             if b_batched and B == 1 and b_np.shape[0] > 1:  # one shared c, per-instance b (Twitter)
                 B = b_np.shape[0]
                 c2 = c2.expand(B, -1)
                 squeeze = False
+                ctx.c_shared = True  # (1-D or (1, n_x) c: the gradients of the instances add up in backward)
             if B == 0:  # nothing to solve: no launch, empty result, empty gradient
                 ctx.saved, ctx.in_shape, ctx.B, ctx.in_dtype = [], c.shape, 0, c.dtype
+                _tock(ev0)
                 return torch.empty_like(c2, dtype=c.dtype)
             # group by the sign pattern of c on unconstrained columns (presolve zero-column rule, :995-1016)
             if zero_cols.size:
@@ -443,16 +484,18 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
             ctx.B = B
             ctx.in_dtype = c.dtype
             state["last"] = saved
-            ev1.record()
-            state["events"].append((ev0, ev1))
+            _tock(ev0)
             out = x_out.to(c.dtype)
             return out[0] if squeeze else out
 
         @staticmethod
         def backward(ctx, del_x):
-            ev0 = torch.cuda.Event(enable_timing=True)
-            ev1 = torch.cuda.Event(enable_timing=True)
-            ev0.record()
+            with torch.cuda.device(del_x.device):
+                return IPOfunc_cls._backward(ctx, del_x)
+
+        @staticmethod
+        def _backward(ctx, del_x):
+            ev0 = _tick()
             L = _capi.lib()
             device = del_x.device
             B = ctx.B
@@ -492,7 +535,7 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                     um.in_idx_dev = dp.var_index32.data_ptr()
                 else:
                     gk = (gg if dp.identity_vars else gg[:, dp.var_index]).double().contiguous()
-                fast_out = fast and single and not (len(ctx.in_shape) == 1 and B > 1)
+                fast_out = fast and single and not ctx.c_shared
                 gfull = None
                 if fast_out:  # ... and writes c_grad[var_index] = dc, zeros elsewhere (:1559-1560), in the caller's dtype
                     gfull = torch.empty(Bg, n_x, dtype=ctx.in_dtype, device=device)
@@ -519,10 +562,9 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                     grad = gfull
                 else:
                     grad[sel] = gfull
-            if len(ctx.in_shape) == 1 and B > 1:  # one shared c, per-instance b: the gradients add up
+            if ctx.c_shared:  # one shared c, per-instance b: the gradients add up
                 grad = grad.sum(dim=0)
-            ev1.record()
-            state["events"].append((ev0, ev1))
+            _tock(ev0)
             return grad.reshape(ctx.in_shape).to(ctx.in_dtype)
 
     def Runtime():

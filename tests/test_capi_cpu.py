@@ -28,7 +28,24 @@ def test_exports_match_header(lib):
     assert declared == set(_capi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.intopt_version() == 3
+    assert lib.intopt_version() == 4
+    # the profiling entry points live in their own header and their own library (never in the product .so)
+    prof = open(os.path.join(ROOT, "include", "intopt_b200_profile.h")).read()
+    assert set(re.findall(r"\b(intopt_[a-z0-9_]+)\s*\(", prof)) == set(_capi.PROFILE_EXPORTS)
+    for name in _capi.PROFILE_EXPORTS:
+        assert not hasattr(lib, name)
+
+
+def test_dense_problems_are_routed_to_the_lock_step_path(lib):
+    # dense A with m >= 192 takes the lock-step dense path (no gather lists, no -5 refusal up to m = 4096)
+    rng = np.random.default_rng(0)
+    for m, n, path in ((64, 128, 0), (192, 384, 1), (1024, 2048, 1)):
+        A = sp.csr_matrix(rng.standard_normal((m, n)))
+        info, perm = _capi.analyze(A)
+        assert info["path"] == path and (info["m"], info["n"], info["nnz"]) == (m, n, m * n)
+        assert info["asm_terms"] == n * m * (m + 1) // 2
+        if path:
+            assert perm.tolist() == list(range(m))
 
 
 def test_structure_analysis_on_reference_shapes(lib):
@@ -59,8 +76,10 @@ def test_malformed_input_is_rejected(lib):
     assert rc != 0 and lib.intopt_last_error()
 
 
-def test_oversized_dense_problem_is_refused_before_allocating(lib):
-    """Dense 1024 x 2048 would need 1.07e9 gather-list terms: refused (-5) by the column-count check, in milliseconds."""
+def test_oversized_problem_is_refused_by_the_gather_list_path(lib, monkeypatch):
+    """On the persistent-CTA path dense 1024 x 2048 would need 1.07e9 gather-list terms: refused (-5) by the column-count
+    check, in milliseconds (by default such a problem takes the lock-step dense path instead)."""
+    monkeypatch.setenv("INTOPT_PATH", "cta")
     m, n = 1024, 2048
     rp = (np.arange(m + 1, dtype=np.int64) * n).astype(np.int32)
     ci = np.tile(np.arange(n, dtype=np.int32), m)

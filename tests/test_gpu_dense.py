@@ -1,0 +1,185 @@
+"""GPU parity tests of the lock-step dense path (csrc/intopt_dense.cu: batched DMMA assembly, tiled Cholesky, blocked
+substitution, per-instance masked iteration) against the CPU oracle, the reference's own golden outputs and the
+persistent-CTA path.  Tolerances are BASELINE.json's: 1e-6 on x* / objective, 1e-5 on dL/dc, equal iteration counts for
+early-stopped runs."""
+import ctypes
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import hsd_numpy as O
+from tests import golden_util as GU
+from tests.test_gpu_parity import _check_case, _rel2, _relinf, _tt
+
+pytestmark = pytest.mark.gpu
+
+
+def gen_dense(m, B, seed=None):
+    """feasible and bounded dense LP, n = 2m, costs c = A^T y0 + s0."""
+    rng = np.random.default_rng(m if seed is None else seed)
+    n = 2 * m
+    A = rng.standard_normal((m, n)).astype(np.float32)
+    x0 = rng.uniform(0.1, 1.0, n)
+    b = (A.astype(np.float64) @ x0).astype(np.float32)
+    y0 = rng.standard_normal((B, m))
+    s0 = rng.uniform(0.1, 1.0, (B, n))
+    c = (y0 @ A.astype(np.float64) + s0).astype(np.float32)
+    return A, b, c
+
+
+@pytest.fixture
+def dense_path(monkeypatch):
+    from neuripsintopt_b200 import ipofunc
+    monkeypatch.setenv("INTOPT_PATH", "dense")
+    ipofunc.clear_cache()
+    yield
+    ipofunc.clear_cache()
+
+
+def _handle(A, b=None):
+    from neuripsintopt_b200 import _capi
+    L = _capi.lib()
+    A = sp.csr_matrix(A)
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+    val = np.ascontiguousarray(A.data, dtype=np.float64)
+    h = ctypes.c_void_p()
+    bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+    _capi.check(L.intopt_problem_create(ctypes.byref(h), A.shape[0], A.shape[1], rp.ctypes.data, ci.ctypes.data,
+                                        val.ctypes.data, None if bb is None else bb.ctypes.data, 0), "create")
+    info = _capi.IntoptInfo()
+    _capi.check(L.intopt_problem_info(h, ctypes.byref(info)), "info")
+    return L, h, info.as_dict()
+
+
+@pytest.mark.parametrize("m,n", [(40, 100), (64, 128), (200, 330), (256, 512)])
+def test_normal_solve_matches_numpy(dense_path, m, n):
+    """Assembly (DMMA SYRK) + tiled Cholesky + blocked substitution against numpy, including shapes that need padding
+    in both dimensions and weights spanning twelve orders of magnitude (d = x / t near convergence)."""
+    rng = np.random.default_rng(m + n)
+    A = rng.standard_normal((m, n))
+    L, h, info = _handle(A)
+    assert info["path"] == 1
+    B = 5
+    d = np.exp(rng.uniform(-14, 14, (B, n)))
+    rhs = rng.standard_normal((B, m))
+    delta = 1e-6
+    dd = torch.tensor(d, device="cuda")
+    rr = torch.tensor(rhs, device="cuda")
+    fail = torch.zeros(B, dtype=torch.int32, device="cuda")
+    nbytes = L.intopt_workspace_bytes(h, B)
+    ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device="cuda")
+    from neuripsintopt_b200 import _capi
+    _capi.check(L.intopt_dense_normal_solve(h, B, dd.data_ptr(), delta, rr.data_ptr(), fail.data_ptr(), ws.data_ptr(),
+                                            ws.numel() * 8, None), "normal_solve")
+    torch.cuda.synchronize()
+    z = rr.cpu().numpy()
+    assert int(fail.sum()) == 0
+    for i in range(B):
+        M = (A * d[i]) @ A.T + delta * np.eye(m)
+        ref = np.linalg.solve(M, rhs[i])
+        # backward-stable solve: the residual is at rounding level relative to |M| |z|
+        res = np.abs(M @ z[i] - rhs[i]).max() / (np.abs(M).max() * np.abs(z[i]).max() * m)
+        err, cond = _rel2(z[i], ref), np.linalg.cond(M)
+        print("normal_solve m=%d n=%d inst %d: scaled residual %.2e, error vs numpy %.2e, cond %.1e" % (m, n, i, res, err, cond))
+        assert res < 1e-13, (m, n, i, res)
+        assert err < 1e-13 * cond + 1e-12, (m, n, i, err, cond)
+    L.intopt_problem_destroy(h)
+
+
+@pytest.mark.parametrize("name", ["dense_m16", "dense_m64"])
+def test_golden_cases_on_the_dense_path(dense_path, name):
+    """The reference's own outputs (tests/golden) and the oracle, early-stopped and converged, whole and alter."""
+    z = GU.load(name)
+    inp = GU.problem_inputs(name, z, 0)
+    for case in GU.cases(z):
+        _check_case(name, z, case, inp, lambda i: inp)
+
+
+@pytest.mark.parametrize("m", [200, 256])
+@pytest.mark.parametrize("thr", [0.1, None])
+def test_config5_against_oracle(m, thr):
+    """Config 5 shapes that take the dense path by default (m >= 192), incl. one that is not a multiple of the tile."""
+    from neuripsintopt_b200 import ipofunc
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    ipofunc.clear_cache()
+    B = 6
+    A, b, c = gen_dense(m, B)
+    f = IPOfunc(torch.tensor(A), torch.tensor(b), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)], thr=thr,
+                damping=1e-6)
+    ct = torch.tensor(c, device="cuda", requires_grad=True)
+    x = f(ct)
+    x.sum().backward()
+    torch.cuda.synchronize()
+    status, iters = IPOfunc.status()
+    info = [v.info for v in ipofunc._PROBLEM_CACHE.values() if hasattr(v, "info")][-1]
+    assert info["path"] == 1
+    assert int((status != 0).sum()) == 0
+    for i in range(3):
+        r = O.ipofunc(c[i], np.ones(2 * m, np.float32), A=A, b=b, bounds=[(0.0, None)], thr=thr, damping=1e-6)
+        xi = x[i].detach().double().cpu().numpy()
+        c64 = c[i].astype(np.float64)
+        assert abs(c64 @ xi - c64 @ r["x"]) <= 1e-6 * max(1.0, abs(c64 @ r["x"])), (m, thr, i)
+        if thr:
+            assert int(iters[i]) == r["iters"], (int(iters[i]), r["iters"])
+            assert _relinf(xi, r["x"]) < 1e-6, (m, thr, i, _relinf(xi, r["x"]))
+            assert _rel2(ct.grad[i].double().cpu().numpy(), r["grad"]) < 1e-5
+        else:
+            assert abs(int(iters[i]) - r["iters"]) <= 1
+            assert _relinf(xi, r["x"]) < 1e-5, (m, thr, i, _relinf(xi, r["x"]))
+
+
+def test_dense_and_cta_paths_agree(monkeypatch):
+    """The same dense problem (m = 96) through both paths: different kernels, same LP layer."""
+    from neuripsintopt_b200 import ipofunc
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    A, b, c = gen_dense(96, 9)
+    outs = []
+    for path in ("cta", "dense"):
+        monkeypatch.setenv("INTOPT_PATH", path)
+        ipofunc.clear_cache()
+        f = IPOfunc(torch.tensor(A), torch.tensor(b), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)], thr=0.1,
+                    damping=1e-6)
+        ct = torch.tensor(c, device="cuda", requires_grad=True)
+        x = f(ct)
+        (x * torch.arange(1, 193, device="cuda")).sum().backward()
+        torch.cuda.synchronize()
+        status, iters = IPOfunc.status()
+        outs.append((x.detach().cpu().numpy(), ct.grad.cpu().numpy(), iters.cpu().numpy()))
+    ipofunc.clear_cache()
+    assert (outs[0][2] == outs[1][2]).all()
+    assert _relinf(outs[0][0], outs[1][0]) < 1e-6
+    assert _rel2(outs[0][1], outs[1][1]) < 1e-5
+
+
+def test_dense_path_per_instance_b_and_warm_start(dense_path):
+    """Per-instance right-hand sides and init_val (end_vectors of a previous solve) on the dense path."""
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    m, B = 24, 4
+    A, b, c = gen_dense(m, B, seed=5)
+    rng = np.random.default_rng(1)
+    bb = np.stack([(A.astype(np.float64) @ rng.uniform(0.1, 1.0, 2 * m)).astype(np.float32) for _ in range(B)])
+    f = IPOfunc(torch.tensor(A), torch.tensor(bb), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)], thr=0.1,
+                damping=1e-6)
+    ct = torch.tensor(c, device="cuda", requires_grad=True)
+    x = f(ct)
+    x.sum().backward()
+    torch.cuda.synchronize()
+    for i in range(B):
+        r = O.ipofunc(c[i], np.ones(2 * m, np.float32), A=A, b=bb[i], bounds=[(0.0, None)], thr=0.1, damping=1e-6)
+        assert _relinf(x[i].detach().double().cpu().numpy(), r["x"]) < 1e-6
+        assert _rel2(ct.grad[i].double().cpu().numpy(), r["grad"]) < 1e-5
+    warm = IPOfunc.end_vectors()
+    f2 = IPOfunc(torch.tensor(A), torch.tensor(bb), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)], thr=1e-3,
+                 damping=1e-6, init_val=warm)
+    x2 = f2(ct.detach())
+    f3 = IPOfunc(torch.tensor(A), torch.tensor(bb), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)], thr=1e-3,
+                 damping=1e-6)
+    x3 = f3(ct.detach())
+    torch.cuda.synchronize()
+    # both end below the same mu threshold: objectives agree to the threshold's accuracy
+    o2 = (x2.double() * ct.detach().double()).sum(1)
+    o3 = (x3.double() * ct.detach().double()).sum(1)
+    assert torch.allclose(o2, o3, rtol=5e-2, atol=5e-2)
