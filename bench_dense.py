@@ -43,7 +43,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="256x1024,512x512,1024x256")
     ap.add_argument("--thr", type=float, default=0.1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--parity", type=int, default=1)
     args = ap.parse_args()
     from neuripsintopt_b200 import _capi, ipofunc
@@ -80,7 +80,7 @@ def main():
                 if thr:
                     assert int(iters[i]) == r["iters"], (int(iters[i]), r["iters"])
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        tf = tb = 0.0
+        tfs, tbs = [], []
         for _ in range(args.steps):
             cc = ct.detach().requires_grad_(True)
             ev[0].record()
@@ -89,10 +89,9 @@ def main():
             xx.backward(g)
             ev[2].record()
             ev[2].synchronize()
-            tf += ev[0].elapsed_time(ev[1])
-            tb += ev[1].elapsed_time(ev[2])
-        tf /= args.steps
-        tb /= args.steps
+            tfs.append(ev[0].elapsed_time(ev[1]))
+            tbs.append(ev[1].elapsed_time(ev[2]))
+        tf, tb = float(np.median(tfs)), float(np.median(tbs))
         ms = tf + tb
         fl = contract_flops(m, n, float(iters.sum()), B)
         tfl = fl / (ms * 1e-3) * 1e-12
@@ -103,7 +102,8 @@ def main():
             "contract_gflop": round(fl * 1e-9, 2), "achieved_tflops": round(tfl, 3),
             "dmma_peak_tflops": round(dmma, 2), "dfma_peak_tflops": round(dfma, 2),
             "roofline_frac_dmma": round(tfl / dmma, 4), "roofline_frac_dfma": round(tfl / dfma, 4),
-            "x_rel_vs_oracle": ex, "grad_rel_vs_oracle": eg, "first_call_s": round(t_first, 2)}), flush=True)
+            "x_rel_vs_oracle": ex, "grad_rel_vs_oracle": eg, "first_call_s": round(t_first, 2),
+            "ms_fwd_all": [round(v, 2) for v in tfs], "ms_bwd_all": [round(v, 2) for v in tbs]}), flush=True)
 
 
 if __name__ == "__main__":

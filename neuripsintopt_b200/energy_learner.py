@@ -46,6 +46,7 @@ class IntoptEnergyLearner:
     def __init__(self, param, input_size, hidden_size=1, num_layers=1, n_items=48, thr=0.1, damping=1e-6,
                  max_iter=None, optimizer=optim.Adam, device="cuda", lp_layer=None, **hyperparams):
         A, b, G, h, F = icon.make_matrix_intopt(**param)
+        self.param = param
         self.n_items = n_items
         self.device = torch.device(device)
         self.F = torch.as_tensor(F.toarray(), dtype=torch.float32, device=self.device)  # (n, 48)
@@ -78,6 +79,91 @@ class IntoptEnergyLearner:
         parallel.allreduce_gradients(self.model.parameters(), group=group)
         self.optimizer.step()
         return float(loss.detach())
+
+    # ---- the epoch / minibatch driver of the reference (Interior/intopt_energy_mlp.py:355-500) -------------
+    def fit(self, X, y, X_validation=None, y_validation=None, epochs=1, batchsize=24, doScale=True, seed=None, shuffle=True,
+            validate_every=7, validation_relax=True, rank=0, world=1, group=None, log=None):
+        """`intopt_energy.fit` (:355-500): standardise the features (:370-372), then for every epoch visit the
+        `n_batches = T // (batchsize * n_items)` minibatches of whole days in a shuffled order (:388-406); a minibatch is
+        ONE batched training step here instead of the reference's loop over its `batchsize` days (:409-453: the order
+        inside a minibatch only permutes a sum of gradients).  Every `validate_every` minibatches, and at the end of an
+        epoch (:464), the regret on the validation days is recorded if validation data was given (:468-485; HiGHS
+        instead of Gurobi, evaluate.EnergySchedule).  Returns a list of dicts, one per minibatch.
+
+        `seed`: the reference shuffles with the global numpy RNG (:404); a seed makes the order reproducible
+        (`shuffle=False` keeps the minibatches in storage order).  All ranks
+        must use the same seed (they see the same global minibatch and take their own shard of it)."""
+        X = np.asarray(X, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        if doScale:
+            self.scaler = StandardScaler().fit(X)
+            X = self.scaler.transform(X)
+        else:
+            self.scaler = None
+        n_items = self.n_items
+        Xd, yd = days(X, y, n_items)
+        n_batches = X.shape[0] // (batchsize * n_items)  # :386
+        order = list(range(n_batches))
+        rng = np.random.RandomState(seed) if seed is not None else np.random
+        history = []
+        for e in range(epochs):
+            if shuffle:
+                rng.shuffle(order)  # :404
+            for i in range(n_batches):
+                lo = batchsize * order[i]
+                loss = self.training_step(Xd[lo:lo + batchsize], yd[lo:lo + batchsize], rank=rank, world=world, group=group)
+                rec = {"epoch": e, "batch": i, "first_day": lo, "loss": loss / batchsize}
+                if X_validation is not None and ((i + 1) % validate_every == 0 or (i + 1) % n_batches == 0):
+                    rec.update(self.validation_result(X_validation, y_validation, relax=validation_relax))
+                history.append(rec)
+                if log is not None:
+                    log(rec)
+        return history
+
+    def predict(self, X, doScale=True):
+        """Predicted prices per slot (:504-506, predict_func): the features go through the scaler fitted by `fit`."""
+        X = np.asarray(X, dtype=np.float64)
+        if doScale and getattr(self, "scaler", None) is not None:
+            X = self.scaler.transform(X)
+        self.model.eval()
+        with torch.no_grad():
+            out = self.model(torch.as_tensor(X, dtype=torch.float32, device=self.device)).squeeze(-1)
+        self.model.train()
+        return out.cpu().numpy().astype(np.float64)
+
+    def validation_result(self, X_validation, y_validation, relax=True, doScale=True, max_days=None):
+        """Regret and MSE on whole validation days (:500-502, validation_func): schedule with the predicted prices, pay the
+        true ones, against the schedule that knew them (evaluate.EnergySchedule: the same program on HiGHS)."""
+        from .evaluate import EnergySchedule
+        if not hasattr(self, "_schedules"):
+            self._schedules = {}
+        if relax not in self._schedules:
+            self._schedules[relax] = EnergySchedule(self.param, relax=relax)
+        sched = self._schedules[relax]
+        y_pred = self.predict(X_validation, doScale=doScale)
+        y_true = np.asarray(y_validation, dtype=np.float64)
+        nd = len(y_true) // self.n_items
+        if max_days is not None:
+            nd = min(nd, max_days)
+        regret = [sched.regret(y_pred[d * self.n_items:(d + 1) * self.n_items], y_true[d * self.n_items:(d + 1) * self.n_items])
+                  for d in range(nd)]
+        T = nd * self.n_items
+        return {"regret": float(np.mean(regret)), "mse": float(np.mean((y_pred[:T] - y_true[:T]) ** 2))}
+
+
+class StandardScaler:
+    """Zero mean / unit (population) variance per column, like sklearn.preprocessing.StandardScaler, which the reference
+    fits on the training features (:370-372); constant columns are left unscaled."""
+
+    def fit(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        self.mean_ = X.mean(axis=0)
+        sd = X.std(axis=0)
+        self.scale_ = np.where(sd == 0.0, 1.0, sd)
+        return self
+
+    def transform(self, X):
+        return (np.asarray(X, dtype=np.float64) - self.mean_) / self.scale_
 
 
 def days(X, y, n_items=48):

@@ -150,3 +150,49 @@ def test_knapsack_regret():
     assert EV.knapsack_regret(true, true, costs, budget=7 / 4)[0] == 0.0
     assert np.isnan(EV.knapsack_value(true, true, costs, budget=0.25)[0])            # cost.x = 1 impossible
     assert EV.knapsack_value(true, true, costs, budget=2.0, equality=False)[0] == 7.0   # cost.x <= 8
+
+
+def test_energy_loader_clamps_and_splits(tmp_path):
+    """data/energy.py: `get_energy` on a Data.npz-style file clamps negative prices (get_energy.py:27-28) and
+    `experiment_split` reproduces exp_run.py:29-39."""
+    from neuripsintopt_b200.data import energy
+    rng = np.random.default_rng(0)
+    n_tr, n_te = 48 * 6, 48 * 70
+    Xtr = np.column_stack([np.repeat(np.arange(6), 48), rng.standard_normal((n_tr, 8))])
+    Xte = np.column_stack([np.repeat(np.arange(70), 48), rng.standard_normal((n_te, 8))])
+    ytr = rng.uniform(-50, 200, n_tr)
+    yte = rng.uniform(5, 300, n_te)
+    f = tmp_path / "Data.npz"
+    np.savez(f, X_1gtrain=Xtr, y_train=ytr, X_1gtest=Xte, y_test=yte)
+    a, b, c, d = energy.get_energy(str(f))
+    assert a.shape == Xtr.shape and (b >= 0).all() and np.array_equal(b, np.maximum(ytr, 0)) and (ytr < 0).any()
+    Xt, yt, Xv, yv, Xs, ys = energy.experiment_split(a, b, c, d)
+    assert Xt.shape == (n_tr, 8) and Xv.shape == (2880, 8) and Xs.shape == (n_te - 2880, 8)
+    assert np.array_equal(yv, yte[:2880]) and np.array_equal(ys, yte[2880:])
+    X, y = energy.synthetic_days(3)
+    assert X.shape == (144, 8) and y.min() >= 20 and y.max() <= 120
+
+
+def test_fit_loop_visits_every_minibatch_once_per_epoch():
+    """IntoptEnergyLearner.fit on CPU with a surrogate LP layer: n_batches = T // (batchsize * 48) minibatches per epoch
+    (intopt_energy_mlp.py:386), shuffled order reproducible by seed, scaler fitted on the training features."""
+    import torch
+    from neuripsintopt_b200.data import energy, icon
+    from neuripsintopt_b200.energy_learner import IntoptEnergyLearner
+    torch.manual_seed(0)
+    surrogate = lambda c: torch.softmax(-c / c.abs().mean(dim=1, keepdim=True), dim=1)  # noqa: E731
+    X, y = energy.synthetic_days(7, n_features=4, seed=3)
+    runs = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        lrn = IntoptEnergyLearner(icon.load1_day01(), input_size=4, device="cpu", lp_layer=surrogate,
+                                  optimizer=torch.optim.SGD, lr=1e-4)
+        hist = lrn.fit(X, y, epochs=2, batchsize=2, seed=11)
+        runs.append(hist)
+        assert len(hist) == 2 * 3  # 7 days -> 3 whole minibatches of 2 days, last day dropped like upstream
+        for e in (0, 1):
+            assert sorted(h["first_day"] for h in hist if h["epoch"] == e) == [0, 2, 4]
+        assert abs(lrn.scaler.transform(X).mean()) < 1e-12
+        assert lrn.predict(X).shape == (7 * 48,)
+    assert [h["first_day"] for h in runs[0]] == [h["first_day"] for h in runs[1]]
+    assert [h["loss"] for h in runs[0]] == [h["loss"] for h in runs[1]]

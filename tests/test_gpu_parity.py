@@ -526,3 +526,35 @@ def test_full_size_batch_properties():
                       damping=1e-6)
         assert _relinf(x[i].detach().double().cpu().numpy(), r["x"]) < X_TOL
         assert _rel2(ct.grad[i].double().cpu().numpy(), r["grad"]) < G_TOL
+
+
+def test_energy_fit_reproduces_the_reference_trajectory():
+    """`IntoptEnergyLearner.fit` (one batched LP call per minibatch) against the reference's own training loop
+    (Interior/intopt_energy_mlp.py:403-453, 24 sequential IPOfunc calls per optimiser step) on real days of Data.npz:
+    the first three Adam steps, generated by oracle/gen_golden_fit.py with the untouched reference.  The reference's
+    backward is float32 (gradients good to ~1e-4), hence the tolerances."""
+    import os
+    from neuripsintopt_b200.data import icon
+    from neuripsintopt_b200.energy_learner import IntoptEnergyLearner
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "energy_fit.npz"))
+    steps, batch = int(z["steps"]), int(z["batch"])
+    lrn = IntoptEnergyLearner(icon.load1_day01(), input_size=z["X_raw"].shape[1], thr=float(z["thr"]),
+                              damping=float(z["damping"]), lr=float(z["lr"]))
+    with torch.no_grad():
+        lrn.model.net.weight.copy_(torch.as_tensor(z["w0"]))
+        lrn.model.net.bias.copy_(torch.as_tensor(z["b0"]))
+    seen = []
+
+    def log(rec):
+        seen.append((rec["loss"], lrn.model.net.weight.detach().cpu().numpy().copy(),
+                     lrn.model.net.bias.detach().cpu().numpy().copy()))
+
+    hist = lrn.fit(z["X_raw"].astype(np.float64), z["y"].astype(np.float64), epochs=1, batchsize=batch, shuffle=False, log=log)
+    assert len(hist) == steps and [h["first_day"] for h in hist] == [0, batch, 2 * batch]
+    for i in range(steps):
+        loss, w, b = seen[i]
+        ref_loss = z["losses"][i].mean()
+        assert abs(loss - ref_loss) <= (1e-5 if i == 0 else 2e-3) * abs(ref_loss), (i, loss, ref_loss)
+        assert np.abs(w - z["weights"][i]).max() <= 2e-3 * max(1.0, np.abs(z["weights"][i]).max()), (i, w, z["weights"][i])
+        assert np.abs(b - z["biases"][i]).max() <= 2e-3 * max(1.0, np.abs(z["biases"][i]).max()), (i, b, z["biases"][i])
+    assert hist[-1]["loss"] < hist[0]["loss"]  # the decision loss goes down on these days, as in the reference run
