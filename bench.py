@@ -50,6 +50,31 @@ def synthetic_costs(F, B, seed):
     return c, g
 
 
+SEED0 = 1000  # rank r draws its shard with seed SEED0 + r; the CPU arm times the first instances of rank 0's shard
+
+
+def workload_name(thr):
+    return ("Energy ICON load1 LP (172x1582 standard form, nnz 22188), thr=%g, damping=1e-6, whole (HSD) backward" % thr)
+
+
+def bench_config(args, world):
+    """The `config` object of the JSON line — built by ONE function for both arms, so that they describe the same
+    workload with the same words (batch per GPU, seeds, L2 policy of the GPU arm)."""
+    B = batch_per_gpu(args, world)
+    return dict(workload=workload_name(args.thr), batch_per_gpu=B, global_batch=B * world, seed=SEED0,
+                l2="inputs rotate over %d device batches, %.0f MB in total (> 126 MB L2)" % (NSETS, NSETS * 2 * B * 1440 * 4 / 1e6),
+                parallelism="dp%d" % world, scaling=args.scaling)
+
+
+def batch_per_gpu(args, world):
+    if args.scaling == "strong":
+        return max(1, args.global_batch // world)
+    return args.batch
+
+
+NSETS = 12  # resident input sets the timed steps rotate over (> L2 in total at the default batch)
+
+
 def algorithmic_flops(info, iters_total, B, k_bwd=2):
     """F_it = 2S + m^3/3 + 6m^2 + 20 nnz + 30 n ;  F_bw = 2S + m^3/3 + 2k m^2 + 12 nnz + 20 n."""
     m, n, nnz, S = info["m"], info["n"], info["nnz"], info["asm_terms"]
@@ -79,29 +104,88 @@ def cpu_reference_pass(A, b, G, h, c, g, count):
     return time.perf_counter() - t0
 
 
+def _mp_worker(job):
+    """One worker of the best-case CPU leg: a share of the sample with ONE BLAS thread (set by the pool initialiser)."""
+    Ad, b, Gd, h, c, g, thr = job
+    from oracle import hsd_numpy as O
+    t0 = time.perf_counter()
+    for i in range(len(c)):
+        O.ipofunc(c[i], g[i], A=Ad, b=b, G=Gd, h=h, bounds=OPTS["bounds"], variant="whole", thr=thr,
+                  max_iter=OPTS["max_iter"], damping=OPTS["damping"], asref=True)
+    return time.perf_counter() - t0
+
+
+def _mp_init():
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+
+
+def cpu_baseline_measure(A, b, G, h, c, g, sample, thr, passes=3):
+    """The reference's CPU path (as-executed oracle port) on this box's host cores, on the first `sample` instances of the
+    GPU arm's batch.  Leg (i): what the reference does — a serial loop, BLAS threads pinned to the core count; median of
+    `passes` passes.  Leg (ii): best case — one process per core with one BLAS thread each, `sample` LPs per worker.
+    `value` is the better of the two (the conservative denominator)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    Ad = A.toarray() if hasattr(A, "toarray") else A
+    Gd = G.toarray() if hasattr(G, "toarray") else G
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=cores)
+    except Exception:
+        limiter = None
+    cpu_reference_pass(Ad, b, Gd, h, c, g, 1)  # warm (imports, caches)
+    times = [cpu_reference_pass(Ad, b, Gd, h, c, g, sample) for _ in range(passes)]
+    if limiter is not None:
+        limiter.restore_original_limits()
+    serial = sample / float(np.median(times))
+    workers = min(cores, 32)
+    per_worker = max(2, sample // 2)
+    multi = None
+    try:
+        ctx = mp.get_context("spawn")
+        jobs = [(Ad, b, Gd, h, c[:per_worker], g[:per_worker], thr) for _ in range(workers)]
+        with ctx.Pool(workers, initializer=_mp_init) as pool:
+            pool.map(_mp_worker, [(Ad, b, Gd, h, c[:1], g[:1], thr)] * workers)  # warm every worker
+            t0 = time.perf_counter()
+            pool.map(_mp_worker, jobs)
+            wall = time.perf_counter() - t0
+        multi = dict(value=workers * per_worker / wall, workers=workers, blas_threads_per_worker=1, lps_per_worker=per_worker)
+    except Exception as e:  # a box that cannot fork workers still reports leg (i)
+        multi = dict(value=None, error=repr(e)[:120])
+    best = max(serial, multi["value"] or 0.0)
+    return dict(value=best, unit=UNIT, cores=cores, kind="port",
+                sample="first %d LPs of rank 0's batch (seed %d); leg (i) serial loop, BLAS threads=%d, median of %d passes; "
+                       "leg (ii) %s processes x 1 BLAS thread; as-executed oracle port incl. per-call host prep and the "
+                       "float32 n-right-hand-side backward; value = the better leg" % (sample, SEED0, cores, passes,
+                                                                                       multi.get("workers")),
+                serial=dict(value=serial, blas_threads=cores, passes_s=[round(t, 3) for t in times]),
+                multiprocess=multi)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     A, b, G, h, F = energy_problem()
-    Ad, Gd = A.toarray(), G.toarray()
-    per_step = args.ref_sample
-    c, g = synthetic_costs(F, per_step, 0)
-    for _ in range(args.warmup):
-        cpu_reference_pass(Ad, b, Gd, h, c, g, min(2, per_step))
-    t = 0.0
-    for _ in range(args.steps):
-        t += cpu_reference_pass(Ad, b, Gd, h, c, g, per_step)
-    value = per_step * args.steps / t
-    cores = os.cpu_count()
+    B = batch_per_gpu(args, world)
+    c, g = synthetic_costs(F, B, SEED0)  # rank 0's shard of the GPU arm
+    t0 = time.perf_counter()
+    cb = cpu_baseline_measure(A, b, G, h, c, g, args.ref_sample, args.thr, passes=max(3, min(args.steps, 5)))
+    wall = time.perf_counter() - t0
+    value = cb["value"]
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * t / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload="Energy ICON load1 LP (172x1582 standard form), thr=0.1, damping=1e-6",
-                            batch_per_step=per_step),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
-                                  sample="%d LPs per step x %d steps, serial loop, BLAS threads=all cores, "
-                                         "as-executed oracle port (float32 n-RHS backward)" % (per_step, args.steps)),
+                ms_per_step=1e3 * B / value, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference", config=bench_config(args, world),
+                cpu_baseline=cb, measure_wall_s=round(wall, 1),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -183,14 +267,14 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, K, W = args.batch, args.steps, args.warmup
+    B, K, W = batch_per_gpu(args, world), args.steps, args.warmup
     sampler = ClockSampler(local) if rank == 0 else None  # started early: its cold start must not hit the timing
 
     A, b, G, h, F = energy_problem()
     tt = lambda M: torch.as_tensor(M.toarray() if hasattr(M, "toarray") else M, dtype=torch.float32)  # noqa: E731
     opts = dict(OPTS, thr=args.thr)
     f = IPOfunc(tt(A), tt(b), tt(G), tt(h), check_finite=False, **opts)
-    c_np, g_np = synthetic_costs(F, B, 1000 + rank)  # every rank owns a different shard of the global batch
+    c_np, g_np = synthetic_costs(F, B, SEED0 + rank)  # every rank owns a different shard of the global batch
     c_dev = torch.tensor(c_np, device=dev)
     g_dev = torch.tensor(g_np, device=dev)
     c_host = torch.empty(c_np.shape, dtype=torch.float32, pin_memory=True).copy_(torch.from_numpy(c_np))
@@ -277,7 +361,6 @@ def run_gpu(args):
 
     per_rank = []
     # Resident inputs rotate over NSETS device batches (> L2 in total) so that no timed step finds its inputs in L2.
-    NSETS = 12
     c_sets = [c_dev] + [torch.tensor(synthetic_costs(F, B, 5000 + 17 * rank + s)[0], device=dev) for s in range(1, NSETS)]
     g_sets = [g_dev] + [g_dev.clone() for _ in range(1, NSETS)]
 
@@ -364,6 +447,45 @@ def run_gpu(args):
             best = ms if best is None else min(best, ms)
         alt = dict(batch_per_gpu=1024, value=1024 * K / (best * 1e-3), ms_per_step=best / K,
                    note="same kernels, batch of 3.46 waves; inputs of this side measurement stay L2 resident")
+    # Strong-scaling side measurement (BASELINE.json configs[3]: "batch 1024 sharded over 8xB200"): a FIXED global batch
+    # of `--global-batch` LPs, this rank solving its 1/world share; max over ranks like the main measurement.  `gpu_ms`
+    # is the device time between the first launch and the last completion of a step (CUDA events on the launching stream),
+    # `ms_per_step` the wall time per step of K back-to-back steps: their difference is host (Python + launch) time the
+    # device spends idle.
+    strong = None
+    if not args.no_strong and args.scaling == "weak":
+        Bs = max(1, args.global_batch // world)
+        cs, gs = synthetic_costs(F, Bs, 4000 + rank)
+        cs_d, gs_d = torch.tensor(cs, device=dev), torch.tensor(gs, device=dev)
+
+        def s_step():
+            cc = cs_d.detach().requires_grad_(True)
+            f(cc).backward(gs_d)
+        for _ in range(10):
+            s_step()
+        best, gpu_best = None, None
+        for _ in range(args.regions):
+            barrier()
+            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(K):
+                evs[i][0].record()
+                s_step()
+                evs[i][1].record()
+            a1.record()
+            a1.synchronize()
+            barrier()
+            ts = torch.tensor([a0.elapsed_time(a1), sum(e[0].elapsed_time(e[1]) for e in evs)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            ms, gms = float(ts[0]), float(ts[1])
+            if best is None or ms < best:
+                best, gpu_best = ms, gms
+        strong = dict(global_batch=Bs * world, batch_per_gpu=Bs, value=Bs * world * K / (best * 1e-3), ms_per_step=best / K,
+                      gpu_ms_per_step=gpu_best / K, waves_per_gpu=Bs / float(info["ctas_per_sm"] * 148),
+                      note="fixed global batch sharded over the ranks (strong scaling); same kernels; value = global batch / "
+                           "max-over-ranks time; gpu_ms_per_step = first launch to last completion on the device")
     # clock samples cover pre-warm + warm-up + both timed regions (identical load); the timed regions alone are
     # only ~K x 4 ms long, too short for more than a couple of 100 ms samples
     clocks = sampler.stop(smi_from) if sampler else None
@@ -385,14 +507,11 @@ def run_gpu(args):
         alg_bytes = 8.0 * (8 * n + 2 * m) * B  # SURVEY §8(d) algorithmic bytes per LP
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=tot_ms / K,
-            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+            higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f64", data="synthetic",
+            iters_per_lp=iters_total / B,
             timing=dict(regions=args.regions, rule="fastest of %d regions of exactly K steps each" % args.regions,
                         ms_per_step_median=tot_ms_median / K, e2e_ms_per_step_median=e2e_ms_median / K),
-            config=dict(workload="Energy ICON load1 LP (172x1582 standard form, nnz 22188), thr=%g, damping=1e-6, "
-                                 "whole (HSD) backward" % args.thr,
-                        batch_per_gpu=B, global_batch=B * world, iters_per_lp=iters_total / B,
-                        l2="inputs rotate over %d device batches, %.0f MB in total (> 126 MB L2)" % (
-                            NSETS, NSETS * 2 * c_dev.numel() * 4 / 1e6), parallelism="dp%d" % world),
+            config=bench_config(args, world),
             e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int(c_host.numel() * 4 + g_host.numel() * 4),
                      d2h_bytes_per_step=int(x_host.numel() * 4 + gc_host.numel() * 4)),
             # per step: intopt_forward_kernel + intopt_backward_kernel (the mapping between the caller's float32 user
@@ -415,22 +534,9 @@ def run_gpu(args):
                                    achieved_gbs=alg_bytes / (tot_ms / K * 1e-3) * 1e-9, peak_gbs=hbm_peak),
                           fwd_ms=fwd_ms / K, bwd_ms=bwd_ms / K),
             problem=info, parity=parity, clocks=clocks, per_rank_ms_per_step=per_rank[-1] if per_rank else [],
-            alt_batch=alt)
+            alt_batch=alt, strong_side=strong)
         if not args.no_cpu and world == 1:
-            Ad, Gd = A.toarray(), G.toarray()
-            cnt = args.ref_sample
-            cpu_reference_pass(Ad, b, Gd, h, c_np, g_np, 1)
-            t = cpu_reference_pass(Ad, b, Gd, h, c_np, g_np, cnt)
-            from oracle import hsd_numpy as O
-            t1 = time.perf_counter()
-            for i in range(cnt):
-                O.ipofunc(c_np[i], g_np[i], A=Ad, b=b, G=Gd, h=h, bounds=opts["bounds"], thr=opts["thr"],
-                          max_iter=opts["max_iter"], damping=opts["damping"])
-            t_vjp = time.perf_counter() - t1
-            line["cpu_baseline"] = dict(value=cnt / t, unit=UNIT, cores=os.cpu_count(), kind="port",
-                                        sample="%d LPs of the same batch, serial loop, BLAS threads=all cores, "
-                                               "as-executed oracle port incl. per-call host prep" % cnt,
-                                        fp64_vjp_port_value=cnt / t_vjp)
+            line["cpu_baseline"] = cpu_baseline_measure(A, b, G, h, c_np, g_np, args.ref_sample, args.thr)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -453,6 +559,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the side measurement at batch 1024")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch LPs per GPU (default, the headline); strong: --global-batch LPs in total, "
+                         "1/N per GPU (BASELINE.json configs[3])")
+    ap.add_argument("--global-batch", type=int, default=1024, help="total LPs per step of the strong-scaling measurements")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling side measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
