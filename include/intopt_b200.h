@@ -72,9 +72,6 @@ typedef struct IntoptInfo {
                              1: lock-step dense path (batch-wide DMMA kernels, factor tiled through HBM) */
   long long asm_padded;   /* gather-list slots incl. padding of the warp-interleaved layout */
   long long solve_macs;   /* MACs of one blocked L L^T solve */
-  int chain_steps;        /* sequential block steps of the factorisation / of one substitution sweep: the number of
-                             level groups (independent block columns are eliminated together), == (m+7)/8 if none */
-  int reserved;
 } IntoptInfo;
 
 int intopt_version(void);

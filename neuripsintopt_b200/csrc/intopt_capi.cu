@@ -80,8 +80,6 @@ void fill_info(const intopt::HostStructure& S, IntoptInfo* info) {
   info->scalar_envelope = S.sky_size;
   info->asm_padded = S.asm_padded;
   info->solve_macs = S.solve_macs;
-  info->chain_steps = intopt::use_levels(S) ? S.n_groups : S.mb;
-  info->reserved = 0;
 }
 
 // The lock-step dense path keeps no block-skyline structure: its "envelope" is the padded square it factors in place.
@@ -98,7 +96,6 @@ void fill_info_dense(int m, int n, int nnz, IntoptInfo* info) {
   info->solve_macs = (long long)m * m;
   info->threads = 512;
   info->path = 1;
-  info->chain_steps = (int)(m64 / 64);
 }
 
 int check_csr(int m, int n, const int* rp, const int* ci, const double* val) {
@@ -427,7 +424,6 @@ int intopt_forward_mapped(const IntoptProblem* p, int B, double* c, long long c_
   a.factor_in_smem = p->info.factor_in_smem;
   a.gather_in_smem = p->info.gather_in_smem;
   a.ws_stride = (long long)ws_per_slot_doubles(p);
-  a.rot_sms = (p->info.ctas_per_sm == 2 && p->info.threads >= 128 && env_int("INTOPT_WARP_ROT", 1)) ? p->sms : 0;
   // the value streams sit at the end of every slot
   a.vals_ws = a.ws + (a.ws_stride - (long long)((vals_ws_doubles(p) + 1) & ~(size_t)1));
   a.vals_ws_stride = a.ws_stride;
@@ -515,7 +511,6 @@ int intopt_backward_mapped(const IntoptProblem* p, int B, int mode, double dampi
   a.factor_in_smem = p->info.factor_in_smem;
   a.gather_in_smem = p->info.gather_in_smem;
   a.ws_stride = (long long)ws_per_slot_doubles(p);
-  a.rot_sms = (p->info.ctas_per_sm == 2 && p->info.threads >= 128 && env_int("INTOPT_WARP_ROT", 1)) ? p->sms : 0;
   // the value streams sit at the end of every slot
   a.vals_ws = a.ws + (a.ws_stride - (long long)((vals_ws_doubles(p) + 1) & ~(size_t)1));
   a.vals_ws_stride = a.ws_stride;

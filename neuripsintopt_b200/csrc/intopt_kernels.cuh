@@ -10,17 +10,13 @@
 
 constexpr int kMaxMetaInts = 4096;  // schedule arrays up to 16 KB are staged in shared memory
 
-// `rot` rotates the LOGICAL warp numbering against the hardware one.  The dependent chains of the factorisation and of
-// the substitutions run on logical warp 0; with two LPs resident per SM the second CTA (blockIdx.x / n_sm odd) rotates by
-// two so that the two chains sit on different SM sub-partitions (warp w issues on sub-partition w % 4).  All reductions
-// follow the logical numbering, so results do not depend on it.
-__device__ __forceinline__ CtaCtx make_ctx(double* red, int rot = 0) {
+__device__ __forceinline__ CtaCtx make_ctx(double* red) {
   CtaCtx cx;
+  cx.tid = threadIdx.x;
   cx.nthreads = blockDim.x;
   cx.lane = threadIdx.x & 31;
+  cx.warp = threadIdx.x >> 5;
   cx.nwarps = blockDim.x >> 5;
-  cx.warp = ((int)(threadIdx.x >> 5) + rot) % cx.nwarps;
-  cx.tid = cx.warp * 32 + cx.lane;
   cx.red = red;
   cx.bar_id = 0;
   cx.bar_n = blockDim.x;
@@ -39,11 +35,11 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
   const intopt::SmemLayout S =
       intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
-  const CtaCtx cx = make_ctx(S.red, (a.rot_sms > 0 && ((blockIdx.x / a.rot_sms) & 1)) ? 2 : 0);
+  const CtaCtx cx = make_ctx(S.red);
   intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
   const bool cold = a.cold_factor != nullptr && a.init == nullptr && *a.cold_ok != 0;  // launch-uniform
-  if (cold && a.factor_in_smem && cx.tid == 0) intopt::mbar_init(S.mbar, 1);
+  if (cold && a.factor_in_smem && threadIdx.x == 0) intopt::mbar_init(S.mbar, 1);
   unsigned served = 0;  // instances this CTA has run = completed phases of the prefetch mbarrier
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
@@ -76,7 +72,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
   const intopt::SmemLayout S =
       intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
-  const CtaCtx cx = make_ctx(S.red, (a.rot_sms > 0 && ((blockIdx.x / a.rot_sms) & 1)) ? 2 : 0);
+  const CtaCtx cx = make_ctx(S.red);
   intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
   for (;;) {

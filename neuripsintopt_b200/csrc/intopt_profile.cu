@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   __syncthreads();
   if (which >= 5 && which <= 7) {  // a valid factor for the factor/solve blocks
     intopt::assemble_normal_matrix(cx, P, M, D, S.G, S.scan, 1e-6, S.L);
-    if (which != 5) intopt::factorize(cx, P, M, S.L, S);
+    if (which != 5) intopt::block_cholesky(cx, P, M, S.L, S.dscr, S.flag);
     __syncthreads();
   }
   const long long t0 = clock64();
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
       case 4: intopt::assemble_normal_matrix(cx, P, M, D, S.G, S.scan, 1e-6, S.L); break;
       case 5:
         intopt::assemble_normal_matrix(cx, P, M, D, S.G, S.scan, 1e-6, S.L);
-        intopt::factorize(cx, P, M, S.L, S);
+        intopt::block_cholesky(cx, P, M, S.L, S.dscr, S.flag);
         break;
       case 6: {
         CTA_FOR(i, P.mv) {
@@ -117,13 +117,13 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
         }
         __syncthreads();
         double* const rhs2[2] = {S.q, S.v};
-        intopt::solve_factored<2>(cx, P, M, S.L, rhs2, S);
+        intopt::block_solve<2>(cx, P, M, S.L, rhs2, S.ybuf);
       } break;
       case 7: {
         CTA_FOR(i, P.mv) S.v[i] = i < P.m ? 2.0 : 0.0;
         __syncthreads();
         double* const rhs1[1] = {S.v};
-        intopt::solve_factored<1>(cx, P, M, S.L, rhs1, S);
+        intopt::block_solve<1>(cx, P, M, S.L, rhs1, S.ybuf);
       } break;
       case 8: CTA_FOR(k, n) intopt::gstore(S.G, k, D[k] * c[k]); break;
       case 9: {

@@ -97,14 +97,7 @@ constexpr int NUC = 1;  // loops that also run a column gather (register pressur
 namespace intopt {
 
 enum { ST_OK = 0, ST_MAXITER = 1, ST_INFEAS = 2, ST_BREAKDOWN = 3, ST_NONFINITE = 4 };
-// work lists of the level schedule (ProblemDev::g_lv / Meta::lv)
-enum LvList { LV_COL_REC = 0, LV_FL_PTR, LV_FL, LV_FO_PTR, LV_FO, LV_FSRC_PTR, LV_FSRC, LV_BL_PTR, LV_BL, LV_BO_PTR, LV_BO,
-              LV_BSRC, LV_NLISTS };
 constexpr int KB = 8;  // block edge, == NB of intopt_structure.hpp
-constexpr int RED_STRIDE = 16;  // per-warp partial sums of the CTA reductions: up to 16 warps (512 threads) x 8 values
-constexpr int LV_MAX = 4;                                 // block columns eliminated together by the level schedule
-constexpr int LV_YBUF = 2 * LV_MAX * 2 * KB;              // pivot vectors of a group, double buffered, 2 rhs
-constexpr int S_SCRATCH_LV = LV_YBUF;                     // extra shared scratch of the level schedule
 
 // The gather buffer is indexed through gpad(): one unused slot after every 32 elements, so that run starts a
 // multiple of 16 or 32 elements apart (the Energy LP: 144 = one task's variables) no longer share a bank.
@@ -138,17 +131,6 @@ struct ProblemDev {
   int n_dummy;
   const int* g_act_ptr;
   const int* g_act_blk;
-  // level schedule (n_groups == 0: not in use, the block columns are eliminated one by one); see intopt_structure.hpp
-  int n_groups, n_rg;
-  const int* g_grp_ptr;
-  const int* g_grp_col;
-  const int* g_col_group;
-  const int* g_rg_ptr;
-  const int* g_rg_blk;
-  const int* g_grp_tab;
-  // work lists of the level schedule (formats: intopt_structure.hpp); lv_cnt = their lengths in LvList order
-  const int* g_lv[12];
-  int lv_cnt[12];
   int meta_ints;  // total ints of {fb, boff, act_ptr, act_blk, csr_ptr, csc_gptr, asm_gptr}: staged in smem if small
   int n_asm;
   const int* g_asm_gptr;
@@ -180,13 +162,6 @@ struct Meta {
   const int* csc_gptr;
   const int* asm_gptr;
   const int* asm_rptr;
-  const int* grp_ptr;
-  const int* grp_col;
-  const int* col_group;
-  const int* rg_ptr;
-  const int* rg_blk;
-  const int* grp_tab;
-  const int* lv[12];  // LvList order
   // value streams of A (by rows, by column groups, assembly weights): the problem's own, or this instance's copies
   // in the CTA's workspace when the values differ per instance (materialize_instance_values)
   const double* csr_val;
@@ -205,13 +180,13 @@ IO_DEV void cta_sum(const CtaCtx& cx, double (&v)[N]) {
   for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
   if (cx.lane == 0) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) cx.red[k * RED_STRIDE + cx.warp] = v[k];
+    for (int k = 0; k < N; ++k) cx.red[k * 32 + cx.warp] = v[k];
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     double s = 0.0;
-    for (int w = 0; w < cx.nwarps; ++w) s += cx.red[k * RED_STRIDE + w];
+    for (int w = 0; w < cx.nwarps; ++w) s += cx.red[k * 32 + w];
     v[k] = s;
   }
   __syncthreads();
@@ -228,13 +203,13 @@ IO_DEV void cta_min(const CtaCtx& cx, double (&v)[N]) {
   for (int k = 0; k < N; ++k) v[k] = warp_min(v[k]);
   if (cx.lane == 0) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) cx.red[k * RED_STRIDE + cx.warp] = v[k];
+    for (int k = 0; k < N; ++k) cx.red[k * 32 + cx.warp] = v[k];
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    double s = cx.red[k * RED_STRIDE];
-    for (int w = 1; w < cx.nwarps; ++w) s = fmin(s, cx.red[k * RED_STRIDE + w]);
+    double s = cx.red[k * 32];
+    for (int w = 1; w < cx.nwarps; ++w) s = fmin(s, cx.red[k * 32 + w]);
     v[k] = s;
   }
   __syncthreads();
@@ -902,8 +877,6 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
   }
 }
 
-#include "intopt_levels.cuh"
-
 IO_FORCEINLINE double run_total(const double* gp, int len) {
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int j = 0;
@@ -1151,66 +1124,43 @@ IO_DEV Meta global_meta(const ProblemDev& P) {
   M.csc_gptr = P.g_csc_gptr;
   M.asm_gptr = P.g_asm_gptr;
   M.asm_rptr = P.g_asm_rptr;
-  M.grp_ptr = P.g_grp_ptr;
-  M.grp_col = P.g_grp_col;
-  M.col_group = P.g_col_group;
-  M.rg_ptr = P.g_rg_ptr;
-  M.rg_blk = P.g_rg_blk;
-  M.grp_tab = P.g_grp_tab;
-  for (int a = 0; a < LV_NLISTS; ++a) M.lv[a] = P.g_lv[a];
   M.csr_val = P.csr_val;
   M.csc_val = P.csc_val;
   M.asm_w = P.asm_w;
   return M;
 }
 
-// Which schedule arrays are worth a shared-memory copy: everything the blocked steps index on their critical path.  Two
-// arrays are only read elsewhere and stay in global memory when their fast-path replacement exists: the row pointers of A
-// (the run-length row kernel does not use them) and the per-term gather pointers (the run-length assembly does not).
-IO_HD int meta_stage_count(const ProblemDev& P, int a) {
-  const int lv = P.n_groups > 0;
-  switch (a) {
-    case 0: return P.mb;
-    case 1: return P.mb + 1;
-    case 2: return P.mb + 1;
-    case 3: return P.n_act;
-    case 4: return P.rs_hdr ? 0 : P.m + 1;
-    case 5: return ((P.n + 31) >> 5) + 1;
-    case 6: return P.asm_run ? 0 : (P.n_asm >> 5) + 1;
-    case 7: return (P.n_asm >> 5) + 1;
-    case 8: return lv ? P.n_groups + 1 : 0;
-    case 9: return lv ? P.mb : 0;
-    case 10: return lv ? P.mb : 0;
-    case 11: return lv ? P.n_groups + 1 : 0;
-    case 12: return lv ? P.n_rg : 0;
-    case 13: return lv ? 16 * P.n_groups : 0;
-    default: return lv ? P.lv_cnt[a - 14] : 0;
-  }
-}
-constexpr int META_ARRAYS = 14 + LV_NLISTS;
-IO_HD int meta_stage_ints(const ProblemDev& P) {
-  int t = 0;
-  for (int a = 0; a < META_ARRAYS; ++a) t += meta_stage_count(P, a);
-  return t;
-}
-
 // Copies the schedule arrays into shared memory (`dst` holds P.meta_ints ints) and returns pointers to the copies.
 IO_DEV Meta stage_meta(const CtaCtx& cx, const ProblemDev& P, int* dst) {
-  Meta M = global_meta(P);
-  const int** slot[14] = {&M.fb,       &M.boff,     &M.act_ptr, &M.act_blk, &M.csr_ptr,   &M.csc_gptr, &M.asm_gptr,
-                          &M.asm_rptr, &M.grp_ptr,  &M.grp_col, &M.col_group, &M.rg_ptr,  &M.rg_blk,   &M.grp_tab};
+  const int cnt[8] = {P.mb, P.mb + 1, P.mb + 1, P.n_act, P.m + 1, ((P.n + 31) >> 5) + 1, (P.n_asm >> 5) + 1,
+                      (P.n_asm >> 5) + 1};
+  const int* src[8] = {P.g_fb, P.g_boff, P.g_act_ptr, P.g_act_blk, P.g_csr_ptr, P.g_csc_gptr, P.g_asm_gptr,
+                       P.g_asm_rptr};
   int* d = dst;
-#pragma unroll
-  for (int a = 0; a < META_ARRAYS; ++a) {
-    const int cnt = meta_stage_count(P, a);
-    const int** dstp = a < 14 ? slot[a] : &M.lv[a - 14];
-    if (cnt > 0) {
-      const int* src = *dstp;
-      CTA_FOR(i, cnt) d[i] = src[i];
-      *dstp = d;
-      d += cnt;
-    }
+  for (int a = 0; a < 8; ++a) {
+    CTA_FOR(i, cnt[a]) d[i] = src[a][i];
+    d += cnt[a];
   }
+  Meta M;
+  d = dst;
+  M.fb = d;
+  d += cnt[0];
+  M.boff = d;
+  d += cnt[1];
+  M.act_ptr = d;
+  d += cnt[2];
+  M.act_blk = d;
+  d += cnt[3];
+  M.csr_ptr = d;
+  d += cnt[4];
+  M.csc_gptr = d;
+  d += cnt[5];
+  M.asm_gptr = d;
+  d += cnt[6];
+  M.asm_rptr = d;
+  M.csr_val = P.csr_val;
+  M.csc_val = P.csc_val;
+  M.asm_w = P.asm_w;
   CTA_SYNC();
   return M;
 }
@@ -1247,12 +1197,10 @@ enum { W_X = 0, W_T, W_D, W_R2, W_P, W_W, W_DX, W_DXDT, W_ATY, W_NVEC };
 IO_HD long long ws_nvec_doubles(int n) { return ((long long)W_NVEC * n + 1) & ~1LL; }
 // shared-memory m-vector slots
 enum { S_B = 0, S_Y, S_R1, S_Q, S_V, S_NVEC };
-constexpr int S_SCRATCH = 4 * KB + (KB + KB * KB) + 8 * RED_STRIDE + 4;  // ybuf (double buffered, 2 rhs) + diag scratch + red + flag + mbarrier
-
+constexpr int S_SCRATCH = 4 * KB + (KB + KB * KB) + 8 * 32 + 4;  // ybuf (double buffered, 2 rhs) + diag scratch + red + flag + mbarrier
 
 struct SmemLayout {
   double *L, *G, *bs, *y, *r1, *q, *v, *ybuf, *dscr, *red;  // G: gather region of 2*gather_len(n) doubles
-  double* ybuf_lv;                                         // pivot vectors of the level schedule (null when not in use)
   D2* scan;  // scratch of the double-double prefix scan: scan_len(n) D2
   int* flag;
   unsigned long long* mbar;  // mbarrier of the cold-start factor prefetch (bulk async copy)
@@ -1300,18 +1248,12 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
   s.ybuf = p;
   s.dscr = p + 4 * KB;
   s.red = s.dscr + KB + KB * KB;
-  s.flag = (int*)(s.red + 8 * RED_STRIDE);
-  s.mbar = reinterpret_cast<unsigned long long*>(s.red + 8 * RED_STRIDE + 2);
+  s.flag = (int*)(s.red + 8 * 32);
+  s.mbar = reinterpret_cast<unsigned long long*>(s.red + 8 * 32 + 2);
   // the prefix-scan scratch aliases the factor storage when it fits (the scan runs before the factor is zero-filled)
   const int own_scan = scan_in_factor(P.bsize, P.n) ? 0 : 2 * scan_len(P.n);
-  s.scan = own_scan ? reinterpret_cast<D2*>(s.red + 8 * RED_STRIDE + 4) : reinterpret_cast<D2*>(s.L);
-  double* after = s.red + 8 * RED_STRIDE + 4 + own_scan;
-  s.ybuf_lv = nullptr;
-  if (P.n_groups > 0) {
-    s.ybuf_lv = after;
-    after += S_SCRATCH_LV;
-  }
-  s.meta = (int*)after;
+  s.scan = own_scan ? reinterpret_cast<D2*>(s.red + 8 * 32 + 4) : reinterpret_cast<D2*>(s.L);
+  s.meta = (int*)(s.red + 8 * 32 + 4 + own_scan);
 #ifndef INTOPT_HOST_EMU
   if (ALLSMEM) {
     __builtin_assume(__isShared(s.L));
@@ -1327,22 +1269,6 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
   __builtin_assume(__isShared(s.red));
 #endif
   return s;
-}
-
-// Factorisation / substitution entry points: the level schedule when the problem has one (independent block columns
-// eliminated together, intopt_levels.cuh), the column-by-column versions otherwise.
-IO_DEV bool factorize(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, const SmemLayout& S,
-                      PhaseTimer* pt = nullptr) {
-  if (P.n_groups > 0) return block_cholesky_lv(cx, P, M, L, S.dscr, S.flag, pt);
-  return block_cholesky(cx, P, M, L, S.dscr, S.flag, pt);
-}
-template <int NR>
-IO_DEV void solve_factored(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const double* L, double* const (&r)[NR],
-                           const SmemLayout& S) {
-  if (P.n_groups > 0)
-    block_solve_lv<NR>(cx, P, M, L, r, S.ybuf_lv);
-  else
-    block_solve<NR>(cx, P, M, L, r, S.ybuf);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1460,7 +1386,6 @@ struct FwdParams {
   long long ws_stride;
   int* counter;  // instance dispenser (zeroed before launch)
   int factor_in_smem, gather_in_smem;
-  int rot_sms;  // > 0: CTAs with (blockIdx.x / rot_sms) odd rotate their logical warp numbering by two (see make_ctx)
   // Cold-start factor: without a warm start every instance begins at x = t = 1, so the first normal matrix
   // A.A^T + delta.I and its factor are constants of the problem; they are computed once (cold_factor_build,
   // same code => same bits) and only copied in at iteration 1.  Null / *cold_ok == 0: assemble + factor as usual.
@@ -1479,10 +1404,7 @@ struct FwdParams {
 // Factor L (block_cholesky) and form the two products out1 = A src1, out2 = A src2 (out2 may be null: one product),
 // side by side when the CTA has at least 4 warps: the products need nothing from the factorisation.  On return
 // (after a full CTA barrier) *S.flag tells whether the factorisation succeeded.
-#ifndef INTOPT_RHS_WARPS
-#define INTOPT_RHS_WARPS 2
-#endif
-constexpr int RHS_WARPS = INTOPT_RHS_WARPS;
+constexpr int RHS_WARPS = 2;
 IO_DEV void factor_and_rhs(const CtaCtx& cx, const ProblemDev& P, const Meta& M, double* L, const SmemLayout& S,
                            const double* src1, const double* src2, double* out1, double* out2, PhaseTimer* pt) {
 #ifndef INTOPT_HOST_EMU
@@ -1494,7 +1416,7 @@ IO_DEV void factor_and_rhs(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
       ca.nwarps = ga;
       ca.bar_id = 1;
       ca.bar_n = ga * 32;
-      factorize(ca, P, M, L, S, pt);
+      block_cholesky(ca, P, M, L, S.dscr, S.flag, pt);
     } else {
       CtaCtx cb = cx;
       cb.tid = cx.tid - ga * 32;
@@ -1512,7 +1434,7 @@ IO_DEV void factor_and_rhs(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
     return;
   }
 #endif
-  factorize(cx, P, M, L, S, pt);
+  block_cholesky(cx, P, M, L, S.dscr, S.flag, pt);
   if (out2)
     spmv_rows_n<2>(cx, P, M, src1, src2, out1, out2);
   else
@@ -1795,7 +1717,7 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
     PHASE_MARK(pt, 4);
     {
       double* const rhs2[2] = {q, v};
-      solve_factored<2>(cx, P, M, L, rhs2, S);
+      block_solve<2>(cx, P, M, L, rhs2, S.ybuf);
     }
     PHASE_MARK(pt, 5);
     double cp_, bq_, cu_, bv_;
@@ -1874,7 +1796,7 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
         PHASE_MARK(pt, 7);
         {
           double* const rhs1[1] = {v};
-          solve_factored<1>(cx, P, M, L, rhs1, S);
+          block_solve<1>(cx, P, M, L, rhs1, S.ybuf);
         }
         PHASE_MARK(pt, 8);
         double acc3[2] = {0.0, 0.0};
@@ -2024,7 +1946,7 @@ IO_DEV void cold_factor_build(const CtaCtx& cx, const ProblemDev& P, const Meta&
   if (cx.tid == 0) S.G[gpad(n)] = 0.0;
   CTA_SYNC();
   assemble_normal_matrix(cx, P, M, D, S.G, S.scan, delta, S.L);
-  const bool ok = factorize(cx, P, M, S.L, S);
+  const bool ok = block_cholesky(cx, P, M, S.L, S.dscr, S.flag);
   CTA_FOR(e, P.bsize) out[e] = S.L[e];
   if (cx.tid == 0) *ok_out = ok ? 1 : 0;
   CTA_SYNC();
@@ -2051,7 +1973,6 @@ struct BwdParams {
   long long ws_stride;
   int* counter;
   int factor_in_smem, gather_in_smem;
-  int rot_sms;
 };
 
 // c_grad[var_index] = dc, zeros elsewhere (:1559-1560), in the caller's layout and precision (after a CTA barrier
@@ -2133,7 +2054,7 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   }
   if (!whole) {
     double* const rhs1[1] = {v};
-    solve_factored<1>(cx, P, M, L, rhs1, S);
+    block_solve<1>(cx, P, M, L, rhs1, S.ybuf);
     at_mult<1>(cx, P, M, v, nullptr, G, nullptr);
     CTA_SYNC();
     CTA_FOR(k, nvar) gc[k] = -x2[k] * (g[k] - G[k]) / mu;
@@ -2149,7 +2070,7 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   CTA_SYNC();
   {
     double* const rhs2[2] = {q, v};
-    solve_factored<2>(cx, P, M, L, rhs2, S);
+    block_solve<2>(cx, P, M, L, rhs2, S.ybuf);
   }
   double* ug = wsi + (long long)W_DX * n;
   double* pp = wsi + (long long)W_P * n;

@@ -62,31 +62,6 @@ struct HostStructure {
   std::vector<int> act_ptr, act_blk;               // block rows I > K with fb[I] <= K
   std::vector<int> pair_ptr, pair_dst, pair_a, pair_b;  // trailing updates of step K: dst -= a * b^T
   std::vector<unsigned char> next_diag_first;      // pair_ptr[K] is the update of block (K+1,K+1)
-  // Level schedule: block columns whose diagonal blocks do not depend on each other (fb[K2] > K1 for K1 < K2 in the
-  // same group) are eliminated together, up to GROUP_MAX at a time; groups are ordered by dependency level, so the
-  // sequential chain of the factorisation / substitutions has n_groups steps instead of mb (Energy: 3 independent
-  // machine bands + border: 10 instead of 22).  lv_act: the act lists again, with bit 16 set on rows that are active in
-  // more than one column of their group (their updates are merged into one task to keep the summation order fixed).
-  std::vector<int> grp_ptr, grp_col, col_group, lv_act, rg_ptr, rg_blk;
-  // per group 16 ints of cumulative work counts over its (up to 4) columns, so that a thread finds its column with three
-  // comparisons against shared memory instead of indexing per-thread arrays:
-  //   [0..4]  panel rows: 8 * (active rows of columns < c)          (substitution items: the same times the rhs count)
-  //   [5..10] trailing-update tiles: 4 * pairs of columns < c, then + 4 * pairs of the shared rows
-  //   [11..15] backward-sweep chunks: 4 * (K - fb[K]) of columns < c
-  std::vector<int> grp_tab;
-  // Work lists of the level schedule, so that the kernels chase no indices on their critical path.  A "source" is one
-  // block of L as  offset | (column slot c of its group) << 16.  A "target" is one block row / block column that a step
-  // updates, as  index | (number of sources) << 11 | (first source) << 14  (sources of a target are contiguous and in
-  // ascending column order: the summation order is fixed).
-  //   lv_col_rec[2 * (4 g + c) ..]  = {K, offset of block (K,K)} of column slot c of group g (K = -1: empty slot)
-  //   forward sweep / factorisation, group g:  lv_fl (targets that are columns of group g+1: the next pivots, warp 0) and
-  //   lv_fo (all other targets) over lv_fsrc;  the sources of group g, lv_fsrc[lv_fsrc_ptr[g] ..), are at the same time the
-  //   panel blocks of the group's columns
-  //   backward sweep, group g (rows I = its columns): lv_bl (targets in group g-1) and lv_bo (the others) over lv_bsrc
-  std::vector<int> lv_col_rec, lv_fl_ptr, lv_fl, lv_fo_ptr, lv_fo, lv_fsrc_ptr, lv_fsrc, lv_bl_ptr, lv_bl, lv_bo_ptr, lv_bo,
-      lv_bsrc;
-  bool lv_ok = false;  // the packed formats fit (bsize < 65536, mb < 2048)
-  int n_groups = 0;
   // assembly gather lists, entries sorted by length (descending), 32 entries per group, interleaved like csc
   int n_asm = 0;  // padded to a multiple of 32
   std::vector<int> asm_gptr, asm_glen, asm_pos;  // asm_pos < 0: padding entry
@@ -458,111 +433,6 @@ inline int analyze(int m, int n, const int* rp, const int* ci, const double* val
     S.pair_ptr[K + 1] = (int)S.pair_dst.size();
     S.chol_macs += (long long)pairs.size() * NB * NB * NB + (long long)act.size() * NB * 36 + 120 + 120;
     S.solve_macs += 2 * ((long long)act.size() * NBB + 36);
-  }
-
-  // ---- level schedule --------------------------------------------------------------------------------------
-  {
-    constexpr int GROUP_MAX = 4;
-    std::vector<int> level(mb, 0);
-    int nlev = 0;
-    for (int K = 0; K < mb; ++K) {
-      int lv = 0;
-      for (int J = S.fb[K]; J < K; ++J) lv = std::max(lv, level[J] + 1);
-      level[K] = lv;
-      nlev = std::max(nlev, lv + 1);
-    }
-    S.grp_ptr.assign(1, 0);
-    S.col_group.assign(mb, 0);
-    for (int lv = 0; lv < nlev; ++lv) {
-      int in_group = 0;
-      for (int K = 0; K < mb; ++K) {
-        if (level[K] != lv) continue;
-        if (in_group == GROUP_MAX) {
-          S.grp_ptr.push_back((int)S.grp_col.size());
-          in_group = 0;
-        }
-        S.col_group[K] = (int)S.grp_ptr.size() - 1;
-        S.grp_col.push_back(K);
-        ++in_group;
-      }
-      S.grp_ptr.push_back((int)S.grp_col.size());
-    }
-    S.n_groups = (int)S.grp_ptr.size() - 1;
-    S.lv_act = S.act_blk;
-    S.rg_ptr.assign(1, 0);
-    for (int g = 0; g < S.n_groups; ++g) {
-      std::vector<int> cnt(mb, 0);
-      for (int c = S.grp_ptr[g]; c < S.grp_ptr[g + 1]; ++c)
-        for (int e = S.act_ptr[S.grp_col[c]]; e < S.act_ptr[S.grp_col[c] + 1]; ++e) cnt[S.act_blk[e]]++;
-      for (int I = 0; I < mb; ++I)
-        if (cnt[I] > 1) S.rg_blk.push_back(I);
-      S.rg_ptr.push_back((int)S.rg_blk.size());
-      for (int c = S.grp_ptr[g]; c < S.grp_ptr[g + 1]; ++c)
-        for (int e = S.act_ptr[S.grp_col[c]]; e < S.act_ptr[S.grp_col[c] + 1]; ++e)
-          if (cnt[S.act_blk[e]] > 1) S.lv_act[e] |= 1 << 16;
-      int tab[16] = {0};
-      const int nc = S.grp_ptr[g + 1] - S.grp_ptr[g];
-      for (int c = 0; c < GROUP_MAX; ++c) {
-        int na = 0, nk = 0;
-        if (c < nc) {
-          const int K = S.grp_col[S.grp_ptr[g] + c];
-          na = S.act_ptr[K + 1] - S.act_ptr[K];
-          nk = K - S.fb[K];
-        }
-        tab[c + 1] = tab[c] + na * NB;
-        tab[5 + c + 1] = tab[5 + c] + na * (na + 1) / 2 * 4;
-        tab[11 + c + 1] = tab[11 + c] + nk * 4;
-      }
-      const int nr = S.rg_ptr[g + 1] - S.rg_ptr[g];
-      tab[10] = tab[9] + nr * (nr + 1) / 2 * 4;
-      S.grp_tab.insert(S.grp_tab.end(), tab, tab + 16);
-    }
-    // ---- work lists
-    S.lv_ok = S.bsize < 65536 && mb < 2048;
-    if (S.lv_ok) {
-      auto off = [&](int I, int K) { return S.boff[I] + (K - S.fb[I]) * NBB; };
-      auto has = [&](int I, int K) { return K >= 0 && K < I && S.fb[I] <= K; };
-      S.lv_col_rec.assign((size_t)S.n_groups * 8, -1);
-      S.lv_fl_ptr.assign(1, 0);
-      S.lv_fo_ptr.assign(1, 0);
-      S.lv_fsrc_ptr.assign(1, 0);
-      S.lv_bl_ptr.assign(1, 0);
-      S.lv_bo_ptr.assign(1, 0);
-      for (int g = 0; g < S.n_groups; ++g) {
-        const int c0 = S.grp_ptr[g], nc = S.grp_ptr[g + 1] - c0;
-        for (int c = 0; c < nc; ++c) {
-          const int K = S.grp_col[c0 + c];
-          S.lv_col_rec[(size_t)(4 * g + c) * 2] = K;
-          S.lv_col_rec[(size_t)(4 * g + c) * 2 + 1] = off(K, K);
-        }
-        // forward targets: rows I below the group's columns, sources = the blocks (I, K_c) present
-        for (int I = 0; I < mb; ++I) {
-          std::vector<int> src;
-          for (int c = 0; c < nc; ++c)
-            if (has(I, S.grp_col[c0 + c])) src.push_back(off(I, S.grp_col[c0 + c]) | (c << 16));
-          if (src.empty()) continue;
-          const int rec = I | ((int)src.size() << 11) | ((int)S.lv_fsrc.size() << 14);
-          S.lv_fsrc.insert(S.lv_fsrc.end(), src.begin(), src.end());
-          (g + 1 < S.n_groups && S.col_group[I] == g + 1 ? S.lv_fl : S.lv_fo).push_back(rec);
-        }
-        S.lv_fl_ptr.push_back((int)S.lv_fl.size());
-        S.lv_fo_ptr.push_back((int)S.lv_fo.size());
-        S.lv_fsrc_ptr.push_back((int)S.lv_fsrc.size());
-        // backward targets: block columns Kc inside the skyline rows of the group's columns
-        for (int Kc = 0; Kc < mb; ++Kc) {
-          std::vector<int> src;
-          for (int c = 0; c < nc; ++c)
-            if (has(S.grp_col[c0 + c], Kc)) src.push_back(off(S.grp_col[c0 + c], Kc) | (c << 16));
-          if (src.empty()) continue;
-          const int rec = Kc | ((int)src.size() << 11) | ((int)S.lv_bsrc.size() << 14);
-          S.lv_bsrc.insert(S.lv_bsrc.end(), src.begin(), src.end());
-          (g > 0 && S.col_group[Kc] == g - 1 ? S.lv_bl : S.lv_bo).push_back(rec);
-        }
-        S.lv_bl_ptr.push_back((int)S.lv_bl.size());
-        S.lv_bo_ptr.push_back((int)S.lv_bo.size());
-      }
-      if (S.lv_fsrc.size() >= (1u << 17) || S.lv_bsrc.size() >= (1u << 17)) S.lv_ok = false;
-    }
   }
 
   // ---- assembly gather lists -------------------------------------------------------------------------------

@@ -14,7 +14,6 @@ LIB = os.path.join(HERE, "libintopt_emu.so")
 def build():
     src = os.path.join(HERE, "emu.cpp")
     deps = [src, os.path.join(HERE, "../../neuripsintopt_b200/csrc/intopt_solver.cuh"),
-            os.path.join(HERE, "../../neuripsintopt_b200/csrc/intopt_levels.cuh"),
             os.path.join(HERE, "../../neuripsintopt_b200/csrc/intopt_structure.hpp"),
             os.path.join(HERE, "../../neuripsintopt_b200/csrc/intopt_bind.hpp")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
