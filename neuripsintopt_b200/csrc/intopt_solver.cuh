@@ -1653,12 +1653,35 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
 
     // ---- M = A D A^T + delta I, factor (:772-777) ------------------------------------------------
     const bool reuse_cold = cold && iters == 1;  // x = t = 1: L already holds chol(A A^T + delta I)
+    // The failure ladder of _get_delta (:798-822).  When cho_factor fails the reference retries the SAME system with
+    // scipy.linalg.solve(assume_a='sym'), then 'pos', and only then reports "not solved" (:855-857).  A non-positive pivot
+    // here means M = A D A^T + delta I is numerically singular (rank-deficient A with tiny damping, or D spanning > 1e16
+    // near convergence); the device analogue of the ladder is two more attempts at this point with the diagonal raised by
+    // eps * dmax, eps = 1e-12 then 1e-8, dmax the largest diagonal entry of M: the smallest perturbations that make the
+    // pivots positive again, far below the accuracy a step needs.  The whole block (assembly, right-hand sides,
+    // factorisation) simply runs again: one copy of the code, nothing added to the first pass.
+    int attempt = 0;
+  factor_again:
     if (!reuse_cold) {
 #ifdef INTOPT_PROFILE
       assemble_normal_matrix(cx, P, M, D, G, S.scan, a.damping, L, a.debug);
 #else
       assemble_normal_matrix(cx, P, M, D, G, S.scan, a.damping, L);
 #endif
+      if (attempt > 0) {
+        double mx[1] = {0.0};
+        CTA_FOR(e, P.n_asm) {
+          const int pos = P.asm_pos[e];
+          if (pos >= 0 && P.asm_diag[e]) mx[0] = fmin(mx[0], -L[pos]);
+        }
+        cta_min<1>(cx, mx);
+        const double boost = (attempt == 1 ? 1e-12 : 1e-8) * -mx[0];
+        CTA_FOR(e, P.n_asm) {
+          const int pos = P.asm_pos[e];
+          if (pos >= 0 && P.asm_diag[e]) L[pos] += boost;
+        }
+        CTA_SYNC();
+      }
     }
     PHASE_MARK(pt, 2);
     // right-hand sides of the (p,q) solve (:800) and of the predictor (gamma = 0, eta = 1): G = D*c and, in the
@@ -1702,6 +1725,10 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
     } else {
       factor_and_rhs(cx, P, M, L, S, G, G2, q, v, &pt);
       solved = *S.flag == 0;
+      if (!solved && attempt < 2) {
+        ++attempt;
+        goto factor_again;
+      }
       CTA_FOR(i, m) {
         q[i] = bs[i] + q[i];
         v[i] = (PLAIN ? eta0 * r1[i] : r1[i]) + v[i];  // :785,666

@@ -558,3 +558,68 @@ def test_energy_fit_reproduces_the_reference_trajectory():
         assert np.abs(w - z["weights"][i]).max() <= 2e-3 * max(1.0, np.abs(z["weights"][i]).max()), (i, w, z["weights"][i])
         assert np.abs(b - z["biases"][i]).max() <= 2e-3 * max(1.0, np.abs(z["biases"][i]).max()), (i, b, z["biases"][i])
     assert hist[-1]["loss"] < hist[0]["loss"]  # the decision loss goes down on these days, as in the reference run
+
+
+def test_breakdown_ladder_recovers_a_numerically_singular_system():
+    """_get_delta's failure ladder (ip_model_whole.py:798-822).  The Twitter incidence matrix is rank deficient (SURVEY
+    C.6): with a slightly NEGATIVE damping, M = A D A^T + damping I has a negative eigenvalue at every iteration and the
+    Cholesky factorisation hits a non-positive pivot.  The reference then re-solves through scipy.linalg.solve(assume_a);
+    the kernel's ladder re-factors M + eps dmax I (eps = 1e-12, then 1e-8) and carries on: the run must end like a run
+    whose damping is what the second rung amounts to, with no breakdown status."""
+    from neuripsintopt_b200 import ip_model_alter
+    z = GU.load("twitter_sp")
+    A = GU.problem_inputs("twitter_sp", z, 0)["A"]
+    case = GU.cases(z)[0]
+    k = len(case["c"])
+    c = torch.tensor(np.asarray(case["c"][:k]), dtype=torch.float32, device="cuda")
+    outs = {}
+    for damping in (-1e-10, 1e-6):
+        f = ip_model_alter.IPOfunc(_tt(A), _tt(z["b_rr"][:k]), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)],
+                                   max_iter=100, thr=0.1, damping=damping)
+        x = f(c)
+        torch.cuda.synchronize()
+        status, iters = ip_model_alter.IPOfunc.status()
+        outs[damping] = (x.double().cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy())
+    x_neg, st_neg, it_neg = outs[-1e-10]
+    x_pos, st_pos, it_pos = outs[1e-6]
+    assert (st_neg == 0).all() and (st_pos == 0).all(), (st_neg, st_pos)
+    assert np.isfinite(x_neg).all()
+    assert (it_neg == it_pos).all(), (it_neg, it_pos)
+    err = max(_relinf(x_neg[i], x_pos[i]) for i in range(k))
+    print("ladder: x vs the damping=1e-6 run, rel-inf %.2e" % err)
+    assert err < 1e-3, err
+    # a damping so negative that no rung can repair it: every attempt fails, the iterate stays where it was (status 3)
+    f = ip_model_alter.IPOfunc(_tt(A), _tt(z["b_rr"][:k]), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)],
+                               max_iter=100, thr=0.1, damping=-1e-2)
+    x = f(c)
+    torch.cuda.synchronize()
+    status, iters = ip_model_alter.IPOfunc.status()
+    assert (status.cpu().numpy() == 3).all() and torch.isfinite(x).all() and (iters.cpu().numpy() == 1).all()
+
+
+def test_breakdown_is_contained_to_its_instance():
+    """An instance whose normal matrix cannot be factored by any rung of the ladder (overflowing entries) ends with
+    status 3 and finite outputs (the unchanged iterate, like upstream's `solved = False` deltas of zero, :855-857) while
+    every other instance of the batch is bitwise what it is without the bad neighbour."""
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = GU.load("knapsack")
+    case = GU.cases(z)[0]
+    k = len(case["c"])
+    costs = np.stack([z["costs"][i][None, :] for i in range(k)]).astype(np.float64)
+    bad = 1
+    c = torch.tensor(np.asarray(case["c"]), dtype=torch.float32, device="cuda")
+    res = []
+    for poison in (False, True):
+        cc = costs.copy()
+        if poison:
+            cc[bad] *= 1e160  # (cost row)^2 overflows in M
+        f = IPOfunc(torch.as_tensor(cc), _tt(z["budget_rhs"]), torch.Tensor(), torch.Tensor(), **case["kw"])
+        x = f(c)
+        torch.cuda.synchronize()
+        status, iters = IPOfunc.status()
+        res.append((x.double().cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy()))
+    (x0, st0, it0), (x1, st1, it1) = res
+    assert st1[bad] == 3 and np.isfinite(x1[bad]).all(), (st1, x1[bad][:4])
+    good = [i for i in range(k) if i != bad]
+    assert (st1[good] == 0).all() and (st0 == 0).all()
+    assert np.array_equal(x0[good], x1[good]) and np.array_equal(it0[good], it1[good])
