@@ -466,7 +466,21 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                 if isinstance(dp, _problem.PresolveComplete):
                     # decided in presolve: upstream returns presolve's x and saves nothing (:1483-1488);
                     # the gradient of such instances is zero here
-                    xg = torch.as_tensor(dp.x, dtype=torch.float64, device=device).expand(cg.shape[0], -1)
+                    if dp.trivial is not None:  # x follows the sign of c (:1136-1142), instance by instance
+                        vi = torch.as_tensor(dp.trivial[0], dtype=torch.long, device=device)
+                        lbt = torch.as_tensor(dp.trivial[1], dtype=torch.float64, device=device)
+                        ubt = torch.as_tensor(dp.trivial[2], dtype=torch.float64, device=device)
+                        cv = cg.double()[:, vi]
+                        zero_c = torch.where(torch.isinf(ubt), torch.zeros_like(ubt), ubt)
+                        xg = torch.as_tensor(dp.x, dtype=torch.float64, device=device).repeat(cg.shape[0], 1)
+                        if dp.fixed is not None and dp.fixed[0].size and b_np is not None:  # singleton rows: b / a
+                            fv = dp.fixed[1] + (dp.fixed[2] @ np.atleast_2d(b_np).T).T  # (1 or B, n_fixed)
+                            fv = fv if fv.shape[0] == 1 or sel is None else fv[idx]
+                            xg[:, torch.as_tensor(dp.fixed[0], dtype=torch.long, device=device)] = torch.as_tensor(
+                                np.ascontiguousarray(fv), dtype=torch.float64, device=device)
+                        xg[:, vi] = torch.where(cv < 0, ubt, torch.where(cv > 0, lbt, zero_c))
+                    else:
+                        xg = torch.as_tensor(dp.x, dtype=torch.float64, device=device).expand(cg.shape[0], -1)
                     if single:
                         xg = xg.to(c.dtype)
                     saved.append((None, sel, None))

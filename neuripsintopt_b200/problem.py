@@ -25,10 +25,29 @@ TOL = 1e-9  # presolve tolerance (:918)
 class PresolveComplete(Exception):
     """Presolve decided the problem (:964-970,1003-1011,1026-1034,1113-1144)."""
 
-    def __init__(self, status, x):
+    def __init__(self, status, x, trivial=None, fixed=None):
         super().__init__("presolve complete, status %d" % status)
         self.status = status
         self.x = x
+        # (fixed_idx, const, map): values of the presolve-fixed variables = const + map @ b_eq (singleton rows, :1020-1041)
+        self.fixed = fixed
+        # (var_index, lb, ub) of the variables that are left when no non-trivial constraint is (:1113-1144): their values
+        # follow the sign of c — x = ub where c < 0, lb where c > 0, the upper bound (or 0 if infinite) where c == 0
+        self.trivial = trivial
+
+    def solution(self, c, b_eq=None):
+        """x (n_x) for the cost vector c (numpy): the presolve values, with the sign rule of :1136-1142 applied to the
+        variables no constraint is left for.  (Upstream returns only those variables, a vector of their number, from
+        its `complete` branch :1483-1488; here every variable is reported, like every other outcome does.)"""
+        x = np.array(self.x, dtype=np.float64)
+        if self.fixed is not None and b_eq is not None and self.fixed[0].size:
+            x[self.fixed[0]] = self.fixed[1] + self.fixed[2] @ np.asarray(b_eq, dtype=np.float64)
+        if self.trivial is not None:
+            vi, lb, ub = self.trivial
+            cv = np.asarray(c, dtype=np.float64)[vi]
+            zero_c = np.where(np.isinf(ub), 0.0, ub)
+            x[vi] = np.where(cv < 0, ub, np.where(cv > 0, lb, zero_c))
+        return x
 
 
 def clean_bounds(bounds, n_x):
@@ -184,6 +203,7 @@ def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=
     if b_eq_v is not None and b_eq_v.ndim != 1:
         raise ValueError("build_standard_form takes a single b_eq; pass batches to StandardForm.b_std")
     lb, ub = clean_bounds(bounds, n_x)
+    lb_raw, ub_raw = lb.copy(), ub.copy()  # the caller's bounds: what upstream's post-solve adjusts with (:1263-1274)
     x_pre = np.zeros(n_x)
 
     # b_eq enters linearly: track every right-hand side as (const, sparse map of b_eq)
@@ -291,9 +311,13 @@ def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=
     nvar = var_index.size
 
     if presolve and A_eq3.nnz == 0 and A_ub3.nnz == 0:
-        # no non-trivial constraints left (:1113-1144): the answer depends on c only through its sign;
-        # callers handle this rare case through the exception (x is filled where it is c-independent).
-        raise PresolveComplete(0, x_pre)
+        # no non-trivial constraints left (:1113-1144): the answer depends on c only through its sign; callers get the
+        # c-independent part (fixed variables) in x and the bounds of the remaining variables for the sign rule
+        x_done = x_pre.copy()
+        if b_eq_v is not None or not fixed_by_row:
+            x_done[fixed_idx] = fixed_const0 + (fixed_from_beq @ b_eq_v if (n_eq and b_eq_v is not None) else 0.0)
+        raise PresolveComplete(0, x_done, trivial=(var_index, lb_k.copy(), ub_k.copy()),
+                               fixed=(fixed_idx, fixed_const0, fixed_from_beq))
 
     # -- _get_Abc (:333-523) ------------------------------------------------------------------------
     lbs, ubs = lb_k.copy(), ub_k.copy()
@@ -326,7 +350,15 @@ def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=
     free_cols[i_free] = nvar + np.arange(i_free.size)
     # lower-bound shift (:510-519)
     shift = np.where(np.isinf(lbs), 0.0, lbs)
-    x_shift = shift.copy()
+    # Post-solve constants (:1263-1274).  Upstream undoes the substitutions with the CALLER's bounds, not with the bounds
+    # presolve tightened through singleton inequality rows (:1048-1072): x = x' + lb_user (or ub_user - x').  The same is
+    # done here whenever the user's bound is of the same kind as the one _get_Abc substituted with; if presolve changed
+    # the kind (a free variable that a singleton row bounded), upstream's loop reads a wrong column, and the
+    # mathematically right constant is used instead.
+    lbr, ubr = lb_raw[var_index], ub_raw[var_index]
+    x_shift = np.where(nolb, 0.0, np.where(np.isfinite(lbr), lbr, shift))  # flipped variables: ub - x' has it all
+    same_kind = nolb & np.isinf(lbr) & np.isfinite(ubr)
+    x_flip_ub[same_kind] = ubr[same_kind]
     b_const = np.concatenate([ubs[has_ub], bub_const, beq_const]) - A_std[:, :nvar] @ shift
     b_map = sp.vstack([sp.csr_matrix((nb, n_eq)), bub_map, beq_map], format="csr")
     sf = StandardForm(

@@ -74,7 +74,10 @@ def standard_form(c, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=None, to
     b_eq = np.zeros(0) if b_eq is None or np.size(b_eq) == 0 else np.array(b_eq, dtype=np.float64).reshape(-1)
     b_ub = np.zeros(0) if b_ub is None or np.size(b_ub) == 0 else np.array(b_ub, dtype=np.float64).reshape(-1)
     lb, ub = _broadcast_bounds(bounds, n_x)
-    out = dict(n_x=n_x, complete=False, status=0)
+    # the caller's list as given (one tuple, or one per variable): _postprocess adjusts with it (:1263-1274)
+    raw_bounds = [tuple(None if (v is None or (isinstance(v, float) and np.isinf(v))) else float(v) for v in bd)
+                  for bd in (bounds or [])]
+    out = dict(n_x=n_x, complete=False, status=0, raw_bounds=raw_bounds)
 
     # ---- _presolve (:918-1161), single pass, rule order preserved -----------------------
     x_pre = np.zeros(n_x)
@@ -203,13 +206,29 @@ def standard_form(c, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=None, to
 
 
 def postprocess(x_hat, sf):
-    """_postprocess (:1241-1285): re-insert fixed variables in ascending index order,
-    truncate to n_x.  The bound 'adjustment' loop (:1263-1274) runs over the caller's raw
-    one-element bounds list, i.e. adds lb to x[0] only; lb=0 in every driver."""
+    """_postprocess (:1241-1285): re-insert fixed variables in ascending index order, undo the variable substitutions,
+    truncate to n_x.  The adjustment loop (:1261-1274) runs over the CALLER's raw bounds list: with the one-element list
+    every driver passes, only x[0] is adjusted (lb = 0 there), with one entry per variable every
+    non-fixed variable is — by the caller's bounds, not by the ones presolve tightened."""
     x = list(np.asarray(x_hat, dtype=np.float64))
     for i, v in zip(sf["fixed_idx"], sf["fixed_val"]):
         x.insert(int(i), float(v))
-    return np.array(x)[: sf["n_x"]]
+    x = np.array(x)
+    n_x = sf["n_x"]
+    no_adjust = set(int(i) for i in sf["fixed_idx"])
+    n_unbounded = 0
+    for i, bnds in enumerate(sf.get("raw_bounds") or []):
+        if i in no_adjust:
+            continue
+        lb, ub = bnds
+        if lb is None and ub is None:
+            n_unbounded += 1
+            x[i] = x[i] - x[n_x + n_unbounded - 1]
+        elif lb is None:
+            x[i] = ub - x[i]
+        else:
+            x[i] += lb
+    return x[:n_x]
 
 
 # --------------------------------------------------------------------------------------

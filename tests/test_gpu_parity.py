@@ -64,16 +64,26 @@ def _check_case(name, z, case, batched_inp, per_instance_inp):
         r = O.ipofunc(case["c"][i], case["g"][i], variant=variant, bounds=kw.get("bounds"), thr=kw.get("thr"),
                       max_iter=kw.get("max_iter", 1000), damping=damping, **inp)
         sf = r["sf"]
-        # x* and objective.  Early-stopped runs (the experiments' mode) pin the whole trajectory: 1e-6 on x.
-        # Converged runs end at cond(M) ~ 1e16: the objective is pinned to 1e-6, but the last
-        # iterate itself is only determined to ~1e-4 (the reference's own float32 output sits at the same
-        # distance from the fp64 oracle), so x gets 1e-3 there.
-        x_tol = X_TOL if thr > 0 else 1e-3
-        assert _relinf(xs[i], r["x"]) < x_tol, (name, variant, thr, i, _relinf(xs[i], r["x"]))
+        # x* and objective: 1e-6 both, early-stopped AND converged (measured: <= 3.2e-8 on every converged fixture,
+        # profiles/r02_converged_parity.txt) — unless the LP itself does not determine x* that well.  That is measured,
+        # not assumed: the oracle is run a second time on the same LP with its constraint rows permuted (identical
+        # mathematics, different rounding).  One converged Energy instance has a degenerate optimal face: the oracle moves
+        # by 5.9e-5 under that permutation (objective: 3.7e-9), and the kernel sits 1.6e-4 from it.  The tolerance on x is
+        # max(1e-6, 10 x the oracle's own permutation noise); the objective keeps 1e-6 everywhere.
+        x_tol, ref_tol = X_TOL, 5e-6
+        if thr == 0:
+            from tests.gpu_converged_parity import permuted
+            rp = O.ipofunc(case["c"][i], case["g"][i], variant=variant, bounds=kw.get("bounds"), thr=kw.get("thr"),
+                           max_iter=kw.get("max_iter", 1000), damping=damping, **permuted(inp))
+            noise = _relinf(rp["x"], r["x"])
+            x_tol, ref_tol = max(X_TOL, 10.0 * noise), max(5e-6, 10.0 * noise)
+        ex = _relinf(xs[i], r["x"])
+        print("parity %s %s thr=%g inst %d: x %.2e (tol %.1e)" % (name, variant, thr, i, ex, x_tol))
+        assert ex < x_tol, (name, variant, thr, i, ex, x_tol)
         c64 = case["c"][i].astype(np.float64)
         assert abs(c64 @ xs[i] - c64 @ r["x"]) <= X_TOL * max(1.0, abs(c64 @ r["x"])), (name, i)
         # the reference's own float32 output
-        assert _relinf(xs[i], case["x"][i].astype(np.float64)) < (5e-6 if thr > 0 else 1e-3), (name, i)
+        assert _relinf(xs[i], case["x"][i].astype(np.float64)) < ref_tol, (name, i)
         if thr > 0:
             assert iters[i] == r["iters"] == case["iters"][i], (name, i, iters[i], r["iters"])
             assert _rel2(gs[i], r["grad"]) < G_TOL, (name, variant, thr, i, _rel2(gs[i], r["grad"]))
@@ -623,3 +633,54 @@ def test_breakdown_is_contained_to_its_instance():
     good = [i for i in range(k) if i != bad]
     assert (st1[good] == 0).all() and (st0 == 0).all()
     assert np.array_equal(x0[good], x1[good]) and np.array_equal(it0[good], it1[good])
+
+
+@pytest.mark.parametrize("variant", ["whole", "alter"])
+def test_mixed_bounds_against_reference_and_oracle(variant):
+    """Finite boxes, shifted lower bounds, upper-only bounds (x = ub - x'), free variables (x = x+ - x-), a
+    presolve-fixed variable and a singleton inequality row on the GPU: against the oracle (1e-6 / 1e-5) and against the
+    untouched reference's float32 outputs (tests/golden/bounds.npz, oracle/gen_golden_bounds.py)."""
+    import os
+    from oracle.gen_golden_bounds import BOUNDS
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "bounds.npz"))
+    assert int(z["n_lps"]) >= 2
+    for k in range(int(z["n_lps"])):
+        inp = dict(A=z["lp%d_A" % k], b=z["lp%d_b" % k], G=z["lp%d_G" % k], h=z["lp%d_h" % k])
+        c, g = z["lp%d_c" % k], z["lp%d_g" % k]
+        for thr, tag in ((0.1, "thr"), (None, "conv")):
+            kw = dict(bounds=BOUNDS, thr=thr, damping=1e-3, max_iter=200)
+            xs, gs, status, iters, _ = _run_gpu(variant, kw, inp, c[None, :], g[None, :])
+            r = O.ipofunc(c, g, variant=variant, **kw, **inp)
+            x_ref = z["lp%d_%s_%s_x" % (k, variant, tag)].astype(np.float64)
+            assert status[0] == 0
+            assert _relinf(xs[0], r["x"]) < X_TOL, (k, variant, thr, _relinf(xs[0], r["x"]))
+            assert _relinf(xs[0], x_ref) < 5e-6, (k, variant, thr, _relinf(xs[0], x_ref))
+            if thr:
+                assert iters[0] == r["iters"] == int(z["lp%d_%s_%s_iters" % (k, variant, tag)])
+                assert _rel2(gs[0], r["grad"]) < G_TOL, (k, variant, _rel2(gs[0], r["grad"]))
+            else:
+                # (not against HiGHS: upstream's post-solve shifts by the caller's lower bound even where a singleton
+                # inequality row tightened it, :1048-1072 vs :1274, so the reported x is not the LP's minimiser there)
+                c64 = c.astype(np.float64)
+                assert abs(c64 @ xs[0] - c64 @ r["x"]) <= 1e-6 * max(1.0, abs(c64 @ r["x"]))
+
+
+def test_trivial_presolve_outcome_on_the_device():
+    """Presolve decides the whole problem (ip_model_whole.py:1113-1144): no launch, x follows the sign of each
+    instance's c, zero gradient.  Values pinned by the reference (tests/golden/bounds.npz)."""
+    import os
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "bounds.npz"))
+    tb = [tuple(float(v) for v in r) for r in z["trivial_bounds"]]
+    f = IPOfunc(_tt(z["trivial_A"]), _tt(z["trivial_b"]), torch.Tensor(), torch.Tensor(), bounds=tb, thr=0.1)
+    ct = torch.tensor(z["trivial_c"], dtype=torch.float32, device="cuda", requires_grad=True)
+    x = f(ct)
+    x.sum().backward()
+    torch.cuda.synchronize()
+    xn = x.detach().cpu().numpy()
+    expect = np.array([[0.0, 1.5, 6.0, 3.0], [5.0, 1.5, 6.0, 1.0], [5.0, 1.5, -2.0, 3.0]])
+    np.testing.assert_allclose(xn, expect, atol=0)
+    kept = [3, 2, 0]  # the one variable presolve leaves in each instance: what upstream returns
+    for i in range(3):
+        assert xn[i, kept[i]] == z["trivial_x"][i][0]
+    assert float(ct.grad.abs().max()) == 0.0

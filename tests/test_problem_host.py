@@ -145,3 +145,25 @@ def test_presolve_outcomes():
         PR.clean_bounds([(2.0, 1.0)], 3)
     with pytest.raises(ValueError):
         PR.build_standard_form(3, np.array([[1.0, np.nan, 0]]), np.array([1.0]))
+
+
+def test_trivial_presolve_outcome_follows_the_sign_of_c():
+    """No non-trivial constraint left after presolve (ip_model_whole.py:1113-1144): x = ub where c < 0, lb where c > 0,
+    the finite upper bound (else 0) where c == 0.  Pinned by the reference's own output (tests/golden/bounds.npz,
+    oracle/gen_golden_bounds.py): upstream returns only the variables presolve did not fix, in order."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "bounds.npz"))
+    A, b = z["trivial_A"].astype(np.float64), z["trivial_b"].astype(np.float64)
+    tb = [tuple(r) for r in z["trivial_bounds"]]
+    for c, x_ref in zip(z["trivial_c"].astype(np.float64), z["trivial_x"]):
+        zc = PR.zero_columns(A, None, 4)
+        with pytest.raises(PR.PresolveComplete) as e:
+            PR.build_standard_form(4, A, b, None, None, tb, np.sign(c[zc]))
+        x = e.value.solution(c)
+        assert e.value.status == 0 and x[1] == 1.5  # the singleton row 2 x1 = 3
+        with pytest.raises(PR.PresolveComplete) as e2:  # right-hand side supplied later (per-instance b): same answer
+            PR.build_standard_form(4, A, None, None, None, tb, np.sign(c[zc]))
+        np.testing.assert_allclose(e2.value.solution(c, b), x, atol=0)
+        np.testing.assert_allclose(x[e.value.trivial[0]], x_ref.astype(np.float64), atol=0)
+        lo, hi = np.array(tb).T
+        assert ((x >= lo) & (x <= hi)).all()
