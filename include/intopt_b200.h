@@ -146,7 +146,8 @@ int intopt_backward_values(const IntoptProblem* p, int B, int mode, double dampi
  *           written to c_dev / grad_x_dev, which are then outputs (the packed c is what the backward call wants as c_dev).
  *   output: user entry i (< n_out) = std[out_idx[i]], or out_const[i] where out_idx[i] < 0 (out_const NULL: 0).  Forward:
  *           x with the presolve-fixed variables re-inserted (_postprocess, ip_model_whole.py:1241-1285; xhat_dev may then
- *           be NULL); backward: c_grad[var_index] = dc, zeros elsewhere (:1559-1560). */
+ *           be NULL); backward: c_grad[var_index] = dc, zeros elsewhere (:1559-1560); grad_c_dev is then NOT written (it must still
+ *           be a valid pointer). */
 typedef struct IntoptUserMap {
   const void* in_dev;
   int in_is_f32;

@@ -7,6 +7,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h>  // CUtensorMap and its enums only: cuTensorMapEncodeTiled is resolved through the runtime (no -lcuda)
+
 #include "intopt_dense.cuh"
 #include "intopt_internal.hpp"
 
@@ -16,6 +18,9 @@ struct IntoptDense {
   double* At = nullptr;      // n64 x m64
   double* rowsum = nullptr;  // A 1
   double* b = nullptr;       // m or null
+  // TMA descriptors of the padded A: box = 16 columns (128 bytes) x 128 / 64 rows, 128-byte swizzle
+  dn::TmaDesc tmap128{}, tmap64{};
+  bool use_tma = false;
   std::vector<void*> allocs;
   // completion signalling of the iteration loop (one forward call at a time per handle)
   mutable std::mutex mu;
@@ -120,6 +125,30 @@ constexpr int kGemmSmem = dn::GemmProd::SMEM_DOUBLES * 8;
 constexpr int kSyrk128Smem = dn::SyrkCfg<128, 512>::G::SMEM_DOUBLES * 8;
 constexpr int kSyrk64Smem = dn::SyrkCfg<64, 128>::G::SMEM_DOUBLES * 8;
 constexpr int kCholSmem = dn::CHOL_SMEM_DOUBLES * 8;
+constexpr int kSyrkTma128Smem = dn::SyrkTma<128, 512>::SMEM_BYTES;
+constexpr int kSyrkTma64Smem = dn::SyrkTma<64, 128>::SMEM_BYTES;
+
+// cuTensorMapEncodeTiled through cudaGetDriverEntryPoint: tiles of `box_rows` rows x 16 doubles of a row-major
+// (rows x cols) fp64 matrix, 128-byte swizzle.  Returns false if the driver entry point is unavailable.
+bool make_tile_map(dn::TmaDesc* out, const double* base, int rows, int cols, int box_rows) {
+  static_assert(sizeof(CUtensorMap) == sizeof(dn::TmaDesc), "CUtensorMap is 128 bytes");
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess)
+    return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * 8};
+  const cuuint32_t box[2] = {(cuuint32_t)dn::KT, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = ((EncodeFn)fn)(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim,
+                                    gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 int solve_smem(int nr, int m64) { return (nr * m64 + nr * dn::NB + 16 * nr * dn::NB) * 8; }
 
 std::once_flag g_attr_once;
@@ -132,6 +161,8 @@ void set_attrs() {
   set((const void*)dn::dense_gemm_kernel, kGemmSmem);
   set((const void*)dn::dense_syrk_kernel<128, 512>, kSyrk128Smem);
   set((const void*)dn::dense_syrk_kernel<64, 128>, kSyrk64Smem);
+  set((const void*)dn::dense_syrk_tma_kernel<128, 512>, kSyrkTma128Smem);
+  set((const void*)dn::dense_syrk_tma_kernel<64, 128>, kSyrkTma64Smem);
   set((const void*)dn::dense_chol_col_kernel, kCholSmem);
   set((const void*)dn::dense_chol_trsm_kernel, kCholSmem);
   set((const void*)dn::dense_solve_kernel<1>, solve_smem(1, 4096));
@@ -148,7 +179,15 @@ void gemm(const double* In, long long ld_in, int rows, const double* W, long lon
 // M_b = A diag(D_b) A^T + delta I for the active instances, then its tiled Cholesky factorisation (in place) with the
 // inverses of the diagonal blocks.
 void assemble_and_factor(const IntoptDense* d, const dn::DenseState& s, int Bc, double delta, cudaStream_t st) {
-  if (d->m64 % 128 == 0) {
+  if (d->use_tma && d->m64 % 128 == 0) {
+    const int T = d->m64 / 128;
+    dn::dense_syrk_tma_kernel<128, 512><<<dim3(T * (T + 1) / 2, Bc), 512, kSyrkTma128Smem, st>>>(
+        d->tmap128, d->n64, d->m, d->m64, s.D, d->n64, delta, s.M, s.active);
+  } else if (d->use_tma) {
+    const int T = d->m64 / 64;
+    dn::dense_syrk_tma_kernel<64, 128><<<dim3(T * (T + 1) / 2, Bc), 128, kSyrkTma64Smem, st>>>(
+        d->tmap64, d->n64, d->m, d->m64, s.D, d->n64, delta, s.M, s.active);
+  } else if (d->m64 % 128 == 0) {
     const int T = d->m64 / 128;
     dn::dense_syrk_kernel<128, 512><<<dim3(T * (T + 1) / 2, Bc), 512, kSyrk128Smem, st>>>(d->A, d->n64, d->m, d->m64, s.D,
                                                                                       d->n64, delta, s.M, s.active);
@@ -253,6 +292,11 @@ int create(IntoptDense** out, int m, int n, const int* rowptr, const int* colidx
     if (err) *err = std::string("dense path set-up: ") + cudaGetErrorString(e);
     destroy(d);
     return -100 - (int)e;
+  }
+  {  // TMA staging of the A tiles (INTOPT_DENSE_TMA=0: the cp.async variant)
+    const char* v = std::getenv("INTOPT_DENSE_TMA");
+    d->use_tma = !(v && v[0] == '0') && make_tile_map(&d->tmap128, d->A, d->m64, d->n64, 128) &&
+                 make_tile_map(&d->tmap64, d->A, d->m64, d->n64, 64);
   }
   const char* gb = std::getenv("INTOPT_DENSE_WS_GB");
   d->ws_budget = (size_t)((gb && *gb ? std::atof(gb) : 32.0) * (double)(1ull << 30));

@@ -214,6 +214,152 @@ __global__ void __launch_bounds__(NTHR) dense_syrk_kernel(const double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The same assembly with the A tiles staged by TMA: one elected thread issues 2-D tensor copies
+// (cp.async.bulk.tensor, the tile box {16 columns x TS rows} described by a CUtensorMap of the padded A, 128-byte
+// swizzle) plus a bulk copy of the 16 weights of the stage; the copies complete on an mbarrier per pipeline stage.  No
+// thread spends issue slots or registers on addresses, and the 128-byte swizzle (16-byte chunk c of row r lands at chunk
+// c ^ (r & 7)) makes the DMMA fragment reads conflict free without padding.  Every instance of the batch pulls the same
+// A tiles: after the first CTAs they come out of L2.
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(64) TmaDesc {
+  unsigned long long opaque[16];  // a CUtensorMap (128 bytes), kept opaque here so that this header needs no <cuda.h>
+};
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const TmaDesc* desc, int x, int y, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(desc), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int TS, int NTHR>
+struct SyrkTma {
+  static constexpr int WM = 32, WN = 32, MT = 4, NT = 4;
+  static constexpr int WARPS_N = TS / WN;
+  static constexpr int TILE_BYTES = TS * KT * 8;                    // one operand tile of a stage (TS rows x 128 bytes)
+  static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 1024;         // two operand tiles + the weights (padded to 1 KB)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 64;  // (+ alignment slack + the mbarriers)
+  static_assert((TS / WM) * (TS / WN) * 32 == NTHR, "warp grid must cover the tile");
+};
+
+template <int TS, int NTHR>
+__global__ void __launch_bounds__(NTHR) dense_syrk_tma_kernel(const __grid_constant__ TmaDesc tmapA, int n64, int m, int m64,
+                                                              const double* __restrict__ D, long long ld_d, double delta,
+                                                              double* __restrict__ Mout, const int* __restrict__ active) {
+  using C = SyrkTma<TS, NTHR>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int b = blockIdx.y;
+  if (active && !active[b]) return;
+  // 1 KB aligned stage buffers (the 128-byte swizzle pattern repeats every 8 rows = 1 KB)
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + STAGES * C::STAGE_BYTES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ti = tri_row(blockIdx.x), tj = blockIdx.x - ti * (ti + 1) / 2;
+  const int wi = warp / C::WARPS_N, wj = warp % C::WARPS_N;
+  const int wm = wi * C::WM, wn = wj * C::WN;
+  const bool compute = !(ti == tj && wj > wi);
+  const double* dsc = D + (long long)b * ld_d;
+  const int nk = n64 / KT;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int kt) {  // one thread: the stage's two tiles and its weights, all on one mbarrier
+    const int s = kt % STAGES;
+    unsigned char* st = base + s * C::STAGE_BYTES;
+    mbar_expect_tx(bars + s, 2 * C::TILE_BYTES + KT * 8);
+    tma_load_2d(st, &tmapA, kt * KT, ti * TS, bars + s);
+    tma_load_2d(st + C::TILE_BYTES, &tmapA, kt * KT, tj * TS, bars + s);
+    bulk_load_1d(st + 2 * C::TILE_BYTES, dsc + kt * KT, KT * 8, bars + s);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < STAGES && s < nk; ++s) issue(s);
+  }
+  double acc[C::MT][C::NT][2];
+#pragma unroll
+  for (int i = 0; i < C::MT; ++i)
+#pragma unroll
+    for (int j = 0; j < C::NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int kk = lane & 3, rr = lane >> 2;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int s = kt % STAGES;
+    mbar_wait(bars + s, (unsigned)((kt / STAGES) & 1));
+    if (compute) {
+      const unsigned char* Pb = base + s * C::STAGE_BYTES;
+      const unsigned char* Qb = Pb + C::TILE_BYTES;
+      const double* Ds = reinterpret_cast<const double*>(Qb + C::TILE_BYTES);
+#pragma unroll
+      for (int k4 = 0; k4 < KT / 4; ++k4) {
+        // element (row r, column k) of a swizzled tile: byte r * 128 + (((k >> 1) ^ (r & 7)) << 4) + (k & 1) * 8
+        const int k = 4 * k4 + kk;
+        double a[C::MT], bq[C::NT];
+#pragma unroll
+        for (int i = 0; i < C::MT; ++i) {
+          const int r = wm + 8 * i + rr;
+          a[i] = *reinterpret_cast<const double*>(Pb + r * 128 + (((k >> 1) ^ (r & 7)) << 4) + (k & 1) * 8);
+        }
+#pragma unroll
+        for (int j = 0; j < C::NT; ++j) {
+          const int r = wn + 8 * j + rr;
+          bq[j] = *reinterpret_cast<const double*>(Qb + r * 128 + (((k >> 1) ^ (r & 7)) << 4) + (k & 1) * 8);
+        }
+        const double d = Ds[k];
+#pragma unroll
+        for (int i = 0; i < C::MT; ++i) a[i] *= d;
+#pragma unroll
+        for (int i = 0; i < C::MT; ++i)
+#pragma unroll
+          for (int j = 0; j < C::NT; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], bq[j]);
+      }
+    }
+    __syncthreads();  // every warp is done with stage s: it may be refilled
+    if (tid == 0 && kt + STAGES < nk) issue(kt + STAGES);
+  }
+  if (!compute) return;
+  double* Mb = Mout + (long long)b * m64 * m64;
+#pragma unroll
+  for (int i = 0; i < C::MT; ++i)
+#pragma unroll
+    for (int j = 0; j < C::NT; ++j) {
+      const int r = ti * TS + wm + 8 * i + rr, c = tj * TS + wn + 8 * j + 2 * kk;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cc = c + e;
+        if (cc > r) continue;
+        double v = acc[i][j][e];
+        if (cc == r) v = r < m ? v + delta : 1.0;
+        Mb[(long long)r * m64 + cc] = v;
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // 64x64 diagonal block: Cholesky in shared memory, then the explicit inverse of the factor (what the panel
 // TRSM and the substitutions multiply by).  S (64 x 64, row stride LDD, lower part valid) is overwritten by L;
 // X (same shape) receives L^-1 (lower, zeros above).  256 threads.  tmp: 64 * LDD doubles, rinv: 64 doubles.

@@ -2002,13 +2002,18 @@ struct BwdParams {
   int factor_in_smem, gather_in_smem;
 };
 
-// c_grad[var_index] = dc, zeros elsewhere (:1559-1560), in the caller's layout and precision (after a CTA barrier
-// that completes gc)
-IO_DEV void backward_unpack(const CtaCtx& cx, const BwdParams& a, int inst, const double* gc) {
-  if (!a.um.out) return;
-  CTA_FOR(i, a.um.n_out) {
-    const int k = a.um.out_idx[i];
-    um_store(a.um, inst, i, k >= 0 ? gc[k] : 0.0);
+// c_grad[var_index] = dc, zeros elsewhere (:1559-1560).  With a mapped output the result goes straight to the caller's
+// layout and precision and the fp64 staging row grad_c_dev is NOT written (27 MB per Energy batch saved); without one it
+// goes to grad_c_dev.  `val(k)` evaluates entry k of dc.
+template <class F>
+IO_DEV void backward_emit(const CtaCtx& cx, const BwdParams& a, int inst, double* gc, F val) {
+  if (a.um.out) {
+    CTA_FOR(i, a.um.n_out) {
+      const int k = a.um.out_idx[i];
+      um_store(a.um, inst, i, k >= 0 ? val(k) : 0.0);
+    }
+  } else {
+    CTA_FOR(k, a.nvar) gc[k] = val(k);
   }
 }
 
@@ -2073,10 +2078,9 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   const bool ok = *S.flag == 0;
   if (!ok) {
     // the reference raises LinAlgError (:1546-1547); here: zero gradient + status
-    CTA_FOR(k, nvar) gc[k] = 0.0;
+    backward_emit(cx, a, inst, gc, [](int) { return 0.0; });
     if (cx.tid == 0) a.status[inst] = ST_BREAKDOWN;
     CTA_SYNC();
-    backward_unpack(cx, a, inst, gc);
     return;
   }
   if (!whole) {
@@ -2084,10 +2088,9 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
     block_solve<1>(cx, P, M, L, rhs1, S.ybuf);
     at_mult<1>(cx, P, M, v, nullptr, G, nullptr);
     CTA_SYNC();
-    CTA_FOR(k, nvar) gc[k] = -x2[k] * (g[k] - G[k]) / mu;
+    backward_emit(cx, a, inst, gc, [&](int k) { return -x2[k] * (g[k] - G[k]) / mu; });
     if (cx.tid == 0) a.status[inst] = ST_OK;
     CTA_SYNC();
-    backward_unpack(cx, a, inst, gc);
     return;
   }
   CTA_FOR(i, m) {
@@ -2120,10 +2123,9 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   }
   cta_sum<4>(cx, acc);
   const double s = (xg + acc[0] - acc[2]) / (acc[3] - acc[1] + mu / (tau * tau));  // :1552-1553
-  CTA_FOR(k, nvar) gc[k] = ug[k] + pp[k] * s;                                      // :1554-1556
+  backward_emit(cx, a, inst, gc, [&](int k) { return ug[k] + pp[k] * s; });  // :1554-1556
   if (cx.tid == 0) a.status[inst] = ST_OK;
   CTA_SYNC();
-  backward_unpack(cx, a, inst, gc);
 }
 
 }  // namespace intopt

@@ -51,6 +51,9 @@ class IntoptEnergyLearner:
         self.device = torch.device(device)
         self.F = torch.as_tensor(F.toarray(), dtype=torch.float32, device=self.device)  # (n, 48)
         self.model = MultilayerRegression(input_size, hidden_size, 1, num_layers).to(self.device)
+        parallel.broadcast_parameters(self.model.parameters())
+        if optimizer is optim.Adam and self.device.type == "cuda":
+            hyperparams.setdefault("capturable", True)  # state on the device: the step can live inside a CUDA graph
         self.optimizer = optimizer(self.model.parameters(), **hyperparams)
         if lp_layer is None:
             from .ip_model_whole import IPOfunc
@@ -71,14 +74,83 @@ class IntoptEnergyLearner:
         self.optimizer.zero_grad()
         X_loc = parallel.shard(torch.as_tensor(X_days, dtype=torch.float32, device=self.device), rank, world)
         y_loc = parallel.shard(torch.as_tensor(y_days, dtype=torch.float32, device=self.device), rank, world)
-        c_true = y_loc @ self.F.t()
-        c_pred = self.costs(X_loc)
-        x = self.lp_layer(c_pred)
-        loss = (x * c_true).mean(dim=1).sum()  # sum over days of the reference's per-day loss (:426)
+        if X_loc.shape[0]:
+            c_true = y_loc @ self.F.t()
+            c_pred = self.costs(X_loc)
+            x = self.lp_layer(c_pred)
+            loss = (x * c_true).mean(dim=1).sum()  # sum over days of the reference's per-day loss (:426)
+        else:  # more ranks than days
+            loss = parallel.zero_loss(self.model.parameters())
         loss.backward()
         parallel.allreduce_gradients(self.model.parameters(), group=group)
         self.optimizer.step()
         return float(loss.detach())
+
+    # ---- the same step as ONE CUDA graph --------------------------------------------------------------------
+    def compile_step(self, batch_days, n_features, rank=0, world=1, group=None):
+        """Capture one training step for a FIXED minibatch size into a CUDA graph and return `step(X_days, y_days)`.
+
+        A step at the reference's batch of 24 days is launch- and Python-bound (a dozen small predictor / optimiser
+        kernels around the two solver launches): captured once, every later step is one graph launch — predictor
+        forward, the batched `IPOfunc` forward + backward (the library only enqueues kernels on the capturing stream),
+        predictor backward, the gradient all-reduce (NCCL is capturable) and the optimiser step.  The optimiser must be
+        capturable (`torch.optim.Adam(..., capturable=True)` — done by `__init__` for Adam on CUDA).  The returned
+        callable copies its inputs into the graph's static buffers, replays, and returns the loss (one device->host
+        read).  The eager `training_step` stays the reference for results: both produce the same numbers."""
+        dev = self.device
+        lo, hi = parallel.shard_bounds(batch_days, rank, world)
+        Xs = torch.zeros(hi - lo, self.n_items, n_features, dtype=torch.float32, device=dev)
+        ys = torch.zeros(hi - lo, self.n_items, dtype=torch.float32, device=dev)
+        loss_buf = torch.zeros((), dtype=torch.float32, device=dev)
+
+        def body():
+            c_true = ys @ self.F.t()
+            x = self.lp_layer(self.costs(Xs))
+            loss = (x * c_true).mean(dim=1).sum()
+            loss.backward()
+            parallel.allreduce_gradients(self.model.parameters(), group=group)
+            self.optimizer.step()
+            return loss
+
+        self.model.train()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        params0 = [p.detach().clone() for p in self.model.parameters()]
+        had_state = len(self.optimizer.state) > 0
+        opt0 = self.optimizer.state_dict() if had_state else None
+        with torch.cuda.stream(side):  # warm-up off the default stream (allocator, cold-start factor, NCCL, autograd)
+            Xs.normal_()
+            ys.uniform_(20.0, 120.0)
+            for _ in range(3):
+                self.optimizer.zero_grad(set_to_none=True)
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        with torch.no_grad():  # the warm-up steps must not count: restore parameters and optimiser state
+            for p, p0 in zip(self.model.parameters(), params0):
+                p.copy_(p0)
+            if had_state:
+                self.optimizer.load_state_dict(opt0)
+            else:
+                # a fresh optimiser: keep the state tensors the warm-up created (a lazy initialisation INSIDE the capture
+                # would be replayed, i.e. reset the moments at every step) and zero them in place
+                for st in self.optimizer.state.values():
+                    for v in st.values():
+                        if isinstance(v, torch.Tensor):
+                            v.zero_()
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            loss_buf.copy_(body().detach())
+        self._graph = graph  # keep alive
+
+        def step(X_days, y_days):
+            Xs.copy_(torch.as_tensor(X_days, dtype=torch.float32)[lo:hi], non_blocking=True)
+            ys.copy_(torch.as_tensor(y_days, dtype=torch.float32)[lo:hi], non_blocking=True)
+            graph.replay()
+            return loss_buf
+
+        return step
 
     # ---- the epoch / minibatch driver of the reference (Interior/intopt_energy_mlp.py:355-500) -------------
     def fit(self, X, y, X_validation=None, y_validation=None, epochs=1, batchsize=24, doScale=True, seed=None, shuffle=True,

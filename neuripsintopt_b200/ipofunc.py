@@ -398,6 +398,8 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
     def _tick():
         """Start a timed region for Runtime(): folds the pairs that have completed into the total first, so the list
         of pending CUDA events stays short however long one IPOfunc lives."""
+        if torch.cuda.is_current_stream_capturing():
+            return None  # inside a CUDA-graph capture: no timing events (they could not be read back anyway)
         ev = state["events"]
         while ev and ev[0][1].query():
             e0, e1 = ev.pop(0)
@@ -411,6 +413,8 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
         return e0
 
     def _tock(e0):
+        if e0 is None:
+            return
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         state["events"].append((e0, e1))

@@ -45,6 +45,7 @@ class IntoptShortestPathLearner:
         self.n_nodes = int(n_nodes)
         self.keep = np.setdiff1d(np.arange(self.n_nodes), np.asarray(removed_rows))
         self.net = net.to(self.device)
+        parallel.broadcast_parameters(self.net.parameters())
         self.optimizer = optimizer(self.net.parameters(), **hyperparams)
         self.opts = dict(bounds=[(0.0, None)], max_iter=max_iter, thr=thr, damping=damping, method=1,
                          check_finite=False)
@@ -71,8 +72,11 @@ class IntoptShortestPathLearner:
         y = torch.as_tensor(y, dtype=torch.float32, device=self.device)
         lo, hi = parallel.shard_bounds(len(pairs), rank, world)
         c_pred = self.net(X).squeeze(-1)
-        x = self.solve(c_pred, list(pairs)[lo:hi])
-        loss = (y * x).mean(dim=1).sum()  # sum over instances of the reference's per-instance loss (:426)
+        if hi > lo:
+            x = self.solve(c_pred, list(pairs)[lo:hi])
+            loss = (y * x).mean(dim=1).sum()  # sum over instances of the reference's per-instance loss (:426)
+        else:  # more ranks than instances: nothing to solve here, but the collective below needs every rank
+            loss = parallel.zero_loss(self.net.parameters())
         loss.backward()
         parallel.allreduce_gradients(self.net.parameters(), group=group)
         self.optimizer.step()
@@ -88,6 +92,7 @@ class IntoptKnapsackLearner:
                  **hyperparams):
         self.device = torch.device(device)
         self.model = model.to(self.device)
+        parallel.broadcast_parameters(self.model.parameters())
         self.optimizer = optimizer(self.model.parameters(), **hyperparams)
         self.budget = float(budget)
         self.opts = dict(bounds=[(0.0, 1.0)], max_iter=max_iter, thr=thr, damping=damping, check_finite=False)
@@ -108,8 +113,11 @@ class IntoptKnapsackLearner:
         y = torch.as_tensor(y, dtype=torch.float32, device=self.device)
         lo, hi = parallel.shard_bounds(y.shape[0], rank, world)
         prices = self.model(features)[lo:hi]
-        x = self.solve(prices, np.asarray(costs)[lo:hi])
-        loss = -(x * y[lo:hi]).mean(dim=1).sum()  # (:406) per minibatch, summed
+        if hi > lo:
+            x = self.solve(prices, np.asarray(costs)[lo:hi])
+            loss = -(x * y[lo:hi]).mean(dim=1).sum()  # (:406) per minibatch, summed
+        else:
+            loss = parallel.zero_loss(self.model.parameters())
         loss.backward()
         parallel.allreduce_gradients(self.model.parameters(), group=group)
         self.optimizer.step()

@@ -32,15 +32,42 @@ def allreduce_gradients(parameters, group=None, average: bool = False):
     is the right granularity on NVSwitch; no bucketing, no overlap machinery."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    params = [p for p in parameters if p.grad is not None]
+    # EVERY parameter takes part, with zeros where a rank has no gradient (an empty shard, an unused head): the flat
+    # buffers must have the same layout on every rank or the collective hangs / mixes parameters up
+    params = [p for p in parameters if p.requires_grad]
     if not params:
         return
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
         flat /= dist.get_world_size(group)
     off = 0
     for p in params:
-        n = p.grad.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        n = p.numel()
+        piece = flat[off:off + n].view_as(p)
+        if p.grad is None:
+            p.grad = piece.clone()
+        else:
+            p.grad.copy_(piece)
         off += n
+
+
+def broadcast_parameters(parameters, src: int = 0, group=None):
+    """Make every rank start from rank `src`'s parameters (data-parallel steps only keep replicas equal if they start
+    equal).  No-op without an initialised process group."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for p in parameters:
+            dist.broadcast(p.data, src=src, group=group)
+
+
+def zero_loss(parameters):
+    """A loss of exactly zero that still touches every parameter: what a rank with an EMPTY shard back-propagates, so
+    that its gradients exist (as zeros) and the all-reduce sees the same layout everywhere."""
+    total = None
+    for p in parameters:
+        if p.requires_grad:
+            t = p.sum() * 0.0
+            total = t if total is None else total + t
+    return total

@@ -8,13 +8,13 @@ from neuripsintopt_b200.ip_model_whole import IPOfunc
 from neuripsintopt_b200 import ipofunc as _ipo
 from oracle import hsd_numpy as O
 
-ladder = [(3, 10), (5, 20), (8, 30)]
-sel = [int(a) for a in sys.argv[1:]] or [0, 1]
+ladder = [(3, 10), (5, 20), (8, 30), (10, 60)]
+sel = [int(a) for a in sys.argv[1:]] or [0, 1, 2]
 for li in sel:
     M_, T_ = ladder[li]
     par = icon.load1_day01() if li == 0 else icon.synthesize(M_, T_, q=30, seed=0)
     A, b, G, h, F = icon.make_matrix_intopt(**par)
-    B = 128
+    B = int(os.environ.get("LADDER_BATCH", "1024" if li < 3 else "256"))  # config 4: batch 1024 (the last rung: 256)
     rng = np.random.default_rng(0)
     P = rng.uniform(20.0, 120.0, (B, F.shape[1]))
     c = np.asarray((F @ P.T).T, dtype=np.float32)
@@ -35,12 +35,16 @@ for li in sel:
         ex = max(ex, float(np.abs(x[i].detach().double().cpu().numpy() - r["x"]).max() / max(1.0, np.abs(r["x"]).max())))
         eg = max(eg, float(np.linalg.norm(ct.grad[i].double().cpu().numpy() - r["grad"]) / np.linalg.norm(r["grad"])))
         assert int(iters[i]) == r["iters"], (int(iters[i]), r["iters"])
+    for _ in range(5):  # warm-up: allocator, cold-start factor, clocks
+        cc = ct.detach().requires_grad_(True); f(cc).backward(gt)
+    torch.cuda.synchronize()
+    reps = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(3):
+    for _ in range(reps):
         cc = ct.detach().requires_grad_(True); f(cc).backward(gt)
     e1.record(); e1.synchronize()
-    ms = e0.elapsed_time(e1) / 3
+    ms = e0.elapsed_time(e1) / reps
     print("(M,T)=(%d,%d): std form %dx%d nnz %d | x_rel %.1e grad_rel %.1e iters %.2f bad %d | B=%d %.0f LP/s (%.2f ms/step) | smem %d B factor_in_smem %d gather_in_smem %d ctas/sm %d threads %d envelope %d | setup+first %.1f s" % (
         M_, T_, info["m"], info["n"], info["nnz"], ex, eg, float(iters.float().mean()), int((status != 0).sum()), B, B / ms * 1e3, ms,
         info["smem_bytes"], info["factor_in_smem"], info["gather_in_smem"], info["ctas_per_sm"], info["threads"], info["envelope"], t_first), flush=True)

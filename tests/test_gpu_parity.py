@@ -684,3 +684,33 @@ def test_trivial_presolve_outcome_on_the_device():
     for i in range(3):
         assert xn[i, kept[i]] == z["trivial_x"][i][0]
     assert float(ct.grad.abs().max()) == 0.0
+
+
+def test_graph_captured_training_step_equals_the_eager_one():
+    """IntoptEnergyLearner.compile_step: one training step (predictor, batched IPOfunc forward + backward, Adam) captured
+    into a CUDA graph gives the same losses and parameters as the eager step, step after step."""
+    from neuripsintopt_b200.data import icon
+    from neuripsintopt_b200.energy_learner import IntoptEnergyLearner
+    rng = np.random.default_rng(3)
+    B = 24
+    X = torch.tensor(rng.standard_normal((B, 48, 8)), dtype=torch.float32, device="cuda")
+    y = torch.tensor(rng.uniform(20.0, 120.0, (B, 48)), dtype=torch.float32, device="cuda")
+    res = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0)
+        lrn = IntoptEnergyLearner(icon.load1_day01(), input_size=8, thr=0.1, damping=1e-6, lr=1e-2)
+        with torch.no_grad():
+            lrn.model.net.weight.fill_(0.0)
+            lrn.model.net.bias.fill_(60.0)
+        step = (lambda: lrn.training_step(X, y)) if mode == "eager" else None
+        if mode == "graph":
+            g = lrn.compile_step(B, 8)
+            step = lambda: float(g(X, y))  # noqa: E731
+        losses = [step() for _ in range(4)]
+        res[mode] = (losses, lrn.model.net.weight.detach().cpu().numpy().copy(), lrn.model.net.bias.detach().cpu().numpy().copy())
+    le, we, be = res["eager"]
+    lg, wg, bg = res["graph"]
+    np.testing.assert_allclose(lg, le, rtol=1e-6)
+    np.testing.assert_allclose(wg, we, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(bg, be, rtol=1e-6)
+    assert le[-1] != le[0]  # the parameters move

@@ -77,6 +77,46 @@ def test_two_rank_step_equals_single_process_step():
     np.testing.assert_allclose(out[1][1], flat, rtol=1e-5, atol=1e-7)
 
 
+def _worker_uneven(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)  # different initial parameters per rank: the constructor must broadcast rank 0's
+        lrn = IntoptEnergyLearner(icon.load1_day01(), input_size=4, hidden_size=3, num_layers=2, device="cpu",
+                                  lp_layer=_surrogate, optimizer=torch.optim.SGD, lr=1e-3)
+        lrn.model.eval()
+        lrn.model.train = lambda *a, **k: lrn.model
+        Xd, yd = _data()
+        loss = lrn.training_step(Xd[:1], yd[:1], rank=rank, world=world)  # ONE day for two ranks: rank 1's shard is empty
+        flat = torch.cat([p.detach().reshape(-1) for p in lrn.model.parameters()])
+        out[rank] = (loss, flat.numpy().copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_more_ranks_than_instances_and_unequal_start():
+    """A rank with an empty shard still joins the gradient all-reduce (zero gradients, same buffer layout), and every
+    rank starts from rank 0's parameters: after the step all replicas are equal and equal to the one-process step."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_uneven, args=(2, port, out), nprocs=2, join=True)
+    torch.manual_seed(100)
+    ref = IntoptEnergyLearner(icon.load1_day01(), input_size=4, hidden_size=3, num_layers=2, device="cpu",
+                              lp_layer=_surrogate, optimizer=torch.optim.SGD, lr=1e-3)
+    ref.model.eval()
+    ref.model.train = lambda *a, **k: ref.model
+    Xd, yd = _data()
+    loss = ref.training_step(Xd[:1], yd[:1])
+    flat = torch.cat([p.detach().reshape(-1) for p in ref.model.parameters()]).numpy()
+    assert out[1][0] == 0.0 and abs(out[0][0] - loss) < 1e-4 * abs(loss)
+    np.testing.assert_allclose(out[0][1], flat, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(out[1][1], flat, rtol=1e-5, atol=1e-7)
+
+
 def test_icon_builder_matches_reference_matrices():
     """make_matrix_intopt (sparse, index-range based) reproduces the reference's dense torch builder output
     stored in the golden fixture (Interior/intopt_energy_mlp.py:124-168)."""
