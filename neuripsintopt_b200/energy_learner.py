@@ -93,7 +93,9 @@ class IntoptEnergyLearner:
         A step at the reference's batch of 24 days is launch- and Python-bound (a dozen small predictor / optimiser
         kernels around the two solver launches): captured once, every later step is one graph launch — predictor
         forward, the batched `IPOfunc` forward + backward (the library only enqueues kernels on the capturing stream),
-        predictor backward, the gradient all-reduce (NCCL is capturable) and the optimiser step.  The optimiser must be
+        predictor backward and the optimiser step.  With several ranks the step is two graphs (forward + backward, then
+        the optimiser) with the flat gradient all-reduce issued eagerly in between, so that no collective lives inside
+        a capture.  The optimiser must be
         capturable (`torch.optim.Adam(..., capturable=True)` — done by `__init__` for Adam on CUDA).  The returned
         callable copies its inputs into the graph's static buffers, replays, and returns the loss (one device->host
         read).  The eager `training_step` stays the reference for results: both produce the same numbers."""
@@ -103,11 +105,17 @@ class IntoptEnergyLearner:
         ys = torch.zeros(hi - lo, self.n_items, dtype=torch.float32, device=dev)
         loss_buf = torch.zeros((), dtype=torch.float32, device=dev)
 
-        def body():
+        distributed = world > 1
+
+        def fwd_bwd():
             c_true = ys @ self.F.t()
             x = self.lp_layer(self.costs(Xs))
             loss = (x * c_true).mean(dim=1).sum()
             loss.backward()
+            return loss
+
+        def body():
+            loss = fwd_bwd()
             parallel.allreduce_gradients(self.model.parameters(), group=group)
             self.optimizer.step()
             return loss
@@ -140,14 +148,25 @@ class IntoptEnergyLearner:
                             v.zero_()
         graph = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph):
-            loss_buf.copy_(body().detach())
-        self._graph = graph  # keep alive
+        if not distributed:
+            with torch.cuda.graph(graph):
+                loss_buf.copy_(body().detach())
+            self._graph = (graph,)  # keep alive
+        else:
+            with torch.cuda.graph(graph):
+                loss_buf.copy_(fwd_bwd().detach())
+            graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_opt, pool=graph.pool()):
+                self.optimizer.step()
+            self._graph = (graph, graph_opt)
 
         def step(X_days, y_days):
             Xs.copy_(torch.as_tensor(X_days, dtype=torch.float32)[lo:hi], non_blocking=True)
             ys.copy_(torch.as_tensor(y_days, dtype=torch.float32)[lo:hi], non_blocking=True)
             graph.replay()
+            if distributed:
+                parallel.allreduce_gradients(self.model.parameters(), group=group)
+                self._graph[1].replay()
             return loss_buf
 
         return step
