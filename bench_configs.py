@@ -27,6 +27,7 @@ def time_steps(fn, steps, warmup=3):
 def main():
     ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=1024); ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--thr", type=float, default=0.1)
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense (config 5) lines")
     args = ap.parse_args()
     from neuripsintopt_b200.ip_model_whole import IPOfunc
     from neuripsintopt_b200 import ipofunc as _ipo
@@ -77,6 +78,16 @@ def main():
                         bad_status=int((status != 0).sum()), smem_bytes=info["smem_bytes"], ctas_per_sm=info["ctas_per_sm"],
                         envelope=info["envelope"]))
         print(json.dumps(out[-1]))
+    # config 5: dense LPs through the lock-step dense path (batched DMMA assembly, tiled Cholesky); roofline against the
+    # MEASURED FP64 tensor-core peak.  Batches chosen so that a step stays within seconds; bench_dense.py runs the sweep.
+    if not args.no_dense:
+        import bench_dense
+        dmma = _capi.measure_dmma_peak(5) * 1e-3
+        for m_, B_ in ((256, 2048), (512, 512), (1024, 256)):
+            line = bench_dense.measure(m_, B_, args.thr if args.thr > 0 else None, steps=3, parity=1, dmma=dmma, dfma=peak)
+            line["roofline"] = dict(bound="fp64 tensor (DMMA)", achieved=line["achieved_tflops"], peak=dmma, unit="TFLOP/s",
+                                    frac=line["roofline_frac_dmma"])
+            print(json.dumps(line))
 
 
 if __name__ == "__main__":

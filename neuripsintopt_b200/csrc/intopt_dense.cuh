@@ -316,17 +316,20 @@ __global__ void __launch_bounds__(NTHR) dense_syrk_tma_kernel(const __grid_const
       const double* Ds = reinterpret_cast<const double*>(Qb + C::TILE_BYTES);
 #pragma unroll
       for (int k4 = 0; k4 < KT / 4; ++k4) {
-        // element (row r, column k) of a swizzled tile: byte r * 128 + (((k >> 1) ^ (r & 7)) << 4) + (k & 1) * 8
+        // element (row r, column k) of a swizzled tile: byte r * 128 + (((k >> 1) ^ (r & 7)) << 4) + (k & 1) * 8.
+        // The 8 rows of a DMMA fragment are taken 2 apart (tile t of a warp = rows 16 (t / 2) + (t % 2) + 2 rr): the
+        // 16 lanes of a half warp then see r & 7 = {0,2,4,6} + t % 2, i.e. eight different 16-byte chunks, and the
+        // 8-byte fragment loads are conflict free (consecutive rows would put two lanes on every chunk).
         const int k = 4 * k4 + kk;
         double a[C::MT], bq[C::NT];
 #pragma unroll
         for (int i = 0; i < C::MT; ++i) {
-          const int r = wm + 8 * i + rr;
+          const int r = wm + 16 * (i >> 1) + (i & 1) + 2 * rr;
           a[i] = *reinterpret_cast<const double*>(Pb + r * 128 + (((k >> 1) ^ (r & 7)) << 4) + (k & 1) * 8);
         }
 #pragma unroll
         for (int j = 0; j < C::NT; ++j) {
-          const int r = wn + 8 * j + rr;
+          const int r = wn + 16 * (j >> 1) + (j & 1) + 2 * rr;
           bq[j] = *reinterpret_cast<const double*>(Qb + r * 128 + (((k >> 1) ^ (r & 7)) << 4) + (k & 1) * 8);
         }
         const double d = Ds[k];
@@ -347,10 +350,11 @@ __global__ void __launch_bounds__(NTHR) dense_syrk_tma_kernel(const __grid_const
   for (int i = 0; i < C::MT; ++i)
 #pragma unroll
     for (int j = 0; j < C::NT; ++j) {
-      const int r = ti * TS + wm + 8 * i + rr, c = tj * TS + wn + 8 * j + 2 * kk;
+      // (same row interleave as the fragment loads: accumulator (rr, 2 kk + e) of tile (i, j))
+      const int r = ti * TS + wm + 16 * (i >> 1) + (i & 1) + 2 * rr;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int cc = c + e;
+        const int cc = tj * TS + wn + 16 * (j >> 1) + (j & 1) + 2 * (2 * kk + e);
         if (cc > r) continue;
         double v = acc[i][j][e];
         if (cc == r) v = r < m ? v + delta : 1.0;

@@ -183,3 +183,66 @@ def test_dense_path_per_instance_b_and_warm_start(dense_path):
     o2 = (x2.double() * ct.detach().double()).sum(1)
     o3 = (x3.double() * ct.detach().double()).sum(1)
     assert torch.allclose(o2, o3, rtol=5e-2, atol=5e-2)
+
+
+@pytest.mark.parametrize("m", [512, 1024])
+def test_large_dense_against_oracle(m):
+    """Config 5 at m = 512 and 1024 (n = 2m): early-stopped forward + backward of a small batch against the oracle —
+    1e-6 on x, 1e-5 on dL/dc, equal iteration counts."""
+    from neuripsintopt_b200 import ipofunc
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    ipofunc.clear_cache()
+    B = 3
+    A, b, c = gen_dense(m, B)
+    f = IPOfunc(torch.tensor(A), torch.tensor(b), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)], thr=0.1,
+                damping=1e-6)
+    ct = torch.tensor(c, device="cuda", requires_grad=True)
+    x = f(ct)
+    x.sum().backward()
+    torch.cuda.synchronize()
+    status, iters = IPOfunc.status()
+    assert int((status != 0).sum()) == 0
+    r = O.ipofunc(c[0], np.ones(2 * m, np.float32), A=A, b=b, bounds=[(0.0, None)], thr=0.1, damping=1e-6)
+    assert int(iters[0]) == r["iters"]
+    ex = _relinf(x[0].detach().double().cpu().numpy(), r["x"])
+    eg = _rel2(ct.grad[0].double().cpu().numpy(), r["grad"])
+    print("dense m=%d: x %.2e grad %.2e iters %d" % (m, ex, eg, r["iters"]))
+    assert ex < 1e-6 and eg < 1e-5, (m, ex, eg)
+    ipofunc.clear_cache()
+
+
+def test_m2048_smoke():
+    """m = 2048, n = 4096 (the largest shape of the sweep; the gather-list path refused anything beyond m ~ 600): the
+    normal-equations primitive against numpy, and one early-stopped forward + backward that ends with status 0 and a
+    finite gradient."""
+    from neuripsintopt_b200 import _capi, ipofunc
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    ipofunc.clear_cache()
+    m, n, B = 2048, 4096, 2
+    A, b, c = gen_dense(m, B)
+    L, h, info = _handle(A.astype(np.float64))
+    assert info["path"] == 1
+    rng = np.random.default_rng(0)
+    d = np.exp(rng.uniform(-3, 3, (1, n)))
+    rhs = rng.standard_normal((1, m))
+    dd, rr = torch.tensor(d, device="cuda"), torch.tensor(rhs, device="cuda")
+    ws = torch.empty(L.intopt_workspace_bytes(h, 1) // 8 + 1, dtype=torch.float64, device="cuda")
+    _capi.check(L.intopt_dense_normal_solve(h, 1, dd.data_ptr(), 1e-6, rr.data_ptr(), None, ws.data_ptr(), ws.numel() * 8,
+                                            None), "normal_solve")
+    torch.cuda.synchronize()
+    Md = torch.tensor(A.astype(np.float64), device="cuda")
+    M = (Md * dd) @ Md.T + 1e-6 * torch.eye(m, dtype=torch.float64, device="cuda")
+    res = (M @ rr[0] - torch.tensor(rhs[0], device="cuda")).abs().max() / (M.abs().max() * rr[0].abs().max() * m)
+    assert float(res) < 1e-13, float(res)
+    L.intopt_problem_destroy(h)
+    del ws, M, Md
+    f = IPOfunc(torch.tensor(A), torch.tensor(b), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)], thr=0.1,
+                damping=1e-6)
+    ct = torch.tensor(c, device="cuda", requires_grad=True)
+    x = f(ct)
+    x.sum().backward()
+    torch.cuda.synchronize()
+    status, iters = IPOfunc.status()
+    assert status.tolist() == [0, 0] and 2 <= int(iters.min()) and int(iters.max()) <= 6
+    assert torch.isfinite(x).all() and torch.isfinite(ct.grad).all() and float(ct.grad.abs().max()) > 0
+    ipofunc.clear_cache()
