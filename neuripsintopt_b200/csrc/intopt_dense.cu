@@ -27,6 +27,21 @@ struct IntoptDense {
   int* h_nactive = nullptr;  // pinned
   cudaEvent_t ev = nullptr;
   size_t ws_budget = 0;
+  // Forward as ONE CUDA graph: init kernel -> while-node whose body is an interior-point iteration -> epilogue.  The
+  // condition is set on the device (dense_loop_cond_kernel), so a forward call enqueues one graph launch and never
+  // waits on the host.  Graphs are cached per (workspace, chunk size, damping, pc, right-hand-side pointer): everything
+  // else a call varies travels through the argument block in device memory.
+  struct FwdGraph {
+    const void* ws;
+    int Bc, plain;
+    double damping;
+    const double* b_batch;
+    long long b_stride;
+    cudaGraphExec_t exec;
+  };
+  mutable std::vector<FwdGraph> graphs;
+  cudaStream_t cap_stream = nullptr;
+  bool use_graph = true;
 };
 
 namespace {
@@ -40,6 +55,8 @@ namespace {
     }                                                                                         \
   } while (0)
 
+constexpr size_t kArgsOffset = 256;
+static_assert(sizeof(dn::DenseFwdArgs) <= 1024, "argument block of the forward graph");
 int up64(int v) { return (v + 63) & ~63; }
 int up128(int v) { return (v + 127) & ~127; }
 
@@ -56,7 +73,7 @@ Layout make_layout(const IntoptDense* d, int Bc) {
   L.Bc = Bc;
   L.Bp = up128(Bc);
   const size_t nv = (size_t)L.Bp * d->n64 * 8, mv = (size_t)L.Bp * d->m64 * 8;
-  size_t o = 256;  // [0,256): n_active counter
+  size_t o = kArgsOffset + 1024;  // [0,256): n_active counter; [256, 256 + 1 KB): the argument block of the forward graph
   auto take = [&](size_t bytes) {
     const size_t at = o;
     o += (bytes + 255) & ~(size_t)255;
@@ -179,7 +196,14 @@ void gemm(const double* In, long long ld_in, int rows, const double* W, long lon
 // M_b = A diag(D_b) A^T + delta I for the active instances, then its tiled Cholesky factorisation (in place) with the
 // inverses of the diagonal blocks.
 void assemble_and_factor(const IntoptDense* d, const dn::DenseState& s, int Bc, double delta, cudaStream_t st) {
-  if (d->use_tma && d->m64 % 128 == 0) {
+  static const int tile_env = [] {
+    const char* v = std::getenv("INTOPT_DENSE_TILE");
+    return v && *v ? std::atoi(v) : 0;
+  }();
+  // 64-wide tiles by default: four 128-thread CTAs per SM hide the TMA / DMMA latencies better than one 512-thread CTA
+  // with 128-wide tiles and waste less on diagonal tiles (measured: m = 256 0.38 -> 0.45 of the DMMA peak, m = 1024
+  // 0.63 -> 0.70, m = 2048 0.70 -> 0.76); INTOPT_DENSE_TILE=128 selects the wide variant.
+  if (d->use_tma && d->m64 % 128 == 0 && tile_env == 128) {
     const int T = d->m64 / 128;
     dn::dense_syrk_tma_kernel<128, 512><<<dim3(T * (T + 1) / 2, Bc), 512, kSyrkTma128Smem, st>>>(
         d->tmap128, d->n64, d->m, d->m64, s.D, d->n64, delta, s.M, s.active);
@@ -281,6 +305,11 @@ int create(IntoptDense** out, int m, int n, const int* rowptr, const int* colidx
   }
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&d->h_nactive, 64, cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking);
+  {
+    const char* v = std::getenv("INTOPT_DENSE_GRAPH");
+    d->use_graph = !(v && v[0] == '0');
+  }
   int dev = 0;
   if (e == cudaSuccess) e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev);
@@ -309,12 +338,126 @@ void destroy(IntoptDense* d) {
   for (void* a : d->allocs) cudaFree(a);
   if (d->h_nactive) cudaFreeHost(d->h_nactive);
   if (d->ev) cudaEventDestroy(d->ev);
+  for (auto& g : d->graphs) cudaGraphExecDestroy(g.exec);
+  if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
   delete d;
 }
 
 size_t workspace_bytes(const IntoptDense* d, int B) {
   if (B <= 0) return 0;
   return make_layout(d, chunk_size(d, B)).total;
+}
+
+// One interior-point iteration of a chunk, enqueued on `st` (the host loop and the graph capture share it).
+// `adev`: the argument block in device memory.
+static void enqueue_iteration(const IntoptDense* d, const dn::DenseState& s, const dn::DenseFwdArgs* adev, int Bc, int Bp,
+                              double damping, bool plain, const double* b_rhs, long long b_rhs_stride, cudaStream_t st) {
+  const int m64 = d->m64, n64 = d->n64;
+  gemm(s.G, n64, 2 * Bp, d->A, n64, m64, n64, s.RHS, m64, st);  // [A(D c) ; A(D w)]
+  assemble_and_factor(d, s, Bc, damping, st);
+  {
+    dn::SolveArgs sa{};
+    sa.rhs[0] = s.RHS;
+    sa.rhs[1] = s.RHS + (size_t)Bp * m64;
+    sa.add[0] = b_rhs;  // q: r = b + A(D c)   (:666 with (c,b))
+    sa.add_stride[0] = b_rhs_stride;
+    sa.add[1] = s.AX;  // v: r = eta r1 + A(D w)                                              (:785,666)
+    sa.add_stride[1] = m64;
+    sa.cadd[1] = s.SC + dn::SC_ETA;
+    sa.coef_stride = dn::SC_N;
+    solve<2>(d, s, Bc, sa, st);
+  }
+  gemm(s.RHS, m64, 2 * Bp, d->At, m64, n64, m64, s.ATQV, n64, st);  // [A^T q ; A^T v]
+  dn::dense_predict_kernel<<<Bc, 256, 0, st>>>(adev);
+  if (!plain) {
+    gemm(s.G, n64, Bp, d->A, n64, m64, n64, s.RHS + (size_t)Bp * m64, m64, st);  // A(D w')
+    {
+      dn::SolveArgs sa{};
+      sa.rhs[0] = s.RHS + (size_t)Bp * m64;
+      sa.add[0] = s.AX;
+      sa.add_stride[0] = m64;
+      sa.cadd[0] = s.SC + dn::SC_ETA;
+      sa.coef_stride = dn::SC_N;
+      solve<1>(d, s, Bc, sa, st);
+    }
+    gemm(s.RHS + (size_t)Bp * m64, m64, Bp, d->At, m64, n64, m64, s.ATQV + (size_t)Bp * n64, n64, st);  // A^T v'
+    dn::dense_step_kernel<<<Bc, 256, 0, st>>>(adev);
+  }
+}
+// loop top: A x, A^T y, residuals + termination tests (counts the instances that enter the iteration)
+static cudaError_t enqueue_loop_top(const IntoptDense* d, const dn::DenseState& s, const dn::DenseFwdArgs* adev, int Bc, int Bp,
+                                    cudaStream_t st, bool zero_count) {
+  const int m64 = d->m64, n64 = d->n64;
+  cudaError_t e = zero_count ? cudaMemsetAsync(s.n_active, 0, sizeof(int), st) : cudaSuccess;
+  gemm(s.X, n64, Bp, d->A, n64, m64, n64, s.AX, m64, st);   // A x
+  gemm(s.Y, m64, Bp, d->At, m64, n64, m64, s.ATY, n64, st);  // A^T y
+  dn::dense_resid_kernel<<<Bc, 256, 0, st>>>(adev);
+  return e;
+}
+
+// Build (or find) the forward graph of a chunk: init -> while (some instance active) { iteration } -> epilogue.
+static cudaGraphExec_t forward_graph(const IntoptDense* d, const dn::DenseState& s, const dn::DenseFwdArgs* adev, void* ws, int Bc,
+                                     int Bp, double damping, bool plain, const double* b_batch, long long b_stride,
+                                     const double* b_rhs, long long b_rhs_stride) {
+  for (const auto& g : d->graphs)
+    if (g.ws == ws && g.Bc == Bc && g.plain == (int)plain && std::memcmp(&g.damping, &damping, sizeof(double)) == 0 &&
+        g.b_batch == b_batch && g.b_stride == b_stride)
+      return g.exec;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  bool ok = cudaGraphCreate(&graph, 0) == cudaSuccess;
+  cudaGraphConditionalHandle handle{};
+  ok = ok && cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+  cudaGraphNode_t n_init = nullptr, n_loop = nullptr, n_epi = nullptr;
+  void* kargs[1] = {(void*)&adev};
+  if (ok) {
+    cudaKernelNodeParams kp{};
+    kp.func = (void*)dn::dense_init_kernel;
+    kp.gridDim = dim3(Bc);
+    kp.blockDim = dim3(256);
+    kp.kernelParams = kargs;
+    ok = cudaGraphAddKernelNode(&n_init, graph, nullptr, 0, &kp) == cudaSuccess;
+  }
+  cudaGraph_t body = nullptr;
+  if (ok) {
+    cudaGraphNodeParams np{};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    ok = cudaGraphAddNode(&n_loop, graph, &n_init, 1, &np) == cudaSuccess;
+    if (ok) body = np.conditional.phGraph_out[0];
+  }
+  if (ok) {
+    ok = cudaStreamBeginCaptureToGraph(d->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      enqueue_loop_top(d, s, adev, Bc, Bp, d->cap_stream, false);  // (the condition kernel re-zeroes the count)
+      dn::dense_loop_cond_kernel<<<1, 32, 0, d->cap_stream>>>(handle, s.n_active);
+      enqueue_iteration(d, s, adev, Bc, Bp, damping, plain, b_rhs, b_rhs_stride, d->cap_stream);
+      cudaGraph_t got = nullptr;
+      ok = cudaStreamEndCapture(d->cap_stream, &got) == cudaSuccess;
+    }
+  }
+  if (ok) {
+    cudaKernelNodeParams kp{};
+    kp.func = (void*)dn::dense_epilogue_kernel;
+    kp.gridDim = dim3(Bc);
+    kp.blockDim = dim3(256);
+    kp.kernelParams = kargs;
+    ok = cudaGraphAddKernelNode(&n_epi, graph, &n_loop, 1, &kp) == cudaSuccess;
+  }
+  ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) {
+    cudaGetLastError();  // clear: the caller falls back to the host-driven loop
+    return nullptr;
+  }
+  if (d->graphs.size() >= 16) {  // bounded cache
+    cudaGraphExecDestroy(d->graphs.front().exec);
+    d->graphs.erase(d->graphs.begin());
+  }
+  d->graphs.push_back({ws, Bc, (int)plain, damping, b_batch, b_stride, exec});
+  return exec;
 }
 
 int forward(const IntoptDense* d, int B, double* c, long long c_stride, const double* b_batch, long long b_stride,
@@ -352,50 +495,30 @@ int forward(const IntoptDense* d, int B, double* c, long long c_stride, const do
     a.max_iter = o->max_iter;
     a.plain = o->plain != 0;
     const dn::DenseState& s = a.s;
-    const int Bp = L.Bp, m64 = d->m64, n64 = d->n64;
-    dn::dense_init_kernel<<<Bc, 256, 0, st>>>(a);
+    const int Bp = L.Bp;
+    const dn::DenseFwdArgs* adev = reinterpret_cast<const dn::DenseFwdArgs*>((char*)ws + kArgsOffset);
+    DN_TRY(cudaMemcpyAsync((void*)adev, &a, sizeof(a), cudaMemcpyHostToDevice, st));
+    const double* b_rhs = b_batch ? b_batch + (long long)b0 * b_stride : d->b;
+    const long long b_rhs_stride = b_batch ? b_stride : 0;
+    if (d->use_graph) {
+      cudaGraphExec_t exec = forward_graph(d, s, adev, ws, Bc, Bp, a.damping, a.plain != 0, b_rhs, b_rhs_stride, b_rhs, b_rhs_stride);
+      if (exec) {
+        DN_TRY(cudaGraphLaunch(exec, st));
+        continue;
+      }
+    }
+    // host-driven loop (INTOPT_DENSE_GRAPH=0, or no conditional-node support): one event wait per iteration
+    dn::dense_init_kernel<<<Bc, 256, 0, st>>>(adev);
     for (long long it = 0;; ++it) {
-      DN_TRY(cudaMemsetAsync(s.n_active, 0, sizeof(int), st));
-      gemm(s.X, n64, Bp, d->A, n64, m64, n64, s.AX, m64, st);   // A x
-      gemm(s.Y, m64, Bp, d->At, m64, n64, m64, s.ATY, n64, st);  // A^T y
-      dn::dense_resid_kernel<<<Bc, 256, 0, st>>>(a);
+      DN_TRY(enqueue_loop_top(d, s, adev, Bc, Bp, st, true));
       DN_TRY(cudaMemcpyAsync(d->h_nactive, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
       DN_TRY(cudaEventRecord(d->ev, st));
-      gemm(s.G, n64, 2 * Bp, d->A, n64, m64, n64, s.RHS, m64, st);  // [A(D c) ; A(D w)]
-      assemble_and_factor(d, s, Bc, a.damping, st);
-      {
-        dn::SolveArgs sa{};
-        sa.rhs[0] = s.RHS;
-        sa.rhs[1] = s.RHS + (size_t)Bp * m64;
-        sa.add[0] = b_batch ? b_batch + (long long)b0 * b_stride : d->b;  // q: r = b + A(D c)   (:666 with (c,b))
-        sa.add_stride[0] = b_batch ? b_stride : 0;
-        sa.add[1] = s.AX;  // v: r = eta r1 + A(D w)                                              (:785,666)
-        sa.add_stride[1] = m64;
-        sa.cadd[1] = s.SC + dn::SC_ETA;
-        sa.coef_stride = dn::SC_N;
-        solve<2>(d, s, Bc, sa, st);
-      }
-      gemm(s.RHS, m64, 2 * Bp, d->At, m64, n64, m64, s.ATQV, n64, st);  // [A^T q ; A^T v]
-      dn::dense_predict_kernel<<<Bc, 256, 0, st>>>(a);
-      if (!a.plain) {
-        gemm(s.G, n64, Bp, d->A, n64, m64, n64, s.RHS + (size_t)Bp * m64, m64, st);  // A(D w')
-        {
-          dn::SolveArgs sa{};
-          sa.rhs[0] = s.RHS + (size_t)Bp * m64;
-          sa.add[0] = s.AX;
-          sa.add_stride[0] = m64;
-          sa.cadd[0] = s.SC + dn::SC_ETA;
-          sa.coef_stride = dn::SC_N;
-          solve<1>(d, s, Bc, sa, st);
-        }
-        gemm(s.RHS + (size_t)Bp * m64, m64, Bp, d->At, m64, n64, m64, s.ATQV + (size_t)Bp * n64, n64, st);  // A^T v'
-        dn::dense_step_kernel<<<Bc, 256, 0, st>>>(a);
-      }
+      enqueue_iteration(d, s, adev, Bc, Bp, a.damping, a.plain != 0, b_rhs, b_rhs_stride, st);
       DN_TRY(cudaEventSynchronize(d->ev));  // how many instances entered this iteration (they all left: stop)
       if (*d->h_nactive == 0) break;
       if (it > (long long)o->max_iter + 2) break;
     }
-    dn::dense_epilogue_kernel<<<Bc, 256, 0, st>>>(a);
+    dn::dense_epilogue_kernel<<<Bc, 256, 0, st>>>(adev);
     DN_TRY(cudaGetLastError());
   }
   return 0;

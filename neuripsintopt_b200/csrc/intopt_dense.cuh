@@ -812,7 +812,8 @@ __device__ __forceinline__ double b_at(const DenseFwdArgs& a, int inst, int i) {
 }
 
 // _initialization (:647-661) + cold-start residual norms (:884,907-910)
-__global__ void __launch_bounds__(256) dense_init_kernel(const DenseFwdArgs a) {
+__global__ void __launch_bounds__(256) dense_init_kernel(const DenseFwdArgs* __restrict__ ap) {
+  const DenseFwdArgs& a = *ap;
   __shared__ double red[4 * 32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const DenseState& s = a.s;
@@ -869,12 +870,14 @@ __global__ void __launch_bounds__(256) dense_init_kernel(const DenseFwdArgs a) {
     a.iters[a.inst0 + b] = 0;
     s.active[b] = nonfinite ? 0 : 1;
     s.fail[b] = 0;
+    if (b == 0) *s.n_active = 0;
   }
 }
 
 // Loop top: residuals (:765-770), indicators and termination tests (:880-917, :1408-1423), then the right-hand-side
 // inputs of the (p,q) solve and of the predictor: G = [D c ; D w].  AX = A x and ATY = A^T y come from the GEMMs.
-__global__ void __launch_bounds__(256) dense_resid_kernel(const DenseFwdArgs a) {
+__global__ void __launch_bounds__(256) dense_resid_kernel(const DenseFwdArgs* __restrict__ ap) {
+  const DenseFwdArgs& a = *ap;
   __shared__ double red[5 * 32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const DenseState& s = a.s;
@@ -960,7 +963,8 @@ struct StepScalars {
 
 // After the (p,q) + predictor solve: p, u, the scalars of :837-842, the predictor's ratio test, gamma (:844), and the
 // corrector's right-hand-side input G = D w' (:792-801).  With pc=False (plain) the first direction is the step.
-__global__ void __launch_bounds__(256) dense_predict_kernel(const DenseFwdArgs a) {
+__global__ void __launch_bounds__(256) dense_predict_kernel(const DenseFwdArgs* __restrict__ ap) {
+  const DenseFwdArgs& a = *ap;
   __shared__ double red[5 * 32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const DenseState& s = a.s;
@@ -1061,7 +1065,8 @@ __global__ void __launch_bounds__(256) dense_predict_kernel(const DenseFwdArgs a
 
 // After the corrector solve: direction (:837-842 with the Mehrotra terms :792-795), ratio test with alpha0 and the
 // step (:1402-1403, :861-868).
-__global__ void __launch_bounds__(256) dense_step_kernel(const DenseFwdArgs a) {
+__global__ void __launch_bounds__(256) dense_step_kernel(const DenseFwdArgs* __restrict__ ap) {
+  const DenseFwdArgs& a = *ap;
   __shared__ double red[2 * 32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const DenseState& s = a.s;
@@ -1120,7 +1125,8 @@ __global__ void __launch_bounds__(256) dense_step_kernel(const DenseFwdArgs a) {
 }
 
 // Epilogue (:1441-1447): x_hat = x / tau, the saved iterate, x in the caller's layout.
-__global__ void __launch_bounds__(256) dense_epilogue_kernel(const DenseFwdArgs a) {
+__global__ void __launch_bounds__(256) dense_epilogue_kernel(const DenseFwdArgs* __restrict__ ap) {
+  const DenseFwdArgs& a = *ap;
   const int b = blockIdx.x, tid = threadIdx.x;
   const DenseState& s = a.s;
   const int n = s.n, m = s.m;
@@ -1260,6 +1266,15 @@ __global__ void __launch_bounds__(256) dense_bwd_final_kernel(const DenseBwdArgs
       const int k = a.um.out_idx[i];
       intopt::um_store(a.um, a.inst0 + b, i, k >= 0 ? gc[k] : 0.0);
     }
+  }
+}
+
+// End of an iteration's termination tests: the while-node of the forward graph runs its body again iff some instance
+// entered this iteration (dense_resid_kernel counted them).
+__global__ void dense_loop_cond_kernel(cudaGraphConditionalHandle handle, int* __restrict__ n_active) {
+  if (threadIdx.x == 0) {
+    cudaGraphSetConditional(handle, *n_active > 0 ? 1u : 0u);
+    *n_active = 0;  // for the next iteration's count (the body graph holds kernels only)
   }
 }
 
