@@ -557,23 +557,33 @@ IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr,
   const int i = cx.lane & 7;
   double a[KB], rinv[KB];
   load_row(blk, i, a);
-  if (panel) {  // fused look-ahead update in registers: row i of C -= P_i . P_k^T with P = L_(K+1,K)
-    double own[KB];
+  if (panel) {
+    // fused look-ahead update in registers: row i of C -= P_i . P_k^T with P = L_(K+1,K).  The four lane octets (which
+    // all hold row i) take two of the eight dot products each and exchange the results by shuffle: a quarter of the
+    // shared-memory loads and FMAs on this warp's critical path, the same sums bit for bit.
+    const int o = cx.lane >> 3;
+    double own[KB], p0[KB], p1[KB];
     load_row(panel, i, own);
+    load_row(panel, 2 * o, p0);
+    load_row(panel, 2 * o + 1, p1);
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int k = 0; k < KB; ++k) {
-      double pk[KB];
-      load_row(panel, k, pk);  // same address on every lane: broadcast
-      double s = 0.0;
-#pragma unroll
-      for (int j = 0; j < KB; ++j) s = fma(own[j], pk[j], s);
-      a[k] -= s;
+    for (int j = 0; j < KB; ++j) {
+      s0 = fma(own[j], p0[j], s0);
+      s1 = fma(own[j], p1[j], s1);
     }
+#pragma unroll
+    for (int k = 0; k < KB; ++k) a[k] -= __shfl_sync(full, (k & 1) ? s1 : s0, (k >> 1) * 8 + i);
   }
   bool bad = false;
 #pragma unroll
   for (int j = 0; j < KB; ++j) {
     double piv = __shfl_sync(full, a[j], j);
+    // the entries of column j travel BEFORE they are scaled (lane k's a[j] is C_kj): the shuffles then overlap the
+    // rsqrt instead of following it on the dependent chain; C_kj * r is formed locally, the same product lane k forms
+    double ckj[KB];
+#pragma unroll
+    for (int k = j + 1; k < KB; ++k) ckj[k] = __shfl_sync(full, a[j], k);
     if (!(piv > 0.0) || !(piv < 1e300)) {
       bad = true;
       piv = 1.0;
@@ -582,10 +592,7 @@ IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr,
     rinv[j] = r;
     a[j] = (i == j) ? piv * r : a[j] * r;  // column j of L (rows above the diagonal hold junk)
 #pragma unroll
-    for (int k = j + 1; k < KB; ++k) {
-      const double lkj = __shfl_sync(full, a[j], k);
-      a[k] = fma(-a[j], lkj, a[k]);
-    }
+    for (int k = j + 1; k < KB; ++k) a[k] = fma(-a[j], ckj[k] * r, a[k]);
   }
   if (bad && cx.lane == 0) *fail = 1;
   // publish L (row i, plain row-major) so that every lane can read the rows below its own column
@@ -745,19 +752,24 @@ IO_FORCEINLINE void pivot_apply(const double* Linv, double* const (&r)[NR], int 
   const int q = idx >> 3, i = idx & 7;
   double rk[KB];
   load_vec8(rhs_sel<NR>(r, q) + blk * KB, rk);
-  double s = 0.0;
+  // two independent half sums (even / odd terms): half the dependent FMA chain on warp 0's critical path
+  double s = 0.0, s2 = 0.0;
   if (!TRANS) {
     double li[KB];
     load_row(Linv, i, li);
 #pragma unroll
-    for (int j = 0; j < KB; ++j)
+    for (int j = 0; j < KB; j += 2) {
       if (j <= i) s = fma(li[j], rk[j], s);
+      if (j + 1 <= i) s2 = fma(li[j + 1], rk[j + 1], s2);
+    }
   } else {
 #pragma unroll
-    for (int j = 0; j < KB; ++j)
+    for (int j = 0; j < KB; j += 2) {
       if (j >= i) s = fma(Linv[bidx(j, i)], rk[j], s);
+      if (j + 1 >= i) s2 = fma(Linv[bidx(j + 1, i)], rk[j + 1], s2);
+    }
   }
-  yout[idx] = s;
+  yout[idx] = s + s2;
 }
 
 template <int NR>
@@ -784,10 +796,13 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
           double row[KB], yk[KB];
           load_row(L + M.boff[K + 1] + (K - M.fb[K + 1]) * 64, rr, row);
           load_vec8(ycur + q * KB, yk);
-          double sacc = 0.0;
+          double sacc = 0.0, sacc2 = 0.0;  // two half sums: half the dependent chain
 #pragma unroll
-          for (int k = 0; k < KB; ++k) sacc = fma(row[k], yk[k], sacc);
-          rhs_sel<NR>(r, q)[(K + 1) * KB + rr] -= sacc;
+          for (int k = 0; k < KB; k += 2) {
+            sacc = fma(row[k], yk[k], sacc);
+            sacc2 = fma(row[k + 1], yk[k + 1], sacc2);
+          }
+          rhs_sel<NR>(r, q)[(K + 1) * KB + rr] -= sacc + sacc2;
         }
       }
       WARP_SYNC();
@@ -831,17 +846,20 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
           const double* blk = L + M.boff[I] + (I - 1 - f) * 64;
           double zi[KB];
           load_vec8(zcur + q * KB, zi);
-          double sx = 0.0, sy = 0.0;
+          double sx = 0.0, sy = 0.0, sx2 = 0.0, sy2 = 0.0;  // half sums: half the dependent chain
 #pragma unroll
-          for (int i = 0; i < KB; ++i) {
+          for (int i = 0; i < KB; i += 2) {
             const D2 t2 = reinterpret_cast<const D2*>(blk + i * KB)[c ^ bswz(i)];
+            const D2 t3 = reinterpret_cast<const D2*>(blk + (i + 1) * KB)[c ^ bswz(i + 1)];
             sx = fma(t2.x, zi[i], sx);
             sy = fma(t2.y, zi[i], sy);
+            sx2 = fma(t3.x, zi[i + 1], sx2);
+            sy2 = fma(t3.y, zi[i + 1], sy2);
           }
           D2* dst = reinterpret_cast<D2*>(rhs_sel<NR>(r, q) + (I - 1) * KB) + c;
           D2 t2 = *dst;
-          t2.x -= sx;
-          t2.y -= sy;
+          t2.x -= sx + sx2;
+          t2.y -= sy + sy2;
           *dst = t2;
         }
       }
