@@ -17,10 +17,12 @@ struct IntoptDense {
   double* A = nullptr;       // m64 x n64, zero padded
   double* At = nullptr;      // n64 x m64
   double* rowsum = nullptr;  // A 1
+  double rowsq_max = 0.0;    // max_i sum_k A_ik^2 (bound of the diagonal of A diag(d) A^T per unit of max d)
   double* b = nullptr;       // m or null
   // TMA descriptors of the padded A: box = 16 columns (128 bytes) x 128 / 64 rows, 128-byte swizzle
   dn::TmaDesc tmap128{}, tmap64{};
   bool use_tma = false;
+  bool use_ladder = true;  // INTOPT_DENSE_LADDER=0: a breakdown ends the instance at once (A/B measurements)
   std::vector<void*> allocs;
   // completion signalling of the iteration loop (one forward call at a time per handle)
   mutable std::mutex mu;
@@ -63,7 +65,7 @@ int up128(int v) { return (v + 127) & ~127; }
 // Workspace of a chunk of Bc instances (doubles unless noted).
 struct Layout {
   int Bc, Bp;
-  size_t X, T, Y, AX, ATY, R2, D, W, P, DX, DXDT, G, RHS, ATQV, SC, M, Linv, ints, total;  // offsets in bytes
+  size_t X, T, Y, AX, ATY, R2, D, W, P, DX, DXDT, G, RHS, ATQV, SC, M, Linv, ints, dretry, total;  // offsets in bytes
 };
 size_t per_instance_bytes(int m64, int n64) {
   return ((size_t)12 * n64 + 4 * (size_t)n64 + 5 * (size_t)m64 + dn::SC_N + (size_t)m64 * m64 + (size_t)m64 * dn::NB) * 8 + 16;
@@ -96,7 +98,8 @@ Layout make_layout(const IntoptDense* d, int Bc) {
   L.SC = take((size_t)L.Bp * dn::SC_N * 8);
   L.M = take((size_t)Bc * d->m64 * d->m64 * 8);
   L.Linv = take((size_t)Bc * d->m64 * dn::NB * 8);
-  L.ints = take((size_t)L.Bp * 2 * sizeof(int));
+  L.ints = take((size_t)L.Bp * 3 * sizeof(int));
+  L.dretry = take((size_t)L.Bp * 8);
   L.total = o;
   return L;
 }
@@ -133,6 +136,8 @@ dn::DenseState bind_state(const IntoptDense* d, const Layout& L, char* ws) {
   s.Linv = at(L.Linv);
   s.active = reinterpret_cast<int*>(ws + L.ints);
   s.fail = s.active + L.Bp;
+  s.retry = s.fail + L.Bp;
+  s.delta_retry = at(L.dretry);
   s.n_active = reinterpret_cast<int*>(ws);
   s.rowsum = d->rowsum;
   return s;
@@ -193,9 +198,10 @@ void gemm(const double* In, long long ld_in, int rows, const double* W, long lon
   dn::dense_gemm_kernel<<<grid, 256, kGemmSmem, st>>>(In, ld_in, W, ld_w, K, Out, ld_out);
 }
 
-// M_b = A diag(D_b) A^T + delta I for the active instances, then its tiled Cholesky factorisation (in place) with the
-// inverses of the diagonal blocks.
-void assemble_and_factor(const IntoptDense* d, const dn::DenseState& s, int Bc, double delta, cudaStream_t st) {
+// M_b = A diag(D_b) A^T + delta I for the instances selected by `mask`, then its tiled Cholesky factorisation (in place)
+// with the inverses of the diagonal blocks.  `delta_arr` (optional): per-instance damping.
+void assemble_and_factor_masked(const IntoptDense* d, const dn::DenseState& s, int Bc, double delta, const int* mask,
+                                const double* delta_arr, cudaStream_t st) {
   static const int tile_env = [] {
     const char* v = std::getenv("INTOPT_DENSE_TILE");
     return v && *v ? std::atoi(v) : 0;
@@ -206,25 +212,37 @@ void assemble_and_factor(const IntoptDense* d, const dn::DenseState& s, int Bc, 
   if (d->use_tma && d->m64 % 128 == 0 && tile_env == 128) {
     const int T = d->m64 / 128;
     dn::dense_syrk_tma_kernel<128, 512><<<dim3(T * (T + 1) / 2, Bc), 512, kSyrkTma128Smem, st>>>(
-        d->tmap128, d->n64, d->m, d->m64, s.D, d->n64, delta, s.M, s.active);
+        d->tmap128, d->n64, d->m, d->m64, s.D, d->n64, delta, s.M, mask, delta_arr);
   } else if (d->use_tma) {
     const int T = d->m64 / 64;
     dn::dense_syrk_tma_kernel<64, 128><<<dim3(T * (T + 1) / 2, Bc), 128, kSyrkTma64Smem, st>>>(
-        d->tmap64, d->n64, d->m, d->m64, s.D, d->n64, delta, s.M, s.active);
+        d->tmap64, d->n64, d->m, d->m64, s.D, d->n64, delta, s.M, mask, delta_arr);
   } else if (d->m64 % 128 == 0) {
     const int T = d->m64 / 128;
     dn::dense_syrk_kernel<128, 512><<<dim3(T * (T + 1) / 2, Bc), 512, kSyrk128Smem, st>>>(d->A, d->n64, d->m, d->m64, s.D,
-                                                                                      d->n64, delta, s.M, s.active);
+                                                                                      d->n64, delta, s.M, mask, delta_arr);
   } else {
     const int T = d->m64 / 64;
     dn::dense_syrk_kernel<64, 128><<<dim3(T * (T + 1) / 2, Bc), 128, kSyrk64Smem, st>>>(d->A, d->n64, d->m, d->m64, s.D,
-                                                                                    d->n64, delta, s.M, s.active);
+                                                                                    d->n64, delta, s.M, mask, delta_arr);
   }
   const int nb = d->m64 / dn::NB;
   for (int k = 0; k < nb; ++k) {
-    dn::dense_chol_col_kernel<<<dim3(nb - k, Bc), 256, kCholSmem, st>>>(s.M, d->m64, k, s.Linv, s.fail, s.active);
+    dn::dense_chol_col_kernel<<<dim3(nb - k, Bc), 256, kCholSmem, st>>>(s.M, d->m64, k, s.Linv, s.fail, mask);
     if (k + 1 < nb)
-      dn::dense_chol_trsm_kernel<<<dim3(nb - k - 1, Bc), 256, kCholSmem, st>>>(s.M, d->m64, k, s.Linv, s.active);
+      dn::dense_chol_trsm_kernel<<<dim3(nb - k - 1, Bc), 256, kCholSmem, st>>>(s.M, d->m64, k, s.Linv, mask);
+  }
+}
+
+// Assembly + factorisation of the active instances, then the two retry rungs of the failure ladder (:798-822) for the
+// instances whose factorisation broke down (`ladder`: the forward; the backward reports a breakdown as the reference does).
+void assemble_and_factor(const IntoptDense* d, const dn::DenseState& s, int Bc, double delta, cudaStream_t st,
+                         bool ladder = false) {
+  assemble_and_factor_masked(d, s, Bc, delta, s.active, nullptr, st);
+  if (!ladder || !d->use_ladder) return;
+  for (int rung = 0; rung < 2; ++rung) {
+    dn::dense_retry_prep_kernel<<<Bc, 256, 0, st>>>(s, delta, d->rowsq_max, rung, nullptr);
+    assemble_and_factor_masked(d, s, Bc, delta, s.retry, s.delta_retry, st);
   }
 }
 
@@ -289,6 +307,9 @@ int create(IntoptDense** out, int m, int n, const int* rowptr, const int* colidx
       s += val[e];
     }
     rs[i] = s;
+    double sq = 0.0;
+    for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) sq += val[e] * val[e];
+    d->rowsq_max = std::max(d->rowsq_max, sq);
   }
   auto upl = [&](const std::vector<double>& h, double** dev) -> cudaError_t {
     cudaError_t e = cudaMalloc((void**)dev, h.size() * sizeof(double));
@@ -309,6 +330,8 @@ int create(IntoptDense** out, int m, int n, const int* rowptr, const int* colidx
   {
     const char* v = std::getenv("INTOPT_DENSE_GRAPH");
     d->use_graph = !(v && v[0] == '0');
+    const char* l = std::getenv("INTOPT_DENSE_LADDER");
+    d->use_ladder = !(l && l[0] == '0');
   }
   int dev = 0;
   if (e == cudaSuccess) e = cudaGetDevice(&dev);
@@ -350,11 +373,17 @@ size_t workspace_bytes(const IntoptDense* d, int B) {
 
 // One interior-point iteration of a chunk, enqueued on `st` (the host loop and the graph capture share it).
 // `adev`: the argument block in device memory.
+static void enqueue_after_factor(const IntoptDense* d, const dn::DenseState& s, const dn::DenseFwdArgs* adev, int Bc, int Bp,
+                                 bool plain, const double* b_rhs, long long b_rhs_stride, cudaStream_t st);
 static void enqueue_iteration(const IntoptDense* d, const dn::DenseState& s, const dn::DenseFwdArgs* adev, int Bc, int Bp,
                               double damping, bool plain, const double* b_rhs, long long b_rhs_stride, cudaStream_t st) {
+  gemm(s.G, d->n64, 2 * Bp, d->A, d->n64, d->m64, d->n64, s.RHS, d->m64, st);  // [A(D c) ; A(D w)]
+  assemble_and_factor(d, s, Bc, damping, st, true);
+  enqueue_after_factor(d, s, adev, Bc, Bp, plain, b_rhs, b_rhs_stride, st);
+}
+static void enqueue_after_factor(const IntoptDense* d, const dn::DenseState& s, const dn::DenseFwdArgs* adev, int Bc, int Bp,
+                                 bool plain, const double* b_rhs, long long b_rhs_stride, cudaStream_t st) {
   const int m64 = d->m64, n64 = d->n64;
-  gemm(s.G, n64, 2 * Bp, d->A, n64, m64, n64, s.RHS, m64, st);  // [A(D c) ; A(D w)]
-  assemble_and_factor(d, s, Bc, damping, st);
   {
     dn::SolveArgs sa{};
     sa.rhs[0] = s.RHS;
@@ -428,15 +457,84 @@ static cudaGraphExec_t forward_graph(const IntoptDense* d, const dn::DenseState&
     ok = cudaGraphAddNode(&n_loop, graph, &n_init, 1, &np) == cudaSuccess;
     if (ok) body = np.conditional.phGraph_out[0];
   }
+  // the leaf of a graph that was filled by capturing one stream (a chain): the node nothing depends on
+  auto leaf_of = [](cudaGraph_t g, cudaGraphNode_t* leaf) {
+    size_t n = 0;
+    if (cudaGraphGetNodes(g, nullptr, &n) != cudaSuccess || n == 0) return false;
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (cudaGraphGetNodes(g, nodes.data(), &n) != cudaSuccess) return false;
+    for (cudaGraphNode_t nd : nodes) {
+      size_t nd_out = 0;
+      if (cudaGraphNodeGetDependentNodes(nd, nullptr, &nd_out) != cudaSuccess) return false;
+      if (nd_out == 0) {
+        *leaf = nd;
+        return true;
+      }
+    }
+    return false;
+  };
+  auto capture_into = [&](cudaGraph_t g, const cudaGraphNode_t* deps, size_t ndeps, auto&& enqueue) {
+    if (cudaStreamBeginCaptureToGraph(d->cap_stream, g, deps, nullptr, ndeps, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+      return false;
+    enqueue();
+    cudaGraph_t got = nullptr;
+    return cudaStreamEndCapture(d->cap_stream, &got) == cudaSuccess;
+  };
+  // IF node (condition set by dense_if_cond_kernel) appended to the chain in `g`; returns its body graph
+  auto add_if = [&](cudaGraph_t g, cudaGraphConditionalHandle h, cudaGraphNode_t* node_out, cudaGraph_t* body_out) {
+    cudaGraphNode_t leaf = nullptr;
+    if (!leaf_of(g, &leaf)) return false;
+    cudaGraphNodeParams np{};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = h;
+    np.conditional.type = cudaGraphCondTypeIf;
+    np.conditional.size = 1;
+    if (cudaGraphAddNode(node_out, g, &leaf, 1, &np) != cudaSuccess) return false;
+    *body_out = np.conditional.phGraph_out[0];
+    return true;
+  };
+  int* n_retry = s.n_active + 1;  // (second word of the counter block at the head of the workspace)
+  const bool ladder = d->use_ladder;
+  cudaGraphConditionalHandle h_r0{}, h_r1{};
+  if (ok && ladder)
+    ok = cudaGraphConditionalHandleCreate(&h_r0, graph, 0, cudaGraphCondAssignDefault) == cudaSuccess &&
+         cudaGraphConditionalHandleCreate(&h_r1, graph, 0, cudaGraphCondAssignDefault) == cudaSuccess;
   if (ok) {
-    ok = cudaStreamBeginCaptureToGraph(d->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-    if (ok) {
+    // segment 1: loop top, loop condition, right-hand-side products, assembly + factorisation, first ladder test
+    ok = capture_into(body, nullptr, 0, [&] {
       enqueue_loop_top(d, s, adev, Bc, Bp, d->cap_stream, false);  // (the condition kernel re-zeroes the count)
       dn::dense_loop_cond_kernel<<<1, 32, 0, d->cap_stream>>>(handle, s.n_active);
-      enqueue_iteration(d, s, adev, Bc, Bp, damping, plain, b_rhs, b_rhs_stride, d->cap_stream);
-      cudaGraph_t got = nullptr;
-      ok = cudaStreamEndCapture(d->cap_stream, &got) == cudaSuccess;
-    }
+      gemm(s.G, d->n64, 2 * Bp, d->A, d->n64, d->m64, d->n64, s.RHS, d->m64, d->cap_stream);
+      assemble_and_factor_masked(d, s, Bc, damping, s.active, nullptr, d->cap_stream);
+      if (ladder) {
+        dn::dense_retry_prep_kernel<<<Bc, 256, 0, d->cap_stream>>>(s, damping, d->rowsq_max, 0, n_retry);
+        dn::dense_if_cond_kernel<<<1, 32, 0, d->cap_stream>>>(h_r0, n_retry);
+      }
+    });
+  }
+  cudaGraphNode_t tail = nullptr;  // what the rest of the iteration depends on
+  if (ok && ladder) {
+    // the retry rungs only exist as bodies of IF nodes: an iteration without a breakdown pays two tiny kernels for them
+    cudaGraphNode_t if0 = nullptr, if1 = nullptr;
+    cudaGraph_t body0 = nullptr, body1 = nullptr;
+    ok = add_if(body, h_r0, &if0, &body0);
+    ok = ok && capture_into(body0, nullptr, 0, [&] {
+      assemble_and_factor_masked(d, s, Bc, damping, s.retry, s.delta_retry, d->cap_stream);
+      dn::dense_retry_prep_kernel<<<Bc, 256, 0, d->cap_stream>>>(s, damping, d->rowsq_max, 1, n_retry);
+      dn::dense_if_cond_kernel<<<1, 32, 0, d->cap_stream>>>(h_r1, n_retry);
+    });
+    ok = ok && add_if(body0, h_r1, &if1, &body1);
+    ok = ok && capture_into(body1, nullptr, 0, [&] {
+      assemble_and_factor_masked(d, s, Bc, damping, s.retry, s.delta_retry, d->cap_stream);
+    });
+    tail = if0;
+  } else if (ok) {
+    ok = leaf_of(body, &tail);
+  }
+  if (ok) {
+    ok = capture_into(body, &tail, 1, [&] {
+      enqueue_after_factor(d, s, adev, Bc, Bp, plain, b_rhs, b_rhs_stride, d->cap_stream);
+    });
   }
   if (ok) {
     cudaKernelNodeParams kp{};

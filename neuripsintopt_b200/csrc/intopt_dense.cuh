@@ -182,11 +182,13 @@ struct SyrkCfg {
 template <int TS, int NTHR>
 __global__ void __launch_bounds__(NTHR) dense_syrk_kernel(const double* __restrict__ A, int n64, int m, int m64,
                                                           const double* __restrict__ D, long long ld_d, double delta,
-                                                          double* __restrict__ Mout, const int* __restrict__ active) {
+                                                          double* __restrict__ Mout, const int* __restrict__ active,
+                                                          const double* __restrict__ delta_arr) {
   using G = typename SyrkCfg<TS, NTHR>::G;
   extern __shared__ __align__(16) double smem[];
   const int b = blockIdx.y;
   if (active && !active[b]) return;
+  if (delta_arr) delta = delta_arr[b];  // (retry rungs of the failure ladder: per-instance damping)
   const int ti = tri_row(blockIdx.x), tj = blockIdx.x - ti * (ti + 1) / 2;
   const int warp = threadIdx.x >> 5;
   const int wi = warp / G::WARPS_N, wj = warp % G::WARPS_N;
@@ -269,11 +271,13 @@ struct SyrkTma {
 template <int TS, int NTHR>
 __global__ void __launch_bounds__(NTHR) dense_syrk_tma_kernel(const __grid_constant__ TmaDesc tmapA, int n64, int m, int m64,
                                                               const double* __restrict__ D, long long ld_d, double delta,
-                                                              double* __restrict__ Mout, const int* __restrict__ active) {
+                                                              double* __restrict__ Mout, const int* __restrict__ active,
+                                                              const double* __restrict__ delta_arr) {
   using C = SyrkTma<TS, NTHR>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int b = blockIdx.y;
   if (active && !active[b]) return;
+  if (delta_arr) delta = delta_arr[b];  // (retry rungs of the failure ladder: per-instance damping)
   // 1 KB aligned stage buffers (the 128-byte swizzle pattern repeats every 8 rows = 1 KB)
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + STAGES * C::STAGE_BYTES);
@@ -784,6 +788,8 @@ struct DenseState {
   double* ATQV;  // 2 Bp x n64: [A^T q ; A^T v]
   double* SC;    // Bp x SC_N
   int *active, *fail, *n_active;
+  int* retry;         // instances whose factorisation is being re-attempted (failure ladder)
+  double* delta_retry;  // their damping for the attempt
   double* M;
   double* Linv;
   const double* rowsum;  // A 1 (m): the cold-start primal residual of _indicators (:884)
@@ -870,7 +876,7 @@ __global__ void __launch_bounds__(256) dense_init_kernel(const DenseFwdArgs* __r
     a.iters[a.inst0 + b] = 0;
     s.active[b] = nonfinite ? 0 : 1;
     s.fail[b] = 0;
-    if (b == 0) *s.n_active = 0;
+    if (b == 0) s.n_active[0] = s.n_active[1] = 0;  // (instance count of the loop test, retry count of the ladder)
   }
 }
 
@@ -1266,6 +1272,39 @@ __global__ void __launch_bounds__(256) dense_bwd_final_kernel(const DenseBwdArgs
       const int k = a.um.out_idx[i];
       intopt::um_store(a.um, a.inst0 + b, i, k >= 0 ? gc[k] : 0.0);
     }
+  }
+}
+
+// The failure ladder of _get_delta (ip_model_whole.py:798-822) on the lock-step path: an active instance whose Cholesky hit
+// a non-positive pivot gets two more attempts with the diagonal raised by eps * dmax, eps = 1e-12 then 1e-8, before it is
+// reported unsolved.  dmax is bounded by max_k d_k * max_i sum_k A_ik^2 (the largest diagonal entry of A diag(d) A^T can
+// be no larger).  This kernel marks the instances of attempt `rung` (0 / 1) and sets their damping; the assembly and the
+// factorisation then run again on exactly those (everyone else leaves at the mask test).
+__global__ void __launch_bounds__(256) dense_retry_prep_kernel(DenseState s, double delta, double rowsq_max, int rung,
+                                                               int* __restrict__ n_retry) {
+  __shared__ double red[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const bool again = s.active[b] && s.fail[b];
+  if (!again) {
+    if (tid == 0) s.retry[b] = 0;
+    return;
+  }
+  if (tid == 0 && n_retry) atomicAdd(n_retry, 1);
+  double mx = 0.0;
+  for (int k = tid; k < s.n; k += blockDim.x) mx = fmin(mx, -s.D[(long long)b * s.n64 + k]);
+  mx = -block_min(mx, red);
+  if (tid == 0) {
+    s.delta_retry[b] = delta + (rung == 0 ? 1e-12 : 1e-8) * mx * rowsq_max;
+    s.retry[b] = 1;
+    s.fail[b] = 0;
+  }
+}
+
+// Graph form of the ladder: the retry pass of a rung is the body of an IF node that only runs when some instance failed.
+__global__ void dense_if_cond_kernel(cudaGraphConditionalHandle handle, int* __restrict__ n_retry) {
+  if (threadIdx.x == 0) {
+    cudaGraphSetConditional(handle, *n_retry > 0 ? 1u : 0u);
+    *n_retry = 0;
   }
 }
 

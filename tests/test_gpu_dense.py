@@ -246,3 +246,34 @@ def test_m2048_smoke():
     assert status.tolist() == [0, 0] and 2 <= int(iters.min()) and int(iters.max()) <= 6
     assert torch.isfinite(x).all() and torch.isfinite(ct.grad).all() and float(ct.grad.abs().max()) > 0
     ipofunc.clear_cache()
+
+
+def test_dense_path_failure_ladder(dense_path):
+    """_get_delta's failure ladder (ip_model_whole.py:798-822) on the lock-step path: a rank-deficient dense A with a
+    slightly negative damping makes every factorisation hit a non-positive pivot; the two retry rungs (diagonal raised by
+    1e-12, 1e-8 x its bound) recover it and the run ends like one with a small positive damping.  A damping that no rung
+    can repair ends with status 3 and the iterate unchanged."""
+    from neuripsintopt_b200 import ip_model_alter
+    m, B = 24, 5
+    A, b, c = gen_dense(m, B, seed=11)
+    A[m - 1] = A[0] + A[1]                      # dependent row: A D A^T is singular for every D
+    b[m - 1] = b[0] + b[1]
+    c = (np.random.default_rng(2).standard_normal((B, m)) @ A.astype(np.float64) + np.random.default_rng(3).uniform(0.1, 1.0, (B, 2 * m))).astype(np.float32)
+    ct = torch.tensor(c, device="cuda")
+    outs = {}
+    for damping in (-1e-9, 1e-6, -1e3):
+        f = ip_model_alter.IPOfunc(torch.tensor(A), torch.tensor(b), torch.Tensor(), torch.Tensor(), bounds=[(0.0, None)],
+                                   thr=0.1, damping=damping, max_iter=50)
+        x = f(ct)
+        torch.cuda.synchronize()
+        status, iters = ip_model_alter.IPOfunc.status()
+        outs[damping] = (x.double().cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy())
+    x_neg, st_neg, it_neg = outs[-1e-9]
+    x_pos, st_pos, it_pos = outs[1e-6]
+    assert (st_pos == 0).all() and (st_neg == 0).all(), (st_pos, st_neg)
+    assert (it_neg == it_pos).all(), (it_neg, it_pos)
+    err = max(_relinf(x_neg[i], x_pos[i]) for i in range(B))
+    print("dense ladder: x vs the damping=1e-6 run, rel-inf %.2e" % err)
+    assert err < 1e-3, err
+    x_bad, st_bad, it_bad = outs[-1e3]
+    assert (st_bad == 3).all() and np.isfinite(x_bad).all() and (it_bad == 1).all()
