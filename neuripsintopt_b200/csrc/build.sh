@@ -10,7 +10,7 @@ OUT="$HERE/../lib"
 MODE="${1:-product}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall)
-UNITS=(intopt_capi intopt_inst_fwd intopt_inst_fwd_plain intopt_inst_bwd intopt_dense)
+UNITS=(intopt_capi intopt_inst_fwd intopt_inst_fwd_plain intopt_inst_fwd_tmem intopt_inst_bwd intopt_dense)
 LIBNAME=libintopt_b200.so
 OBJDIR="$HERE/../../build/obj"
 if [ "$MODE" = profile ]; then
@@ -21,6 +21,11 @@ if [ "$MODE" = profile ]; then
 fi
 # shellcheck disable=SC2206
 FLAGS+=(${INTOPT_NVCC_EXTRA:-})
+# A/B builds: INTOPT_VARIANT=name (with INTOPT_NVCC_EXTRA="-D...") -> ../lib/libintopt_b200_name.so, objects apart
+if [ -n "${INTOPT_VARIANT:-}" ]; then
+  LIBNAME="${LIBNAME%.so}_${INTOPT_VARIANT}.so"
+  OBJDIR="${OBJDIR}_${INTOPT_VARIANT}"
+fi
 mkdir -p "$OUT" "$OBJDIR"
 newest_dep=$(ls -t "$HERE"/*.cuh "$HERE"/*.hpp "$HERE"/../../include/*.h "$HERE/build.sh" | head -1)
 pids=()

@@ -171,6 +171,7 @@ static std::vector<const void*> all_kernels() {
   std::vector<const void*> v;
   intopt_k::list_forward(v);
   intopt_k::list_forward_plain(v);
+  intopt_k::list_tmem(v);
   intopt_k::list_backward(v);
   return v;
 }
@@ -178,6 +179,13 @@ static const void* pick_kernel(bool forward, int threads, bool allsmem, bool pla
   return forward ? intopt_k::pick_forward(threads, allsmem, plain) : intopt_k::pick_backward(threads, allsmem);
 }
 static const void* pick_cold_kernel(int threads, bool allsmem) { return intopt_k::pick_cold(threads, allsmem); }
+// The tensor-memory kernels (element-wise n-vectors in TMEM instead of the L2-resident workspace): 256-thread CTAs, at most
+// two per SM (each takes half of the SM's 512 columns), and every thread's share of an n-vector must fit its columns.
+static bool tmem_variant(const IntoptProblem* p) {
+  const int th = p->info.threads;
+  return th > 128 && th <= 256 && p->info.ctas_per_sm <= 2 && (p->info.n + th - 1) / th <= intopt::NV_EMAX &&
+         env_int("INTOPT_TMEM", 1) != 0;
+}
 
 namespace {
 // Returns the cold-start factor for `delta` (computing it on `stream` the first time) or nulls if unavailable.
@@ -446,8 +454,10 @@ int intopt_forward_mapped(const IntoptProblem* p, int B, double* c, long long c_
   CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
   {
     void* args[2] = {(void*)&p->dev, (void*)&a};
-    CU_TRY(cudaLaunchKernel(pick_kernel(true, p->info.threads, a.factor_in_smem && a.gather_in_smem, a.plain != 0), dim3(grid),
-                            dim3(p->info.threads), args, (size_t)p->info.smem_bytes, (cudaStream_t)stream));
+    const bool allsmem = a.factor_in_smem && a.gather_in_smem;
+    const int th = p->info.threads;
+    const void* kern = (!a.plain && tmem_variant(p)) ? intopt_k::pick_forward_tmem(allsmem) : pick_kernel(true, th, allsmem, a.plain != 0);
+    CU_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(th), args, (size_t)p->info.smem_bytes, (cudaStream_t)stream));
   }
   CU_TRY(cudaGetLastError());
   return 0;
@@ -518,8 +528,9 @@ int intopt_backward_mapped(const IntoptProblem* p, int B, int mode, double dampi
   CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
   {
     void* args[2] = {(void*)&p->dev, (void*)&a};
-    CU_TRY(cudaLaunchKernel(pick_kernel(false, p->info.threads, a.factor_in_smem && a.gather_in_smem), dim3(grid),
-                            dim3(p->info.threads), args, (size_t)p->info.smem_bytes, (cudaStream_t)stream));
+    const bool allsmem = a.factor_in_smem && a.gather_in_smem;
+    const void* kern = tmem_variant(p) ? intopt_k::pick_backward_tmem(allsmem) : pick_kernel(false, p->info.threads, allsmem);
+    CU_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(p->info.threads), args, (size_t)p->info.smem_bytes, (cudaStream_t)stream));
   }
   CU_TRY(cudaGetLastError());
   return 0;

@@ -52,6 +52,59 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   }
 }
 
+// Tensor memory of a 256-thread CTA: NV_COLS columns for each of its two groups of four warps (half of the SM's 512 columns,
+// so two CTAs fit).  Warp 0 allocates and frees; the address travels through shared memory.
+constexpr int kTmemCols = intopt::NV_COLS * 2;
+__device__ __forceinline__ uint32_t tmem_acquire(const CtaCtx& cx, uint32_t* slot) {
+  if (cx.warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *slot;
+}
+__device__ __forceinline__ void tmem_release(const CtaCtx& cx, uint32_t tmem) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (cx.warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+}
+
+// The same forward with the element-wise n-vectors in tensor memory (see NVTmem): 256-thread CTAs, two per SM, each
+// owning 256 of the SM's 512 columns (two groups of four warps x 128 columns).  Picked at launch when every thread's share
+// of an n-vector fits (n <= 7 * 256).
+template <bool ALLSMEM>
+__global__ void __launch_bounds__(256, 2) intopt_forward_tmem_kernel(const __grid_constant__ intopt::ProblemDev P,
+                                                                     const __grid_constant__ intopt::FwdParams a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_inst;
+  __shared__ uint32_t s_tmem;
+  double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
+  const intopt::SmemLayout S =
+      intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
+  const CtaCtx cx = make_ctx(S.red);
+  const uint32_t tmem = tmem_acquire(cx, &s_tmem);
+  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  const bool cold = a.cold_factor != nullptr && a.init == nullptr && *a.cold_ok != 0;  // launch-uniform
+  if (cold && a.factor_in_smem && threadIdx.x == 0) intopt::mbar_init(S.mbar, 1);
+  unsigned served = 0;
+  for (;;) {
+    if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int inst = s_inst;
+    __syncthreads();
+    if (inst >= a.B) break;
+    intopt::forward_instance_tmem(cx, P, M, a, inst, wsi, S, tmem, cold, served & 1u);
+    ++served;
+  }
+  tmem_release(cx, tmem);
+}
+
 // One CTA computes the cold-start factor chol(A A^T + delta I) with the instance code path (same CTA size).
 template <int TMAX, bool ALLSMEM>
 __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_coldfactor_kernel(const __grid_constant__ intopt::ProblemDev P,
@@ -86,6 +139,29 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
 }
 
 
+template <bool ALLSMEM>
+__global__ void __launch_bounds__(256, 2) intopt_backward_tmem_kernel(const __grid_constant__ intopt::ProblemDev P,
+                                                                      const __grid_constant__ intopt::BwdParams a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_inst;
+  __shared__ uint32_t s_tmem;
+  double* wsi = a.ws + (long long)blockIdx.x * a.ws_stride;
+  const intopt::SmemLayout S =
+      intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
+  const CtaCtx cx = make_ctx(S.red);
+  const uint32_t tmem = tmem_acquire(cx, &s_tmem);
+  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  for (;;) {
+    if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int inst = s_inst;
+    __syncthreads();
+    if (inst >= a.B) break;
+    intopt::backward_instance_tmem(cx, P, M, a, inst, wsi, S, tmem);
+  }
+  tmem_release(cx, tmem);
+}
+
 // Kernel variants: CTA size cap (128: 4 CTAs/SM x 128 registers, 256: 2 x 128, 512: 1 x 128; 192: 2 x 168 only in
 // profiling builds) x whether every buffer is in shared memory.
 #ifdef INTOPT_PROFILE
@@ -97,9 +173,12 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
 
 namespace intopt_k {
 const void* pick_forward(int threads, bool allsmem, bool plain);
+const void* pick_forward_tmem(bool allsmem);
+const void* pick_backward_tmem(bool allsmem);
 const void* pick_backward(int threads, bool allsmem);
 const void* pick_cold(int threads, bool allsmem);
 void list_forward(std::vector<const void*>& v);
 void list_forward_plain(std::vector<const void*>& v);
+void list_tmem(std::vector<const void*>& v);
 void list_backward(std::vector<const void*>& v);
 }  // namespace intopt_k

@@ -395,6 +395,65 @@ IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const 
     // sorted by run count) are contiguous and fetched with up to three 16-byte loads that are all in flight
     // together; groups of 4 / 8 headers take the shorter batches, so padding headers cost nothing beyond the
     // rounding of R to a multiple of four.
+#ifndef INTOPT_HOST_EMU
+    // A group costs one L2 round trip for its headers (and one for its target position) before any arithmetic can
+    // start, and a warp walks ~36 groups: the first four headers, the position and the diagonal flag of the warp's NEXT
+    // group are requested before the current group is summed (same sums, same order: bit-identical).
+    {
+      struct Pre {
+        int r0, R, pos, dg;
+        U4 h;
+      };
+      auto fetch = [&](int g) {
+        Pre f;
+        f.r0 = M.asm_rptr[g];
+        f.R = M.asm_rptr[g + 1] - f.r0;
+        f.h.x = f.h.y = f.h.z = f.h.w = 0u;  // (len 0 runs contribute exactly 0)
+        if (f.R > 0) f.h = *reinterpret_cast<const U4*>(P.asm_run + (size_t)f.r0 * 32 + (size_t)cx.lane * f.R);
+        const int e = g * 32 + cx.lane;
+        f.pos = P.asm_pos[e];
+        f.dg = P.asm_diag[e];
+        return f;
+      };
+      int grp = cx.warp;
+      Pre cur{};
+      if (grp < ngrp) cur = fetch(grp);
+      while (grp < ngrp) {
+        const int nxt = grp + cx.nwarps;
+        Pre nx = cur;
+        if (nxt < ngrp) nx = fetch(nxt);
+        double s0 = 0.0, s1 = 0.0;
+        {
+          const uint32_t h[4] = {cur.h.x, cur.h.y, cur.h.z, cur.h.w};
+#pragma unroll
+          for (int u = 0; u < 4; u += 2) {
+            const int a0 = (int)(h[u] & 0xffffu), a1 = (int)(h[u + 1] & 0xffffu);
+            const D2 lo0 = PP[a0], hi0 = PP[a0 + (int)(h[u] >> 16)];
+            const D2 lo1 = PP[a1], hi1 = PP[a1 + (int)(h[u + 1] >> 16)];
+            s0 += dd_diff(hi0, lo0);
+            s1 += dd_diff(hi1, lo1);
+          }
+        }
+        const uint32_t* __restrict__ hp = P.asm_run + (size_t)cur.r0 * 32 + (size_t)cx.lane * cur.R;
+        for (int rb = 4; rb < cur.R;) {
+          const int left = cur.R - rb;
+          if (left >= 12) {
+            asm_run_batch<3>(hp + rb, PP, s0, s1);
+            rb += 12;
+          } else if (left >= 8) {
+            asm_run_batch<2>(hp + rb, PP, s0, s1);
+            rb += 8;
+          } else {
+            asm_run_batch<1>(hp + rb, PP, s0, s1);
+            rb += 4;
+          }
+        }
+        if (cur.pos >= 0) L[cur.pos] = cur.dg ? (s0 + s1) + delta : (s0 + s1);
+        cur = nx;
+        grp = nxt;
+      }
+    }
+#else
     WARP_ROWS(grp, ngrp) {
       const int r0 = M.asm_rptr[grp], R = M.asm_rptr[grp + 1] - r0;
       LANE_FOR(l, 0, 32) {
@@ -417,6 +476,7 @@ IO_DEV void assemble_normal_matrix(const CtaCtx& cx, const ProblemDev& P, const 
         if (pos >= 0) L[pos] = P.asm_diag[e] ? (s0 + s1) + delta : (s0 + s1);
       }
     }
+#endif
     CTA_SYNC();
     return;
   }
@@ -812,17 +872,21 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
       }
     }
     if (cx.nwarps == 1 || cx.warp > 0) {
+      // one item = one row of a block, applied to every right-hand side (the row is read from shared memory once)
       const int nrest = na - lead;
-      for (int idx = o_tid; idx < nrest * KB * NR; idx += o_n) {
-        const int q = idx / (nrest * KB), rem = idx - q * (nrest * KB);
-        const int I = M.act_blk[a0 + lead + (rem >> 3)], rr = rem & 7;
-        double row[KB], yk[KB];
+      for (int idx = o_tid; idx < nrest * KB; idx += o_n) {
+        const int I = M.act_blk[a0 + lead + (idx >> 3)], rr = idx & 7;
+        double row[KB];
         load_row(L + M.boff[I] + (K - M.fb[I]) * 64, rr, row);
-        load_vec8(ycur + q * KB, yk);
-        double sacc = 0.0;
 #pragma unroll
-        for (int k = 0; k < KB; ++k) sacc = fma(row[k], yk[k], sacc);
-        rhs_sel<NR>(r, q)[I * KB + rr] -= sacc;
+        for (int q = 0; q < NR; ++q) {
+          double yk[KB];
+          load_vec8(ycur + q * KB, yk);
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = 0; k < KB; ++k) sacc = fma(row[k], yk[k], sacc);
+          rhs_sel<NR>(r, q)[I * KB + rr] -= sacc;
+        }
       }
     }
     CTA_SYNC();
@@ -871,24 +935,28 @@ IO_DEV void block_solve(const CtaCtx& cx, const ProblemDev& P, const Meta& M, co
     }
     if (cx.nwarps == 1 || cx.warp > 0) {
       const int nk = I - f - lead;  // block columns f .. I-1-lead
-      for (int idx = o_tid; idx < nk * 4 * NR; idx += o_n) {
-        const int q = idx / (nk * 4), rem = idx - q * (nk * 4);
-        const int Kc = f + (rem >> 2), c = rem & 3;
+      for (int idx = o_tid; idx < nk * 4; idx += o_n) {  // (two columns of a block, for every right-hand side)
+        const int Kc = f + (idx >> 2), c = idx & 3;
         const double* blk = L + M.boff[I] + (Kc - f) * 64;
-        double zi[KB];
-        load_vec8(zcur + q * KB, zi);
-        double sx = 0.0, sy = 0.0;
+        D2 col[KB];
 #pragma unroll
-        for (int i = 0; i < KB; ++i) {
-          const D2 t2 = reinterpret_cast<const D2*>(blk + i * KB)[c ^ bswz(i)];
-          sx = fma(t2.x, zi[i], sx);
-          sy = fma(t2.y, zi[i], sy);
+        for (int i = 0; i < KB; ++i) col[i] = reinterpret_cast<const D2*>(blk + i * KB)[c ^ bswz(i)];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+          double zi[KB];
+          load_vec8(zcur + q * KB, zi);
+          double sx = 0.0, sy = 0.0;
+#pragma unroll
+          for (int i = 0; i < KB; ++i) {
+            sx = fma(col[i].x, zi[i], sx);
+            sy = fma(col[i].y, zi[i], sy);
+          }
+          D2* dst = reinterpret_cast<D2*>(rhs_sel<NR>(r, q) + Kc * KB) + c;
+          D2 t2 = *dst;
+          t2.x -= sx;
+          t2.y -= sy;
+          *dst = t2;
         }
-        D2* dst = reinterpret_cast<D2*>(rhs_sel<NR>(r, q) + Kc * KB) + c;
-        D2 t2 = *dst;
-        t2.x -= sx;
-        t2.y -= sy;
-        *dst = t2;
       }
     }
     CTA_SYNC();
@@ -1460,24 +1528,79 @@ IO_DEV void factor_and_rhs(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
   CTA_SYNC();
 }
 
+// ---- where the forward's element-wise n-vectors live ---------------------------------------------------------------
+// Nine n-vectors (x, t, c, D, r_d, w, p, d_x, d_x*d_t) are only ever touched element-wise, and always by the same thread:
+// element k belongs to thread k % nthreads.  In the workspace in global memory every pass over them is a chain of L2 round
+// trips (the loops are not batched: registers).  Tensor memory is the other place that can hold them: 256 KB per SM
+// that this kernel does not otherwise use, addressed per lane (a thread reads and writes only its own 32-bit cells, which
+// is exactly the access pattern here), with a load-to-use latency of some 40 cycles instead of an L2 hit's ~700.  The loops
+// below are written once against an accessor; NVGlobal is the workspace version, NVTmem the tensor-memory version
+// (tcgen05.ld / tcgen05.st, shape 32x32b.x2 = one double per thread and access).
+enum { V_X = 0, V_T, V_C, V_D, V_R2, V_W, V_P, V_DX, V_DXDT, V_SLOTS };
+constexpr int NV_EMAX = 7;     // elements per thread and vector: 9 vectors * 7 elements * 2 columns = 126 <= 128
+constexpr int NV_COLS = 128;   // tensor-memory columns of one group of four warps (warps w and w + 4 share lanes)
+
+struct NVGlobal {
+  static constexpr bool kTmem = false;
+  typedef double Val;
+  double* v[V_SLOTS];
+  int n;
+  IO_DEV Val ld(int s, int, int k) const { return k < n ? v[s][k] : 1.0; }
+  IO_DEV void ld_wait() const {}
+  IO_DEV double get(Val& r) const { return r; }
+  IO_DEV void st(int s, int, int k, double val) const {
+    if (k < n) v[s][k] = val;
+  }
+  IO_DEV void st_wait() const {}
+};
+
+#ifndef INTOPT_HOST_EMU
+struct NVTmem {
+  static constexpr bool kTmem = true;
+  struct Val {
+    uint32_t lo, hi;
+  };
+  uint32_t base;  // this thread's lane (bits 31:16) and the first column of its warp group
+  __device__ __forceinline__ Val ld(int s, int j, int) const {
+    Val r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
+                 : "=r"(r.lo), "=r"(r.hi)
+                 : "r"(base + 2u * (unsigned)(s * NV_EMAX + j))
+                 : "memory");
+    return r;
+  }
+  __device__ __forceinline__ void ld_wait() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+  __device__ __forceinline__ double get(Val& r) const {
+    asm volatile("" : "+r"(r.lo), "+r"(r.hi));  // (pins the first use behind the wait)
+    return __hiloint2double((int)r.hi, (int)r.lo);
+  }
+  __device__ __forceinline__ void st(int s, int j, int, double val) const {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(base + 2u * (unsigned)(s * NV_EMAX + j)),
+                 "r"((uint32_t)__double2loint(val)), "r"((uint32_t)__double2hiint(val))
+                 : "memory");
+  }
+  __device__ __forceinline__ void st_wait() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+};
+#endif
+
+// With tensor memory every thread runs the same number of trips (the accesses are warp-collective) and the element index
+// is checked where it matters; with the workspace the loop is CTA_FOR.  Per thread the elements come in ascending order.
+#define NV_FOR(j, k) for (int j = 0, k = cx.tid; TM ? j < nv_trips : k < n; ++j, k += cx.nthreads)
+
 // PLAIN = false: Mehrotra predictor-corrector (pc=True upstream, every reference driver).  PLAIN = true: pc=False.  A
 // template parameter, and one kernel per value, rather than a run-time switch: the run-time version cost the
 // predictor-corrector path 0.45 %, both instantiations inside one kernel 3.8 % (register allocation).
-template <bool PLAIN>
-IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst, double* wsi,
-                               const SmemLayout& S, bool cold = false, unsigned cold_parity = 0) {
+template <bool PLAIN, class NV>
+IO_DEV void forward_instance_nv(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst, double* wsi,
+                                const SmemLayout& S, const NV& nv, bool cold = false, unsigned cold_parity = 0) {
+  constexpr bool TM = NV::kTmem;
   if (a.a_vals)  // (M already points at the CTA's value streams, see instance_value_streams)
     fill_instance_values(cx, P, a.a_vals + (long long)inst * a.a_stride, a.vals_ws + (long long)blockIdx_x() * a.vals_ws_stride);
   const int m = P.m, n = P.n, mv = P.mv;
+  const int nv_trips = (n + cx.nthreads - 1) / cx.nthreads;
   double *L = S.L, *G = S.G, *bs = S.bs, *y = S.y, *r1 = S.r1, *q = S.q, *v = S.v;
-  double* __restrict__ x = wsi + (long long)W_X * n;
-  double* __restrict__ t = wsi + (long long)W_T * n;
-  double* __restrict__ D = wsi + (long long)W_D * n;
-  double* __restrict__ r2 = wsi + (long long)W_R2 * n;
-  double* __restrict__ p = wsi + (long long)W_P * n;
-  double* __restrict__ w = wsi + (long long)W_W * n;
-  double* __restrict__ dx = wsi + (long long)W_DX * n;
-  double* __restrict__ dxdt = wsi + (long long)W_DXDT * n;
+  // D is also kept in the workspace (the assembly's prefix sums read it in their own order)
+  double* __restrict__ Dg = wsi + (long long)W_D * n;
   // A^T y, carried along the iteration: y only ever changes by alpha * (v + q dtau), and A^T(v + q dtau) is what the
   // direction was built from, so the product never has to be formed again after the starting point
   double* __restrict__ aty = wsi + (long long)W_ATY * n;
@@ -1491,11 +1614,18 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
   PHASE_START(pt);
   if (a.um.in) {  // the caller's cost vector -> this instance's standard-form row (kept for the backward)
     double* cw = const_cast<double*>(a.c) + (long long)inst * a.c_stride;
-    CTA_FOR(k, n) {
-      const int src = a.um.in_idx[k];
-      cw[k] = src >= 0 ? (a.um.in_scale ? a.um.in_scale[k] : 1.0) * um_load(a.um, inst, src) : 0.0;
+    NV_FOR(j, k) {
+      double ck = 0.0;
+      if (k < n) {
+        const int src = a.um.in_idx[k];
+        ck = src >= 0 ? (a.um.in_scale ? a.um.in_scale[k] : 1.0) * um_load(a.um, inst, src) : 0.0;
+        cw[k] = ck;
+      }
+      if (TM) nv.st(V_C, j, k, ck);
     }
     CTA_SYNC();
+  } else if (TM) {
+    NV_FOR(j, k) nv.st(V_C, j, k, k < n ? c[k] : 0.0);
   }
   const bool l_in_smem = a.factor_in_smem != 0;
   if (cold) cold_copy_begin(cx, P, a.cold_factor, L, S.mbar, l_in_smem);
@@ -1515,10 +1645,15 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
   CTA_SYNC();
   if (a.init) {
     const double* s0 = a.init + (long long)inst * slen;
-    CTA_FOR(k, n) {
-      x[k] = s0[k];
-      gstore(G, k, s0[k]);
-      t[k] = s0[n + m + k];
+    NV_FOR(j, k) {
+      double xk = 1.0, tk = 1.0;
+      if (k < n) {
+        xk = s0[k];
+        tk = s0[n + m + k];
+        gstore(G, k, xk);
+      }
+      nv.st(V_X, j, k, xk);
+      nv.st(V_T, j, k, tk);
     }
     CTA_FOR(i, m) y[i] = s0[n + P.perm[i]];
     tau = s0[2 * n + m];
@@ -1526,13 +1661,16 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
     CTA_SYNC();
     CTA_FOR(k, n) aty[k] = col_dot(P, M, k, y);
   } else {
-    CTA_FOR(k, n) {
-      aty[k] = 0.0;  // y = 0
-      x[k] = 1.0;
-      gstore(G, k, 1.0);  // G mirrors x at every loop top: the residual A x gathers from shared memory
-      t[k] = 1.0;
+    NV_FOR(j, k) {
+      if (k < n) {
+        aty[k] = 0.0;       // y = 0
+        gstore(G, k, 1.0);  // G mirrors x at every loop top: the residual A x gathers from shared memory
+      }
+      nv.st(V_X, j, k, 1.0);
+      nv.st(V_T, j, k, 1.0);
     }
   }
+  nv.st_wait();
   CTA_SYNC();
 
   // ---- cold-start residual norms for the indicators (:884,907-910) -----------------------------
@@ -1540,12 +1678,16 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
   int nonfinite = 0;
   {
     double acc[3] = {0.0, 0.0, 0.0};
-    CTA_FOR(k, n) {
-      const double ck = c[k];
-      const double e = ck - 1.0;
-      acc[0] = fma(e, e, acc[0]);
-      acc[1] += ck;
-      if (!(fabs(ck) < 1e300)) acc[2] += 1.0;
+    NV_FOR(j, k) {
+      typename NV::Val cr = nv.ld(V_C, j, k);
+      nv.ld_wait();
+      const double ck = nv.get(cr);
+      if (k < n) {
+        const double e = ck - 1.0;
+        acc[0] = fma(e, e, acc[0]);
+        acc[1] += ck;
+        if (!(fabs(ck) < 1e300)) acc[2] += 1.0;
+      }
     }
     double accp = 0.0;  // ||b - A 1||
     if (P.a_unit) {  // row sum of a 0/1 matrix = its entry count (exactly what summing the ones gives)
@@ -1581,25 +1723,24 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
   while (status != ST_NONFINITE) {
     // ---- residuals at the current iterate (:765-770; the same r_p, r_d as _indicators :887-894) ----
     double acc[3] = {0.0, 0.0, 0.0};
-    CTA_BATCH_FOR(k0, n, NUC) {
-      double xv[NUC], tv[NUC], cv[NUC], av[NUC];
-      BATCH_EACH(u, k, k0, n, NUC) {
-        xv[u] = x[k];
-        tv[u] = t[k];
-        cv[u] = c[k];
-        av[u] = aty[k];
-      }
-      BATCH_EACH(u, k, k0, n, NUC) {
-        const double xk = xv[u], tk = tv[u], ck = cv[u];
-        const double r = -(av[u] + tk - ck * tau);  // :766
-        const double dk = xk / tk;                // :772
-        r2[k] = r;
-        D[k] = dk;
+    NV_FOR(j, k) {
+      typename NV::Val xr = nv.ld(V_X, j, k), tr = nv.ld(V_T, j, k), cr = nv.ld(V_C, j, k);
+      const bool ok = k < n;
+      const double av = ok ? aty[k] : 0.0;
+      nv.ld_wait();
+      const double xk = nv.get(xr), tk = nv.get(tr), ck = nv.get(cr);
+      const double r = -(av + tk - ck * tau);  // :766
+      const double dk = xk / tk;               // :772
+      nv.st(V_R2, j, k, r);
+      nv.st(V_D, j, k, dk);
+      if (ok) {
+        if (TM) Dg[k] = dk;
         acc[0] = fma(xk, tk, acc[0]);
         acc[1] = fma(ck, xk, acc[1]);
         acc[2] = fma(r, r, acc[2]);
       }
     }
+    nv.st_wait();
     if (iters > 0 && a.thr > 0.0) {
       // Early stop (:1408): with thr > 0 the loop usually ends because mu <= thr, which makes `go` false whatever the
       // residuals are.  If moreover tau is not tiny, both infeasibility tests (:1409-1413) are false without looking
@@ -1682,9 +1823,9 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
   factor_again:
     if (!reuse_cold) {
 #ifdef INTOPT_PROFILE
-      assemble_normal_matrix(cx, P, M, D, G, S.scan, a.damping, L, a.debug);
+      assemble_normal_matrix(cx, P, M, Dg, G, S.scan, a.damping, L, a.debug);
 #else
-      assemble_normal_matrix(cx, P, M, D, G, S.scan, a.damping, L);
+      assemble_normal_matrix(cx, P, M, Dg, G, S.scan, a.damping, L);
 #endif
       if (attempt > 0) {
         double mx[1] = {0.0};
@@ -1705,29 +1846,26 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
     // right-hand sides of the (p,q) solve (:800) and of the predictor (gamma = 0, eta = 1): G = D*c and, in the
     // upper half of the gather region (only the assembly's prefix sums use it), G2 = D*w
     double* G2 = G + gather_len(n);
-    CTA_BATCH_FOR(k0, n, NU) {
-      double dv[NU], cv[NU], xv[NU], tv[NU], rv[NU];
-      BATCH_EACH(u, k, k0, n, NU) {
-        dv[u] = D[k];
-        cv[u] = c[k];
-        xv[u] = x[k];
-        tv[u] = t[k];
-        rv[u] = r2[k];
+    NV_FOR(j, k) {
+      typename NV::Val dr = nv.ld(V_D, j, k), cr = nv.ld(V_C, j, k), xr = nv.ld(V_X, j, k), tr = nv.ld(V_T, j, k),
+                       rr = nv.ld(V_R2, j, k);
+      nv.ld_wait();
+      const double dk = nv.get(dr), ck = nv.get(cr), xk = nv.get(xr), tk = nv.get(tr), rk = nv.get(rr);
+      double wk;
+      if (!PLAIN) {
+        const double rxt = -(xk * tk);    // :788 with gamma = 0
+        wk = rk - (1.0 / xk) * rxt;       // :801 with eta(0) = 1
+      } else {
+        const double rxt = -(xk * tk - gm0);
+        wk = eta0 * rk - (1.0 / xk) * rxt;
       }
-      BATCH_EACH(u, k, k0, n, NU) {
-        gstore(G, k, dv[u] * cv[u]);
-        double wk;
-        if (!PLAIN) {
-          const double rxt = -(xv[u] * tv[u]);      // :788 with gamma = 0
-          wk = rv[u] - (1.0 / xv[u]) * rxt;         // :801 with eta(0) = 1
-        } else {
-          const double rxt = -(xv[u] * tv[u] - gm0);
-          wk = eta0 * rv[u] - (1.0 / xv[u]) * rxt;
-        }
-        w[k] = wk;
-        gstore(G2, k, dv[u] * wk);
+      nv.st(V_W, j, k, wk);
+      if (k < n) {
+        gstore(G, k, dk * ck);
+        gstore(G2, k, dk * wk);
       }
     }
+    nv.st_wait();
     CTA_SYNC();  // G, G2 complete
     // The factorisation is a dependent chain that keeps few warps busy, and the two products A(D c), A(D w) do not
     // depend on it: with enough warps the CTA splits, the last RHS_WARPS warps form the right-hand sides while the
@@ -1755,7 +1893,12 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
     CTA_SYNC();
     PHASE_MARK(pt, 3);
     if (!solved) {  // deltas = 0 (:855-857): the iterate is unchanged, the tests run at loop top
-      CTA_FOR(k, n) gstore(G, k, x[k]);  // G must mirror x again
+      NV_FOR(j, k) {  // G must mirror x again
+        typename NV::Val xr = nv.ld(V_X, j, k);
+        nv.ld_wait();
+        const double xk = nv.get(xr);
+        if (k < n) gstore(G, k, xk);
+      }
       CTA_SYNC();
       continue;
     }
@@ -1768,26 +1911,24 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
     double cp_, bq_, cu_, bv_;
     {
       double acc2[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-      CTA_BATCH_FOR(k0, n, NUC) {
-        double dv[NUC], cv[NUC], wv[NUC];
-        BATCH_EACH(u, k, k0, n, NUC) {
-          dv[u] = D[k];
-          cv[u] = c[k];
-          wv[u] = w[k];
-        }
-        BATCH_EACH(u, k, k0, n, NUC) {
-          double atq, atv;
-          col_dot2(P, M, k, q, v, atq, atv);
-          const double dk = dv[u], ck = cv[u];
-          const double pk = dk * (atq - ck);     // :678 for (c,b)
-          const double uk = dk * (atv - wv[u]);  // :678 for the predictor
-          p[k] = pk;
-          dx[k] = uk;
+      NV_FOR(j, k) {
+        typename NV::Val dr = nv.ld(V_D, j, k), cr = nv.ld(V_C, j, k), wr = nv.ld(V_W, j, k);
+        const bool ok = k < n;
+        double atq = 0.0, atv = 0.0;
+        if (ok) col_dot2(P, M, k, q, v, atq, atv);
+        nv.ld_wait();
+        const double dk = nv.get(dr), ck = nv.get(cr), wk = nv.get(wr);
+        const double pk = dk * (atq - ck);  // :678 for (c,b)
+        const double uk = dk * (atv - wk);  // :678 for the predictor
+        nv.st(V_P, j, k, pk);
+        nv.st(V_DX, j, k, uk);
+        if (ok) {
           acc2[0] = fma(ck, pk, acc2[0]);
           acc2[2] = fma(ck, uk, acc2[2]);
           if (!(fabs(pk) < 1e300)) acc2[4] += 1.0;
         }
       }
+      nv.st_wait();
       CTA_FOR(i, m) {
         acc2[1] = fma(bs[i], q[i], acc2[1]);
         acc2[3] = fma(bs[i], v[i], acc2[3]);
@@ -1800,7 +1941,12 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
       bv_ = acc2[3];
       if (acc2[4] > 0.0) {  // NaN in p or q (:805-806) -> unsolved
         solved = false;
-        CTA_FOR(k, n) gstore(G, k, x[k]);
+        NV_FOR(j, k) {  // G must mirror x again
+          typename NV::Val xr = nv.ld(V_X, j, k);
+          nv.ld_wait();
+          const double xk = nv.get(xr);
+          if (k < n) gstore(G, k, xk);
+        }
         CTA_SYNC();
         continue;
       }
@@ -1815,22 +1961,17 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
       double rtk = -(tau * kappa - gm);     // :789
       if (pass == 1) rtk -= dtau * dkappa;  // :795
       if (pass == 1) {
-        CTA_BATCH_FOR(k0, n, NU) {
-          double xv[NU], tv[NU], rv[NU], dv[NU], ev[NU];
-          BATCH_EACH(u, k, k0, n, NU) {
-            xv[u] = x[k];
-            tv[u] = t[k];
-            rv[u] = r2[k];
-            dv[u] = D[k];
-            ev[u] = dxdt[k];
-          }
-          BATCH_EACH(u, k, k0, n, NU) {
-            const double rxt = -(xv[u] * tv[u] - gm) - ev[u];      // :788,793
-            const double wk = eta * rv[u] - (1.0 / xv[u]) * rxt;  // :801
-            w[k] = wk;
-            gstore(G, k, dv[u] * wk);
-          }
+        NV_FOR(j, k) {
+          typename NV::Val xr = nv.ld(V_X, j, k), tr = nv.ld(V_T, j, k), rr = nv.ld(V_R2, j, k), dr = nv.ld(V_D, j, k),
+                           er = nv.ld(V_DXDT, j, k);
+          nv.ld_wait();
+          const double xk = nv.get(xr), tk = nv.get(tr), rk = nv.get(rr), dk = nv.get(dr), ek = nv.get(er);
+          const double rxt = -(xk * tk - gm) - ek;         // :788,793
+          const double wk = eta * rk - (1.0 / xk) * rxt;  // :801
+          nv.st(V_W, j, k, wk);
+          if (k < n) gstore(G, k, dk * wk);
         }
+        nv.st_wait();
         CTA_SYNC();
         PHASE_MARK(pt, 21);
         spmv_rows(cx, P, M, G, v);
@@ -1845,20 +1986,17 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
         }
         PHASE_MARK(pt, 8);
         double acc3[2] = {0.0, 0.0};
-        CTA_BATCH_FOR(k0, n, NUC) {
-          double dv[NUC], cv[NUC], wv[NUC];
-          BATCH_EACH(u, k, k0, n, NUC) {
-            dv[u] = D[k];
-            cv[u] = c[k];
-            wv[u] = w[k];
-          }
-          BATCH_EACH(u, k, k0, n, NUC) {
-            const double atv = col_dot(P, M, k, v);
-            const double uk = dv[u] * (atv - wv[u]);  // :678
-            dx[k] = uk;
-            acc3[0] = fma(cv[u], uk, acc3[0]);
-          }
+        NV_FOR(j, k) {
+          typename NV::Val dr = nv.ld(V_D, j, k), cr = nv.ld(V_C, j, k), wr = nv.ld(V_W, j, k);
+          const bool ok = k < n;
+          const double atv = ok ? col_dot(P, M, k, v) : 0.0;
+          nv.ld_wait();
+          const double dk = nv.get(dr), ck = nv.get(cr), wk = nv.get(wr);
+          const double uk = dk * (atv - wk);  // :678
+          nv.st(V_DX, j, k, uk);
+          if (ok) acc3[0] = fma(ck, uk, acc3[0]);
         }
+        nv.st_wait();
         CTA_FOR(i, m) acc3[1] = fma(bs[i], v[i], acc3[1]);
         cta_sum<2>(cx, acc3);
         cu_ = acc3[0];
@@ -1869,30 +2007,26 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
       // ratio test (:871-875): min over x/-dx and t/-dt of the decreasing components = 1 / max(-dx/x, -dt/t); the
       // reciprocals come from 1/x (needed for d_t anyway) and 1/t = D/x, so the loop has one division instead of three
       double mn[1] = {INFINITY};
-      CTA_BATCH_FOR(k0, n, NU) {
-        double xv[NU], tv[NU], uv[NU], pv[NU], ev[NU], dv[NU];
-        BATCH_EACH(u, k, k0, n, NU) {
-          xv[u] = x[k];
-          tv[u] = t[k];
-          uv[u] = dx[k];
-          pv[u] = p[k];
-          dv[u] = D[k];
-          ev[u] = pass == 1 ? dxdt[k] : 0.0;
-        }
-        BATCH_EACH(u, k, k0, n, NU) {
-          const double xk = xv[u], tk = tv[u];
-          double rxt = -(xk * tk - gm);
-          if (pass == 1) rxt -= ev[u];
-          const double dxk = uv[u] + pv[u] * dtau;  // :839
-          const double rx = 1.0 / xk;
-          const double dtk = rx * (rxt - tk * dxk);  // :841
-          dx[k] = dxk;
-          if (pass == 0) dxdt[k] = dxk * dtk;
+      NV_FOR(j, k) {
+        typename NV::Val xr = nv.ld(V_X, j, k), tr = nv.ld(V_T, j, k), ur = nv.ld(V_DX, j, k), pr = nv.ld(V_P, j, k),
+                         dr = nv.ld(V_D, j, k), er = xr;
+        if (pass == 1) er = nv.ld(V_DXDT, j, k);
+        nv.ld_wait();
+        const double xk = nv.get(xr), tk = nv.get(tr), uk = nv.get(ur), pk = nv.get(pr), dk = nv.get(dr);
+        double rxt = -(xk * tk - gm);
+        if (pass == 1) rxt -= nv.get(er);
+        const double dxk = uk + pk * dtau;  // :839
+        const double rx = 1.0 / xk;
+        const double dtk = rx * (rxt - tk * dxk);  // :841
+        nv.st(V_DX, j, k, dxk);
+        if (pass == 0) nv.st(V_DXDT, j, k, dxk * dtk);
+        if (k < n) {
           // -mn[0] tracks max(-dx/x, -dt/t) over the decreasing components (as a min of the negated values)
           if (dxk < 0.0) mn[0] = fmin(mn[0], dxk * rx);
-          if (dtk < 0.0) mn[0] = fmin(mn[0], dtk * (dv[u] * rx));
+          if (dtk < 0.0) mn[0] = fmin(mn[0], dtk * (dk * rx));
         }
       }
+      nv.st_wait();
       cta_min<1>(cx, mn);
       minr = mn[0] < 0.0 ? -1.0 / mn[0] : INFINITY;
       PHASE_MARK(pt, 23);
@@ -1907,28 +2041,28 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
         double al = fmin(1.0, a.alpha0 * minr);
         if (dtau < 0.0) al = fmin(al, a.alpha0 * tau / -dtau);  // evaluation order of :874,876
         if (dkappa < 0.0) al = fmin(al, a.alpha0 * kappa / -dkappa);
-        CTA_BATCH_FOR(k0, n, NU) {
-          double xv[NU], tv[NU], uv[NU], ev[NU];
-          BATCH_EACH(u, k, k0, n, NU) {
-            xv[u] = x[k];
-            tv[u] = t[k];
-            uv[u] = dx[k];
-            ev[u] = pass == 1 ? dxdt[k] : 0.0;  // Mehrotra term of the corrector only (:793)
-          }
-          BATCH_EACH(u, k, k0, n, NU) {
-            const double xk = xv[u], tk = tv[u];
-            const double rxt = -(xk * tk - gm) - ev[u];
-            const double dxk = uv[u];
-            const double rx = 1.0 / xk;
-            const double dtk = rx * (rxt - tk * dxk);
-            const double xn = xk + al * dxk;
-            x[k] = xn;
+        NV_FOR(j, k) {
+          typename NV::Val xr = nv.ld(V_X, j, k), tr = nv.ld(V_T, j, k), ur = nv.ld(V_DX, j, k), wr = nv.ld(V_W, j, k),
+                           cr = nv.ld(V_C, j, k), er = xr;
+          if (pass == 1) er = nv.ld(V_DXDT, j, k);
+          const bool ok = k < n;
+          const double av = ok ? aty[k] : 0.0;
+          nv.ld_wait();
+          const double xk = nv.get(xr), tk = nv.get(tr), dxk = nv.get(ur), wk = nv.get(wr), ck = nv.get(cr);
+          const double ek = pass == 1 ? nv.get(er) : 0.0;  // Mehrotra term of the corrector only (:793)
+          const double rxt = -(xk * tk - gm) - ek;
+          const double rx = 1.0 / xk;
+          const double dtk = rx * (rxt - tk * dxk);
+          const double xn = xk + al * dxk;
+          nv.st(V_X, j, k, xn);
+          nv.st(V_T, j, k, tk + al * dtk);
+          if (ok) {
             gstore(G, k, xn);
-            t[k] = tk + al * dtk;
             // A^T d_y = A^T v + dtau A^T q, recovered from d_x = D (A^T v - w) + D (A^T q - c) dtau with 1/D = t/x
-            aty[k] = aty[k] + al * (dxk * tk * rx + w[k] + dtau * c[k]);
+            aty[k] = av + al * (dxk * tk * rx + wk + dtau * ck);
           }
         }
+        nv.st_wait();
         CTA_FOR(i, m) y[i] = y[i] + al * (v[i] + q[i] * dtau);  // d_y = v + q d_tau (:840)
         tau = tau + al * dtau;
         kappa = kappa + al * dkappa;
@@ -1942,22 +2076,21 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
   // ---- epilogue (:1441-1447): x_hat = x / tau, save the iterate ------------------------------------
   double* st = a.state + (long long)inst * slen;
   double* xh = a.xhat ? a.xhat + (long long)inst * n : nullptr;
-  CTA_BATCH_FOR(k0, n, NU) {
-    double xv[NU], tv[NU];
-    BATCH_EACH(u, k, k0, n, NU) {
-      xv[u] = x[k];
-      tv[u] = t[k];
-    }
-    BATCH_EACH(u, k, k0, n, NU) {
-      if (xh) xh[k] = xv[u] / tau;
-      st[k] = xv[u];
-      st[n + m + k] = tv[u];
+  NV_FOR(j, k) {
+    typename NV::Val xr = nv.ld(V_X, j, k), tr = nv.ld(V_T, j, k);
+    nv.ld_wait();
+    const double xk = nv.get(xr), tk = nv.get(tr);
+    if (k < n) {
+      if (xh) xh[k] = xk / tau;
+      st[k] = xk;
+      st[n + m + k] = tk;
     }
   }
   if (a.um.out) {  // x in the caller's layout and precision, presolve-fixed variables re-inserted (_postprocess :1241-1285)
+    // (any element, not only this thread's: G mirrors x whenever the loop is left, and a barrier has passed since)
     CTA_FOR(i, a.um.n_out) {
       const int k = a.um.out_idx[i];
-      um_store(a.um, inst, i, k >= 0 ? x[k] / tau : (a.um.out_const ? a.um.out_const[i] : 0.0));
+      um_store(a.um, inst, i, k >= 0 ? G[gpad(k)] / tau : (a.um.out_const ? a.um.out_const[i] : 0.0));
     }
   }
   CTA_FOR(i, m) st[n + P.perm[i]] = y[i];
@@ -1970,6 +2103,35 @@ IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta
   CTA_SYNC();
   PHASE_MARK(pt, 10);
 }
+
+template <bool PLAIN>
+IO_DEV void forward_instance_t(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst, double* wsi,
+                               const SmemLayout& S, bool cold = false, unsigned cold_parity = 0) {
+  const int n = P.n;
+  NVGlobal nv;
+  nv.n = n;
+  nv.v[V_X] = wsi + (long long)W_X * n;
+  nv.v[V_T] = wsi + (long long)W_T * n;
+  nv.v[V_C] = const_cast<double*>(a.c) + (long long)inst * a.c_stride;  // (never stored to)
+  nv.v[V_D] = wsi + (long long)W_D * n;
+  nv.v[V_R2] = wsi + (long long)W_R2 * n;
+  nv.v[V_W] = wsi + (long long)W_W * n;
+  nv.v[V_P] = wsi + (long long)W_P * n;
+  nv.v[V_DX] = wsi + (long long)W_DX * n;
+  nv.v[V_DXDT] = wsi + (long long)W_DXDT * n;
+  forward_instance_nv<PLAIN>(cx, P, M, a, inst, wsi, S, nv, cold, cold_parity);
+}
+
+#ifndef INTOPT_HOST_EMU
+// The predictor-corrector forward with the nine element-wise n-vectors in tensor memory (tmem_base: the CTA's allocation of
+// NV_COLS columns per group of four warps).
+IO_DEV void forward_instance_tmem(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst,
+                                  double* wsi, const SmemLayout& S, uint32_t tmem_base, bool cold, unsigned cold_parity) {
+  NVTmem nv;
+  nv.base = tmem_base + ((uint32_t)(32 * (cx.warp & 3)) << 16) + (uint32_t)(NV_COLS * (cx.warp >> 2));
+  forward_instance_nv<false>(cx, P, M, a, inst, wsi, S, nv, cold, cold_parity);
+}
+#endif
 
 #ifdef INTOPT_HOST_EMU  // (the CUDA kernels pick the instantiation at launch: one kernel per value of PLAIN)
 IO_DEV void forward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const FwdParams& a, int inst, double* wsi,
@@ -2040,13 +2202,19 @@ IO_DEV void backward_emit(const CtaCtx& cx, const BwdParams& a, int inst, double
 //          s = (x.g + c.ug - b.w)/(b.q - c.p + mu/tau^2), dc = ug + p s        (ip_model_whole.py:1515-1556)
 //   alter: dc = -X2 (g - A^T M^-1 A (X2 g)) / mu  with x,t normalised by tau   (ip_model_alter.py:1524-1620)
 // with M = A diag(x^2) A^T + damping I in both.
-IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const BwdParams& a, int inst, double* wsi,
-                              const SmemLayout& S) {
+// (its five element-wise n-vectors - x^2, g, c, u_g, p - through the same accessor as the forward's: workspace or tensor
+// memory)
+enum { B_X2 = 0, B_G, B_C, B_UG, B_PP };
+template <class NV>
+IO_DEV void backward_instance_nv(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const BwdParams& a, int inst, double* wsi,
+                                 const SmemLayout& S, const NV& nv) {
+  constexpr bool TM = NV::kTmem;
   if (a.a_vals)
     fill_instance_values(cx, P, a.a_vals + (long long)inst * a.a_stride, a.vals_ws + (long long)blockIdx_x() * a.vals_ws_stride);
   const int m = P.m, n = P.n, nvar = a.nvar, mv = P.mv;
+  const int nv_trips = (n + cx.nthreads - 1) / cx.nthreads;
   double *L = S.L, *G = S.G, *bs = S.bs, *q = S.q, *v = S.v;
-  double* x2 = wsi + (long long)W_D * n;
+  double* x2 = wsi + (long long)W_D * n;  // (also with tensor memory: the assembly's prefix sums read it in their own order)
   const long long slen = 2LL * n + m + 2;
   const double* st = a.state + (long long)inst * slen;
   const double* __restrict__ c = a.c + (long long)inst * a.c_stride;
@@ -2072,14 +2240,29 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   }
   if (cx.tid == 0) G[gpad(n)] = 0.0;
   double xt[2] = {0.0, 0.0};
-  CTA_FOR(k, n) {
-    const double xk = whole ? xs[k] : xs[k] / tau;  // alter saves x/tau, t/tau (ip_model_alter.py:1459-1461)
-    const double tk = whole ? ts[k] : ts[k] / tau;
-    const double xx = xk * xk;
-    x2[k] = xx;
-    xt[0] = fma(xk, tk, xt[0]);
-    if (k < nvar) xt[1] = fma(xk, g[k], xt[1]);
+  NV_FOR(j, k) {
+    double xx = 1.0, gk = 0.0, ck = 0.0;
+    if (k < n) {
+      const double xk = whole ? xs[k] : xs[k] / tau;  // alter saves x/tau, t/tau (ip_model_alter.py:1459-1461)
+      const double tk = whole ? ts[k] : ts[k] / tau;
+      xx = xk * xk;
+      xt[0] = fma(xk, tk, xt[0]);
+      if (k < nvar) {
+        gk = g[k];
+        xt[1] = fma(xk, gk, xt[1]);
+      }
+      if (TM) {
+        x2[k] = xx;
+        ck = c[k];
+      }
+    }
+    nv.st(B_X2, j, k, xx);
+    if (TM) {
+      nv.st(B_G, j, k, gk);
+      nv.st(B_C, j, k, ck);
+    }
   }
+  nv.st_wait();
   cta_sum<2>(cx, xt);
   const double mu = whole ? (xt[0] + tau * kappa) / (double)(n + 1) : xt[0] / (double)n;  // :1517 | alter :1525
   const double xg = xt[1];
@@ -2087,9 +2270,15 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
   CTA_SYNC();
   assemble_normal_matrix(cx, P, M, x2, G, S.scan, a.damping, L);  // :1525-1527,1535
   double* G2 = G + gather_len(n);  // upper half of the gather region: X2 c beside X2 g, one pass over A for both
-  CTA_FOR(k, n) {
-    gstore(G, k, (k < nvar) ? x2[k] * g[k] : 0.0);
-    if (whole) gstore(G2, k, x2[k] * c[k]);
+  NV_FOR(j, k) {
+    typename NV::Val xr = nv.ld(B_X2, j, k), cr = nv.ld(B_C, j, k), gr = xr;
+    if (TM || k < nvar) gr = nv.ld(B_G, j, k);  // (g has nvar entries; its tensor-memory copy is zero beyond them)
+    nv.ld_wait();
+    const double xx = nv.get(xr), gk = nv.get(gr), ck = nv.get(cr);
+    if (k < n) {
+      gstore(G, k, (k < nvar) ? xx * gk : 0.0);
+      if (whole) gstore(G2, k, xx * ck);
+    }
   }
   CTA_SYNC();  // G, G2 complete
   factor_and_rhs(cx, P, M, L, S, G, whole ? G2 : nullptr, v, whole ? q : nullptr, nullptr);  // A (X2 g_hat) [, A (X2 c)]
@@ -2120,30 +2309,74 @@ IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta&
     double* const rhs2[2] = {q, v};
     block_solve<2>(cx, P, M, L, rhs2, S.ybuf);
   }
-  double* ug = wsi + (long long)W_DX * n;
-  double* pp = wsi + (long long)W_P * n;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   at_mult<2>(cx, P, M, q, v, G, G + gather_len(n));
   CTA_SYNC();
-  CTA_FOR(k, n) {
-    const double atq = G[k], atv = G[gather_len(n) + k];
-    const double gk = (k < nvar) ? g[k] : 0.0;
-    const double ugk = x2[k] * (atv - tau * gk) / mu;  // :1549 applied to g
-    const double pk = x2[k] * (atq - c[k]) / mu;       // :1548
-    ug[k] = ugk;
-    pp[k] = pk;
-    acc[0] = fma(c[k], ugk, acc[0]);
-    acc[1] = fma(c[k], pk, acc[1]);
+  NV_FOR(j, k) {
+    typename NV::Val xr = nv.ld(B_X2, j, k), cr = nv.ld(B_C, j, k), gr = xr;
+    if (TM || k < nvar) gr = nv.ld(B_G, j, k);
+    const bool in = k < n;
+    const double atq = in ? G[k] : 0.0, atv = in ? G[gather_len(n) + k] : 0.0;
+    nv.ld_wait();
+    const double xx = nv.get(xr), ck = nv.get(cr);
+    const double gk = (TM || k < nvar) ? nv.get(gr) : 0.0;
+    const double ugk = xx * (atv - tau * gk) / mu;  // :1549 applied to g
+    const double pk = xx * (atq - ck) / mu;         // :1548
+    nv.st(B_UG, j, k, ugk);
+    nv.st(B_PP, j, k, pk);
+    if (in) {
+      acc[0] = fma(ck, ugk, acc[0]);
+      acc[1] = fma(ck, pk, acc[1]);
+    }
   }
+  nv.st_wait();
   CTA_FOR(i, m) {
     acc[2] = fma(bs[i], v[i], acc[2]);
     acc[3] = fma(bs[i], q[i], acc[3]);
   }
-  cta_sum<4>(cx, acc);
+  cta_sum<4>(cx, acc);  // (its barriers: every thread is past its reads of G)
   const double s = (xg + acc[0] - acc[2]) / (acc[3] - acc[1] + mu / (tau * tau));  // :1552-1553
-  backward_emit(cx, a, inst, gc, [&](int k) { return ug[k] + pp[k] * s; });  // :1554-1556
+  if (TM) {
+    // dc = u_g + p s (:1554-1556) is formed by the owner of each element and passed through the gather region: the
+    // emission may ask for any element
+    NV_FOR(j, k) {
+      typename NV::Val ur = nv.ld(B_UG, j, k), pr = nv.ld(B_PP, j, k);
+      nv.ld_wait();
+      const double dc = nv.get(ur) + nv.get(pr) * s;
+      if (k < n) G[k] = dc;
+    }
+    CTA_SYNC();
+    backward_emit(cx, a, inst, gc, [&](int k) { return G[k]; });
+  } else {
+    const double* ug = wsi + (long long)W_DX * n;
+    const double* pp = wsi + (long long)W_P * n;
+    backward_emit(cx, a, inst, gc, [&](int k) { return ug[k] + pp[k] * s; });  // :1554-1556
+  }
   if (cx.tid == 0) a.status[inst] = ST_OK;
   CTA_SYNC();
 }
+
+IO_DEV void backward_instance(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const BwdParams& a, int inst, double* wsi,
+                              const SmemLayout& S) {
+  const int n = P.n;
+  NVGlobal nv;
+  nv.n = n;
+  for (int sidx = 0; sidx < V_SLOTS; ++sidx) nv.v[sidx] = nullptr;
+  nv.v[B_X2] = wsi + (long long)W_D * n;
+  nv.v[B_G] = const_cast<double*>(a.gx) + (long long)inst * a.nvar;  // (never stored to)
+  nv.v[B_C] = const_cast<double*>(a.c) + (long long)inst * a.c_stride;  // (never stored to)
+  nv.v[B_UG] = wsi + (long long)W_DX * n;
+  nv.v[B_PP] = wsi + (long long)W_P * n;
+  backward_instance_nv(cx, P, M, a, inst, wsi, S, nv);
+}
+
+#ifndef INTOPT_HOST_EMU
+IO_DEV void backward_instance_tmem(const CtaCtx& cx, const ProblemDev& P, const Meta& M, const BwdParams& a, int inst,
+                                   double* wsi, const SmemLayout& S, uint32_t tmem_base) {
+  NVTmem nv;
+  nv.base = tmem_base + ((uint32_t)(32 * (cx.warp & 3)) << 16) + (uint32_t)(NV_COLS * (cx.warp >> 2));
+  backward_instance_nv(cx, P, M, a, inst, wsi, S, nv);
+}
+#endif
 
 }  // namespace intopt

@@ -1,0 +1,7 @@
+# A/B of library variants on the GPU box: bash tests/ab_variants.sh old main ... (writes gpurun_out/ab_*.json)
+for v in "$@"; do
+  if [ "$v" = main ]; then unset INTOPT_LIB_OVERRIDE; else export INTOPT_LIB_OVERRIDE=$PWD/neuripsintopt_b200/lib/libintopt_b200_$v.so; fi
+  timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu --no-alt --no-strong --regions 3 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  timeout 200 python bench_configs.py --no-dense --batch 2368 > gpurun_out/abcfg_$v.jsonl 2> gpurun_out/abcfg_$v.err
+done
+echo done

@@ -152,6 +152,41 @@ def test_cold_start_factor_cache_is_bit_identical(monkeypatch):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("thr", [0.1, 0.0])
+def test_tensor_memory_forward_is_bit_identical(monkeypatch, thr):
+    """The Energy forward keeps its nine element-wise n-vectors in tensor memory (tcgen05.ld / tcgen05.st) instead of the
+    L2-resident workspace.  Same arithmetic in the same order: not one bit of x, of the saved iterate (through the
+    gradient) or of the iteration count may differ from the workspace version (INTOPT_TMEM=0), short runs and converged."""
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    z = GU.load("energy_load1")
+    case = GU.cases(z)[0]
+    inp = GU.problem_inputs("energy_load1", z, 0)
+    kw = dict(case["kw"])
+    kw["thr"] = thr
+    f = IPOfunc(_tt(inp["A"]), _tt(inp["b"]), _tt(inp["G"]), _tt(inp["h"]), **kw)
+    import scipy.sparse as sp
+    from neuripsintopt_b200 import _capi
+    info, _ = _capi.analyze(sp.csr_matrix(GU.dense(z, "stdA")))
+    assert info["threads"] == 256 and info["n"] <= 7 * 256 and info["ctas_per_sm"] <= 2  # what the variant is picked for
+    rng = np.random.default_rng(7)
+    F = GU.dense(z, "F")
+    c = torch.tensor((rng.uniform(20, 120, (700, 48)) @ F.T), dtype=torch.float64, device="cuda")  # > two waves
+    outs = []
+    for tm in ("1", "0"):
+        monkeypatch.setenv("INTOPT_TMEM", tm)
+        cc = c.clone().requires_grad_(True)
+        x = f(cc)
+        x.sum().backward()
+        torch.cuda.synchronize()
+        st, it = IPOfunc.status()
+        ev = IPOfunc.end_vectors()
+        outs.append((x.detach().clone(), cc.grad.clone(), it.clone(), st.clone(), ev["t"].clone(), ev["y"].clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert int(outs[0][2].max()) >= (2 if thr > 0 else 8)
+    assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[0][1]).all()
+
+
 def test_larger_energy_instance_spilled_buffers():
     """a synthesised (5 machines, 20 tasks) ICON instance - standard form 297 x 5037, odd n,
     gather buffers spilled to the workspace (one LP fills an SM, 512 threads).  Guards the 16-byte alignment of the
