@@ -179,6 +179,10 @@ static const void* pick_kernel(bool forward, int threads, bool allsmem, bool pla
   return forward ? intopt_k::pick_forward(threads, allsmem, plain) : intopt_k::pick_backward(threads, allsmem);
 }
 static const void* pick_cold_kernel(int threads, bool allsmem) { return intopt_k::pick_cold(threads, allsmem); }
+// factor, gather region AND schedule arrays in shared memory: the kernels compiled for exactly that
+static bool all_in_smem(const IntoptProblem* p) {
+  return p->info.factor_in_smem && p->info.gather_in_smem && p->dev.meta_ints <= kMaxMetaInts;
+}
 // The tensor-memory kernels (element-wise n-vectors in TMEM instead of the L2-resident workspace): 256-thread CTAs, at most
 // two per SM (each takes half of the SM's 512 columns), and every thread's share of an n-vector must fit its columns.
 static bool tmem_variant(const IntoptProblem* p) {
@@ -222,7 +226,7 @@ int cold_factor_for(const IntoptProblem* p, double delta, cudaStream_t stream, c
   {
     int fis = p->info.factor_in_smem, gis = p->info.gather_in_smem;
     void* args[7] = {(void*)&p->dev, (void*)&delta, (void*)&ws, (void*)&fis, (void*)&gis, (void*)&e.factor, (void*)&e.ok};
-    CU_TRY(cudaLaunchKernel(pick_cold_kernel(p->info.threads, fis && gis), dim3(1), dim3(p->info.threads), args,
+    CU_TRY(cudaLaunchKernel(pick_cold_kernel(p->info.threads, all_in_smem(p)), dim3(1), dim3(p->info.threads), args,
                             (size_t)p->info.smem_bytes, stream));
   }
   CU_TRY(cudaEventRecord(e.ready, stream));
@@ -320,7 +324,7 @@ int intopt_problem_create(IntoptProblem** out, int m, int n, const int* rowptr, 
     CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   int occ = 0;
   CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &occ, pick_kernel(true, p->info.threads, p->info.factor_in_smem && p->info.gather_in_smem), p->info.threads,
+      &occ, pick_kernel(true, p->info.threads, all_in_smem(p)), p->info.threads,
       (size_t)p->info.smem_bytes));
   if (occ < 1) {
     intopt_problem_destroy(p);
@@ -454,7 +458,7 @@ int intopt_forward_mapped(const IntoptProblem* p, int B, double* c, long long c_
   CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
   {
     void* args[2] = {(void*)&p->dev, (void*)&a};
-    const bool allsmem = a.factor_in_smem && a.gather_in_smem;
+    const bool allsmem = all_in_smem(p);
     const int th = p->info.threads;
     const void* kern = (!a.plain && tmem_variant(p)) ? intopt_k::pick_forward_tmem(allsmem) : pick_kernel(true, th, allsmem, a.plain != 0);
     CU_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(th), args, (size_t)p->info.smem_bytes, (cudaStream_t)stream));
@@ -528,7 +532,7 @@ int intopt_backward_mapped(const IntoptProblem* p, int B, int mode, double dampi
   CU_TRY(cudaMemsetAsync(ws, 0, kCounterBytes, (cudaStream_t)stream));
   {
     void* args[2] = {(void*)&p->dev, (void*)&a};
-    const bool allsmem = a.factor_in_smem && a.gather_in_smem;
+    const bool allsmem = all_in_smem(p);
     const void* kern = tmem_variant(p) ? intopt_k::pick_backward_tmem(allsmem) : pick_kernel(false, p->info.threads, allsmem);
     CU_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(p->info.threads), args, (size_t)p->info.smem_bytes, (cudaStream_t)stream));
   }

@@ -9,6 +9,9 @@
 #include "intopt_solver.cuh"
 
 constexpr int kMaxMetaInts = 4096;  // schedule arrays up to 16 KB are staged in shared memory
+// (The ALLSMEM kernels are launched only when the schedule is staged: the choice is then known at compile time, every
+// schedule pointer provably points into shared memory and the lookups compile to LDS instead of generic loads - they sit
+// on the dependent chain of every substitution / factorisation step.)
 
 __device__ __forceinline__ CtaCtx make_ctx(double* red) {
   CtaCtx cx;
@@ -36,7 +39,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   const intopt::SmemLayout S =
       intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
-  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  intopt::Meta M = (ALLSMEM || P.meta_ints <= kMaxMetaInts) ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
   const bool cold = a.cold_factor != nullptr && a.init == nullptr && *a.cold_ok != 0;  // launch-uniform
   if (cold && a.factor_in_smem && threadIdx.x == 0) intopt::mbar_init(S.mbar, 1);
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(256, 2) intopt_forward_tmem_kernel(const __gri
       intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
   const uint32_t tmem = tmem_acquire(cx, &s_tmem);
-  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  intopt::Meta M = (ALLSMEM || P.meta_ints <= kMaxMetaInts) ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   const bool cold = a.cold_factor != nullptr && a.init == nullptr && *a.cold_ok != 0;  // launch-uniform
   if (cold && a.factor_in_smem && threadIdx.x == 0) intopt::mbar_init(S.mbar, 1);
   unsigned served = 0;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   extern __shared__ __align__(16) double smem[];
   const intopt::SmemLayout S = intopt::carve<ALLSMEM>(P, smem, ws + intopt::ws_nvec_doubles(P.n), factor_in_smem, gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
-  const intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  const intopt::Meta M = (ALLSMEM || P.meta_ints <= kMaxMetaInts) ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   intopt::cold_factor_build(cx, P, M, delta, ws, S, out, ok);
 }
 
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   const intopt::SmemLayout S =
       intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
-  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  intopt::Meta M = (ALLSMEM || P.meta_ints <= kMaxMetaInts) ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(256, 2) intopt_backward_tmem_kernel(const __gr
       intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
   const uint32_t tmem = tmem_acquire(cx, &s_tmem);
-  intopt::Meta M = P.meta_ints <= kMaxMetaInts ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  intopt::Meta M = (ALLSMEM || P.meta_ints <= kMaxMetaInts) ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
     __syncthreads();
