@@ -208,6 +208,54 @@ class DeviceProblem(_DeviceHandle):
         return (self.val_const + self.val_sign * A_flat[:, self.val_src]).contiguous()
 
 
+def _needs_instance_loop(n_x, A_tagged, G_np, h_np, bounds, presolve):
+    """True when presolve of the tagged pattern fixes variables or shifts / flips them: what it then does to b depends on
+    the per-instance numbers of A (ip_model_whole.py:1020-1041 singleton rows, :1096-1097 b - A lb)."""
+    zero_cols = _problem.zero_columns(A_tagged, G_np, n_x) if presolve else np.zeros(0, dtype=np.int64)
+    try:
+        sf = _problem.build_standard_form(n_x, A_tagged, None, G_np, h_np, bounds,
+                                          None if not zero_cols.size else np.ones(zero_cols.size), presolve=bool(presolve))
+    except Exception:  # (decided in presolve, or rejected on the tag numbers: the instances give the real answer)
+        return True
+    return bool(sf.meta["number_dependent"])
+
+
+def _instance_loop(variant, A_all, b_np, G, h, kw):
+    """IPOfunc for a batch of equality matrices as B independent functions (see make_ipofunc).  Gradients flow through
+    torch.stack; the hooks aggregate over the instances."""
+    B = A_all.shape[0]
+    if kw.get("init_val") is not None:
+        raise ValueError("init_val is not supported for a batch of equality matrices with number-dependent presolve")
+    if b_np is not None and b_np.ndim == 2 and b_np.shape[0] != B:
+        raise ValueError("b has %d rows for %d equality matrices" % (b_np.shape[0], B))
+    subs = [make_ipofunc(variant, A_all[i], None if b_np is None else (b_np[i] if b_np.ndim == 2 else b_np), G, h, **kw)
+            for i in range(B)]
+
+    def apply(c):
+        if c.dim() == 1 or (c.dim() == 2 and c.shape[0] == 1 and B > 1):
+            rows = [c.reshape(-1)] * B
+        elif c.dim() == 2 and c.shape[0] == B:
+            rows = [c[i] for i in range(B)]
+        else:
+            raise ValueError("c must have one row, or one row per equality matrix (%d)" % B)
+        return torch.stack([subs[i][0](rows[i]).reshape(-1) for i in range(B)])
+
+    def status():
+        pairs = [sub[1]["status"]() for sub in subs]
+        return torch.cat([p[0] for p in pairs]), torch.cat([p[1] for p in pairs])
+
+    def end_vectors():
+        ev = [sub[1]["end_vectors"]() for sub in subs]
+        if len({tuple(e["x"].shape) for e in ev}) != 1:
+            raise RuntimeError("end_vectors(): the instances have different standard forms")
+        return {k: torch.cat([e[k] for e in ev]) for k in ev[0]}
+
+    hooks = dict(Runtime=lambda: sum(sub[1]["Runtime"]() for sub in subs), end_vectors=end_vectors,
+                 forward_solved=lambda: all(sub[1]["forward_solved"]() for sub in subs), status=status,
+                 get_problem=None, instances=subs)
+    return apply, hooks
+
+
 def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.1, pc=True, tol=1e-8,
                  max_iter=1000, init_val=None, method=1, mu0=None, smoothing=False, bounds=None, thr=None,
                  new_grad=True, presolve=True, A_eq_rr=True, damping=1e-2, check_finite=True):
@@ -249,6 +297,14 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
         A_np.flat[tag_flatpos] = _TAG0 + np.arange(tag_flatpos.size)
     n_x = (A_np if A_np is not None else G_np).shape[1]
     b_batched = b_np is not None and b_np.ndim == 2
+    if a_batched and _needs_instance_loop(n_x, A_np, G_np, h_np, bounds, presolve):
+        # Presolve outcomes that depend on the NUMBERS of A (a singleton row fixes x_j = b_i / a_ij; a non-zero lower bound
+        # moves b by A lb) cannot be read off the shared pattern.  Such a batch runs the way upstream runs every batch of
+        # matrices - one function object per instance - each on the device path; only the batching is lost.
+        return _instance_loop(variant, A_all, b_np, G, h, dict(
+            alpha0=alpha0, beta=beta, pc=pc, tol=tol, max_iter=max_iter, init_val=init_val, method=method, mu0=mu0,
+            smoothing=smoothing, bounds=bounds, thr=thr, new_grad=new_grad, presolve=presolve, A_eq_rr=A_eq_rr,
+            damping=damping, check_finite=check_finite))
     a_dev_cache = {}
     structure_key = _digest(A_np, G_np, h_np) + repr([tuple(bd) for bd in bounds]) + ("" if presolve else "|raw")
     zero_cols = _problem.zero_columns(A_np, G_np, n_x) if presolve else np.zeros(0, dtype=np.int64)
@@ -265,11 +321,8 @@ def make_ipofunc(variant, A=None, b=None, G=None, h=None, alpha0=0.9995, beta=0.
                     n_x, A_np, None, G_np, h_np, bounds,
                     None if not zero_cols.size else np.asarray(sign_key, dtype=np.float64), presolve=bool(presolve))
                 if a_batched:
-                    if sf.fixed_idx.size:
-                        raise NotImplementedError("per-instance A with variables fixed by presolve (singleton rows)")
-                    if np.any(sf.x_shift != 0) or np.isfinite(sf.x_flip_ub).any():
-                        # the shift term of b (b - A lb, ip_model_whole.py:1096-1097) would be formed from the pattern tags
-                        raise NotImplementedError("per-instance A with non-zero lower bounds or upper-only bounds")
+                    # (number-dependent presolve outcomes were routed to _instance_loop at construction)
+                    assert not sf.meta["number_dependent"]
                     sf.tag_flatpos = tag_flatpos
                 hit = DeviceProblem(sf, device, inst_values=a_batched)
             except _problem.PresolveComplete as done:

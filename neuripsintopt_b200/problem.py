@@ -50,6 +50,19 @@ class PresolveComplete(Exception):
         return x
 
 
+def raw_bounds_count(bounds, n_x):
+    """Number of leading variables upstream's post-solve loop visits: the length of the caller's bounds list when it is
+    a list of pairs (ip_model_whole.py:1263), every variable for the other accepted forms."""
+    if bounds is None or isinstance(bounds, str) or len(bounds) == 0:
+        return n_x
+    try:
+        if all(len(bd) == 2 for bd in bounds):
+            return min(len(bounds), n_x)
+    except TypeError:
+        pass
+    return n_x
+
+
 def clean_bounds(bounds, n_x):
     """`_clean_inputs` bounds handling (:256-317) -> (lb, ub) float arrays with ±inf for None."""
     if isinstance(bounds, str):
@@ -359,6 +372,16 @@ def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=
     x_shift = np.where(nolb, 0.0, np.where(np.isfinite(lbr), lbr, shift))  # flipped variables: ub - x' has it all
     same_kind = nolb & np.isinf(lbr) & np.isfinite(ubr)
     x_flip_ub[same_kind] = ubr[same_kind]
+    # Upstream's loop runs over the caller's bounds LIST (:1263 `enumerate(bounds)` with the raw argument, :1376): a
+    # one-element list - broadcast to every variable by _clean_inputs for the solve - undoes the substitution of x[0]
+    # only; every other variable is returned as the standard-form value x' (SURVEY C.8).  With the (0, None) / (0, 1)
+    # lists the drivers pass nothing changes (lb = 0); with any other one-element list the result is upstream's, not
+    # the LP's.
+    n_raw = raw_bounds_count(bounds, n_x)
+    beyond = var_index >= n_raw
+    x_shift = np.where(beyond, 0.0, x_shift)
+    x_flip_ub = np.where(beyond, np.nan, x_flip_ub)
+    free_cols = np.where(beyond, -1, free_cols)
     b_const = np.concatenate([ubs[has_ub], bub_const, beq_const]) - A_std[:, :nvar] @ shift
     b_map = sp.vstack([sp.csr_matrix((nb, n_eq)), bub_map, beq_map], format="csr")
     sf = StandardForm(
@@ -367,7 +390,9 @@ def build_standard_form(n_x, A_eq=None, b_eq=None, A_ub=None, b_ub=None, bounds=
         b_const=b_const, b_from_beq=b_map, b=None, zero_rows_eq=zero_rows_eq,
         singleton=(s_rows, s_cols, s_coef, s_lo, s_hi), x_shift=x_shift, x_flip_ub=x_flip_ub,
         free_cols=free_cols, n_eq_user=n_eq,
-        meta=dict(m_ub=m_ub, n_free=int(i_free.size), n_bound_rows=int(nb), eq_keep=eq_keep, ub_keep=ub_keep))
+        meta=dict(m_ub=m_ub, n_free=int(i_free.size), n_bound_rows=int(nb), eq_keep=eq_keep, ub_keep=ub_keep,
+                  # b was moved by A lb / A ub, or variables were fixed: presolve acted on the NUMBERS of A
+                  number_dependent=bool(fixed_idx.size or np.any(shift != 0) or np.any(nolb))))
     if b_eq_v is not None:
         sf.b = b_const + (b_map @ b_eq_v if n_eq else 0.0)
         sf.fixed_const = fixed_const0 + (fixed_from_beq @ b_eq_v if n_eq else 0.0)

@@ -416,6 +416,49 @@ def test_method_2_with_per_instance_A():
         assert _rel2(ct.grad[i].double().cpu().numpy(), r["grad"]) < G_TOL
 
 
+@pytest.mark.parametrize("kind", ["fixed", "shifted"])
+@pytest.mark.parametrize("variant", ["whole", "alter"])
+def test_per_instance_A_with_number_dependent_presolve(variant, kind):
+    """A batch of equality matrices whose presolve depends on the numbers of A - a singleton row fixes x_j = b_i / a_ij
+    (ip_model_whole.py:1020-1041), a non-zero lower bound moves b by A lb (:1096-1097) - runs as one device function per
+    instance (upstream's own way of handling a batch of matrices); every instance against the oracle on its own LP."""
+    mod = _module(variant)
+    rng = np.random.default_rng(11)
+    B, n = 3, 6
+    A = np.zeros((B, 2, n))
+    A[:, 1, :] = rng.uniform(0.5, 2.0, (B, n))
+    b = np.zeros((B, 2))
+    if kind == "fixed":
+        A[:, 0, 2] = rng.uniform(1.0, 2.0, B)     # singleton row: x_2 = b_0 / a_02, different in every instance
+        b[:, 0] = 1.5
+        bounds = [(0.0, None)]
+    else:
+        A[:, 0, :] = rng.uniform(0.5, 2.0, (B, n))
+        b[:, 0] = A[:, 0, :].sum(axis=1) * 1.2
+        bounds = [(0.25, None)]
+    b[:, 1] = A[:, 1, :].sum(axis=1) * 1.1
+    G = np.zeros((1, n))
+    G[0, :2] = 1.0
+    h = np.array([3.0])
+    c = rng.uniform(0.5, 2.0, (B, n))
+    g = rng.standard_normal((B, n))
+    kw = dict(bounds=bounds, thr=0.1, damping=1e-3, max_iter=200)
+    f = mod.IPOfunc(torch.as_tensor(A), torch.as_tensor(b), _tt(G), _tt(h), **kw)
+    ct = torch.tensor(c, dtype=torch.float64, device="cuda", requires_grad=True)
+    x = f(ct)
+    (x * torch.tensor(g, dtype=torch.float64, device="cuda")).sum().backward()
+    torch.cuda.synchronize()
+    status, iters = mod.IPOfunc.status()
+    assert tuple(x.shape) == (B, n) and (status.cpu().numpy() == 0).all()
+    for i in range(B):
+        r = O.ipofunc(c[i], g[i], variant=variant, A=A[i], b=b[i], G=G, h=h, **kw)
+        assert _relinf(x[i].detach().cpu().numpy(), r["x"]) < X_TOL, (i, _relinf(x[i].detach().cpu().numpy(), r["x"]))
+        assert _rel2(ct.grad[i].cpu().numpy(), r["grad"]) < G_TOL, (i, _rel2(ct.grad[i].cpu().numpy(), r["grad"]))
+        assert int(iters[i]) == r["iters"]
+    if kind == "fixed":
+        assert np.allclose(x[:, 2].detach().cpu().numpy(), 1.5 / A[:, 0, 2], rtol=1e-12)
+
+
 def test_batch_position_independence():
     """Instances are independent: the same LP gives bitwise identical results wherever it sits in a batch
     (this is what makes 1-GPU and N-GPU shards agree exactly)."""

@@ -167,3 +167,22 @@ def test_trivial_presolve_outcome_follows_the_sign_of_c():
         np.testing.assert_allclose(x[e.value.trivial[0]], x_ref.astype(np.float64), atol=0)
         lo, hi = np.array(tb).T
         assert ((x >= lo) & (x <= hi)).all()
+
+
+def test_batched_A_with_number_dependent_presolve_is_split_per_instance():
+    """A batch of equality matrices is analysed once on its shared pattern - unless presolve would act on the numbers
+    (singleton row -> fixed variable, non-zero lower bound -> shifted b): then one function per instance is built."""
+    import torch
+    from neuripsintopt_b200.ipofunc import make_ipofunc
+    rng = np.random.default_rng(0)
+    A = rng.uniform(0.5, 2.0, (3, 1, 5))
+    b = A.sum(axis=2) * 1.1
+    _, hooks = make_ipofunc("whole", torch.as_tensor(A), torch.as_tensor(b), None, None, bounds=[(0.0, None)])
+    assert "instances" not in hooks
+    _, hooks = make_ipofunc("whole", torch.as_tensor(A), torch.as_tensor(b), None, None, bounds=[(0.25, None)])
+    assert len(hooks["instances"]) == 3
+    A2 = np.zeros((2, 2, 4))
+    A2[:, 0, 1] = [1.0, 2.0]
+    A2[:, 1, :] = 1.0
+    _, hooks = make_ipofunc("alter", torch.as_tensor(A2), torch.as_tensor(np.ones((2, 2))), None, None, bounds=[(0.0, 1.0)])
+    assert len(hooks["instances"]) == 2
