@@ -517,15 +517,18 @@ def run_gpu(args):
             # per step: intopt_forward_kernel + intopt_backward_kernel (the mapping between the caller's float32 user
             # layout and the standard form runs inside them)
             gpu_launches=2 * K,
-            roofline=dict(bound="fp64", kernel="intopt_forward_kernel", achieved=ach_fwd, peak=fp64_peak,
+            roofline=dict(bound="fp64", kernel=("intopt_forward_tmem_kernel" if info.get("tmem") else "intopt_forward_kernel"),
+                          achieved=ach_fwd, peak=fp64_peak,
                           unit="TFLOP/s", frac=ach_fwd / fp64_peak,
                           # DRAM bytes of one forward launch from the committed `ncu --set full` capture of this
-                          # default configuration (profiles/r01_final_ncu_summary.txt: 14.3 MB read + 105.6 MB written for
-                          # 2368 LPs = float32 c in, packed c + saved iterate + float32 x out); null for other configurations
-                          traffic=(119.9e6 if (B == 2368 and args.thr == 0.1) else None),
+                          # default configuration (profiles/r02_energy_fwd_ncu.txt: 14.4 MB read + 61.2 MB written for
+                          # 2368 LPs = float32 c in, packed c + saved iterate + float32 x out; 117 MB before the n-vectors
+                          # moved from the workspace to tensor memory); null for other configurations
+                          traffic=(75.6e6 if (B == 2368 and args.thr == 0.1 and info.get("tmem")) else None),
                           peak_source="DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
                           flops_per_iter=f_it, flops_backward=f_bw,
-                          backward=dict(kernel="intopt_backward_kernel", achieved=ach_bwd, frac=ach_bwd / fp64_peak),
+                          backward=dict(kernel=("intopt_backward_tmem_kernel" if info.get("tmem") else "intopt_backward_kernel"),
+                                        achieved=ach_bwd, frac=ach_bwd / fp64_peak),
                           step=dict(achieved=ach_all, frac=ach_all / fp64_peak,
                                     executed_achieved=exe_all, executed_frac=exe_all / fp64_peak,
                                     note="achieved uses the contract's dense m^3/3 Cholesky count; executed_* uses the "

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define INTOPT_B200_VERSION 4
+#define INTOPT_B200_VERSION 5
 
 /* intopt_problem_create flag: the VALUES of A's non-zeros differ per instance (same sparsity pattern), e.g. the
  * knapsack driver whose equality row is the minibatch's cost vector (experiments/Building Knapsack/optimizer.py:396-405).
@@ -72,6 +72,9 @@ typedef struct IntoptInfo {
                              1: lock-step dense path (batch-wide DMMA kernels, factor tiled through HBM) */
   long long asm_padded;   /* gather-list slots incl. padding of the warp-interleaved layout */
   long long solve_macs;   /* MACs of one blocked L L^T solve */
+  int tmem;               /* 1 if the kernels keep their element-wise n-vectors in tensor memory (tcgen05.ld/st) instead of
+                             the L2-resident workspace: 256-thread CTAs, n <= 7 * 256, env INTOPT_TMEM != 0 (set by
+                             intopt_problem_create, 0 from intopt_analyze) */
 } IntoptInfo;
 
 int intopt_version(void);

@@ -34,7 +34,7 @@ class IntoptInfo(ctypes.Structure):
                 ("smem_bytes", ctypes.c_int), ("factor_in_smem", ctypes.c_int), ("threads", ctypes.c_int),
                 ("ordering", ctypes.c_int), ("gather_in_smem", ctypes.c_int), ("ctas_per_sm", ctypes.c_int),
                 ("scalar_envelope", ctypes.c_int), ("path", ctypes.c_int), ("asm_padded", ctypes.c_longlong),
-                ("solve_macs", ctypes.c_longlong)]
+                ("solve_macs", ctypes.c_longlong), ("tmem", ctypes.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -332,6 +332,7 @@ int intopt_problem_create(IntoptProblem** out, int m, int n, const int* rowptr, 
   }
   occ = std::min(occ, env_int("INTOPT_MAX_CTAS_PER_SM", 8));
   p->info.ctas_per_sm = occ;
+  p->info.tmem = tmem_variant(p) ? 1 : 0;
   p->slots = p->sms * occ;
   CU_TRY(cudaDeviceSynchronize());
   *out = p;

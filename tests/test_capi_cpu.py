@@ -28,7 +28,7 @@ def test_exports_match_header(lib):
     assert declared == set(_capi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.intopt_version() == 4
+    assert lib.intopt_version() == 5
     # the profiling entry points live in their own header and their own library (never in the product .so)
     prof = open(os.path.join(ROOT, "include", "intopt_b200_profile.h")).read()
     assert set(re.findall(r"\b(intopt_[a-z0-9_]+)\s*\(", prof)) == set(_capi.PROFILE_EXPORTS)
