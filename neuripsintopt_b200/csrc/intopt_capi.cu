@@ -183,12 +183,13 @@ static const void* pick_cold_kernel(int threads, bool allsmem) { return intopt_k
 static bool all_in_smem(const IntoptProblem* p) {
   return p->info.factor_in_smem && p->info.gather_in_smem && p->dev.meta_ints <= kMaxMetaInts;
 }
-// The tensor-memory kernels (element-wise n-vectors in TMEM instead of the L2-resident workspace): 256-thread CTAs, at most
-// two per SM (each takes half of the SM's 512 columns), and every thread's share of an n-vector must fit its columns.
+// The tensor-memory kernels (element-wise n-vectors in TMEM instead of the L2-resident workspace): CTAs of up to 256 threads,
+// at most two per SM (each takes half of the SM's 512 columns), or larger CTAs, one per SM (all 512 columns); every
+// thread's share of an n-vector must fit its columns.
 static bool tmem_variant(const IntoptProblem* p) {
   const int th = p->info.threads;
-  return th > 128 && th <= 256 && p->info.ctas_per_sm <= 2 && (p->info.n + th - 1) / th <= intopt::NV_EMAX &&
-         env_int("INTOPT_TMEM", 1) != 0;
+  const bool fits = th > 128 && (th <= 256 ? p->info.ctas_per_sm <= 2 : p->info.ctas_per_sm == 1);
+  return fits && (p->info.n + th - 1) / th <= intopt::NV_EMAX && env_int("INTOPT_TMEM", 1) != 0;
 }
 
 namespace {
@@ -461,7 +462,7 @@ int intopt_forward_mapped(const IntoptProblem* p, int B, double* c, long long c_
     void* args[2] = {(void*)&p->dev, (void*)&a};
     const bool allsmem = all_in_smem(p);
     const int th = p->info.threads;
-    const void* kern = (!a.plain && tmem_variant(p)) ? intopt_k::pick_forward_tmem(allsmem) : pick_kernel(true, th, allsmem, a.plain != 0);
+    const void* kern = (!a.plain && tmem_variant(p)) ? intopt_k::pick_forward_tmem(th, allsmem) : pick_kernel(true, th, allsmem, a.plain != 0);
     CU_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(th), args, (size_t)p->info.smem_bytes, (cudaStream_t)stream));
   }
   CU_TRY(cudaGetLastError());
@@ -534,7 +535,7 @@ int intopt_backward_mapped(const IntoptProblem* p, int B, int mode, double dampi
   {
     void* args[2] = {(void*)&p->dev, (void*)&a};
     const bool allsmem = all_in_smem(p);
-    const void* kern = tmem_variant(p) ? intopt_k::pick_backward_tmem(allsmem) : pick_kernel(false, p->info.threads, allsmem);
+    const void* kern = tmem_variant(p) ? intopt_k::pick_backward_tmem(p->info.threads, allsmem) : pick_kernel(false, p->info.threads, allsmem);
     CU_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(p->info.threads), args, (size_t)p->info.smem_bytes, (cudaStream_t)stream));
   }
   CU_TRY(cudaGetLastError());

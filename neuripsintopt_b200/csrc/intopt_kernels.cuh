@@ -55,14 +55,15 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   }
 }
 
-// Tensor memory of a 256-thread CTA: NV_COLS columns for each of its two groups of four warps (half of the SM's 512 columns,
-// so two CTAs fit).  Warp 0 allocates and frees; the address travels through shared memory.
-constexpr int kTmemCols = intopt::NV_COLS * 2;
+// Tensor memory of a CTA: NV_COLS columns for each of its groups of four warps - 256 columns for a 256-thread CTA (half
+// of the SM's 512, so two CTAs fit), all 512 for a 512-thread CTA (one per SM).  Warp 0 allocates and frees; the address
+// travels through shared memory.
+template <int COLS>
 __device__ __forceinline__ uint32_t tmem_acquire(const CtaCtx& cx, uint32_t* slot) {
   if (cx.warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(slot)),
-                 "n"(kTmemCols)
+                 "n"(COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -71,18 +72,19 @@ __device__ __forceinline__ uint32_t tmem_acquire(const CtaCtx& cx, uint32_t* slo
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   return *slot;
 }
+template <int COLS>
 __device__ __forceinline__ void tmem_release(const CtaCtx& cx, uint32_t tmem) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (cx.warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(COLS) : "memory");
 }
 
 // The same forward with the element-wise n-vectors in tensor memory (see NVTmem): 256-thread CTAs, two per SM, each
-// owning 256 of the SM's 512 columns (two groups of four warps x 128 columns).  Picked at launch when every thread's share
-// of an n-vector fits (n <= 7 * 256).
-template <bool ALLSMEM>
-__global__ void __launch_bounds__(256, 2) intopt_forward_tmem_kernel(const __grid_constant__ intopt::ProblemDev P,
+// owning 256 of the SM's 512 columns (two groups of four warps x 128 columns), or one 512-thread CTA per SM owning all of
+// them.  Picked at launch when every thread's share of an n-vector fits (n <= 7 * threads).
+template <int TMAX, bool ALLSMEM>
+__global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_forward_tmem_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                      const __grid_constant__ intopt::FwdParams a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_inst;
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(256, 2) intopt_forward_tmem_kernel(const __gri
   const intopt::SmemLayout S =
       intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
-  const uint32_t tmem = tmem_acquire(cx, &s_tmem);
+  const uint32_t tmem = tmem_acquire<intopt::NV_COLS * (TMAX / 128)>(cx, &s_tmem);
   intopt::Meta M = (ALLSMEM || P.meta_ints <= kMaxMetaInts) ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   const bool cold = a.cold_factor != nullptr && a.init == nullptr && *a.cold_ok != 0;  // launch-uniform
   if (cold && a.factor_in_smem && threadIdx.x == 0) intopt::mbar_init(S.mbar, 1);
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(256, 2) intopt_forward_tmem_kernel(const __gri
     intopt::forward_instance_tmem(cx, P, M, a, inst, wsi, S, tmem, cold, served & 1u);
     ++served;
   }
-  tmem_release(cx, tmem);
+  tmem_release<intopt::NV_COLS * (TMAX / 128)>(cx, tmem);
 }
 
 // One CTA computes the cold-start factor chol(A A^T + delta I) with the instance code path (same CTA size).
@@ -142,8 +144,8 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
 }
 
 
-template <bool ALLSMEM>
-__global__ void __launch_bounds__(256, 2) intopt_backward_tmem_kernel(const __grid_constant__ intopt::ProblemDev P,
+template <int TMAX, bool ALLSMEM>
+__global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_backward_tmem_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                       const __grid_constant__ intopt::BwdParams a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_inst;
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256, 2) intopt_backward_tmem_kernel(const __gr
   const intopt::SmemLayout S =
       intopt::carve<ALLSMEM>(P, smem, wsi + intopt::ws_nvec_doubles(P.n), a.factor_in_smem, a.gather_in_smem);
   const CtaCtx cx = make_ctx(S.red);
-  const uint32_t tmem = tmem_acquire(cx, &s_tmem);
+  const uint32_t tmem = tmem_acquire<intopt::NV_COLS * (TMAX / 128)>(cx, &s_tmem);
   intopt::Meta M = (ALLSMEM || P.meta_ints <= kMaxMetaInts) ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(256, 2) intopt_backward_tmem_kernel(const __gr
     if (inst >= a.B) break;
     intopt::backward_instance_tmem(cx, P, M, a, inst, wsi, S, tmem);
   }
-  tmem_release(cx, tmem);
+  tmem_release<intopt::NV_COLS * (TMAX / 128)>(cx, tmem);
 }
 
 // Kernel variants: CTA size cap (128: 4 CTAs/SM x 128 registers, 256: 2 x 128, 512: 1 x 128; 192: 2 x 168 only in
@@ -176,8 +178,8 @@ __global__ void __launch_bounds__(256, 2) intopt_backward_tmem_kernel(const __gr
 
 namespace intopt_k {
 const void* pick_forward(int threads, bool allsmem, bool plain);
-const void* pick_forward_tmem(bool allsmem);
-const void* pick_backward_tmem(bool allsmem);
+const void* pick_forward_tmem(int threads, bool allsmem);
+const void* pick_backward_tmem(int threads, bool allsmem);
 const void* pick_backward(int threads, bool allsmem);
 const void* pick_cold(int threads, bool allsmem);
 void list_forward(std::vector<const void*>& v);

@@ -187,6 +187,38 @@ def test_tensor_memory_forward_is_bit_identical(monkeypatch, thr):
     assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[0][1]).all()
 
 
+def test_tensor_memory_twitter_512_thread_ctas_bit_identical(monkeypatch):
+    """The Twitter LP runs one 512-thread CTA per SM; that CTA owns all 512 tensor-memory columns (four groups of four
+    warps) and 2852 / 512 -> 6 elements per thread and vector fit.  Same check as for the Energy shape: not a bit differs
+    from the workspace version, per-instance right-hand sides and a shared cost vector's summed gradient included."""
+    from neuripsintopt_b200.ip_model_whole import IPOfunc
+    import scipy.sparse as sp
+    from neuripsintopt_b200 import _capi
+    z = GU.load("twitter_sp")
+    case = GU.cases(z)[0]
+    inp = GU.problem_inputs("twitter_sp", z, 0)
+    info, _ = _capi.analyze(sp.csr_matrix(GU.dense(z, "stdA")))
+    assert info["threads"] == 512 and (info["n"] + 511) // 512 <= 7
+    B = 200
+    bb = np.tile(z["b_rr"], (B // len(z["b_rr"]) + 1, 1))[:B]
+    rng = np.random.default_rng(3)
+    c0 = case["c"][0].astype(np.float64)
+    c = torch.tensor(c0 * np.abs(1 + 0.3 * rng.standard_normal((B, c0.size))), dtype=torch.float64, device="cuda")
+    f = IPOfunc(_tt(inp["A"]), _tt(bb), torch.Tensor(), torch.Tensor(), **dict(case["kw"], thr=0.1))
+    outs = []
+    for tm in ("1", "0"):
+        monkeypatch.setenv("INTOPT_TMEM", tm)
+        cc = c.clone().requires_grad_(True)
+        x = f(cc)
+        (x * x).sum().backward()
+        torch.cuda.synchronize()
+        st, it = IPOfunc.status()
+        outs.append((x.detach().clone(), cc.grad.clone(), it.clone(), st.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert (outs[0][3] == 0).all() and torch.isfinite(outs[0][1]).all()
+
+
 def test_larger_energy_instance_spilled_buffers():
     """a synthesised (5 machines, 20 tasks) ICON instance - standard form 297 x 5037, odd n,
     gather buffers spilled to the workspace (one LP fills an SM, 512 threads).  Guards the 16-byte alignment of the
