@@ -53,7 +53,10 @@ def redundant_rows(A_eq, small_nullspace=5):
     if rank >= A.shape[0]:
         return []
     if A.shape[0] - rank > small_nullspace:
-        raise NotImplementedError("large row nullspace: the reference switches to its dense pivoting removal")
+        # upstream switches to its pivoting removal here (ip_model_whole.py:1192-1194) - and raises a TypeError, because
+        # that function still has SciPy's (A, rhs) signature (remove_redundancy.py:107).  What it was meant
+        # to return is restated in dependent_rows_pivot: the dependent rows in the ORIGINAL numbering.
+        return dependent_rows_pivot(A)
     eps = np.finfo(float).eps
     removed = []
     U, s, _ = np.linalg.svd(A)
@@ -68,6 +71,67 @@ def redundant_rows(A_eq, small_nullspace=5):
         U, s, _ = np.linalg.svd(A)
         s_min = s[-1] if A.shape[0] <= A.shape[1] else 0.0
     return removed
+
+
+def dependent_rows_pivot(A_eq, rhs=None, tolapiv=1e-8, tolprimal=1e-8):
+    """Linearly dependent rows of `A_eq` by the basis-pivoting method of Andersen (1995) that
+    `remove_redundancy.py:107-230` (dense, Bartels-Golub updates) and `:233-355` (sparse LU) implement: start from the
+    basis of artificial columns [I | A]; for row i, pi = B^-T e_i; if some structural column outside the basis has
+    |A_j . pi| > tolapiv it replaces artificial column i, otherwise row i is a combination of the others - dependent, or,
+    if pi . rhs is not ~0, the system is inconsistent (upstream: status 2).  Accepts dense or scipy.sparse input (the
+    sparse branch factors the basis with SuperLU, the dense one with LAPACK; the basis is refactored per row instead of
+    updated, which only costs time on a host-side one-off).  Returns the list of dependent row indices; zero rows count
+    as dependent (upstream removes them first, :139).  Raises ValueError for an inconsistent system."""
+    import scipy.linalg as sla
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    sparse = sp.issparse(A_eq)
+    A = sp.csc_matrix(A_eq, dtype=np.float64) if sparse else np.array(A_eq, dtype=np.float64)
+    m, n = A.shape
+    if m == 0:
+        return []
+    nz_row = np.asarray((abs(A) > 1e-13).sum(axis=1)).ravel() > 0
+    rhs_v = None if rhs is None else np.asarray(rhs, dtype=np.float64).ravel()
+    if rhs_v is not None and np.any(~nz_row & (np.abs(rhs_v) > tolprimal)):
+        raise ValueError("a zero row of A_eq has a non-zero right-hand side: infeasible")
+    rows = np.flatnonzero(nz_row)                # the algorithm runs on the non-zero rows
+    Ar = A[rows, :]
+    mr = rows.size
+    basis = list(range(mr))                      # columns of [I | Ar]; < mr: artificial
+    in_basis = np.zeros(mr + n, dtype=bool)
+    in_basis[:mr] = True
+    dependent = [int(i) for i in np.flatnonzero(~nz_row)]
+
+    def column(j):
+        if j < mr:
+            e = np.zeros(mr)
+            e[j] = 1.0
+            return e
+        col = Ar[:, j - mr]
+        return np.asarray(col.todense()).ravel() if sparse else col
+
+    bnorm = 0.0 if rhs_v is None else float(np.linalg.norm(rhs_v[rows]))
+    for i in range(mr):
+        Bm = np.column_stack([column(j) for j in basis])
+        e = np.zeros(mr)
+        e[i] = 1.0
+        if sparse:
+            pi = spla.splu(sp.csc_matrix(Bm)).solve(e, trans="T")
+        else:
+            pi = sla.lu_solve(sla.lu_factor(Bm), e, trans=1)
+        score = np.abs(np.asarray(Ar.T @ pi).ravel())
+        score[in_basis[mr:]] = 0.0
+        if score.size and score.max() > tolapiv:
+            j = mr + int(np.argmax(score))       # a very independent column takes the place of artificial column i
+            in_basis[basis[i]] = False
+            basis[i] = j
+            in_basis[j] = True
+        else:
+            if rhs_v is not None and abs(float(pi @ rhs_v[rows])) / (1.0 + bnorm) > tolprimal:
+                raise ValueError("a combination of rows of A_eq vanishes while the same combination of b_eq does not: "
+                                 "infeasible")
+            dependent.append(int(rows[i]))
+    return sorted(dependent)
 
 
 def prepare(A):

@@ -42,6 +42,34 @@ def test_row_removal_full_rank_and_small_cases():
     assert twitter.redundant_rows(np.zeros((0, 4))) == []
 
 
+def test_large_row_nullspace_takes_the_pivoting_removal():
+    """More than five dependent rows: upstream switches to its pivoting removal (Andersen 1995; its own call into it
+    raises).  The restatement must find exactly the rows SciPy's implementation of the same algorithm finds,
+    dense and sparse, count zero rows as dependent and flag an inconsistent right-hand side."""
+    import warnings
+    from scipy.optimize._remove_redundancy import _remove_redundancy_pivot_dense
+    rng = np.random.default_rng(0)
+    for trial in range(4):
+        m, n, r = 30, 45, 21 - 2 * trial
+        base = rng.standard_normal((r, n))
+        A = np.vstack([base, rng.standard_normal((m - r, r)) @ base])[rng.permutation(m)]
+        if trial % 2:
+            A[int(rng.integers(m))] = 0.0
+        b = A @ rng.standard_normal(n)
+        d = twitter.dependent_rows_pivot(A, b)
+        assert d == twitter.dependent_rows_pivot(sp.csr_matrix(A), b) == twitter.redundant_rows(A)
+        keep = [i for i in range(m) if i not in d]
+        assert len(d) == m - np.linalg.matrix_rank(A) and np.linalg.matrix_rank(A[keep]) == len(keep)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            A2, _, status, _ = _remove_redundancy_pivot_dense(A.copy(), b.copy())
+        assert status == 0 and np.array_equal(A2, A[keep])
+    b_bad = b.copy()
+    b_bad[d[0]] += 1.0
+    with pytest.raises(ValueError):
+        twitter.dependent_rows_pivot(A, b_bad)
+
+
 def test_graph_file_round_trip(tmp_path):
     rng = np.random.default_rng(1)
     A, X, c = rng.integers(-1, 2, (4, 6)).astype(float), rng.normal(size=(6, 3)), rng.uniform(size=6)
