@@ -84,7 +84,7 @@ const char* intopt_last_error(void);
  * row_perm_host[m] (internal row i = original row row_perm_host[i]).  Needs no GPU.
  * Returns 0, -1..-4 for malformed input (NULL / non-monotone rowptr / column out of range / m too large for the
  * 16-bit row indices), -5 when a SPARSE problem is too large for the gather-list assembly (asm_terms > 2^28);
- * intopt_problem_create returns the same codes.  Dense problems (nnz >= m n / 4) with m >= 192 take the lock-step dense
+ * intopt_problem_create returns the same codes.  Dense problems (nnz >= m n / 4) with m >= 128 take the lock-step dense
  * path (info.path = 1, m <= 4096) and are not subject to that limit. */
 int intopt_analyze(int m, int n, const int* rowptr_host, const int* colidx_host, const double* val_host,
                    IntoptInfo* info, int* row_perm_host);

@@ -287,7 +287,9 @@ bool wanted(int m, int n, long long nnz, int flags) {
   if (v && !std::strcmp(v, "dense")) return true;
   if (v && !std::strcmp(v, "cta")) return false;
   // dense problems whose factor is too large to share an SM's shared memory between resident LPs
-  return m >= 192 && (double)nnz >= 0.25 * (double)m * (double)n;
+  // (measured crossover against the persistent-CTA path: m = 128 wins at every batch size from 64 up - 341 k vs 196 k LP/s at
+  // batch 1024 - m = 96 only from batch ~1000)
+  return m >= 128 && (double)nnz >= 0.25 * (double)m * (double)n;
 }
 
 int create(IntoptDense** out, int m, int n, const int* rowptr, const int* colidx, const double* val, const double* b,

@@ -37,9 +37,9 @@ def test_exports_match_header(lib):
 
 
 def test_dense_problems_are_routed_to_the_lock_step_path(lib):
-    # dense A with m >= 192 takes the lock-step dense path (no gather lists, no -5 refusal up to m = 4096)
+    # dense A with m >= 128 takes the lock-step dense path (no gather lists, no -5 refusal up to m = 4096)
     rng = np.random.default_rng(0)
-    for m, n, path in ((64, 128, 0), (192, 384, 1), (1024, 2048, 1)):
+    for m, n, path in ((64, 128, 0), (96, 192, 0), (128, 256, 1), (192, 384, 1), (1024, 2048, 1)):
         A = sp.csr_matrix(rng.standard_normal((m, n)))
         info, perm = _capi.analyze(A)
         assert info["path"] == path and (info["m"], info["n"], info["nnz"]) == (m, n, m * n)

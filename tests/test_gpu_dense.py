@@ -98,10 +98,10 @@ def test_golden_cases_on_the_dense_path(dense_path, name):
         _check_case(name, z, case, inp, lambda i: inp)
 
 
-@pytest.mark.parametrize("m", [200, 256])
+@pytest.mark.parametrize("m", [128, 200, 256])
 @pytest.mark.parametrize("thr", [0.1, None])
 def test_config5_against_oracle(m, thr):
-    """Config 5 shapes that take the dense path by default (m >= 192), incl. one that is not a multiple of the tile."""
+    """Config 5 shapes that take the dense path by default (m >= 128), incl. one that is not a multiple of the tile."""
     from neuripsintopt_b200 import ipofunc
     from neuripsintopt_b200.ip_model_whole import IPOfunc
     ipofunc.clear_cache()
