@@ -498,8 +498,12 @@ __device__ void chol64_factor_invert(double* S, double* X, double* tmp, double* 
 // M is B x m64 x m64 row-major (lower part), Linv is B x nb x 64 x 64.
 // ---------------------------------------------------------------------------------------------------------
 using GemmChol = GemmNT<64, 64, 32, 16, 256, false>;
-constexpr int CHOL_SMEM_DOUBLES =
-    (GemmChol::SMEM_DOUBLES > 3 * NB * LDD + NB + 8) ? GemmChol::SMEM_DOUBLES : 3 * NB * LDD + NB + 8;
+// (the factor-and-invert step needs the block, its inverse and 7 x 64 doubles of scratch: 71 KB, three CTAs per SM - the
+// diagonal-tile CTAs run a serial pivot chain, so residency is what hides it)
+constexpr int CHOL_TMP_DOUBLES = 7 * 64;
+constexpr int CHOL_SMEM_DOUBLES = (GemmChol::SMEM_DOUBLES > 2 * NB * LDD + CHOL_TMP_DOUBLES + NB + 8)
+                                      ? GemmChol::SMEM_DOUBLES
+                                      : 2 * NB * LDD + CHOL_TMP_DOUBLES + NB + 8;
 
 __global__ void __launch_bounds__(256) dense_chol_col_kernel(double* __restrict__ M, int m64, int k,
                                                              double* __restrict__ Linv, int* __restrict__ fail,
@@ -530,7 +534,7 @@ __global__ void __launch_bounds__(256) dense_chol_col_kernel(double* __restrict_
   double* S = smem;
   double* X = S + NB * LDD;
   double* tmp = X + NB * LDD;
-  double* rinv = tmp + NB * LDD;
+  double* rinv = tmp + CHOL_TMP_DOUBLES;
   int* sfail = reinterpret_cast<int*>(rinv + NB);
   if (threadIdx.x == 0) *sfail = 0;
 #pragma unroll
