@@ -39,7 +39,7 @@ if [ "$PART" = ncudense ]; then
     $T 900 ncu --set full --clock-control none --import-source on -f -o /tmp/rep/$name -k "regex:$k" -s $skip -c 1 "$@" > /tmp/rep/$name.log 2>&1
     python profiles/summarize_rep.py /tmp/rep/$name.ncu-rep $O/r02_${name}_ncu.txt $name > /dev/null 2>&1 || echo "summary of $name failed"
   }
-  cap dense_syrk 'dense_syrk' 4 $DENSE
+  cap dense_syrk 'dense_syrk' 3 $DENSE   # (launches 1, 2 of an iteration are the masked retry rungs: 3 is a full one)
   cap dense_solve 'dense_solve_kernel' 8 $DENSE
 fi
 if want ncu; then
@@ -61,8 +61,8 @@ if want ncu; then
   cap energy_fwd 'intopt_forward.*kernel' 2 $BENCH
   cap energy_bwd 'intopt_backward.*kernel' 2 $BENCH
   cap twitter_fwd 'intopt_forward.*kernel' 1 python tests/gpu_twitter_step.py
-  cap dense_syrk 'dense_syrk' 4 $DENSE
-  cap dense_cholcol 'dense_chol_col_kernel' 40 $DENSE
+  cap dense_syrk 'dense_syrk' 3 $DENSE   # (launches 1, 2 of an iteration are the masked retry rungs: 3 is a full one)
+  cap dense_cholcol 'dense_chol_col_kernel' 8 $DENSE   # (block column 8 of the first factorisation)
   cap dense_solve 'dense_solve_kernel' 8 $DENSE
 fi
 ls -la $O | head -60
