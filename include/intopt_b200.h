@@ -73,7 +73,7 @@ typedef struct IntoptInfo {
   long long asm_padded;   /* gather-list slots incl. padding of the warp-interleaved layout */
   long long solve_macs;   /* MACs of one blocked L L^T solve */
   int tmem;               /* 1 if the kernels keep their element-wise n-vectors in tensor memory (tcgen05.ld/st) instead of
-                             the L2-resident workspace: n <= 7 * threads, CTAs of 256 (two per SM) or 512 threads (one per SM), env INTOPT_TMEM != 0 (set by
+                             the L2-resident workspace: n <= 7 * threads (and n >= threads on 128-thread CTAs); CTAs of 128 (four per SM), 256 (two) or 512 threads (one); env INTOPT_TMEM != 0 (set by
                              intopt_problem_create, 0 from intopt_analyze) */
 } IntoptInfo;
 

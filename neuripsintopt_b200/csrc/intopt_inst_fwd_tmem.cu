@@ -1,9 +1,9 @@
 // Instantiations of the predictor-corrector forward kernel and of the backward kernel that keep their element-wise
-// n-vectors in tensor memory (256-thread CTAs, two per SM; 512-thread CTAs, one per SM).
+// n-vectors in tensor memory (128-thread CTAs, four per SM; 256-thread CTAs, two per SM; 512-thread CTAs, one per SM).
 #include "intopt_kernels.cuh"
 
 namespace intopt_k {
-#define INTOPT_TMEM_VARIANTS(F) F(256, true) F(256, false) F(512, true) F(512, false)
+#define INTOPT_TMEM_VARIANTS(F) F(128, true) F(128, false) F(256, true) F(256, false) F(512, true) F(512, false)
 const void* pick_forward_tmem(int threads, bool allsmem) {
 #define PICK_(T, A) \
   if (threads <= T && allsmem == A) return (const void*)intopt_forward_tmem_kernel<T, A>;

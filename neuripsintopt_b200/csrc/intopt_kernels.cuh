@@ -55,8 +55,9 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
   }
 }
 
-// Tensor memory of a CTA: NV_COLS columns for each of its groups of four warps - 256 columns for a 256-thread CTA (half
-// of the SM's 512, so two CTAs fit), all 512 for a 512-thread CTA (one per SM).  Warp 0 allocates and frees; the address
+// Tensor memory of a CTA: NV_COLS columns for each of its groups of four warps - 128 columns for a 128-thread CTA (four
+// CTAs per SM), 256 for a 256-thread CTA (two), all 512 for a 512-thread CTA (one): CTAs x columns never exceeds the SM's 512
+// because registers (128 per thread) admit at most 512 threads of these kernels per SM.  Warp 0 allocates and frees; the address
 // travels through shared memory.
 template <int COLS>
 __device__ __forceinline__ uint32_t tmem_acquire(const CtaCtx& cx, uint32_t* slot) {
@@ -81,10 +82,10 @@ __device__ __forceinline__ void tmem_release(const CtaCtx& cx, uint32_t tmem) {
 }
 
 // The same forward with the element-wise n-vectors in tensor memory (see NVTmem): 256-thread CTAs, two per SM, each
-// owning 256 of the SM's 512 columns (two groups of four warps x 128 columns), or one 512-thread CTA per SM owning all of
-// them.  Picked at launch when every thread's share of an n-vector fits (n <= 7 * threads).
+// owning 256 of the SM's 512 columns (two groups of four warps x 128 columns), one 512-thread CTA per SM owning all of
+// them, or four 128-thread CTAs with 128 columns each.  Picked at launch when every thread's share of an n-vector fits (n <= 7 * threads).
 template <int TMAX, bool ALLSMEM>
-__global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_forward_tmem_kernel(const __grid_constant__ intopt::ProblemDev P,
+__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_forward_tmem_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                      const __grid_constant__ intopt::FwdParams a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_inst;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_forward_tmem
   const CtaCtx cx = make_ctx(S.red);
   const uint32_t tmem = tmem_acquire<intopt::NV_COLS * (TMAX / 128)>(cx, &s_tmem);
   intopt::Meta M = (ALLSMEM || P.meta_ints <= kMaxMetaInts) ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
   const bool cold = a.cold_factor != nullptr && a.init == nullptr && *a.cold_ok != 0;  // launch-uniform
   if (cold && a.factor_in_smem && threadIdx.x == 0) intopt::mbar_init(S.mbar, 1);
   unsigned served = 0;
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) i
 
 
 template <int TMAX, bool ALLSMEM>
-__global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_backward_tmem_kernel(const __grid_constant__ intopt::ProblemDev P,
+__global__ void __launch_bounds__(TMAX, TMAX <= 128 ? 4 : TMAX <= 256 ? 2 : 1) intopt_backward_tmem_kernel(const __grid_constant__ intopt::ProblemDev P,
                                                                       const __grid_constant__ intopt::BwdParams a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_inst;
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 256 ? 2 : 1) intopt_backward_tme
   const CtaCtx cx = make_ctx(S.red);
   const uint32_t tmem = tmem_acquire<intopt::NV_COLS * (TMAX / 128)>(cx, &s_tmem);
   intopt::Meta M = (ALLSMEM || P.meta_ints <= kMaxMetaInts) ? intopt::stage_meta(cx, P, S.meta) : intopt::global_meta(P);
+  if (a.a_vals) intopt::instance_value_streams(P, M, a.vals_ws + (long long)blockIdx.x * a.vals_ws_stride);
   for (;;) {
     if (threadIdx.x == 0) s_inst = atomicAdd(a.counter, 1);
     __syncthreads();
