@@ -98,6 +98,7 @@ namespace intopt {
 
 enum { ST_OK = 0, ST_MAXITER = 1, ST_INFEAS = 2, ST_BREAKDOWN = 3, ST_NONFINITE = 4 };
 constexpr int KB = 8;  // block edge, == NB of intopt_structure.hpp
+constexpr int S_DSCR = KB + KB * KB;  // one diagonal-block scratch: reciprocal pivots + the factored block (row-major)
 
 // The gather buffer is indexed through gpad(): one unused slot after every 32 elements, so that run starts a
 // multiple of 16 or 32 elements apart (the Energy LP: 144 = one task's variables) no longer share a bank.
@@ -611,8 +612,11 @@ IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr,
 #else
 // CUDA build: the block lives in registers (lane i & 7 owns row i, lanes 8..31 mirror lanes 0..7), pivots
 // and columns travel by warp shuffles, pivots use rsqrt so the dependent chain has no fp64 divide/sqrt.
-IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr, int* fail,
-                                     const double* panel = nullptr) {
+// Factor only: L (row-major rows) and the reciprocal pivots are left in `scr` (KB + KB*KB doubles: rinv, then L) for
+// whoever forms the inverse - this warp right away (diag_block_factor_invert) or another warp off the pivot chain
+// (diag_block_invert_published).  `blk` itself is not written.
+IO_DEV void diag_block_factor_publish(const CtaCtx& cx, const double* blk, double* scr, int* fail,
+                                      const double* panel = nullptr) {
   const unsigned full = 0xffffffffu;
   const int i = cx.lane & 7;
   double a[KB], rinv[KB];
@@ -661,7 +665,20 @@ IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr,
 #pragma unroll
     for (int k = 0; k < KB; ++k) Ls[i * KB + k] = a[k];
   }
+  if (cx.lane == KB) {  // (every lane holds the same reciprocal pivots)
+#pragma unroll
+    for (int k = 0; k < KB; ++k) scr[k] = rinv[k];
+  }
   __syncwarp();
+}
+
+// Column i = lane & 7 of Linv from a published factor (see above), written over the diagonal block.  One warp.
+IO_DEV void diag_block_invert_published(const CtaCtx& cx, double* blk, const double* scr) {
+  const int i = cx.lane & 7;
+  const double* Ls = scr + KB;
+  double rinv[KB];
+#pragma unroll
+  for (int k = 0; k < KB; ++k) rinv[k] = scr[k];
   // column c = i of Linv by forward substitution with reciprocal pivots: x_c = rinv_c,
   // x_r = -rinv_r * sum_{k=c}^{r-1} L_rk x_k
   double x[KB];
@@ -680,6 +697,28 @@ IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr,
       if (r >= i) blk[bidx(r, i)] = x[r];
   }
   __syncwarp();
+}
+
+IO_DEV void diag_block_factor_invert(const CtaCtx& cx, double* blk, double* scr, int* fail,
+                                     const double* panel = nullptr) {
+  diag_block_factor_publish(cx, blk, scr, fail, panel);
+  diag_block_invert_published(cx, blk, scr);
+}
+
+// One row of the panel block the pivot chain needs, L_(K+1,K) = C L_KK^-T, by substitution against the PUBLISHED factor of
+// block K (its inverse is being formed by another warp at the same time): out_c = (c_c - sum_{k<c} out_k L_ck) / L_cc.
+IO_FORCEINLINE void chol_panel_row_subst(double* blk, const double* scr, int row) {
+  const double* Ls = scr + KB;
+  double c[KB];
+  load_row(blk, row, c);
+#pragma unroll
+  for (int j = 0; j < KB; ++j) {
+    const double xj = c[j] * scr[j];
+    c[j] = xj;
+#pragma unroll
+    for (int k = j + 1; k < KB; ++k) c[k] = fma(-xj, Ls[k * KB + j], c[k]);
+  }
+  store_row(blk, row, c);
 }
 #endif
 
@@ -814,19 +853,27 @@ IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
   const int mb = P.mb;
   if (cx.tid == 0) *fail_flag = 0;
   CTA_SYNC();
+#ifndef INTOPT_HOST_EMU
+  if (cx.nwarps > 2) {
+    if (cx.warp == 0) diag_block_factor_publish(cx, L + M.boff[0] + (0 - M.fb[0]) * 64, scratch, fail_flag);
+  } else
+#endif
   if (cx.warp == 0) diag_block_factor_invert(cx, L + M.boff[0] + (0 - M.fb[0]) * 64, scratch, fail_flag);
   CTA_SYNC();
   const int o_tid = cx.nwarps > 1 ? cx.tid - cx.warpsize : 0;
   const int o_n = cx.nwarps > 1 ? cx.nthreads - cx.warpsize : 1;
 #ifndef INTOPT_HOST_EMU
-  if (cx.nwarps > 1) {
-    // The pivot chain runs on warp 0: factor + invert diagonal block K+1, and for that it needs ONE block of step K's
-    // panel, L_(K+1,K).  Warp 0 therefore forms that block itself and goes straight on to the diagonal block, while the
-    // other warps form the rest of the panel, meet on a named barrier of their own (warp 0 only ARRIVES there, after its
-    // block is written: it never waits for the panel) and apply the trailing updates.  One full barrier per step instead
-    // of two, and the panel is off the chain.  Same sums in the same order as the plain schedule below.
+  if (cx.nwarps > 2) {
+    // The pivot chain runs on warp 0: factor diagonal block K+1, and for that it needs ONE block of step K's panel,
+    // L_(K+1,K), and the FACTOR of block K - not its inverse.  Warp 0 therefore forms that block itself, by substitution
+    // against the factor it published a step earlier, and goes straight on to the next diagonal block; the inverse of
+    // block K (which only the substitution sweeps act through) is formed by warp 1 in the meantime, warps 2.. form the
+    // rest of the panel the same way as warp 0, all meet on a named barrier (warp 0 only ARRIVES there, after its block is
+    // written: it never waits) and apply the trailing updates on the tensor core.  One full barrier per step; panel,
+    // inversion and updates are all off the chain.
     for (int K = 0; K < mb; ++K) {
-      const double* Linv = L + M.boff[K] + (K - M.fb[K]) * 64;
+      double* diagK = L + M.boff[K] + (K - M.fb[K]) * 64;
+      double* scrK = scratch + (K & 1) * S_DSCR;  // factor + reciprocal pivots of diagonal block K (published by warp 0)
       const int a0 = M.act_ptr[K], na = M.act_ptr[K + 1] - a0;
       const int lead = (na > 0 && M.act_blk[a0] == K + 1) ? 1 : 0;
       const int np = na * (na + 1) / 2;
@@ -835,22 +882,30 @@ IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
         const double* lead_panel = nullptr;
         if (lead) {
           double* blk = L + M.boff[K + 1] + (K - M.fb[K + 1]) * 64;
-          if (cx.lane < KB) chol_panel_row(blk, Linv, cx.lane);
+          if (cx.lane < KB) chol_panel_row_subst(blk, scrK, cx.lane);
           __syncwarp();
           lead_panel = blk;
         }
         asm volatile("bar.arrive 3, %0;" ::"r"(cx.nthreads) : "memory");
         if (pt) { PHASE_MARK(*pt, 11); }
         if (K + 1 < mb)
-          diag_block_factor_invert(cx, L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64, scratch, fail_flag, lead_panel);
+          diag_block_factor_publish(cx, L + M.boff[K + 1] + (K + 1 - M.fb[K + 1]) * 64, scratch + ((K + 1) & 1) * S_DSCR,
+                                    fail_flag, lead_panel);
         if (pt) { PHASE_MARK(*pt, 13); }
       } else {
-        for (int idx = o_tid; idx < (na - lead) * KB; idx += o_n) {
-          const int I = M.act_blk[a0 + lead + (idx >> 3)];
-          chol_panel_row(L + M.boff[I] + (K - M.fb[I]) * 64, Linv, idx & 7);
+        // the inverse of diagonal block K (only the substitution sweeps act through it: every panel row is formed by
+        // substitution against the published factor) is written here, off everybody's chain, by warp 1, while warps 2.. form
+        // the panel
+        if (cx.warp == 1) {
+          diag_block_invert_published(cx, diagK, scrK);
+        } else {
+          for (int idx = cx.tid - 2 * cx.warpsize; idx < (na - lead) * KB; idx += cx.nthreads - 2 * cx.warpsize) {
+            const int I = M.act_blk[a0 + lead + (idx >> 3)];
+            chol_panel_row_subst(L + M.boff[I] + (K - M.fb[I]) * 64, scrK, idx & 7);
+          }
         }
         asm volatile("bar.sync 3, %0;" ::"r"(cx.nthreads) : "memory");
-        constexpr int UNR = 1;  // one warp per block pair (2 / 3 pairs in flight per warp measured 0.5 % / 1.7 % slower)
+        constexpr int UNR = 1;  // one warp per block pair (two pairs of a warp in flight measured 1 % slower, three 2 %)
         for (int pair = lead + cx.warp - 1; pair < np; pair += UNR * (cx.nwarps - 1))
           chol_update_pairs_dmma<UNR>(M, L, K, a0, pair, cx.nwarps - 1, np, cx.lane);
       }
@@ -1379,7 +1434,7 @@ enum { W_X = 0, W_T, W_D, W_R2, W_P, W_W, W_DX, W_DXDT, W_ATY, W_NVEC };
 IO_HD long long ws_nvec_doubles(int n) { return ((long long)W_NVEC * n + 1) & ~1LL; }
 // shared-memory m-vector slots
 enum { S_B = 0, S_Y, S_R1, S_Q, S_V, S_NVEC };
-constexpr int S_SCRATCH = 4 * KB + (KB + KB * KB) + 8 * 32 + 4;  // ybuf (double buffered, 2 rhs) + diag scratch + red + flag + mbarrier
+constexpr int S_SCRATCH = 4 * KB + 2 * S_DSCR + 8 * 32 + 4;  // ybuf (double buffered, 2 rhs) + diag scratch (double buffered) + red + flag + mbarrier
 
 struct SmemLayout {
   double *L, *G, *bs, *y, *r1, *q, *v, *ybuf, *dscr, *red;  // G: gather region of 2*gather_len(n) doubles
@@ -1429,7 +1484,7 @@ IO_DEV SmemLayout carve(const ProblemDev& P, double* smem, double* ws_tail, int 
   p += S_NVEC * P.mv;
   s.ybuf = p;
   s.dscr = p + 4 * KB;
-  s.red = s.dscr + KB + KB * KB;
+  s.red = s.dscr + 2 * S_DSCR;
   s.flag = (int*)(s.red + 8 * 32);
   s.mbar = reinterpret_cast<unsigned long long*>(s.red + 8 * 32 + 2);
   // the prefix-scan scratch aliases the factor storage when it fits (the scan runs before the factor is zero-filled)
