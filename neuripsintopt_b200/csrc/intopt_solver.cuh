@@ -905,9 +905,49 @@ IO_DEV bool block_cholesky(const CtaCtx& cx, const ProblemDev& P, const Meta& M,
           }
         }
         asm volatile("bar.sync 3, %0;" ::"r"(cx.nthreads) : "memory");
-        constexpr int UNR = 1;  // one warp per block pair (two pairs of a warp in flight measured 1 % slower, three 2 %)
-        for (int pair = lead + cx.warp - 1; pair < np; pair += UNR * (cx.nwarps - 1))
-          chol_update_pairs_dmma<UNR>(M, L, K, a0, pair, cx.nwarps - 1, np, cx.lane);
+        // one warp per block pair (two pairs of a warp in flight measured 1 % slower, three 2 %)
+        if (na <= 32) {
+          // Lane l holds the addressing of active block row l of this column; a pair's three block addresses then come from
+          // five shuffles instead of two levels of dependent schedule lookups, and the pair's (row, column) position in the
+          // lower triangle is advanced incrementally instead of being recomputed (a square root) per pair.
+          int r_I = 0, r_f = 0, r_bo = 0, r_pk = 0;
+          if (cx.lane < na) {
+            r_I = M.act_blk[a0 + cx.lane];
+            r_f = M.fb[r_I];
+            r_bo = M.boff[r_I];
+            r_pk = r_bo + (K - r_f) * 64;
+          }
+          const int stride = cx.nwarps - 1;
+          int pair = lead + cx.warp - 1;
+          int ia = tri_row(pair), ib = pair - ia * (ia + 1) / 2;
+          const int rr = cx.lane >> 2, q = cx.lane & 3;
+          const int o_lo = bidx(rr, q), o_hi = bidx(rr, q + 4), o_c = rr * KB + ((q ^ bswz(rr)) << 1);
+          while (pair < np) {
+            const unsigned full = 0xffffffffu;
+            const int pkA = __shfl_sync(full, r_pk, ia), pkB = __shfl_sync(full, r_pk, ib);
+            const int boA = __shfl_sync(full, r_bo, ia), fA = __shfl_sync(full, r_f, ia), J = __shfl_sync(full, r_I, ib);
+            const double* A = L + pkA;
+            const double* Bm = L + pkB;
+            double* cdst = L + boA + (J - fA) * 64 + o_c;
+            const double a_lo = A[o_lo], a_hi = A[o_hi], b_lo = Bm[o_lo], b_hi = Bm[o_hi];
+            D2 t = *reinterpret_cast<const D2*>(cdst);
+            double acc0 = 0.0, acc1 = 0.0;
+            dmma_884(acc0, acc1, a_lo, b_lo);
+            dmma_884(acc0, acc1, a_hi, b_hi);
+            t.x -= acc0;
+            t.y -= acc1;
+            *reinterpret_cast<D2*>(cdst) = t;
+            pair += stride;
+            ib += stride;
+            while (ib > ia) {
+              ib -= ia + 1;
+              ++ia;
+            }
+          }
+        } else {
+          for (int pair = lead + cx.warp - 1; pair < np; pair += cx.nwarps - 1)
+            chol_update_pairs_dmma<1>(M, L, K, a0, pair, cx.nwarps - 1, np, cx.lane);
+        }
       }
       CTA_SYNC();
     }
