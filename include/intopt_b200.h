@@ -108,7 +108,9 @@ size_t intopt_workspace_bytes(const IntoptProblem* p, int B);
  *   init_dev     optional warm start, B x (2n+m+2) in the `state` layout (init_val, :655-660), or NULL
  *   xhat_dev     out, B x n:  x / tau  (:1441)
  *   state_dev    out, B x (2n+m+2): x[n], y[m], t[n], tau, kappa — what forward saves for backward (:1463)
- *   status_dev, iters_dev  out, int32[B]
+ *   status_dev, iters_dev  out, int32[B]; status 0 ok, 1 max_iter reached, 2 infeasible / unbounded by the indicators
+ *                (:1409-1413), 3 factorisation breakdown that two retries with a raised diagonal did not cure (the
+ *                ladder of :798-822; the iterate is left unchanged, :855-857), 4 non-finite cost vector
  */
 int intopt_forward(const IntoptProblem* p, int B, const double* c_dev, long long c_stride,
                    const double* b_batch_dev, long long b_stride, const IntoptOpts* opts,
